@@ -1,0 +1,198 @@
+"""Torch-CPU restatement of hopwise's four KGE recommenders (oracle; test infrastructure only).
+
+One spec-driven class replaces the reference's four files.  It uses the same torch
+operators the reference calls, so on the CPU it reproduces the reference's fp32
+results (the golden fixtures under tests/golden pin that).
+
+Reference call sites followed (relative to /root/reference/hopwise/model/
+knowledge_graph_embedding_recommender/):
+  transe.py:36-53 (tables, TripletMarginLoss p=2), :55-57 (score), :59-98 (loss),
+      :100-126 (predict / full_sort_predict), :128-154 (kg twins)
+  distmult.py:32-48, :50-51, :53-95, :97-133, :110-146
+  rotate.py:36-59 (phase table re-initialised U(0, 2pi)), :61-69 (single L2 norm over
+      the stacked (re, im) residual), :98-131 (two BCE means), :133-190
+  complex.py:31-51, :53-62 (4th term uses tail_im, as written), :95-128, :130-190
+  ../init.py:13-29 (xavier_normal_ on every nn.Embedding)
+  ../abstract_recommender.py:204-223 (field names, n_users/n_items/n_entities/n_relations)
+Optimiser: torch.optim.Adam(lr, weight_decay) as built in trainer/trainer.py:189-190;
+step order as in trainer/trainer.py:243-265.
+"""
+
+from __future__ import annotations
+
+import math
+from dataclasses import dataclass
+
+import torch
+from torch import nn
+
+# table-name layout per model: (user parts, entity parts, relation parts).  Creation
+# order (users, entities, relations; re before im) is the reference's constructor
+# order, which fixes the RNG stream of the initialisation.
+TABLE_NAMES = {
+    "TransE": (["user_embedding"], ["entity_embedding"], ["relation_embedding"]),
+    "DistMult": (["user_embedding"], ["entity_embedding"], ["relation_embedding"]),
+    "RotatE": (
+        ["user_embedding", "user_embedding_im"],
+        ["entity_embedding", "entity_embedding_im"],
+        ["relation_embedding"],
+    ),
+    "ComplEx": (
+        ["user_re_embedding", "user_im_embedding"],
+        ["entity_re_embedding", "entity_im_embedding"],
+        ["relation_re_embedding", "relation_im_embedding"],
+    ),
+}
+
+
+@dataclass
+class Shapes:
+    n_users: int
+    n_items: int
+    n_entities: int
+    n_relations: int
+    embedding_size: int
+    margin: float = 1.0
+    ui_relation: int | None = None  # token id of [UI-Relation]; default = last row
+
+    def __post_init__(self):
+        if self.ui_relation is None:
+            self.ui_relation = self.n_relations - 1
+
+
+class OracleKGE(nn.Module):
+    """CPU oracle with the KnowledgeRecommender call surface (tensor-dict batches)."""
+
+    def __init__(self, model: str, shapes: Shapes):
+        super().__init__()
+        if model not in TABLE_NAMES:
+            raise ValueError(model)
+        self.model = model
+        self.shapes = shapes
+        d = shapes.embedding_size
+        unames, enames, rnames = TABLE_NAMES[model]
+        for n in unames:
+            setattr(self, n, nn.Embedding(shapes.n_users, d))
+        for n in enames:
+            setattr(self, n, nn.Embedding(shapes.n_entities, d))
+        for n in rnames:
+            setattr(self, n, nn.Embedding(shapes.n_relations, d))
+        for mod in self.modules():  # same traversal order as nn.Module.apply on children
+            if isinstance(mod, nn.Embedding):
+                nn.init.xavier_normal_(mod.weight.data)
+        if model == "RotatE":
+            nn.init.uniform_(self.relation_embedding.weight, 0, 2 * math.pi)
+        self._u = [getattr(self, n) for n in unames]
+        self._e = [getattr(self, n) for n in enames]
+        self._r = [getattr(self, n) for n in rnames]
+
+    # ---- relation row used for user->item triples -------------------------------------
+    def _ui_row(self, full_sort: bool) -> int:
+        # TransE / DistMult always take weight[-1]; RotatE always the token id; ComplEx the
+        # token id for loss/predict and weight[-1] for full_sort_predict.
+        if self.model in ("TransE", "DistMult"):
+            return self.shapes.n_relations - 1
+        if self.model == "ComplEx" and full_sort:
+            return self.shapes.n_relations - 1
+        return self.shapes.ui_relation
+
+    # ---- scorers (broadcast over leading dims; reduce the last) -----------------------
+    def score(self, h, r, t):
+        m = self.model
+        if m == "TransE":
+            return -torch.norm(h[0] + r[0] - t[0], p=2, dim=-1)
+        if m == "DistMult":
+            return (h[0] * r[0] * t[0]).sum(dim=-1)
+        if m == "RotatE":
+            c, s = torch.cos(r[0]), torch.sin(r[0])
+            re = (c * h[0] - s * h[1]) - t[0]
+            im = (c * h[1] + s * h[0]) - t[1]
+            both = torch.stack([re, im], dim=-1)
+            return self.shapes.margin - torch.linalg.vector_norm(both, dim=(-2, -1))
+        # ComplEx, with the reference's fourth term on tail_im
+        hr, hi = h
+        rr, ri = r
+        tr, ti = t
+        return (
+            (hr * rr * tr).sum(-1) + (hi * rr * ti).sum(-1) + (hr * ri * ti).sum(-1) - (hi * ri * ti).sum(-1)
+        )
+
+    def _rows(self, tabs, idx):
+        return [tab(idx) for tab in tabs]
+
+    # ---- training loss ----------------------------------------------------------------
+    def calculate_loss(self, batch: dict) -> torch.Tensor:
+        user, item, neg_item = batch["user_id"], batch["item_id"], batch["neg_item_id"]
+        head, rel = batch["head_id"], batch["relation_id"]
+        tail, neg_tail = batch["tail_id"], batch["neg_tail_id"]
+        ui = torch.full_like(user, self._ui_row(full_sort=False))
+
+        u = self._rows(self._u, user)
+        ur = self._rows(self._r, ui)
+        ip, ineg = self._rows(self._e, item), self._rows(self._e, neg_item)
+        h = self._rows(self._e, head)
+        kr = self._rows(self._r, rel)
+        tp, tn = self._rows(self._e, tail), self._rows(self._e, neg_tail)
+
+        if self.model == "TransE":
+            anchor = torch.cat([u[0] + ur[0], h[0] + kr[0]])
+            pos, neg = torch.cat([ip[0], tp[0]]), torch.cat([ineg[0], tn[0]])
+            return nn.functional.triplet_margin_loss(anchor, pos, neg, margin=self.shapes.margin, p=2)
+        if self.model == "DistMult":
+            cat = lambda a, b: [torch.cat([x, y]) for x, y in zip(a, b)]  # noqa: E731
+            hh, rr = cat(u, h), cat(ur, kr)
+            s_pos, s_neg = self.score(hh, rr, cat(ip, tp)), self.score(hh, rr, cat(ineg, tn))
+            return nn.functional.margin_ranking_loss(
+                s_pos, s_neg, torch.ones_like(s_pos), margin=self.shapes.margin
+            )
+        # RotatE / ComplEx: one BCE-with-logits mean per task, summed
+        total = 0
+        for hh, rr, p, n in ((u, ur, ip, ineg), (h, kr, tp, tn)):
+            sp, sn = self.score(hh, rr, p), self.score(hh, rr, n)
+            logits = torch.cat([sp, sn])
+            labels = torch.cat([torch.ones_like(sp), torch.zeros_like(sn)])
+            total = total + nn.functional.binary_cross_entropy_with_logits(logits, labels)
+        return total
+
+    # ---- inference ----------------------------------------------------------------------
+    def predict(self, batch: dict) -> torch.Tensor:
+        user, item = batch["user_id"], batch["item_id"]
+        ui = torch.full_like(user, self._ui_row(full_sort=False))
+        return self.score(self._rows(self._u, user), self._rows(self._r, ui), self._rows(self._e, item))
+
+    def predict_kg(self, batch: dict) -> torch.Tensor:
+        return self.score(
+            self._rows(self._e, batch["head_id"]),
+            self._rows(self._r, batch["relation_id"]),
+            self._rows(self._e, batch["tail_id"]),
+        )
+
+    def full_sort_predict(self, batch: dict) -> torch.Tensor:
+        user = batch["user_id"]
+        ui = torch.full_like(user, self._ui_row(full_sort=True))
+        items = torch.arange(self.shapes.n_items)
+        h = [x.unsqueeze(1) for x in self._rows(self._u, user)]
+        r = [x.unsqueeze(1) for x in self._rows(self._r, ui)]
+        t = [x.unsqueeze(0) for x in self._rows(self._e, items)]
+        return self.score(h, r, t)
+
+    def full_sort_predict_kg(self, batch: dict) -> torch.Tensor:
+        ents = torch.arange(self.shapes.n_entities)
+        h = [x.unsqueeze(1) for x in self._rows(self._e, batch["head_id"])]
+        r = [x.unsqueeze(1) for x in self._rows(self._r, batch["relation_id"])]
+        t = [x.unsqueeze(0) for x in self._rows(self._e, ents)]
+        return self.score(h, r, t)
+
+
+def make_optimizer(model: nn.Module, lr: float = 1e-3, weight_decay: float = 0.0):
+    return torch.optim.Adam(model.parameters(), lr=lr, weight_decay=weight_decay)
+
+
+def train_step(model: OracleKGE, opt, batch: dict) -> float:
+    """One optimisation step in the trainer's order (trainer.py:243-265)."""
+    opt.zero_grad()
+    loss = model.calculate_loss(batch)
+    value = loss.item()
+    loss.backward()
+    opt.step()
+    return value
