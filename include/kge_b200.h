@@ -1,0 +1,183 @@
+/*
+ * kge_b200.h -- C ABI of the B200-native KGE hot path (libkge_b200.so).
+ *
+ * Drop-in boundary for tail-unica/hopwise's knowledge-graph-embedding recommenders
+ * (TransE / DistMult / RotatE / ComplEx).  The reference has no FFI of its own (it is
+ * pure Python on torch); each entry point below names the reference Python interface it
+ * replaces (paths relative to /root/reference/hopwise/).  INTEGRATION.md shows the ctypes
+ * binding a hopwise maintainer would add.
+ *
+ * Conventions
+ *   - every pointer is DEVICE memory owned by the caller (torch tensors) unless a
+ *     parameter is documented "host"; the library allocates nothing persistent;
+ *   - all ids are int64 (torch.long), all embedding data fp32, row-major [rows, d];
+ *   - every call is asynchronous on the given cudaStream_t (passed as void*);
+ *   - return value: 0 = ok, >0 = cudaError_t, <0 = KGE_E_* argument error;
+ *     kge_last_error() gives a thread-local message.  No exceptions cross the ABI;
+ *   - re-entrant, no global state; one process per GPU.
+ */
+#ifndef KGE_B200_H
+#define KGE_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define KGE_ABI_VERSION 1
+
+typedef void* kge_stream_t; /* cudaStream_t */
+
+enum kge_model_kind { KGE_TRANSE = 0, KGE_DISTMULT = 1, KGE_ROTATE = 2, KGE_COMPLEX = 3 };
+
+enum kge_error {
+  KGE_E_ARG = -1,         /* null pointer / negative size */
+  KGE_E_UNSUPPORTED = -2, /* embedding_size or k outside the compiled range */
+  KGE_E_STATE = -3        /* optimiser state missing for a call that needs it */
+};
+
+/* One family of embedding tables (user / entity / relation): `parts` fp32 matrices
+ * [rows, d] (1 = real models, 2 = re/im) plus the row-lazy Adam state that rides with it.
+ * m, v, g, last_step, touch_step, uniq may be NULL for an inference-only model. */
+typedef struct {
+  int64_t rows;
+  int32_t parts;
+  int32_t _pad;
+  float* w[2];         /* parameters: nn.Embedding.weight.data_ptr() */
+  float* m[2];         /* Adam exp_avg */
+  float* v[2];         /* Adam exp_avg_sq */
+  float* g[2];         /* gradient accumulators; all-zero between steps (invariant) */
+  int32_t* last_step;  /* [rows] optimiser step the stored (w,m,v) are current for; -1 = never updated */
+  int32_t* touch_step; /* [rows] step whose unique-row list already holds the row */
+  int32_t* uniq;       /* [rows] rows touched by the step being accumulated */
+} kge_table_t;
+
+typedef struct {
+  int32_t model;                /* enum kge_model_kind */
+  int32_t d;                    /* embedding_size */
+  float margin;                 /* TransE / DistMult / RotatE */
+  int32_t ui_relation;          /* relation row for user->item triples in loss / predict
+                                   (transe.py:63, distmult.py:57: weight[-1]; rotate.py:43,
+                                   complex.py:38: the [UI-Relation] token id) */
+  int32_t ui_relation_fullsort; /* row used by full_sort_predict (complex.py:168-169 takes weight[-1]) */
+  int32_t _pad;
+  int64_t n_items;              /* items are entity rows [0, n_items) (kg_dataset.py:556-588) */
+  kge_table_t user, entity, relation;
+  int32_t* counters;            /* [8] unique-row counts: [parity*4 + {user,entity,relation}] */
+  const float* adam_table;      /* [2*adam_table_len]: {lr/(1-b1^j), 1/sqrt(1-b2^j)} for j = 0..len-1 */
+  int32_t adam_table_len;
+  int32_t _pad2;
+} kge_model_t;
+
+/* One training batch, the fields Interaction carries into calculate_loss
+ * (transe.py:75-87).  neg_* hold k negatives per positive in the reference's j-major
+ * layout out[j*n + i] (sampler.py:146-153); k = 1 is what the reference's loaders produce
+ * for KG triples (knowledge_dataloader.py:51). */
+typedef struct {
+  const int64_t* user;
+  const int64_t* item;
+  const int64_t* neg_item;
+  int64_t n_rec;
+  const int64_t* head;
+  const int64_t* relation;
+  const int64_t* tail;
+  const int64_t* neg_tail;
+  int64_t n_kg;
+  int32_t k_rec;
+  int32_t k_kg;
+} kge_batch_t;
+
+/* torch.optim.Adam hyper-parameters (trainer.py:189-190) + the step about to be applied. */
+typedef struct {
+  float lr, beta1, beta2, eps;
+  int32_t step;       /* 1-based index of the update this batch produces */
+  int32_t replay_cap; /* zero-gradient steps replayed exactly per row before the closed-form tail */
+} kge_adam_t;
+
+int kge_abi_version(void);
+const char* kge_last_error(void);
+
+/* host: fill `out[2*len]` with the Adam bias-correction table; returns the length needed
+ * for (beta1, beta2) when out == NULL. */
+int kge_adam_table_fill(float lr, float beta1, float beta2, float* out_host, int32_t len);
+
+/* ---- training ------------------------------------------------------------------------
+ * kge_train_forward: replaces <Model>.calculate_loss (transe.py:75-98, distmult.py:68-95,
+ * rotate.py:98-131, complex.py:95-128) AND the autograd backward of it
+ * (trainer.py:261): gathers rows (catching lazily-updated rows up to step-1 on the fly),
+ * scores, adds the scalar loss into *loss_out (caller zeroes it), and when with_grad != 0
+ * accumulates analytic gradients into table.g and records the touched rows. */
+int kge_train_forward(const kge_model_t* model, const kge_batch_t* batch, const kge_adam_t* adam,
+                      int with_grad, float* loss_out, kge_stream_t stream);
+
+/* kge_adam_apply: replaces optimizer.step() (trainer.py:264, torch.optim.Adam) for the rows
+ * touched by the accumulated gradient: replays the skipped zero-gradient steps of each row,
+ * applies step `adam->step` with gradient g*grad_scale, zeroes g.  Untouched rows are caught
+ * up later (next touch or kge_adam_flush), which is exactly dense Adam's trajectory. */
+int kge_adam_apply(const kge_model_t* model, const kge_adam_t* adam, float grad_scale, kge_stream_t stream);
+
+/* Bring every row of every table to step `adam->step` (dense pass).  Must run before
+ * weights are read by anything but this library (state_dict, predict, checkpoints). */
+int kge_adam_flush(const kge_model_t* model, const kge_adam_t* adam, kge_stream_t stream);
+
+/* Drop a gradient that was accumulated but will not be applied. */
+int kge_grad_discard(const kge_model_t* model, int32_t step, kge_stream_t stream);
+
+/* Row-sparse gradient exchange (replaces DDP's dense all-reduce, trainer.py:82-112).
+ * pack: copy this rank's touched rows of table `which` (0 user, 1 entity, 2 relation) into
+ *       ids_out[count] / rows_out[count, parts*d], zero them in g and clear their touch
+ *       marks; *count_out (device) receives the count.
+ * add:  add a (possibly remote) packed list into g and the unique-row list. */
+int kge_grad_pack(const kge_model_t* model, int32_t which, int32_t step, int64_t* ids_out, float* rows_out,
+                  int32_t* count_out, kge_stream_t stream);
+int kge_grad_add(const kge_model_t* model, int32_t which, int32_t step, const int64_t* ids, const float* rows,
+                 const int32_t* count_dev, int64_t max_count, kge_stream_t stream);
+
+/* ---- scoring --------------------------------------------------------------------------
+ * kge_predict: <Model>.predict / predict_kg (transe.py:100-110,128-137 and twins).
+ * heads index the user tables when head_is_user != 0, else the entity tables; rels == NULL
+ * means the user->item relation row. */
+int kge_predict(const kge_model_t* model, const int64_t* heads, const int64_t* rels, const int64_t* tails,
+                int64_t n, int head_is_user, float* out, kge_stream_t stream);
+
+/* kge_full_sort_scores: <Model>.full_sort_predict / full_sort_predict_kg
+ * (transe.py:112-126,139-154 and twins): out[n, n_targets] over entity rows [0, n_targets). */
+int kge_full_sort_scores(const kge_model_t* model, const int64_t* heads, const int64_t* rels, int64_t n,
+                         int head_is_user, int64_t n_targets, float* out, kge_stream_t stream);
+
+/* kge_full_sort_topk: fuses full_sort_predict + the trainer's masking
+ * (trainer.py:731-734: column 0 and history -> -inf) + torch.topk (collector.py:177) without
+ * materialising [n, n_targets].  History is CSR over the n query rows (hist_off[n+1],
+ * hist_items sorted ascending per row).  Order: score descending, id ascending.
+ * Outputs ids_out[n,k] (int64), scores_out[n,k] (fp32; -inf where fewer than k unmasked). */
+int kge_full_sort_topk(const kge_model_t* model, const int64_t* heads, const int64_t* rels, int64_t n,
+                       int head_is_user, int64_t n_targets, const int64_t* hist_off, const int64_t* hist_items,
+                       int32_t k, int64_t* ids_out, float* scores_out, kge_stream_t stream);
+
+/* kge_topk_hits: collector.py:178-183 without the [n, I] pos_matrix: out[n, k+1] int32 =
+ * hit flags of ids[n,k] against the positives CSR (pos_off[n+1], pos_items sorted) then pos_len. */
+int kge_topk_hits(const int64_t* ids, int64_t n, int32_t k, const int64_t* pos_off, const int64_t* pos_items,
+                  int32_t* out, kge_stream_t stream);
+
+/* kge_topk_metric_sums: metrics.py:67-69,93-101,164-165,191-207,231-232 summed over users:
+ * sums[5*k] float64 = per-cutoff sums of recall, mrr, ndcg, hit, precision (caller zeroes). */
+int kge_topk_metric_sums(const int32_t* rec_topk, int64_t n, int32_t k, double* sums, kge_stream_t stream);
+
+/* ---- negative sampling -------------------------------------------------------------------
+ * kge_sample_negatives: AbstractSampler.sample_by_key_ids with uniform sampling
+ * (sampler.py:140-183, 226-227, 315-316) on numpy's MT19937 stream, bit for bit.
+ * mt_state[625] (device): 624 key words + pos, read and advanced.  used_off[n_keys+1] /
+ * used_vals: CSR of sorted forbidden values per key.  out[n*num] int64, j-major.
+ * workspace: int32 scratch of kge_sample_workspace_bytes(n*num) bytes. */
+int64_t kge_sample_workspace_bytes(int64_t total);
+int kge_sample_negatives(uint32_t* mt_state, const int64_t* keys, int64_t n, int32_t num, const int64_t* used_off,
+                         const int64_t* used_vals, int64_t low, int64_t high, int64_t* out, void* workspace,
+                         kge_stream_t stream);
+/* np.random.seed(seed) (legacy init_genrand) into a device state. */
+int kge_mt19937_seed(uint32_t* mt_state, uint32_t seed, kge_stream_t stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* KGE_B200_H */
