@@ -1,0 +1,410 @@
+#!/usr/bin/env python
+"""Benchmark of the KGE hot path: KG triples/s of the fused train step (headline) plus users/s of
+the fused full-sort top-k, on synthetic KGs of BASELINE.json's shapes.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
+
+One JSON line on stdout (rank 0).  `value` = positive (rec + KG) triples per second over all
+ranks with the id tensors resident in HBM; `e2e` = the same step driven the way hopwise's trainer
+drives it, from pinned HOST id buffers: H2D of the 7 id arrays -> calculate_loss -> backward ->
+loss.item() (D2H) every step.  `roofline` follows SURVEY.md 8(d): algorithmic bytes per positive
+triple = 24*d*T*(2+K) + 8*(3+K), over the measured HBM peak.  `--impl reference` times the
+reference's own algorithm on the host cores (the torch-CPU oracle port: the same torch operators
+the reference's Python calls, dense autograd + dense torch.optim.Adam).
+"""
+
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+import torch
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+
+# ---- workloads ---------------------------------------------------------------
+WORKLOADS = {
+    # BASELINE.json configs[1]: TransE L2, synthetic ML-1M-small-shaped KG, d=100, 1 negative
+    "cfg2_transe_ml1m": dict(model="TransE", U=6041, I=3001, E=30001, R=22, d=100, k=1,
+                             n_rec=262144, n_kg=262144, triples=1_000_000, inters=1_000_000),
+    # the reference's default batch on the same KG (latency-bound: ~30 MB per step)
+    "cfg2_transe_ml1m_b2048": dict(model="TransE", U=6041, I=3001, E=30001, R=22, d=100, k=1,
+                                   n_rec=2048, n_kg=2048, triples=1_000_000, inters=1_000_000),
+    # BASELINE.json configs[4] shape on one GPU: tables far larger than L2 (no-duplicate regime)
+    "cfg5_transe_alibaba": dict(model="TransE", U=115001, I=30001, E=1000001, R=54, d=128, k=1,
+                                n_rec=262144, n_kg=262144, triples=50_000_000, inters=5_000_000),
+    # BASELINE.json configs[2]: RotatE d=256, 64 negatives per triple
+    "cfg3_rotate_yelp": dict(model="RotatE", U=45920, I=45539, E=90001, R=44, d=256, k=64,
+                             n_rec=2048, n_kg=2048, triples=1_800_000, inters=1_200_000),
+}
+FULLSORT = {
+    # BASELINE.json configs[3]: DistMult / ComplEx full-sort, 1M users x 200k items, top-20
+    "cfg4_distmult": dict(model="DistMult", U=1_000_001, I=200_001, E=200_001, R=3, d=64, k=20, hist=50),
+    "cfg4_complex": dict(model="ComplEx", U=1_000_001, I=200_001, E=200_001, R=3, d=64, k=20, hist=50),
+}
+PARTS = {"TransE": 1, "DistMult": 1, "RotatE": 2, "ComplEx": 2}
+
+
+def bytes_per_triple(model, d, k):
+    return 24 * d * PARTS[model] * (2 + k) + 8 * (3 + k)
+
+
+def measured_peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        p = json.load(open(path))
+        return dict(hbm_gbs=float(p["hbm_gbs"]), bf16_tflops=float(p["bf16_tflops"]), source="measured")
+    return dict(hbm_gbs=6650.0, bf16_tflops=1590.0, source="fallback")
+
+
+def synth_batches(w, n_batches, seed):
+    """Positive triples drawn from a fixed synthetic KG + uniform negatives (ids only)."""
+    rng = np.random.default_rng(seed)
+    out = []
+    for _ in range(n_batches):
+        out.append({
+            "user_id": rng.integers(1, w["U"], w["n_rec"]),
+            "item_id": rng.integers(1, w["I"], w["n_rec"]),
+            "neg_item_id": rng.integers(1, w["I"], w["n_rec"] * w["k"]),
+            "head_id": rng.integers(1, w["E"], w["n_kg"]),
+            "relation_id": rng.integers(1, w["R"] - 1, w["n_kg"]),
+            "tail_id": rng.integers(1, w["E"], w["n_kg"]),
+            "neg_tail_id": rng.integers(1, w["E"], w["n_kg"] * w["k"]),
+        })
+    return out
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons while the timed region runs."""
+
+    Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index, self.rows, self.proc = index, [], None
+
+    def __enter__(self):
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100", "-i",
+                 str(self.index)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._read, daemon=True)
+            self.thread.start()
+        except Exception:
+            self.proc = None
+        return self
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([x.strip() for x in line.split(",")])
+
+    def __exit__(self, *exc):
+        if self.proc is not None:
+            time.sleep(0.15)
+            self.proc.terminate()
+            try:
+                self.proc.wait(timeout=2)
+            except Exception:
+                self.proc.kill()
+
+    def summary(self):
+        sm, mx, reasons = [], 0, set()
+        names = ("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap")
+        for r in self.rows:
+            try:
+                sm.append(float(r[0]))
+                mx = max(mx, float(r[1]))
+                for n, v in zip(names, r[2:6]):
+                    if v.lower().startswith("active"):
+                        reasons.add(n)
+            except (ValueError, IndexError):
+                continue
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": mx or None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def make_model(w, device, seed=2024):
+    from kge_helpers import make_product_model
+
+    return make_product_model(w["model"], w["U"], w["I"], w["E"], w["R"], w["d"], device=device, seed=seed)
+
+
+def dist_info():
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    return rank, world, local
+
+
+def max_over_ranks(x, device, world):
+    if world == 1:
+        return x
+    import torch.distributed as dist
+
+    t = torch.tensor([x], dtype=torch.float64, device=device)
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    return float(t.item())
+
+
+def barrier(world):
+    if world > 1:
+        import torch.distributed as dist
+
+        dist.barrier()
+    torch.cuda.synchronize()
+
+
+# ---- timed legs -------------------------------------------------------------------------------
+def time_train_device(model, dev_batches, steps, warmup, flush_buf, world):
+    """K steps with ids resident in HBM; per-step CUDA events, L2 flushed (untimed) in between."""
+    nb = len(dev_batches)
+    for i in range(warmup):
+        model.calculate_loss(dev_batches[i % nb]).backward()
+    ev = [[torch.cuda.Event(enable_timing=True) for _ in range(3)] for _ in range(steps)]
+    barrier(world)
+    for i in range(steps):
+        if flush_buf is not None:
+            flush_buf.zero_()
+        b = dev_batches[(warmup + i) % nb]
+        ev[i][0].record()
+        loss = model.calculate_loss(b)
+        ev[i][1].record()
+        loss.backward()
+        ev[i][2].record()
+    barrier(world)
+    fwd = sum(e[0].elapsed_time(e[1]) for e in ev)
+    upd = sum(e[1].elapsed_time(e[2]) for e in ev)
+    return fwd, upd, float(loss.item())
+
+
+def time_train_e2e(model, host_batches, steps, warmup, world, device):
+    """The trainer's loop body from pinned host ids: H2D, loss, backward, loss.item() (D2H)."""
+    nb = len(host_batches)
+    stream = torch.cuda.current_stream()
+
+    def one(b):
+        db = {k: v.to(device, non_blocking=True) for k, v in b.items()}
+        loss = model.calculate_loss(db)
+        val = loss.item()   # trainer.py:259 -- the per-step device->host sync of the reference loop
+        loss.backward()
+        return val
+
+    for i in range(warmup):
+        one(host_batches[i % nb])
+    barrier(world)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record(stream)
+    for i in range(steps):
+        one(host_batches[(warmup + i) % nb])
+    e1.record(stream)
+    barrier(world)
+    return e0.elapsed_time(e1)
+
+
+def time_fullsort(fs, device, n_users_step, steps, warmup, world, rank):
+    """users/s of fused full-sort + mask + top-k on a block of users per step."""
+    from kge_helpers import make_product_model
+
+    m = make_product_model(fs["model"], fs["U"], fs["I"], fs["E"], fs["R"], fs["d"], device=device)
+    rng = np.random.default_rng(2024 + rank)
+    blocks = []
+    for _ in range(min(4, steps + warmup)):
+        users = torch.from_numpy(rng.integers(1, fs["U"], n_users_step)).to(device)
+        hist = np.sort(rng.integers(1, fs["I"], (n_users_step, fs["hist"])), axis=1)
+        off = torch.arange(0, fs["hist"] * n_users_step + 1, fs["hist"], dtype=torch.long, device=device)
+        blocks.append((users, off, torch.from_numpy(hist.reshape(-1)).to(device)))
+    for i in range(warmup):
+        u, o, h = blocks[i % len(blocks)]
+        m.full_sort_topk(u, fs["k"], o, h, return_scores=False)
+    barrier(world)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for i in range(steps):
+        u, o, h = blocks[(warmup + i) % len(blocks)]
+        ids, _ = m.full_sort_topk(u, fs["k"], o, h, return_scores=False)
+    e1.record()
+    barrier(world)
+    ms = e0.elapsed_time(e1)
+    del m
+    return ms
+
+
+def cpu_reference_steps(w, steps, warmup, budget_s=None, threads=None):
+    """The reference's train step on the host cores (torch-CPU oracle port): returns (triples/s,
+    steps timed, threads).  budget_s bounds the sample."""
+    from kge_helpers import make_oracle_model, to_cpu_batch
+    from oracle.kge_torch import make_optimizer, train_step
+
+    if threads:
+        torch.set_num_threads(threads)
+    ora = make_oracle_model(w["model"], w["U"], w["I"], w["E"], w["R"], w["d"])
+    opt = make_optimizer(ora)
+    from kge_helpers import tile_batch
+
+    batches = [to_cpu_batch(tile_batch(b, w["k"], w["k"])) for b in synth_batches(w, 2, 99)]
+    for i in range(warmup):
+        train_step(ora, opt, batches[i % 2])
+    t0 = time.perf_counter()
+    done = 0
+    for i in range(steps):
+        train_step(ora, opt, batches[i % 2])
+        done += 1
+        if budget_s is not None and time.perf_counter() - t0 > budget_s:
+            break
+    dt = time.perf_counter() - t0
+    return done * (w["n_rec"] + w["n_kg"]) / dt, done, torch.get_num_threads(), dt
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="cfg2_transe_ml1m", choices=sorted(WORKLOADS))
+    ap.add_argument("--no-extras", action="store_true", help="headline only (used under ncu)")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3)
+    rank, world, local = dist_info()
+    w = WORKLOADS[args.workload]
+    triples_step = w["n_rec"] + w["n_kg"]
+    config = {"workload": f"{args.workload}: {w['model']} d={w['d']} U={w['U']} I={w['I']} E={w['E']} R={w['R']} "
+                          f"K={w['k']} batch={w['n_rec']}rec+{w['n_kg']}kg positives/step/GPU, uniform synthetic KG, Adam lr=1e-3",
+              "parallelism": f"dp{world}" if world > 1 else "single",
+              "l2": "L2 flushed (256 MiB memset) between timed steps"}
+
+    if args.impl == "reference":
+        if rank != 0:
+            return
+        # bounded sample: one step is the full batch when it fits a few seconds, else a slice
+        wr = dict(w)
+        tps, done, threads, dt = cpu_reference_steps(wr, args.steps, min(args.warmup, 2), budget_s=150)
+        line = {"metric": "KG triples/sec (train step)", "value": tps, "unit": "triples/s", "n_gpus": args.gpus,
+                "steps": done, "warmup": min(args.warmup, 2), "ms_per_step": 1e3 * dt / done,
+                "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
+                "data": "synthetic", "impl": "reference", "config": config,
+                "cpu_baseline": {"value": tps, "unit": "triples/s", "cores": threads, "kind": "port",
+                                 "sample": f"{done} steps of the full {triples_step}-triple batch (torch CPU, dense Adam)"},
+                "e2e": {"value": tps, "unit": "triples/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+                "gpu_launches": 0}
+        print(json.dumps(line))
+        return
+
+    assert torch.cuda.is_available(), "bench.py --impl ours needs a CUDA device"
+    torch.cuda.set_device(local)
+    device = torch.device("cuda", local)
+    if world > 1:
+        import torch.distributed as dist
+
+        dist.init_process_group("nccl", device_id=device)
+    from hopwise_b200 import _abi
+
+    _abi.lib()
+    model = make_model(w, device)
+    exchange = None
+    if world > 1:
+        from hopwise_b200.distributed import broadcast_weights, enable_row_sparse_data_parallel
+
+        broadcast_weights(model)
+        exchange = enable_row_sparse_data_parallel(model)
+
+    n_batches = 4
+    host = synth_batches(w, n_batches, seed=2024 + rank)
+    host_t = [{k: torch.from_numpy(v).pin_memory() for k, v in b.items()} for b in host]
+    dev_t = [{k: v.to(device) for k, v in b.items()} for b in host_t]
+    flush_buf = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device=device)
+    h2d = sum(v.numel() * 8 for v in host_t[0].values())
+
+    with ClockSampler(local) as clocks:
+        fwd_ms, upd_ms, last_loss = time_train_device(model, dev_t, args.steps, args.warmup, flush_buf, world)
+    clk = clocks.summary()
+    step_ms = max_over_ranks((fwd_ms + upd_ms) / args.steps, device, world)
+    fwd_ms_avg = max_over_ranks(fwd_ms / args.steps, device, world)
+    upd_ms_avg = max_over_ranks(upd_ms / args.steps, device, world)
+    value = world * triples_step / (step_ms * 1e-3)
+
+    e2e_ms = time_train_e2e(model, host_t, args.steps, args.warmup, world, device)
+    e2e_ms = max_over_ranks(e2e_ms / args.steps, device, world)
+    e2e_value = world * triples_step / (e2e_ms * 1e-3)
+
+    peaks = measured_peaks()
+    bpt = bytes_per_triple(w["model"], w["d"], w["k"])
+    achieved = triples_step * bpt / (step_ms * 1e-3) / 1e9
+    roof = {"bound": "hbm", "achieved": achieved, "peak": peaks["hbm_gbs"], "unit": "GB/s",
+            "frac": achieved / peaks["hbm_gbs"], "traffic": None, "peak_source": peaks["source"],
+            "kernels": "train_fwd_kernel + adam_apply_kernel (the two launches of one step)",
+            "fwd_ms": fwd_ms_avg, "adam_ms": upd_ms_avg, "bytes_per_triple": bpt}
+
+    line = {"metric": "KG triples/sec (train step)", "value": value, "unit": "triples/s", "n_gpus": world,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": step_ms, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": config,
+            "e2e": {"value": e2e_value, "unit": "triples/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4,
+                    "ms_per_step": e2e_ms},
+            "gpu_launches": 2 * args.steps * (1 if world == 1 else 1) + (0 if world == 1 else 6 * args.steps),
+            "roofline": roof, "clocks": clk, "final_loss": last_loss}
+    if exchange is not None:
+        line["exchange_bytes_per_rank_per_step"] = exchange.bytes_per_step
+
+    if not args.no_extras:
+        extras = {}
+        # the reference's default batch on the same KG (launch/latency-bound)
+        if args.workload == "cfg2_transe_ml1m" and world == 1:
+            for name in ("cfg2_transe_ml1m_b2048", "cfg5_transe_alibaba", "cfg3_rotate_yelp"):
+                wx = WORKLOADS[name]
+                try:
+                    mx = make_model(wx, device)
+                    hb = synth_batches(wx, 4, seed=7)
+                    db = [{k: torch.from_numpy(v).to(device) for k, v in b.items()} for b in hb]
+                    f, u, _ = time_train_device(mx, db, args.steps, args.warmup, flush_buf, 1)
+                    ms = (f + u) / args.steps
+                    t = wx["n_rec"] + wx["n_kg"]
+                    bx = bytes_per_triple(wx["model"], wx["d"], wx["k"])
+                    extras[name] = {"triples_per_s": t / (ms * 1e-3), "ms_per_step": ms, "fwd_ms": f / args.steps,
+                                    "adam_ms": u / args.steps, "bytes_per_triple": bx,
+                                    "hbm_frac": t * bx / (ms * 1e-3) / 1e9 / peaks["hbm_gbs"]}
+                    del mx, db
+                    torch.cuda.empty_cache()
+                except Exception as exc:  # report, never hide
+                    extras[name] = {"error": repr(exc)}
+        # second headline metric: users/s of full-sort top-k (user blocks sharded across ranks)
+        for name, fs in FULLSORT.items():
+            try:
+                n_users_step = 32768
+                ms = time_fullsort(fs, device, n_users_step, max(3, args.steps // 4), 3, world, rank)
+                ms = max_over_ranks(ms / max(3, args.steps // 4), device, world)
+                ups = world * n_users_step / (ms * 1e-3)
+                flops = 2.0 * fs["I"] * fs["d"] * PARTS[fs["model"]]
+                extras[name] = {"metric": "users/sec (full-sort top-20)", "users_per_s": ups, "ms_per_block": ms,
+                                "users_per_block_per_gpu": n_users_step, "path": "cuda-core fp32 tile kernel",
+                                "algorithmic_tflops": ups * flops / 1e12,
+                                "tensor_frac_of_bf16_peak": ups / world * flops / 1e12 / peaks["bf16_tflops"]}
+                torch.cuda.empty_cache()
+            except Exception as exc:
+                extras[name] = {"error": repr(exc)}
+        line["extras"] = extras
+
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        tps, done, threads, dt = cpu_reference_steps(w, 1000, 1, budget_s=15)
+        line["cpu_baseline"] = {"value": tps, "unit": "triples/s", "cores": threads, "kind": "port",
+                                "sample": f"{done} steps of the full {triples_step}-triple batch in {dt:.1f}s "
+                                          "(torch CPU ops of the reference, dense autograd + dense Adam)"}
+    if rank == 0:
+        print(json.dumps(line))
+    if world > 1:
+        import torch.distributed as dist
+
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

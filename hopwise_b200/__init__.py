@@ -1,0 +1,13 @@
+"""hopwise_b200: B200-native (sm_100a) drop-in for hopwise's knowledge-graph-embedding hot path.
+
+Public surface (mirrors the reference names so a hopwise user can switch imports):
+  TransE, DistMult, RotatE, ComplEx      KnowledgeRecommender-compatible models (recommender.py)
+  KGSampler, RecSampler                  bit-exact GPU negative samplers (sampler.py)
+  FusedCollector, evaluate_full_sort     fused full-sort top-k evaluation (evaluator.py)
+  RowSparseDataParallel                  row-sparse gradient exchange over NCCL (distributed.py)
+"""
+
+from .recommender import ComplEx, DistMult, FusedKGEModel, KnowledgeRecommender, RotatE, TransE, MODELS  # noqa: F401
+
+__all__ = ["TransE", "DistMult", "RotatE", "ComplEx", "FusedKGEModel", "KnowledgeRecommender", "MODELS"]
+__version__ = "0.1.0"

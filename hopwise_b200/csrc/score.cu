@@ -1,0 +1,705 @@
+// Scoring side of the KGE hot path for sm_100a: predict, dense full-sort scores and the fused
+// full-sort + mask + per-user top-k, all on the CUDA cores in exact fp32.
+//
+// Replaces (paths under /root/reference/hopwise/):
+//   model/knowledge_graph_embedding_recommender/{transe.py:100-154, distmult.py:97-146,
+//   rotate.py:133-220, complex.py:130-219}         (predict / full_sort_predict and _kg twins)
+//   trainer/trainer.py:716-735                     (scores[:, 0] = -inf; scores[history] = -inf)
+//   evaluator/collector.py:176-177                 (torch.topk over [n, I])
+//
+// All four scorers are "transform the (head, relation) pair into one query vector q of
+// Kdim = parts*d floats, then reduce against the target row t":
+//   TransE   q = h + r                      score = -||q - t||
+//   RotatE   q = rot(h, theta) (re | im)    score = margin - ||q - t||   (one L2 norm, rotate.py:61-69)
+//   DistMult q = h * r                      score = q . t
+//   ComplEx  q = (hr*rr | hi*rr + hr*ri - hi*ri)   score = q . t        (complex.py:53-62 as written)
+// so one tile kernel serves them all: a CTA owns BU=32 query rows (q kept in shared memory for
+// the whole sweep) and streams target tiles of BT=128 rows through shared memory in K-chunks
+// of 32 floats; each thread accumulates a 4x4 register block.  The epilogue either stores
+// the dense [n, n_targets] scores (API parity: the unchanged trainer mutates that tensor) or
+// keeps a per-row sorted top-k list of 64-bit (score, ~id) keys in shared memory, so the dense
+// matrix never exists (800 GB at 1M x 200k).  Order: score descending, id ascending.
+#include <math.h>
+
+#include "common.cuh"
+
+namespace {
+
+constexpr int BU = 32;    // query rows per CTA
+constexpr int BT = 128;   // target rows per tile
+constexpr int KC = 32;    // K chunk (floats)
+constexpr int TS = KC + 4;  // padded row stride of the target tile: conflict-free LDS.128
+constexpr int TILE_THREADS = 256;
+constexpr int KMAX = 128;  // largest supported k
+
+__device__ __forceinline__ uint64_t make_key(float score, uint32_t id) {
+  uint32_t b = __float_as_uint(score);
+  b = (b & 0x80000000u) ? ~b : (b | 0x80000000u);  // order-preserving map of fp32 to uint32
+  return ((uint64_t)b << 32) | (uint64_t)(0xFFFFFFFFu - id);  // larger key = better (score desc, id asc)
+}
+__device__ __forceinline__ float key_score(uint64_t key) {
+  uint32_t b = (uint32_t)(key >> 32);
+  b = (b & 0x80000000u) ? (b & 0x7FFFFFFFu) : ~b;
+  return __uint_as_float(b);
+}
+__device__ __forceinline__ int64_t key_id(uint64_t key) { return (int64_t)(0xFFFFFFFFu - (uint32_t)key); }
+
+// Insert `c` into the descending list (capacity k) cooperatively by one warp.  `len` is warp-uniform.
+__device__ __forceinline__ void warp_insert(uint64_t* list, int& len, int k, uint64_t c, int lane) {
+  if (len == k && c <= list[k - 1]) return;
+  int pos = 0;
+  for (int base = 0; base < len; base += 32) {
+    const int i = base + lane;
+    const bool gt = (i < len) && (list[i] > c);
+    pos += __popc(__ballot_sync(0xffffffffu, gt));
+  }
+  const int newlen = len < k ? len + 1 : k;
+  uint64_t moved[KMAX / 32];
+#pragma unroll
+  for (int q = 0; q < KMAX / 32; ++q) {
+    const int i = q * 32 + lane;
+    moved[q] = (i > pos && i < newlen) ? list[i - 1] : 0ull;
+  }
+  __syncwarp();
+#pragma unroll
+  for (int q = 0; q < KMAX / 32; ++q) {
+    const int i = q * 32 + lane;
+    if (i > pos && i < newlen) list[i] = moved[q];
+  }
+  if (lane == 0) list[pos] = c;
+  len = newlen;
+  __syncwarp();
+}
+
+struct ScoreArgs {
+  kge_model_t m;
+  const int64_t* heads;
+  const int64_t* rels;   // NULL: the user->item relation row
+  const int64_t* tails;  // predict only
+  int64_t n;
+  int head_is_user;
+  int rel_row;  // row used when rels == NULL
+};
+
+// ---- predict: one lane group per (head, relation, tail) -------------------------------------
+template <int MODEL, int VEC, int G, int NCH>
+__global__ void __launch_bounds__(256) predict_kernel(const ScoreArgs a, float* __restrict__ out) {
+  constexpr int E = VEC * NCH;
+  constexpr int PH = (MODEL == KGE_ROTATE || MODEL == KGE_COMPLEX) ? 2 : 1;
+  constexpr int PR = (MODEL == KGE_COMPLEX) ? 2 : 1;
+  const int d = a.m.d;
+  const int gl = (threadIdx.x & 31) % G;
+  const int groups_per_cta = blockDim.x / G;
+  const int64_t n_groups = (int64_t)gridDim.x * groups_per_cta;
+  const kge_table_t& HT = a.head_is_user ? a.m.user : a.m.entity;
+  for (int64_t i = (int64_t)blockIdx.x * groups_per_cta + threadIdx.x / G; i < a.n; i += n_groups) {
+    const int64_t h_id = __ldg(a.heads + i);
+    const int64_t r_id = a.rels ? __ldg(a.rels + i) : (int64_t)a.rel_row;
+    const int64_t t_id = __ldg(a.tails + i);
+    float h[PH][E], r[PR][E], t[PH][E];
+#pragma unroll
+    for (int p = 0; p < PH; ++p) {
+      frag_load<VEC, G, NCH>(HT.w[p], h_id, d, gl, h[p]);
+      frag_load<VEC, G, NCH>(a.m.entity.w[p], t_id, d, gl, t[p]);
+    }
+#pragma unroll
+    for (int p = 0; p < PR; ++p) frag_load<VEC, G, NCH>(a.m.relation.w[p], r_id, d, gl, r[p]);
+    float s = 0.f;
+    if (MODEL == KGE_TRANSE) {
+#pragma unroll
+      for (int e = 0; e < E; ++e) {
+        const float x = h[0][e] + r[0][e] - t[0][e];
+        s += x * x;
+      }
+      s = -sqrtf(group_sum<G>(s));
+    } else if (MODEL == KGE_DISTMULT) {
+#pragma unroll
+      for (int e = 0; e < E; ++e) s += h[0][e] * r[0][e] * t[0][e];
+      s = group_sum<G>(s);
+    } else if (MODEL == KGE_ROTATE) {
+#pragma unroll
+      for (int e = 0; e < E; ++e) {
+        float sn, cs;
+        sincosf(r[0][e], &sn, &cs);
+        const float re = (cs * h[0][e] - sn * h[1][e]) - t[0][e];
+        const float im = (cs * h[1][e] + sn * h[0][e]) - t[1][e];
+        s += re * re + im * im;
+      }
+      s = a.m.margin - sqrtf(group_sum<G>(s));
+    } else {
+#pragma unroll
+      for (int e = 0; e < E; ++e) {
+        const float A_ = h[0][e] * r[0][e];
+        const float B_ = h[1][e] * r[0][e] + h[0][e] * r[1][e] - h[1][e] * r[1][e];
+        s += t[0][e] * A_ + t[1][e] * B_;
+      }
+      s = group_sum<G>(s);
+    }
+    if (gl == 0) out[i] = s;
+  }
+}
+
+// ---- the tile kernel ---------------------------------------------------------------------------
+struct TileArgs {
+  ScoreArgs s;
+  int64_t n_targets;
+  int kpad;            // padded floats per part = ceil(d / KC) * KC
+  int tiles_per_split; // target tiles handled by one blockIdx.y
+  // dense epilogue
+  float* out;
+  // top-k epilogue
+  const int64_t* hist_off;
+  const int64_t* hist_items;
+  int mask_first;
+  int k;
+  uint64_t* part_keys;  // [n, n_splits, k]
+  int n_splits;
+};
+
+__device__ __forceinline__ void build_queries(const ScoreArgs& a, int64_t row0, int nrows, int kpad, float* Qs) {
+  const int d = a.m.d;
+  const int model = a.m.model;
+  const int parts = (model == KGE_ROTATE || model == KGE_COMPLEX) ? 2 : 1;
+  const int qstride = parts * kpad;
+  const kge_table_t& HT = a.head_is_user ? a.m.user : a.m.entity;
+  for (int idx = threadIdx.x; idx < BU * kpad; idx += blockDim.x) {
+    const int u = idx / kpad, c = idx - u * kpad;
+    float q0 = 0.f, q1 = 0.f;
+    if (u < nrows && c < d) {
+      const int64_t h_id = __ldg(a.heads + row0 + u);
+      const int64_t r_id = a.rels ? __ldg(a.rels + row0 + u) : (int64_t)a.rel_row;
+      const float h0 = __ldg(HT.w[0] + h_id * d + c);
+      const float r0 = __ldg(a.m.relation.w[0] + r_id * d + c);
+      if (model == KGE_TRANSE) {
+        q0 = h0 + r0;
+      } else if (model == KGE_DISTMULT) {
+        q0 = h0 * r0;
+      } else if (model == KGE_ROTATE) {
+        const float h1 = __ldg(HT.w[1] + h_id * d + c);
+        float sn, cs;
+        sincosf(r0, &sn, &cs);
+        q0 = cs * h0 - sn * h1;
+        q1 = cs * h1 + sn * h0;
+      } else {
+        const float h1 = __ldg(HT.w[1] + h_id * d + c);
+        const float r1 = __ldg(a.m.relation.w[1] + r_id * d + c);
+        q0 = h0 * r0;
+        q1 = h1 * r0 + h0 * r1 - h1 * r1;
+      }
+    }
+    Qs[u * qstride + c] = q0;
+    if (parts == 2) Qs[u * qstride + kpad + c] = q1;
+  }
+}
+
+// Stage target rows [t0, t0+BT) x columns [c0, c0+KC) of one part into Ts (zero padded).
+__device__ __forceinline__ void load_target_chunk(const float* __restrict__ W, int d, int64_t n_targets, int64_t t0,
+                                                  int c0, float* Ts) {
+  if ((d & 3) == 0) {
+    // 8 float4 per row chunk; consecutive lanes take consecutive rows -> conflict-free STS.128
+    for (int idx = threadIdx.x; idx < BT * (KC / 4); idx += blockDim.x) {
+      const int q = idx / BT, j = idx - q * BT;
+      const int c = c0 + q * 4;
+      float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+      const int64_t t = t0 + j;
+      if (t < n_targets && c < d) v = __ldg(reinterpret_cast<const float4*>(W + t * d + c));
+      *reinterpret_cast<float4*>(Ts + j * TS + q * 4) = v;
+    }
+  } else {
+    for (int idx = threadIdx.x; idx < BT * KC; idx += blockDim.x) {
+      const int j = idx / KC, q = idx - j * KC;
+      const int c = c0 + q;
+      const int64_t t = t0 + j;
+      Ts[j * TS + q] = (t < n_targets && c < d) ? __ldg(W + t * d + c) : 0.f;
+    }
+  }
+}
+
+template <bool DIST, bool TOPK>
+__global__ void __launch_bounds__(TILE_THREADS) fullsort_tile_kernel(const TileArgs a) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  const int model = a.s.m.model;
+  const int parts = (model == KGE_ROTATE || model == KGE_COMPLEX) ? 2 : 1;
+  const int d = a.s.m.d;
+  const int kpad = a.kpad;
+  const int qstride = parts * kpad;
+  const int k = a.k;
+
+  float* Qs = reinterpret_cast<float*>(smem_raw);  // [BU][qstride]
+  float* Ts = Qs + BU * qstride;                   // [BT][TS]
+  // top-k only
+  uint64_t* lists = reinterpret_cast<uint64_t*>(Ts + BT * TS);  // [BU][k]
+  uint64_t* cand = lists + (TOPK ? BU * k : 0);                 // [BU][BT]
+  uint64_t* thr = cand + (TOPK ? BU * BT : 0);                  // [BU]
+  uint32_t* maskbits = reinterpret_cast<uint32_t*>(thr + (TOPK ? BU : 0));  // [BU][BT/32]
+  int* cnt = reinterpret_cast<int*>(maskbits + (TOPK ? BU * (BT / 32) : 0));  // [BU]
+  int* llen = cnt + (TOPK ? BU : 0);                                        // [BU]
+  int64_t* cursor = reinterpret_cast<int64_t*>(llen + (TOPK ? BU : 0));     // [BU] (8-byte aligned by layout)
+
+  const int64_t row0 = (int64_t)blockIdx.x * BU;
+  const int nrows = (int)min((int64_t)BU, a.s.n - row0);
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int tu = warp;  // users 4*tu .. 4*tu+3
+
+  const int64_t n_tiles = (a.n_targets + BT - 1) / BT;
+  const int64_t tile_lo = (int64_t)blockIdx.y * a.tiles_per_split;
+  const int64_t tile_hi = min(n_tiles, tile_lo + a.tiles_per_split);
+
+  build_queries(a.s, row0, nrows, kpad, Qs);
+  if (TOPK) {
+    for (int u = threadIdx.x; u < BU; u += blockDim.x) {
+      thr[u] = 0ull;
+      llen[u] = 0;
+      cnt[u] = 0;
+      int64_t cur = 0;
+      if (u < nrows && a.hist_off) {
+        // first history entry >= tile_lo * BT (history sorted ascending per row)
+        int64_t lo = a.hist_off[row0 + u], hi = a.hist_off[row0 + u + 1];
+        const int64_t first = tile_lo * BT;
+        while (lo < hi) {
+          const int64_t mid = (lo + hi) >> 1;
+          if (a.hist_items[mid] < first) lo = mid + 1; else hi = mid;
+        }
+        cur = lo;
+      }
+      cursor[u] = cur;
+    }
+  }
+  __syncthreads();
+
+  for (int64_t tile = tile_lo; tile < tile_hi; ++tile) {
+    const int64_t t0 = tile * BT;
+    float acc[4][4];
+#pragma unroll
+    for (int x = 0; x < 4; ++x)
+#pragma unroll
+      for (int y = 0; y < 4; ++y) acc[x][y] = 0.f;
+
+    if (TOPK) {
+      // history bits of this tile
+      for (int i = threadIdx.x; i < BU * (BT / 32); i += blockDim.x) maskbits[i] = 0u;
+      __syncthreads();
+      if (a.hist_off) {
+        for (int u = warp; u < nrows; u += TILE_THREADS / 32) {
+          const int64_t end = a.hist_off[row0 + u + 1];
+          int64_t cur = cursor[u];
+          const int64_t limit = t0 + BT;
+          while (true) {
+            const int64_t idx = cur + lane;
+            int64_t item = limit;
+            if (idx < end) item = a.hist_items[idx];
+            const bool in = item < limit;
+            if (in && item >= t0) {
+              const int off = (int)(item - t0);
+              atomicOr(&maskbits[u * (BT / 32) + (off >> 5)], 1u << (off & 31));
+            }
+            const unsigned b = __ballot_sync(0xffffffffu, in);
+            cur += __popc(b);
+            if (b != 0xffffffffu) break;
+          }
+          if (lane == 0) cursor[u] = cur;
+        }
+      }
+    }
+
+    for (int p = 0; p < parts; ++p) {
+      const float* W = a.s.m.entity.w[p];
+      for (int c0 = 0; c0 < kpad; c0 += KC) {
+        __syncthreads();  // previous chunk consumed
+        load_target_chunk(W, d, a.n_targets, t0, c0, Ts);
+        __syncthreads();
+        const float* qbase = Qs + (4 * tu) * qstride + p * kpad + c0;
+#pragma unroll
+        for (int kk = 0; kk < KC; kk += 4) {
+          float4 qv[4], tv[4];
+#pragma unroll
+          for (int x = 0; x < 4; ++x) qv[x] = *reinterpret_cast<const float4*>(qbase + x * qstride + kk);
+#pragma unroll
+          for (int y = 0; y < 4; ++y) tv[y] = *reinterpret_cast<const float4*>(Ts + (lane + 32 * y) * TS + kk);
+#pragma unroll
+          for (int x = 0; x < 4; ++x)
+#pragma unroll
+            for (int y = 0; y < 4; ++y) {
+              if (DIST) {
+                const float e0 = qv[x].x - tv[y].x, e1 = qv[x].y - tv[y].y;
+                const float e2 = qv[x].z - tv[y].z, e3 = qv[x].w - tv[y].w;
+                acc[x][y] = fmaf(e0, e0, acc[x][y]);
+                acc[x][y] = fmaf(e1, e1, acc[x][y]);
+                acc[x][y] = fmaf(e2, e2, acc[x][y]);
+                acc[x][y] = fmaf(e3, e3, acc[x][y]);
+              } else {
+                acc[x][y] = fmaf(qv[x].x, tv[y].x, acc[x][y]);
+                acc[x][y] = fmaf(qv[x].y, tv[y].y, acc[x][y]);
+                acc[x][y] = fmaf(qv[x].z, tv[y].z, acc[x][y]);
+                acc[x][y] = fmaf(qv[x].w, tv[y].w, acc[x][y]);
+              }
+            }
+        }
+      }
+    }
+
+    // ---- epilogue of this tile ------------------------------------------------------------
+    const float margin = (model == KGE_ROTATE) ? a.s.m.margin : 0.f;
+#pragma unroll
+    for (int x = 0; x < 4; ++x) {
+      const int u = 4 * tu + x;
+      if (u >= nrows) continue;
+#pragma unroll
+      for (int y = 0; y < 4; ++y) {
+        const int jo = lane + 32 * y;
+        const int64_t j = t0 + jo;
+        if (j >= a.n_targets) continue;
+        float sc = DIST ? (margin - sqrtf(acc[x][y])) : acc[x][y];
+        if (!TOPK) {
+          a.out[(row0 + u) * a.n_targets + j] = sc;
+        } else {
+          const bool masked = (a.mask_first && j == 0) || ((maskbits[u * (BT / 32) + (jo >> 5)] >> (jo & 31)) & 1u);
+          if (masked) sc = -INFINITY;
+          const uint64_t key = make_key(sc, (uint32_t)j);
+          if (key > thr[u]) {
+            const int slot = atomicAdd(&cnt[u], 1);
+            cand[u * BT + slot] = key;
+          }
+        }
+      }
+    }
+    if (TOPK) {
+      __syncthreads();
+      for (int u = warp; u < nrows; u += TILE_THREADS / 32) {
+        const int c = cnt[u];
+        if (c == 0) continue;
+        int len = llen[u];
+        uint64_t* list = lists + u * k;
+        for (int i = 0; i < c; ++i) warp_insert(list, len, k, cand[u * BT + i], lane);
+        if (lane == 0) {
+          llen[u] = len;
+          cnt[u] = 0;
+          thr[u] = (len == k) ? list[k - 1] : 0ull;
+        }
+      }
+      // the next tile's first __syncthreads orders these writes before its reads
+    }
+  }
+
+  if (TOPK) {
+    __syncthreads();
+    for (int idx = threadIdx.x; idx < nrows * k; idx += blockDim.x) {
+      const int u = idx / k, i = idx - u * k;
+      const uint64_t key = (i < llen[u]) ? lists[u * k + i] : 0ull;
+      a.part_keys[((row0 + u) * a.n_splits + blockIdx.y) * k + i] = key;
+    }
+  }
+}
+
+// Merge the per-split lists of one row (one warp per row) and decode.
+__global__ void __launch_bounds__(256) topk_merge_kernel(const uint64_t* __restrict__ part_keys, int64_t n,
+                                                         int n_splits, int k, int64_t* __restrict__ ids_out,
+                                                         float* __restrict__ scores_out) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  uint64_t* lists = reinterpret_cast<uint64_t*>(smem_raw);  // [warps][k]
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int64_t row = (int64_t)blockIdx.x * (blockDim.x >> 5) + warp;
+  if (row >= n) return;
+  uint64_t* list = lists + warp * k;
+  int len = 0;
+  const uint64_t* src = part_keys + row * (int64_t)n_splits * k;
+  if (n_splits == 1) {
+    for (int i = lane; i < k; i += 32) list[i] = src[i];
+    len = k;
+    __syncwarp();
+  } else {
+    for (int i = 0; i < n_splits * k; ++i) {
+      const uint64_t key = src[i];
+      if (key != 0ull) warp_insert(list, len, k, key, lane);
+    }
+    for (int i = len + lane; i < k; i += 32) list[i] = 0ull;
+    __syncwarp();
+  }
+  for (int i = lane; i < k; i += 32) {
+    const uint64_t key = list[i];
+    ids_out[row * k + i] = key ? key_id(key) : -1;
+    if (scores_out) scores_out[row * k + i] = key ? key_score(key) : -INFINITY;
+  }
+}
+
+// ---- collector.py:178-183 without the [n, I] matrix ---------------------------------------------
+__global__ void __launch_bounds__(256) topk_hits_kernel(const int64_t* __restrict__ ids, int64_t n, int k,
+                                                        const int64_t* __restrict__ pos_off,
+                                                        const int64_t* __restrict__ pos_items,
+                                                        int32_t* __restrict__ out) {
+  const int64_t total = n * (int64_t)(k + 1);
+  for (int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total;
+       idx += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t u = idx / (k + 1);
+    const int i = (int)(idx - u * (k + 1));
+    int64_t lo = pos_off[u], hi = pos_off[u + 1];
+    if (i == k) {
+      out[idx] = (int32_t)(hi - lo);
+      continue;
+    }
+    const int64_t id = ids[u * k + i];
+    int hit = 0;
+    while (lo < hi) {
+      const int64_t mid = (lo + hi) >> 1;
+      const int64_t v = pos_items[mid];
+      if (v == id) { hit = 1; break; }
+      if (v < id) lo = mid + 1; else hi = mid;
+    }
+    out[idx] = hit;
+  }
+}
+
+// ---- metrics.py summed over users ---------------------------------------------------------------
+// sums[5][k]: recall, mrr, ndcg, hit, precision (the order of overall.yaml's default metrics).
+__device__ __forceinline__ double warp_sum_f64(double x) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) x += __shfl_xor_sync(0xffffffffu, x, o);
+  return x;
+}
+
+__global__ void __launch_bounds__(256) topk_metric_sums_kernel(const int32_t* __restrict__ rec, int64_t n, int k,
+                                                               double* __restrict__ sums) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  double* acc = reinterpret_cast<double*>(smem_raw);  // [warps][5*k]
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, warps = blockDim.x >> 5;
+  for (int i = threadIdx.x; i < warps * 5 * k; i += blockDim.x) acc[i] = 0.0;
+  __syncthreads();
+  double* mine = acc + warp * 5 * k;
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t base = (int64_t)blockIdx.x * blockDim.x + warp * 32; base < n; base += stride) {
+    const int64_t u = base + lane;
+    const bool valid = u < n;
+    const int32_t* row = rec + (valid ? u : 0) * (int64_t)(k + 1);
+    const int pos_len = row[k];
+    const int ilen = pos_len < k ? pos_len : k;
+    int cum = 0, first = -1;
+    double dcg = 0.0, idcg = 0.0;
+    for (int j = 0; j < k; ++j) {
+      const int hit = row[j] != 0;
+      const double disc = 1.0 / log2((double)(j + 2));
+      if (hit) {
+        if (first < 0) first = j;
+        dcg += disc;
+      }
+      cum += hit;
+      if (j < ilen) idcg += disc;  // idcg freezes after min(pos_len, k) terms (metrics.py:191-207)
+      double v0 = (double)cum / (double)pos_len;
+      double v1 = first >= 0 ? 1.0 / (double)(first + 1) : 0.0;
+      double v2 = dcg / idcg;
+      double v3 = cum > 0 ? 1.0 : 0.0;
+      double v4 = (double)cum / (double)(j + 1);
+      if (!valid) v0 = v1 = v2 = v3 = v4 = 0.0;
+      v0 = warp_sum_f64(v0);
+      v1 = warp_sum_f64(v1);
+      v2 = warp_sum_f64(v2);
+      v3 = warp_sum_f64(v3);
+      v4 = warp_sum_f64(v4);
+      if (lane == 0) {
+        mine[0 * k + j] += v0;
+        mine[1 * k + j] += v1;
+        mine[2 * k + j] += v2;
+        mine[3 * k + j] += v3;
+        mine[4 * k + j] += v4;
+      }
+    }
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < 5 * k; i += blockDim.x) {
+    double t = 0.0;
+    for (int w = 0; w < warps; ++w) t += acc[w * 5 * k + i];
+    atomicAdd(&sums[i], t);
+  }
+}
+
+int check_score_model(const kge_model_t* m) {
+  KGE_REQUIRE(m, KGE_E_ARG, "model is NULL");
+  KGE_REQUIRE(m->model >= KGE_TRANSE && m->model <= KGE_COMPLEX, KGE_E_ARG, "unknown model kind %d", m->model);
+  const int ph = (m->model == KGE_ROTATE || m->model == KGE_COMPLEX) ? 2 : 1;
+  const int pr = (m->model == KGE_COMPLEX) ? 2 : 1;
+  for (int p = 0; p < ph; ++p) KGE_REQUIRE(m->user.w[p] && m->entity.w[p], KGE_E_ARG, "NULL weight table");
+  for (int p = 0; p < pr; ++p) KGE_REQUIRE(m->relation.w[p], KGE_E_ARG, "NULL relation table");
+  KGE_REQUIRE(m->d >= 1, KGE_E_UNSUPPORTED, "embedding_size %d unsupported", m->d);
+  return 0;
+}
+
+struct TilePlan {
+  int kpad, n_splits, tiles_per_split;
+  size_t smem;
+  int64_t n_blocks;
+};
+
+int plan_tiles(const kge_model_t* m, int64_t n, int64_t n_targets, int k, bool topk, TilePlan& pl) {
+  const int parts = (m->model == KGE_ROTATE || m->model == KGE_COMPLEX) ? 2 : 1;
+  pl.kpad = (m->d + KC - 1) / KC * KC;
+  size_t smem = (size_t)BU * parts * pl.kpad * 4 + (size_t)BT * TS * 4;
+  if (topk) smem += (size_t)BU * k * 8 + (size_t)BU * BT * 8 + BU * 8 + BU * (BT / 32) * 4 + BU * 4 * 2 + BU * 8;
+  pl.smem = smem;
+  KGE_REQUIRE(smem <= 220 * 1024, KGE_E_UNSUPPORTED, "embedding_size %d needs %zu bytes of shared memory", m->d, smem);
+  pl.n_blocks = (n + BU - 1) / BU;
+  const int64_t n_tiles = (n_targets + BT - 1) / BT;
+  int splits = 1;
+  if (topk) {
+    // enough CTAs for two waves at 2 CTAs/SM, but at least 8 tiles per split
+    const int64_t want = (int64_t)kge_num_sms() * 4;
+    int64_t s = (want + pl.n_blocks - 1) / pl.n_blocks;
+    const int64_t max_s = (n_tiles + 7) / 8;
+    if (s > max_s) s = max_s;
+    if (s < 1) s = 1;
+    if (s > 65535) s = 65535;
+    splits = (int)s;
+  }
+  pl.tiles_per_split = (int)((n_tiles + splits - 1) / splits);
+  pl.n_splits = (int)((n_tiles + pl.tiles_per_split - 1) / pl.tiles_per_split);
+  if (pl.n_splits < 1) pl.n_splits = 1;
+  return 0;
+}
+
+bool is_dist(int model) { return model == KGE_TRANSE || model == KGE_ROTATE; }
+
+}  // namespace
+
+extern "C" int kge_predict(const kge_model_t* model, const int64_t* heads, const int64_t* rels, const int64_t* tails,
+                           int64_t n, int head_is_user, float* out, kge_stream_t stream) {
+  if (int e = check_score_model(model)) return e;
+  KGE_REQUIRE(n >= 0, KGE_E_ARG, "negative n");
+  if (n == 0) return 0;
+  KGE_REQUIRE(heads && tails && out, KGE_E_ARG, "NULL heads / tails / out");
+  RowCfg c;
+  KGE_REQUIRE(kge_pick_rowcfg(model->d, c), KGE_E_UNSUPPORTED, "embedding_size %d unsupported", model->d);
+  ScoreArgs a;
+  a.m = *model;
+  a.heads = heads;
+  a.rels = rels;
+  a.tails = tails;
+  a.n = n;
+  a.head_is_user = head_is_user;
+  a.rel_row = model->ui_relation;
+  const int threads = 256;
+  int64_t g = (n + threads / c.g - 1) / (threads / c.g);
+  const int64_t cap = (int64_t)kge_num_sms() * 8;
+  const int grid = (int)(g < cap ? g : cap);
+  cudaStream_t st = (cudaStream_t)stream;
+#define CALL(V, G, N)                                                                          \
+  switch (model->model) {                                                                      \
+    case KGE_TRANSE: predict_kernel<KGE_TRANSE, V, G, N><<<grid, threads, 0, st>>>(a, out); break;     \
+    case KGE_DISTMULT: predict_kernel<KGE_DISTMULT, V, G, N><<<grid, threads, 0, st>>>(a, out); break; \
+    case KGE_ROTATE: predict_kernel<KGE_ROTATE, V, G, N><<<grid, threads, 0, st>>>(a, out); break;     \
+    default: predict_kernel<KGE_COMPLEX, V, G, N><<<grid, threads, 0, st>>>(a, out); break;            \
+  }
+  KGE_DISPATCH_ROWCFG(c, CALL);
+#undef CALL
+  KGE_LAUNCH_CHECK();
+  return 0;
+}
+
+template <bool DIST, bool TOPK>
+static int launch_tile(const TileArgs& a, const TilePlan& pl, cudaStream_t st) {
+  auto kern = fullsort_tile_kernel<DIST, TOPK>;
+  KGE_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pl.smem));
+  // blockIdx.x is limited to 2^31-1 rows/BU: fine for any table that fits the device
+  dim3 grid((unsigned)pl.n_blocks, (unsigned)pl.n_splits);
+  kern<<<grid, TILE_THREADS, pl.smem, st>>>(a);
+  KGE_LAUNCH_CHECK();
+  return 0;
+}
+
+extern "C" int kge_full_sort_scores(const kge_model_t* model, const int64_t* heads, const int64_t* rels, int64_t n,
+                                    int head_is_user, int64_t n_targets, float* out, kge_stream_t stream) {
+  if (int e = check_score_model(model)) return e;
+  KGE_REQUIRE(n >= 0 && n_targets >= 1 && n_targets <= model->entity.rows, KGE_E_ARG, "bad n / n_targets");
+  if (n == 0) return 0;
+  KGE_REQUIRE(heads && out, KGE_E_ARG, "NULL heads / out");
+  TilePlan pl;
+  if (int e = plan_tiles(model, n, n_targets, 0, false, pl)) return e;
+  TileArgs a = {};
+  a.s.m = *model;
+  a.s.heads = heads;
+  a.s.rels = rels;
+  a.s.tails = nullptr;
+  a.s.n = n;
+  a.s.head_is_user = head_is_user;
+  a.s.rel_row = model->ui_relation_fullsort;
+  a.n_targets = n_targets;
+  a.kpad = pl.kpad;
+  a.tiles_per_split = pl.tiles_per_split;
+  a.out = out;
+  a.n_splits = 1;
+  return is_dist(model->model) ? launch_tile<true, false>(a, pl, (cudaStream_t)stream)
+                               : launch_tile<false, false>(a, pl, (cudaStream_t)stream);
+}
+
+extern "C" int64_t kge_full_sort_topk_workspace_bytes(const kge_model_t* model, int64_t n, int64_t n_targets,
+                                                      int32_t k) {
+  if (!model || n < 0 || n_targets < 1 || k < 1 || k > KMAX) return -1;
+  TilePlan pl;
+  if (plan_tiles(model, n > 0 ? n : 1, n_targets, k, true, pl)) return -1;
+  return (int64_t)n * pl.n_splits * k * 8;
+}
+
+extern "C" int kge_full_sort_topk(const kge_model_t* model, const int64_t* heads, const int64_t* rels, int64_t n,
+                                  int head_is_user, int64_t n_targets, const int64_t* hist_off,
+                                  const int64_t* hist_items, int mask_first, int32_t k, int64_t* ids_out,
+                                  float* scores_out, void* workspace, int64_t workspace_bytes, kge_stream_t stream) {
+  if (int e = check_score_model(model)) return e;
+  KGE_REQUIRE(n >= 0 && n_targets >= 1 && n_targets <= model->entity.rows, KGE_E_ARG, "bad n / n_targets");
+  KGE_REQUIRE(k >= 1 && k <= KMAX, KGE_E_UNSUPPORTED, "k=%d outside [1, %d]", k, KMAX);
+  KGE_REQUIRE(k <= n_targets, KGE_E_ARG, "k=%d larger than the number of targets", k);
+  KGE_REQUIRE(n_targets < 0xFFFFFFFFll, KGE_E_UNSUPPORTED, "more than 2^32-2 targets");
+  if (n == 0) return 0;
+  KGE_REQUIRE(heads && ids_out, KGE_E_ARG, "NULL heads / ids_out");
+  KGE_REQUIRE((hist_off == nullptr) == (hist_items == nullptr) || hist_off, KGE_E_ARG, "hist_items without hist_off");
+  TilePlan pl;
+  if (int e = plan_tiles(model, n, n_targets, k, true, pl)) return e;
+  const int64_t need = n * pl.n_splits * k * 8;
+  KGE_REQUIRE(workspace && workspace_bytes >= need, KGE_E_ARG, "workspace too small: need %lld bytes", (long long)need);
+  TileArgs a = {};
+  a.s.m = *model;
+  a.s.heads = heads;
+  a.s.rels = rels;
+  a.s.tails = nullptr;
+  a.s.n = n;
+  a.s.head_is_user = head_is_user;
+  a.s.rel_row = model->ui_relation_fullsort;
+  a.n_targets = n_targets;
+  a.kpad = pl.kpad;
+  a.tiles_per_split = pl.tiles_per_split;
+  a.hist_off = hist_off;
+  a.hist_items = hist_items;
+  a.mask_first = mask_first;
+  a.k = k;
+  a.part_keys = reinterpret_cast<uint64_t*>(workspace);
+  a.n_splits = pl.n_splits;
+  cudaStream_t st = (cudaStream_t)stream;
+  if (int e = is_dist(model->model) ? launch_tile<true, true>(a, pl, st) : launch_tile<false, true>(a, pl, st)) return e;
+  const int warps = 8;
+  const int64_t mg = (n + warps - 1) / warps;
+  topk_merge_kernel<<<(unsigned)mg, warps * 32, (size_t)warps * k * 8, st>>>(a.part_keys, n, pl.n_splits, k, ids_out,
+                                                                            scores_out);
+  KGE_LAUNCH_CHECK();
+  return 0;
+}
+
+extern "C" int kge_topk_hits(const int64_t* ids, int64_t n, int32_t k, const int64_t* pos_off, const int64_t* pos_items,
+                             int32_t* out, kge_stream_t stream) {
+  KGE_REQUIRE(n >= 0 && k >= 1, KGE_E_ARG, "bad n / k");
+  if (n == 0) return 0;
+  KGE_REQUIRE(ids && pos_off && pos_items && out, KGE_E_ARG, "NULL argument");
+  const int64_t total = n * (int64_t)(k + 1);
+  int64_t g = (total + 255) / 256;
+  const int64_t cap = (int64_t)kge_num_sms() * 8;
+  topk_hits_kernel<<<(unsigned)(g < cap ? g : cap), 256, 0, (cudaStream_t)stream>>>(ids, n, k, pos_off, pos_items, out);
+  KGE_LAUNCH_CHECK();
+  return 0;
+}
+
+extern "C" int kge_topk_metric_sums(const int32_t* rec_topk, int64_t n, int32_t k, double* sums, kge_stream_t stream) {
+  KGE_REQUIRE(n >= 0 && k >= 1 && k <= 128, KGE_E_ARG, "bad n / k");
+  if (n == 0) return 0;
+  KGE_REQUIRE(rec_topk && sums, KGE_E_ARG, "NULL argument");
+  int64_t g = (n + 255) / 256;
+  const int64_t cap = (int64_t)kge_num_sms() * 4;
+  topk_metric_sums_kernel<<<(unsigned)(g < cap ? g : cap), 256, (size_t)8 * 5 * k * 8, (cudaStream_t)stream>>>(rec_topk, n, k,
+                                                                                                         sums);
+  KGE_LAUNCH_CHECK();
+  return 0;
+}

@@ -469,6 +469,7 @@ struct ApplyArgs {
   kge_model_t m;
   AdamDev adam;
   float scale;
+  const float* scale_dev;  // optional device-side factor (the incoming grad of the loss)
 };
 
 template <int VEC, int G, int NCH>
@@ -499,6 +500,7 @@ __device__ __forceinline__ void adam_row(const kge_table_t& T, int64_t row, int 
     frag_store<VEC, G, NCH>(T.v[part], row, d, gl, v);
     frag_store<VEC, G, NCH>(T.g[part], row, d, gl, z);
   }
+  __syncwarp(group_mask<G>());  // every lane has read last_step
   if (gl == 0) T.last_step[row] = A.step;
 }
 
@@ -510,10 +512,11 @@ __global__ void __launch_bounds__(256) adam_apply_kernel(const ApplyArgs a) {
   const int32_t* cnt = a.m.counters + (a.adam.step & 1) * 4;
   const int64_t cu = cnt[0], ce = cnt[1], cr = cnt[2];
   const int64_t total = cu + ce + cr;
+  const float scale = a.scale_dev ? a.scale * __ldg(a.scale_dev) : a.scale;
   for (int64_t idx = (int64_t)blockIdx.x * groups_per_cta + threadIdx.x / G; idx < total; idx += n_groups) {
-    if (idx < cu) adam_row<VEC, G, NCH>(a.m.user, a.m.user.uniq[idx], a.m.d, gl, a.adam, a.scale);
-    else if (idx < cu + ce) adam_row<VEC, G, NCH>(a.m.entity, a.m.entity.uniq[idx - cu], a.m.d, gl, a.adam, a.scale);
-    else adam_row<VEC, G, NCH>(a.m.relation, a.m.relation.uniq[idx - cu - ce], a.m.d, gl, a.adam, a.scale);
+    if (idx < cu) adam_row<VEC, G, NCH>(a.m.user, a.m.user.uniq[idx], a.m.d, gl, a.adam, scale);
+    else if (idx < cu + ce) adam_row<VEC, G, NCH>(a.m.entity, a.m.entity.uniq[idx - cu], a.m.d, gl, a.adam, scale);
+    else adam_row<VEC, G, NCH>(a.m.relation, a.m.relation.uniq[idx - cu - ce], a.m.d, gl, a.adam, scale);
   }
   // hand the next step a zeroed set of counters (the other parity)
   if (blockIdx.x == 0 && threadIdx.x < 4) a.m.counters[((a.adam.step + 1) & 1) * 4 + threadIdx.x] = 0;
@@ -707,13 +710,14 @@ extern "C" int kge_train_forward(const kge_model_t* model, const kge_batch_t* b,
 }
 
 extern "C" int kge_adam_apply(const kge_model_t* model, const kge_adam_t* adam, float grad_scale,
-                              kge_stream_t stream) {
+                              const float* grad_scale_dev, kge_stream_t stream) {
   if (int e = check_model(model, true)) return e;
   KGE_REQUIRE(adam && adam->step >= 1, KGE_E_ARG, "bad adam");
   ApplyArgs a;
   a.m = *model;
   a.adam = make_adam_dev(model, adam);
   a.scale = grad_scale;
+  a.scale_dev = grad_scale_dev;
   RowCfg c;
   kge_pick_rowcfg(model->d, c);
   const int threads = 256;

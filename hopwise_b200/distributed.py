@@ -1,0 +1,150 @@
+"""Data parallelism for the fused KGE path: row-sparse gradient exchange and user-block sharding.
+
+What it replaces (paths under /root/reference/hopwise/):
+  trainer/trainer.py:82-112    DistributedDataParallel wrap + set_reduce_hook / sync_grad_loss:
+                               a dense all-reduce (mean) of every embedding table each step
+  trainer/trainer.py:592-609   _map_reduce: all_gather of per-rank metric means
+  data/dataloader/abstract_dataloader.py:59-64   per-rank DistributedSampler shards
+
+One process per GPU (torch.distributed, NCCL over NVLink).  Tables and Adam state are
+replicated.  Per step every rank packs the rows its batch touched (ids + gradient rows) into one
+flat buffer, a single all-gather moves the buffers, and every rank adds all lists -- its own
+included -- into its (zeroed) gradient accumulators in rank order, then applies Adam with the
+gradient scaled by 1/world_size (DDP's mean).  The adds see the same values in the same
+order on every rank, so the replicas stay bit-identical without ever moving a dense table.
+Bytes per rank per step: sum over tables of min(rows, touched) * (8 + parts*d*4), instead of
+4 bytes * every parameter.
+"""
+
+from __future__ import annotations
+
+import ctypes as C
+
+import torch
+import torch.distributed as dist
+
+from . import _abi
+
+FAMILIES = ("user", "entity", "relation")
+
+
+def shard_bounds(n: int, rank: int, world: int):
+    """Contiguous block [lo, hi) of `n` units for `rank`; sizes differ by at most one."""
+    base, rem = divmod(n, world)
+    lo = rank * base + min(rank, rem)
+    return lo, lo + base + (1 if rank < rem else 0)
+
+
+class FlatLayout:
+    """Byte layout of one rank's packed gradient message: per table
+    [count int32 (padded to 8 B) | ids int64[cap] | rows fp32[cap, parts*d]]."""
+
+    def __init__(self, caps, parts, d):
+        self.caps, self.parts, self.d = list(caps), list(parts), int(d)
+        self.offsets = []
+        off = 0
+        for cap, p in zip(self.caps, self.parts):
+            cnt = off
+            ids = cnt + 8
+            rows = ids + 8 * cap
+            off = rows + 4 * cap * p * self.d
+            off = (off + 15) // 16 * 16
+            self.offsets.append((cnt, ids, rows))
+        self.nbytes = off
+
+    def views(self, buf: torch.Tensor, which: int):
+        """(count int32[1], ids int64[cap], rows fp32[cap, parts*d]) views into a uint8 buffer."""
+        cnt, ids, rows = self.offsets[which]
+        cap, p = self.caps[which], self.parts[which]
+        return (
+            buf[cnt : cnt + 4].view(torch.int32),
+            buf[ids : ids + 8 * cap].view(torch.int64),
+            buf[rows : rows + 4 * cap * p * self.d].view(torch.float32).view(cap, p * self.d),
+        )
+
+
+def _cuda_pack(model, which, step, count, ids, rows):
+    m = model._model_struct(True)
+    _abi.check(
+        _abi.lib().kge_grad_pack(C.byref(m), which, step, ids.data_ptr(), rows.data_ptr(), count.data_ptr(),
+                                 _abi.stream_ptr()),
+        "kge_grad_pack",
+    )
+
+
+def _cuda_add(model, which, step, count, ids, rows):
+    m = model._model_struct(True)
+    _abi.check(
+        _abi.lib().kge_grad_add(C.byref(m), which, step, ids.data_ptr(), rows.data_ptr(), count.data_ptr(),
+                                ids.numel(), _abi.stream_ptr()),
+        "kge_grad_add",
+    )
+
+
+class RowSparseExchange:
+    """Callable installed as ``model._grad_sync``; runs between the forward/gradient kernel and
+    the Adam kernel of every step."""
+
+    def __init__(self, model, group=None, pack_fn=_cuda_pack, add_fn=_cuda_add, device=None):
+        self.group = group
+        self.world = dist.get_world_size(group)
+        self.rank = dist.get_rank(group)
+        self.pack_fn, self.add_fn = pack_fn, add_fn
+        rows = (model.n_users, model.n_entities, model.n_relations)
+        parts = (len(model.USER_TABLES), len(model.ENTITY_TABLES), len(model.RELATION_TABLES))
+        # a step cannot touch more distinct rows than the table has
+        self.layout = FlatLayout(rows, parts, model.embedding_size)
+        self._caps_for = None
+        self.device = device
+        self.send = self.recv = None
+        self.bytes_per_step = 0
+
+    def _plan(self, model, batch_rows):
+        """Tighten the per-table capacity to what this batch shape can touch."""
+        rows = (model.n_users, model.n_entities, model.n_relations)
+        parts = self.layout.parts
+        caps = [max(1, min(r, b)) for r, b in zip(rows, batch_rows)]
+        if self.send is None or caps != self.layout.caps:
+            self.layout = FlatLayout(caps, parts, model.embedding_size)
+            device = self.device or next(model.parameters()).device
+            self.send = torch.zeros(self.layout.nbytes, dtype=torch.uint8, device=device)
+            self.recv = torch.zeros(self.world * self.layout.nbytes, dtype=torch.uint8, device=device)
+            self.bytes_per_step = self.layout.nbytes
+
+    def __call__(self, model):
+        step = model._step + 1
+        self._plan(model, model._touch_bounds)
+        for which in range(3):
+            count, ids, rows = self.layout.views(self.send, which)
+            self.pack_fn(model, which, step, count, ids, rows)
+        dist.all_gather_into_tensor(self.recv, self.send, group=self.group)
+        n = self.layout.nbytes
+        for r in range(self.world):  # fixed order on every rank => identical fp32 sums
+            chunk = self.recv[r * n : (r + 1) * n]
+            for which in range(3):
+                count, ids, rows = self.layout.views(chunk, which)
+                self.add_fn(model, which, step, count, ids, rows)
+
+
+def enable_row_sparse_data_parallel(model, group=None):
+    """Turn a FusedKGEModel replica into a data-parallel one (call once, after model.to(device),
+    on every rank, with identical initial weights: the reference gets that from DDP's rank-0
+    broadcast, here `broadcast_weights` does it)."""
+    ex = RowSparseExchange(model, group=group)
+    model._grad_sync = ex
+    model._grad_scale = 1.0 / ex.world
+    return ex
+
+
+def broadcast_weights(model, src: int = 0, group=None):
+    for p in model.parameters():
+        dist.broadcast(p.data, src=src, group=group)
+
+
+def reduce_metric_sums(sums: torch.Tensor, n_users: int, group=None):
+    """Exact global metric means from per-rank sums (the reference all-gathers rounded per-rank
+    means weighted by a batch count, trainer.py:592-609; this is the unrounded global mean)."""
+    buf = torch.cat([sums.reshape(-1).to(torch.float64), torch.tensor([float(n_users)], dtype=torch.float64,
+                                                                       device=sums.device)])
+    dist.all_reduce(buf, op=dist.ReduceOp.SUM, group=group)
+    return buf[:-1].reshape(sums.shape), int(round(buf[-1].item()))

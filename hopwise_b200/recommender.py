@@ -1,0 +1,562 @@
+"""KnowledgeRecommender-compatible TransE / DistMult / RotatE / ComplEx on the fused CUDA path.
+
+Host-side mirror of hopwise's model API (paths under /root/reference/hopwise/):
+  model/abstract_recommender.py:36-108, 197-223   AbstractRecommender / KnowledgeRecommender
+  model/knowledge_graph_embedding_recommender/transe.py:22-154, distmult.py:22-146,
+      rotate.py:24-220, complex.py:22-219          (constructor, calculate_loss, predict,
+                                                    full_sort_predict and the _kg twins)
+  model/init.py:13-29                              xavier_normal_ on every nn.Embedding
+  trainer/trainer.py:165-206, 243-265              optimiser choice and the step loop
+
+Same class names, constructor signature ``(config, dataset)``, attribute names and
+``state_dict`` keys as the reference, so the unchanged ``KGTrainer`` drives these models:
+
+  optimizer.zero_grad(); loss = model.calculate_loss(batch); loss.backward(); optimizer.step()
+
+What differs underneath: ``calculate_loss`` launches one kernel that gathers the rows, scores,
+accumulates the scalar loss and scatters analytic gradients; ``loss.backward()`` launches the
+exact row-lazy Adam on the touched rows (scaled by the incoming grad).  The embedding
+parameters never receive a ``.grad``, so the trainer's ``torch.optim.Adam.step()`` is a no-op
+by construction.  Rows a step did not touch are caught up lazily (dense Adam keeps moving a row
+after its last gradient); ``flush()`` brings every row up to date and runs automatically before
+the weights are read (``state_dict``, ``eval``, ``predict*``).
+
+All compute goes through the C ABI in include/kge_b200.h.  There is no CPU fallback: calling a
+compute method on CPU tensors raises.
+"""
+
+from __future__ import annotations
+
+import ctypes as C
+import enum
+import math
+
+import torch
+from torch import nn
+
+from . import _abi
+
+try:  # use hopwise's own enums when it is importable so Config(model=cls) accepts the classes
+    from hopwise.utils import InputType, ModelType  # type: ignore
+except Exception:  # pragma: no cover - exercised on boxes without hopwise
+
+    class ModelType(enum.Enum):
+        GENERAL = 1
+        SEQUENTIAL = 2
+        CONTEXT = 3
+        KNOWLEDGE = 4
+        TRADITIONAL = 5
+        DECISIONTREE = 6
+
+    class InputType(enum.Enum):
+        POINTWISE = 1
+        PAIRWISE = 2
+        LISTWISE = 3
+
+
+def _cfg_get(config, key, default=None):
+    try:
+        if key in config:
+            return config[key]
+    except TypeError:
+        pass
+    try:
+        v = config[key]
+        return default if v is None else v
+    except (KeyError, AttributeError):
+        return default
+
+
+class KnowledgeRecommender(nn.Module):
+    """Field names and entity counts, as abstract_recommender.py:197-223."""
+
+    type = ModelType.KNOWLEDGE
+
+    def __init__(self, config, dataset):
+        super().__init__()
+        self.USER_ID = config["USER_ID_FIELD"]
+        self.ITEM_ID = config["ITEM_ID_FIELD"]
+        self.NEG_ITEM_ID = config["NEG_PREFIX"] + self.ITEM_ID
+        self.ENTITY_ID = config["ENTITY_ID_FIELD"]
+        self.RELATION_ID = config["RELATION_ID_FIELD"]
+        self.HEAD_ENTITY_ID = config["HEAD_ENTITY_ID_FIELD"]
+        self.TAIL_ENTITY_ID = config["TAIL_ENTITY_ID_FIELD"]
+        self.NEG_TAIL_ENTITY_ID = config["NEG_PREFIX"] + self.TAIL_ENTITY_ID
+        self.n_users = dataset.num(self.USER_ID)
+        self.n_items = dataset.num(self.ITEM_ID)
+        self.n_entities = dataset.num(self.ENTITY_ID)
+        self.n_relations = dataset.num(self.RELATION_ID)
+        self.device = config["device"]
+
+    # abstract_recommender.py:93-102
+    def other_parameter(self):
+        if hasattr(self, "other_parameter_name"):
+            return {key: getattr(self, key) for key in self.other_parameter_name}
+        return dict()
+
+    def load_other_parameter(self, para):
+        if para is None:
+            return
+        for key, value in para.items():
+            setattr(self, key, value)
+
+    def __str__(self):
+        params = sum(p.numel() for p in self.parameters() if p.requires_grad)
+        return super().__str__() + f"\nTrainable parameters: {params}"
+
+
+class _FusedStep(torch.autograd.Function):
+    """loss = forward kernel; backward = Adam on the touched rows, scaled by grad_output."""
+
+    @staticmethod
+    def forward(ctx, anchor, model, batch):
+        ctx.model = model
+        return model._launch_forward(batch, with_grad=True)
+
+    @staticmethod
+    def backward(ctx, grad_out):
+        ctx.model._launch_apply(grad_out)
+        return torch.zeros_like(grad_out).reshape(1), None, None
+
+
+class FusedKGEModel(KnowledgeRecommender):
+    """Shared machinery; the four public classes only name their tables."""
+
+    input_type = InputType.PAIRWISE
+    KIND: str = ""
+    USER_TABLES: tuple = ()
+    ENTITY_TABLES: tuple = ()
+    RELATION_TABLES: tuple = ()
+    HAS_MARGIN = True
+    # rotate.py:43 / complex.py:38 look the [UI-Relation] token up; transe/distmult take weight[-1]
+    UI_BY_TOKEN = False
+    UI_FULLSORT_BY_TOKEN = False
+    # extra state the reference checkpoints through other_parameter() (trainer.py:296-304)
+    other_parameter_name = ["kge_optimizer_state"]
+
+    def __init__(self, config, dataset):
+        super().__init__(config, dataset)
+        self.embedding_size = int(config["embedding_size"])
+        self.margin = float(config["margin"]) if self.HAS_MARGIN else 0.0
+        if self.UI_BY_TOKEN or self.UI_FULLSORT_BY_TOKEN:
+            self.ui_relation = int(dataset.field2token_id["relation_id"][dataset.ui_relation])
+        # tables in the reference's creation order (fixes the RNG stream of the initialisation)
+        d = self.embedding_size
+        for name in self.USER_TABLES:
+            setattr(self, name, nn.Embedding(self.n_users, d))
+        for name in self.ENTITY_TABLES:
+            setattr(self, name, nn.Embedding(self.n_entities, d))
+        for name in self.RELATION_TABLES:
+            setattr(self, name, nn.Embedding(self.n_relations, d))
+        self.apply(_xavier_normal_initialization)
+        if self.KIND == "RotatE":
+            nn.init.uniform_(self.relation_embedding.weight, 0, 2 * math.pi)  # rotate.py:59
+
+        # optimiser hyper-parameters: the trainer's (trainer.py:165-206); anything the fused
+        # update does not reproduce is refused instead of silently diverging
+        learner = str(_cfg_get(config, "learner", "adam")).lower()
+        if learner != "adam":
+            raise NotImplementedError(f"fused KGE step implements learner 'adam' only, got {learner!r}")
+        if float(_cfg_get(config, "weight_decay", 0.0) or 0.0) != 0.0:
+            raise NotImplementedError("fused KGE step implements weight_decay 0.0 only")
+        if _cfg_get(config, "clip_grad_norm", None):
+            raise NotImplementedError("clip_grad_norm is not supported by the fused KGE step")
+        if _cfg_get(config, "enable_amp", False) or _cfg_get(config, "enable_scaler", False):
+            raise NotImplementedError("AMP / GradScaler are not supported: the kernels are fp32")
+        self.learning_rate = float(_cfg_get(config, "learning_rate", 1e-3))
+        self.betas = (0.9, 0.999)
+        self.adam_eps = 1e-8
+        self.replay_cap = int(_cfg_get(config, "kge_replay_cap", 200))
+
+        self._step = 0          # optimiser steps applied so far
+        self._pending = False   # a gradient was accumulated and not yet applied
+        self._dirty = False     # some rows lag behind self._step (lazy Adam)
+        self._state = None      # device-side optimiser state, allocated on first training step
+        self._anchor = None
+        self._grad_sync = None  # optional callable(model) run between forward and apply (multi-GPU)
+        self._grad_scale = 1.0  # 1 / world_size under data parallelism (DDP averages gradients)
+        self._keepalive = None
+        self._touch_bounds = (0, 0, 0)
+
+    # ------------------------------------------------------------------ tables
+    def _tables(self, names):
+        return [getattr(self, n).weight for n in names]
+
+    def _check_ready(self):
+        w = self._tables(self.ENTITY_TABLES)[0]
+        if not w.is_cuda:
+            raise RuntimeError(
+                f"{type(self).__name__}: the fused KGE path runs on CUDA only (weights are on {w.device}); "
+                "there is no CPU fallback"
+            )
+        for names in (self.USER_TABLES, self.ENTITY_TABLES, self.RELATION_TABLES):
+            for t in self._tables(names):
+                if t.dtype != torch.float32 or not t.is_contiguous():
+                    raise RuntimeError("the fused KGE kernels need contiguous float32 tables (weight_precision float32)")
+        return w.device
+
+    def _ui_row(self, full_sort: bool) -> int:
+        by_token = self.UI_FULLSORT_BY_TOKEN if full_sort else self.UI_BY_TOKEN
+        return self.ui_relation if by_token else self.n_relations - 1
+
+    def _ensure_state(self, device):
+        if self._state is not None and self._state["device"] == device:
+            return self._state
+        st = {"device": device}
+        for fam, names, rows in (
+            ("user", self.USER_TABLES, self.n_users),
+            ("entity", self.ENTITY_TABLES, self.n_entities),
+            ("relation", self.RELATION_TABLES, self.n_relations),
+        ):
+            d = self.embedding_size
+            st[fam] = {
+                "m": [torch.zeros(rows, d, device=device) for _ in names],
+                "v": [torch.zeros(rows, d, device=device) for _ in names],
+                "g": [torch.zeros(rows, d, device=device) for _ in names],
+                "last_step": torch.full((rows,), -1, dtype=torch.int32, device=device),
+                "touch_step": torch.full((rows,), -1, dtype=torch.int32, device=device),
+                "uniq": torch.zeros(rows, dtype=torch.int32, device=device),
+            }
+        st["counters"] = torch.zeros(8, dtype=torch.int32, device=device)
+        lib = _abi.lib()
+        n = lib.kge_adam_table_fill(self.learning_rate, self.betas[0], self.betas[1], None, 0)
+        host = (C.c_float * (2 * n))()
+        lib.kge_adam_table_fill(self.learning_rate, self.betas[0], self.betas[1], host, n)
+        st["adam_table"] = torch.tensor(list(host), dtype=torch.float32).to(device)
+        st["adam_table_len"] = n
+        st["loss"] = torch.zeros(1, device=device)
+        self._state = st
+        return st
+
+    def _model_struct(self, with_state: bool) -> _abi.kge_model_t:
+        m = _abi.kge_model_t()
+        m.model = _abi.MODEL_KINDS[self.KIND]
+        m.d = self.embedding_size
+        m.margin = self.margin
+        m.ui_relation = self._ui_row(False)
+        m.ui_relation_fullsort = self._ui_row(True)
+        m.n_items = self.n_items
+        st = self._state if with_state else None
+        for fam, names, rows in (
+            ("user", self.USER_TABLES, self.n_users),
+            ("entity", self.ENTITY_TABLES, self.n_entities),
+            ("relation", self.RELATION_TABLES, self.n_relations),
+        ):
+            t = getattr(m, fam)
+            t.rows = rows
+            t.parts = len(names)
+            for p, w in enumerate(self._tables(names)):
+                t.w[p] = w.data_ptr()
+                if st is not None:
+                    t.m[p] = st[fam]["m"][p].data_ptr()
+                    t.v[p] = st[fam]["v"][p].data_ptr()
+                    t.g[p] = st[fam]["g"][p].data_ptr()
+            if st is not None:
+                t.last_step = st[fam]["last_step"].data_ptr()
+                t.touch_step = st[fam]["touch_step"].data_ptr()
+                t.uniq = st[fam]["uniq"].data_ptr()
+        if st is not None:
+            m.counters = st["counters"].data_ptr()
+            m.adam_table = st["adam_table"].data_ptr()
+            m.adam_table_len = st["adam_table_len"]
+        return m
+
+    def _adam_struct(self, step: int) -> _abi.kge_adam_t:
+        a = _abi.kge_adam_t()
+        a.lr, a.beta1, a.beta2, a.eps = self.learning_rate, self.betas[0], self.betas[1], self.adam_eps
+        a.step = step
+        a.replay_cap = self.replay_cap
+        return a
+
+    # ------------------------------------------------------------------ training
+    @staticmethod
+    def _ids(x, device):
+        if not torch.is_tensor(x):
+            x = torch.as_tensor(x)
+        if x.device != device:
+            raise RuntimeError(f"batch ids are on {x.device}, the model is on {device} (call interaction.to(device))")
+        return x.to(torch.int64).contiguous()
+
+    def _batch_struct(self, interaction, device):
+        def get(key):
+            try:
+                return self._ids(interaction[key], device)
+            except KeyError:
+                return None
+
+        user, item, neg_item = get(self.USER_ID), get(self.ITEM_ID), get(self.NEG_ITEM_ID)
+        head, rel = get(self.HEAD_ENTITY_ID), get(self.RELATION_ID)
+        tail, neg_tail = get(self.TAIL_ENTITY_ID), get(self.NEG_TAIL_ENTITY_ID)
+        b = _abi.kge_batch_t()
+        keep = []
+        b.k_rec = b.k_kg = 1
+        if user is not None and user.numel():
+            if item is None or neg_item is None:
+                raise KeyError("recommendation half of the batch needs item and negative-item ids")
+            n = user.numel()
+            if item.numel() != n or neg_item.numel() % n:
+                raise ValueError("user / item / neg_item lengths do not line up")
+            b.user, b.item, b.neg_item, b.n_rec = user.data_ptr(), item.data_ptr(), neg_item.data_ptr(), n
+            b.k_rec = neg_item.numel() // n
+            keep += [user, item, neg_item]
+        if head is not None and head.numel():
+            if rel is None or tail is None or neg_tail is None:
+                raise KeyError("KG half of the batch needs relation, tail and negative-tail ids")
+            n = head.numel()
+            if rel.numel() != n or tail.numel() != n or neg_tail.numel() % n:
+                raise ValueError("head / relation / tail / neg_tail lengths do not line up")
+            b.head, b.relation, b.tail, b.neg_tail, b.n_kg = (
+                head.data_ptr(), rel.data_ptr(), tail.data_ptr(), neg_tail.data_ptr(), n,
+            )
+            b.k_kg = neg_tail.numel() // n
+            keep += [head, rel, tail, neg_tail]
+        return b, keep
+
+    def _launch_forward(self, interaction, with_grad: bool):
+        device = self._check_ready()
+        lib = _abi.lib()
+        stream = _abi.stream_ptr()
+        lazy = self._state is not None
+        if with_grad:
+            self._ensure_state(device)
+            lazy = True
+        if self._pending:  # a loss whose backward never ran: drop its gradient
+            m = self._model_struct(True)
+            _abi.check(lib.kge_grad_discard(C.byref(m), self._step + 1, stream), "kge_grad_discard")
+            self._pending = False
+        m = self._model_struct(lazy)
+        b, keep = self._batch_struct(interaction, device)
+        a = self._adam_struct(self._step + 1)
+        loss = torch.zeros(1, device=device)
+        _abi.check(
+            lib.kge_train_forward(C.byref(m), C.byref(b), C.byref(a), 1 if with_grad else 0, loss.data_ptr(), stream),
+            "kge_train_forward",
+        )
+        self._keepalive = keep
+        # upper bounds on the distinct rows this batch can touch (sizes the row-sparse exchange)
+        self._touch_bounds = (
+            int(b.n_rec),
+            int(b.n_rec) * (1 + int(b.k_rec)) + int(b.n_kg) * (2 + int(b.k_kg)),
+            int(b.n_kg) + 1,
+        )
+        if with_grad:
+            self._pending = True
+        return loss.reshape(())
+
+    def _launch_apply(self, grad_out):
+        if not self._pending:
+            raise RuntimeError("backward called twice for one calculate_loss (the fused step keeps no graph)")
+        lib = _abi.lib()
+        if self._grad_sync is not None:
+            self._grad_sync(self)
+        # the incoming grad stays on the device: no host sync inside backward
+        g = grad_out.detach().to(torch.float32).reshape(1).contiguous()
+        m = self._model_struct(True)
+        a = self._adam_struct(self._step + 1)
+        _abi.check(
+            lib.kge_adam_apply(C.byref(m), C.byref(a), float(self._grad_scale), g.data_ptr(), _abi.stream_ptr()),
+            "kge_adam_apply",
+        )
+        self._step += 1
+        self._pending = False
+        self._dirty = True
+
+    def calculate_loss(self, interaction):
+        """transe.py:75-98 / distmult.py:68-95 / rotate.py:98-131 / complex.py:95-128."""
+        device = self._check_ready()
+        if not torch.is_grad_enabled():
+            return self._launch_forward(interaction, with_grad=False)
+        if self._anchor is None or self._anchor.device != device:
+            self._anchor = torch.zeros(1, device=device, requires_grad=True)
+        return _FusedStep.apply(self._anchor, self, interaction)
+
+    def flush(self):
+        """Bring every row of every table to the current optimiser step (dense pass)."""
+        if self._state is None or not self._dirty:
+            return
+        lib = _abi.lib()
+        if self._pending:
+            m = self._model_struct(True)
+            _abi.check(lib.kge_grad_discard(C.byref(m), self._step + 1, _abi.stream_ptr()), "kge_grad_discard")
+            self._pending = False
+        m = self._model_struct(True)
+        a = self._adam_struct(self._step)
+        _abi.check(lib.kge_adam_flush(C.byref(m), C.byref(a), _abi.stream_ptr()), "kge_adam_flush")
+        self._dirty = False
+
+    # ------------------------------------------------------------------ nn.Module hooks
+    def train(self, mode: bool = True):
+        if not mode:
+            self.flush()
+        return super().train(mode)
+
+    def state_dict(self, *args, **kwargs):
+        self.flush()
+        return super().state_dict(*args, **kwargs)
+
+    def load_state_dict(self, state_dict, *args, **kwargs):
+        self.flush()  # every row current before the weights are overwritten
+        return super().load_state_dict(state_dict, *args, **kwargs)
+
+    def _apply(self, fn, *args, **kwargs):
+        # .to(device): optimiser state is rebuilt lazily on the new device (after a flush)
+        if self._state is not None:
+            self.flush()
+        return super()._apply(fn, *args, **kwargs)
+
+    @property
+    def kge_optimizer_state(self):
+        """Adam moments for checkpoints (rides in other_parameter(), trainer.py:296-304)."""
+        if self._state is None:
+            return None
+        self.flush()
+        out = {"step": self._step}
+        for fam in ("user", "entity", "relation"):
+            out[fam] = {
+                "m": [t.detach().cpu() for t in self._state[fam]["m"]],
+                "v": [t.detach().cpu() for t in self._state[fam]["v"]],
+                "last_step": self._state[fam]["last_step"].detach().cpu(),
+            }
+        return out
+
+    @kge_optimizer_state.setter
+    def kge_optimizer_state(self, value):
+        if value is None:
+            return
+        device = self._check_ready()
+        st = self._ensure_state(device)
+        self._step = int(value["step"])
+        for fam in ("user", "entity", "relation"):
+            for dst, src in zip(st[fam]["m"], value[fam]["m"]):
+                dst.copy_(src)
+            for dst, src in zip(st[fam]["v"], value[fam]["v"]):
+                dst.copy_(src)
+            st[fam]["last_step"].copy_(value[fam]["last_step"])
+        self._dirty = False
+        self._pending = False
+
+    # ------------------------------------------------------------------ scoring
+    def _score_rows(self, heads, rels, tails, head_is_user: bool):
+        device = self._check_ready()
+        self.flush()
+        heads, tails = self._ids(heads, device), self._ids(tails, device)
+        rels = None if rels is None else self._ids(rels, device)
+        out = torch.empty(heads.numel(), dtype=torch.float32, device=device)
+        m = self._model_struct(False)
+        _abi.check(
+            _abi.lib().kge_predict(
+                C.byref(m), heads.data_ptr(), _abi.ptr(rels), tails.data_ptr(), heads.numel(),
+                1 if head_is_user else 0, out.data_ptr(), _abi.stream_ptr(),
+            ),
+            "kge_predict",
+        )
+        return out
+
+    def _full_sort(self, heads, rels, head_is_user: bool, n_targets: int):
+        device = self._check_ready()
+        self.flush()
+        heads = self._ids(heads, device)
+        rels = None if rels is None else self._ids(rels, device)
+        out = torch.empty(heads.numel(), n_targets, dtype=torch.float32, device=device)
+        m = self._model_struct(False)
+        _abi.check(
+            _abi.lib().kge_full_sort_scores(
+                C.byref(m), heads.data_ptr(), _abi.ptr(rels), heads.numel(), 1 if head_is_user else 0,
+                n_targets, out.data_ptr(), _abi.stream_ptr(),
+            ),
+            "kge_full_sort_scores",
+        )
+        return out
+
+    def predict(self, interaction):
+        return self._score_rows(interaction[self.USER_ID], None, interaction[self.ITEM_ID], True)
+
+    def predict_kg(self, interaction):
+        return self._score_rows(
+            interaction[self.HEAD_ENTITY_ID], interaction[self.RELATION_ID], interaction[self.TAIL_ENTITY_ID], False
+        )
+
+    def full_sort_predict(self, interaction):
+        """[n_batch_users, n_items] fp32 the caller owns (trainer.py:731-734 masks it in place)."""
+        return self._full_sort(interaction[self.USER_ID], None, True, self.n_items)
+
+    def full_sort_predict_kg(self, interaction):
+        return self._full_sort(interaction[self.HEAD_ENTITY_ID], interaction[self.RELATION_ID], False, self.n_entities)
+
+    def full_sort_topk(self, user_ids, k: int, hist_off=None, hist_items=None, mask_pad: bool = True,
+                       return_scores: bool = True):
+        """Fused full_sort_predict + trainer masking + top-k (trainer.py:716-735, collector.py:176-177).
+
+        ``hist_off`` [n+1] / ``hist_items`` (sorted ascending per user) is the CSR of the items to
+        mask for each of the ``user_ids``.  Returns (ids [n,k] int64, scores [n,k] fp32 or None),
+        ordered by (score desc, id asc).
+        """
+        device = self._check_ready()
+        self.flush()
+        users = self._ids(user_ids, device)
+        n = users.numel()
+        if hist_off is not None:
+            hist_off, hist_items = self._ids(hist_off, device), self._ids(hist_items, device)
+            if hist_off.numel() != n + 1:
+                raise ValueError("hist_off must have n_users + 1 entries")
+        ids = torch.empty(n, k, dtype=torch.int64, device=device)
+        scores = torch.empty(n, k, dtype=torch.float32, device=device) if return_scores else None
+        m = self._model_struct(False)
+        lib = _abi.lib()
+        need = lib.kge_full_sort_topk_workspace_bytes(C.byref(m), n, self.n_items, k)
+        if need < 0:
+            raise _abi.KgeError(f"kge_full_sort_topk: unsupported shape (k={k}, d={self.embedding_size})")
+        ws = torch.empty(max(need, 8), dtype=torch.uint8, device=device)
+        _abi.check(
+            lib.kge_full_sort_topk(
+                C.byref(m), users.data_ptr(), None, n, 1, self.n_items, _abi.ptr(hist_off), _abi.ptr(hist_items),
+                1 if mask_pad else 0, k, ids.data_ptr(), _abi.ptr(scores), ws.data_ptr(), ws.numel(),
+                _abi.stream_ptr(),
+            ),
+            "kge_full_sort_topk",
+        )
+        return ids, scores
+
+    def forward(self, *args, **kwargs):  # the reference's forward is the scorer on gathered rows
+        raise NotImplementedError("use calculate_loss / predict / full_sort_predict")
+
+
+def _xavier_normal_initialization(module):
+    if isinstance(module, nn.Embedding):  # model/init.py:24-25
+        nn.init.xavier_normal_(module.weight.data)
+
+
+class TransE(FusedKGEModel):
+    KIND = "TransE"
+    USER_TABLES = ("user_embedding",)
+    ENTITY_TABLES = ("entity_embedding",)
+    RELATION_TABLES = ("relation_embedding",)
+
+
+class DistMult(FusedKGEModel):
+    KIND = "DistMult"
+    USER_TABLES = ("user_embedding",)
+    ENTITY_TABLES = ("entity_embedding",)
+    RELATION_TABLES = ("relation_embedding",)
+
+
+class RotatE(FusedKGEModel):
+    KIND = "RotatE"
+    USER_TABLES = ("user_embedding", "user_embedding_im")
+    ENTITY_TABLES = ("entity_embedding", "entity_embedding_im")
+    RELATION_TABLES = ("relation_embedding",)
+    UI_BY_TOKEN = True
+    UI_FULLSORT_BY_TOKEN = True  # rotate.py:136, 163
+
+
+class ComplEx(FusedKGEModel):
+    KIND = "ComplEx"
+    USER_TABLES = ("user_re_embedding", "user_im_embedding")
+    ENTITY_TABLES = ("entity_re_embedding", "entity_im_embedding")
+    RELATION_TABLES = ("relation_re_embedding", "relation_im_embedding")
+    HAS_MARGIN = False
+    UI_BY_TOKEN = True            # complex.py:103-104, 137-138 (loss / predict)
+    UI_FULLSORT_BY_TOKEN = False  # complex.py:168-169 take weight[-1]
+
+
+MODELS = {"TransE": TransE, "DistMult": DistMult, "RotatE": RotatE, "ComplEx": ComplEx}

@@ -113,9 +113,12 @@ int kge_train_forward(const kge_model_t* model, const kge_batch_t* batch, const 
 
 /* kge_adam_apply: replaces optimizer.step() (trainer.py:264, torch.optim.Adam) for the rows
  * touched by the accumulated gradient: replays the skipped zero-gradient steps of each row,
- * applies step `adam->step` with gradient g*grad_scale, zeroes g.  Untouched rows are caught
- * up later (next touch or kge_adam_flush), which is exactly dense Adam's trajectory. */
-int kge_adam_apply(const kge_model_t* model, const kge_adam_t* adam, float grad_scale, kge_stream_t stream);
+ * applies step `adam->step` with gradient g * grad_scale * (*grad_scale_dev), zeroes g.
+ * grad_scale_dev (device, may be NULL) is the incoming gradient of the scalar loss, so that
+ * loss.backward() needs no host synchronisation.  Untouched rows are caught up later (next
+ * touch or kge_adam_flush), which is exactly dense Adam's trajectory. */
+int kge_adam_apply(const kge_model_t* model, const kge_adam_t* adam, float grad_scale, const float* grad_scale_dev,
+                   kge_stream_t stream);
 
 /* Bring every row of every table to step `adam->step` (dense pass).  Must run before
  * weights are read by anything but this library (state_dict, predict, checkpoints). */
@@ -149,11 +152,16 @@ int kge_full_sort_scores(const kge_model_t* model, const int64_t* heads, const i
 /* kge_full_sort_topk: fuses full_sort_predict + the trainer's masking
  * (trainer.py:731-734: column 0 and history -> -inf) + torch.topk (collector.py:177) without
  * materialising [n, n_targets].  History is CSR over the n query rows (hist_off[n+1],
- * hist_items sorted ascending per row).  Order: score descending, id ascending.
- * Outputs ids_out[n,k] (int64), scores_out[n,k] (fp32; -inf where fewer than k unmasked). */
+ * hist_items sorted ascending per row; both NULL = no history).  mask_first != 0 masks target 0
+ * (the [PAD] item).  Order: score descending, id ascending (masked targets, score -inf, rank
+ * last and enter only when a row has fewer than k unmasked targets).
+ * Outputs ids_out[n,k] (int64), scores_out[n,k] (fp32, may be NULL).  workspace: device
+ * scratch of kge_full_sort_topk_workspace_bytes(model, n, n_targets, k) bytes. */
+int64_t kge_full_sort_topk_workspace_bytes(const kge_model_t* model, int64_t n, int64_t n_targets, int32_t k);
 int kge_full_sort_topk(const kge_model_t* model, const int64_t* heads, const int64_t* rels, int64_t n,
                        int head_is_user, int64_t n_targets, const int64_t* hist_off, const int64_t* hist_items,
-                       int32_t k, int64_t* ids_out, float* scores_out, kge_stream_t stream);
+                       int mask_first, int32_t k, int64_t* ids_out, float* scores_out, void* workspace,
+                       int64_t workspace_bytes, kge_stream_t stream);
 
 /* kge_topk_hits: collector.py:178-183 without the [n, I] pos_matrix: out[n, k+1] int32 =
  * hit flags of ids[n,k] against the positives CSR (pos_off[n+1], pos_items sorted) then pos_len. */
@@ -167,8 +175,10 @@ int kge_topk_metric_sums(const int32_t* rec_topk, int64_t n, int32_t k, double* 
 /* ---- negative sampling -------------------------------------------------------------------
  * kge_sample_negatives: AbstractSampler.sample_by_key_ids with uniform sampling
  * (sampler.py:140-183, 226-227, 315-316) on numpy's MT19937 stream, bit for bit.
- * mt_state[625] (device): 624 key words + pos, read and advanced.  used_off[n_keys+1] /
- * used_vals: CSR of sorted forbidden values per key.  out[n*num] int64, j-major.
+ * mt_state[626] (device): 624 key words, pos, status; read and advanced.  status becomes 1
+ * (sticky) when some key's forbidden list covers the whole range (the reference raises for
+ * that up front, sampler.py:318-336).  used_off[n_keys+1] / used_vals: CSR of sorted forbidden
+ * values per key.  out[n*num] int64, j-major.
  * workspace: int32 scratch of kge_sample_workspace_bytes(n*num) bytes. */
 int64_t kge_sample_workspace_bytes(int64_t total);
 int kge_sample_negatives(uint32_t* mt_state, const int64_t* keys, int64_t n, int32_t num, const int64_t* used_off,

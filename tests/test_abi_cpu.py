@@ -1,0 +1,102 @@
+"""CPU-side checks of the boundary: the library builds for sm_100a, loads without a GPU and
+exports every symbol include/kge_b200.h declares; the ctypes structs match the header."""
+
+import ctypes as C
+import os
+import re
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+HEADER = os.path.join(ROOT, "include", "kge_b200.h")
+
+
+def _declared_functions():
+    text = open(HEADER).read()
+    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+    return sorted(set(re.findall(r"\b(kge_[a-z0-9_]+)\s*\(", text)))
+
+
+def test_library_exports_every_declared_symbol():
+    from hopwise_b200 import _abi, _build
+
+    _build.build()
+    lib = _abi.lib()
+    names = _declared_functions()
+    assert len(names) >= 15
+    for n in names:
+        assert hasattr(lib, n), f"{n} declared in kge_b200.h but not exported"
+    assert set(names) == set(_abi.PROTOTYPES), "ctypes prototypes and header disagree"
+    assert lib.kge_abi_version() == _abi.KGE_ABI_VERSION
+
+
+def test_struct_layout_matches_header():
+    from hopwise_b200 import _abi
+
+    # sizes computed from the header's field lists (LP64)
+    assert C.sizeof(_abi.kge_table_t) == 8 + 4 + 4 + 4 * 16 + 3 * 8
+    assert C.sizeof(_abi.kge_model_t) == 4 * 6 + 8 + 3 * C.sizeof(_abi.kge_table_t) + 8 + 8 + 8
+    assert C.sizeof(_abi.kge_batch_t) == 3 * 8 + 8 + 4 * 8 + 8 + 8
+    assert C.sizeof(_abi.kge_adam_t) == 24
+
+
+def test_host_only_entry_points():
+    from hopwise_b200 import _abi
+
+    lib = _abi.lib()
+    n = lib.kge_adam_table_fill(1e-3, 0.9, 0.999, None, 0)
+    assert n > 20000
+    buf = (C.c_float * (2 * n))()
+    lib.kge_adam_table_fill(1e-3, 0.9, 0.999, buf, n)
+    assert abs(buf[2] - 1e-3 / (1 - 0.9)) < 1e-8  # lr / (1 - b1^1)
+    assert abs(buf[3] - 1 / (1 - 0.999) ** 0.5) < 1e-3
+    assert abs(buf[2 * (n - 1)] - 1e-3) < 1e-10 and abs(buf[2 * (n - 1) + 1] - 1.0) < 1e-6
+    assert lib.kge_sample_workspace_bytes(100) == 800
+    # argument errors come back as codes + message, never exceptions or crashes
+    assert lib.kge_train_forward(None, None, None, 1, None, None) < 0
+    assert b"NULL" in lib.kge_last_error()
+
+
+def test_product_has_no_cpu_fallback_and_no_oracle_import():
+    import torch
+
+    from kge_helpers import make_product_model, random_batch, to_cpu_batch
+    import numpy as np
+
+    m = make_product_model("TransE", 10, 8, 20, 5, 16, device="cpu")
+    b = to_cpu_batch(random_batch(np.random.default_rng(0), 10, 8, 20, 5, 4, 4))
+    with pytest.raises(RuntimeError, match="CUDA only"):
+        m.calculate_loss(b)
+    with pytest.raises(RuntimeError, match="CUDA only"):
+        m.full_sort_predict({"user_id": torch.arange(1, 3)})
+    pkg = os.path.join(ROOT, "hopwise_b200")
+    for dirpath, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".h")):
+                src = open(os.path.join(dirpath, f)).read()
+                assert not re.search(r"^\s*(from|import)\s+oracle\b", src, flags=re.M), f"{f} imports the oracle"
+
+
+def test_state_dict_keys_match_reference_names(golden):
+    from kge_helpers import make_product_model
+
+    for name in ("TransE", "RotatE", "DistMult", "ComplEx"):
+        g = golden(f"model_{name}_d10.npz")
+        U, I, E, R, d = (int(x) for x in g["shape"])
+        m = make_product_model(name, U, I, E, R, d, device="cpu")
+        want = sorted(k[5:] for k in g.files if k.startswith("init/"))
+        assert sorted(m.state_dict().keys()) == want
+        # same seed, same constructor order => the reference's initial weights, bit for bit
+        for k, v in m.state_dict().items():
+            assert (v.numpy() == g["init/" + k]).all(), (name, k)
+
+
+def test_unsupported_configs_are_refused():
+    from kge_helpers import make_product_model
+
+    with pytest.raises(NotImplementedError):
+        make_product_model("TransE", 10, 8, 20, 5, 16, device="cpu", learner="sgd")
+    with pytest.raises(NotImplementedError):
+        make_product_model("TransE", 10, 8, 20, 5, 16, device="cpu", weight_decay=0.1)
+    with pytest.raises(NotImplementedError):
+        make_product_model("TransE", 10, 8, 20, 5, 16, device="cpu", clip_grad_norm={"max_norm": 5})
