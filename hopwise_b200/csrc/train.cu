@@ -44,6 +44,7 @@ struct TrainArgs {
   float wpos_rec, wpos_kg; // BCE models: weight of the positive term (= w * k)
   int with_grad;
   float* loss;
+  int cap_user, cap_entity, cap_relation;  // per-CTA capacity of the staged unique-row lists
 };
 
 __device__ __forceinline__ float2 adam_consts(const AdamDev& A, int j) {
@@ -111,6 +112,27 @@ __device__ __forceinline__ void touch_row(const kge_table_t& T, int32_t* counter
   }
 }
 
+// Same, but the new row goes to a per-CTA list in shared memory (table index t: 0 user, 1 entity,
+// 2 relation); the CTA publishes its lists with one global atomicAdd per table at the end, so
+// the unique-row counters are not hammered by one returning atomic per touched row.
+struct StageLists {
+  int* cnt;      // [3]
+  int32_t* list[3];
+};
+template <int G>
+__device__ __forceinline__ void touch_row_staged(const kge_table_t& T, const StageLists& S, int t, int64_t row,
+                                                 int step, int gl) {
+  if (gl == 0) {
+    if (*reinterpret_cast<volatile int32_t*>(T.touch_step + row) != step) {
+      const int old = atomicExch(T.touch_step + row, step);
+      if (old != step) {
+        const int pos = atomicAdd(&S.cnt[t], 1);
+        S.list[t][pos] = (int32_t)row;
+      }
+    }
+  }
+}
+
 __device__ __forceinline__ float softplusf(float z) { return fmaxf(z, 0.f) + log1pf(expf(-fabsf(z))); }
 __device__ __forceinline__ float sigmoidf(float z) { return 1.f / (1.f + expf(-z)); }
 
@@ -119,8 +141,16 @@ __global__ void __launch_bounds__(256) train_fwd_kernel(const TrainArgs a) {
   constexpr int E = VEC * NCH;
   constexpr int PH = (MODEL == KGE_ROTATE || MODEL == KGE_COMPLEX) ? 2 : 1;  // head / tail parts
   constexpr int PR = (MODEL == KGE_COMPLEX) ? 2 : 1;                          // relation parts
-  extern __shared__ float s_racc[];  // [PR][d] user->item relation gradient of this CTA
+  extern __shared__ float s_racc[];  // [PR][d] user->item relation gradient of this CTA, then the staged lists
   __shared__ float s_loss[8];
+  __shared__ int s_cnt[3];
+  __shared__ int s_base[3];
+  StageLists S;
+  S.cnt = s_cnt;
+  S.list[0] = reinterpret_cast<int32_t*>(s_racc + PR * a.m.d);
+  S.list[1] = S.list[0] + a.cap_user;
+  S.list[2] = S.list[1] + a.cap_entity;
+  if (threadIdx.x < 3) s_cnt[threadIdx.x] = 0;
 
   const int d = a.m.d;
   const int gl = (threadIdx.x & 31) % G;
@@ -192,8 +222,10 @@ __global__ void __launch_bounds__(256) train_fwd_kernel(const TrainArgs a) {
       }
       const float np_ = sqrtf(group_sum<G>(sp));
       const float inv_p = np_ > 0.f ? 1.f / np_ : 0.f;
+      // the positive and the negative term are formed by the same operations, so that a pair
+      // whose negative equals its positive cancels exactly, as it does under autograd
 #pragma unroll
-      for (int e = 0; e < E; ++e) up[e] *= inv_p;
+      for (int e = 0; e < E; ++e) up[e] = w * (up[e] * inv_p);
       float nact = 0.f;
       for (int j = 0; j < K; ++j) {
         const int64_t tn_id = __ldg(negs + (int64_t)j * n_seg + i);
@@ -211,27 +243,23 @@ __global__ void __launch_bounds__(256) train_fwd_kernel(const TrainArgs a) {
         if (z >= 0.f) {
           inst_loss += z * w;
           if (a.with_grad) {
-            const float inv_n = nn_ > 0.f ? w / nn_ : 0.f;
+            const float inv_n = nn_ > 0.f ? 1.f / nn_ : 0.f;
             nact += 1.f;
 #pragma unroll
             for (int e = 0; e < E; ++e) {
-              tn[e] *= inv_n;       // gradient of the negative tail
-              gh[0][e] -= tn[e];
+              tn[e] = w * (tn[e] * inv_n);  // gradient of the negative tail
+              gh[0][e] += up[e] - tn[e];
+              gtp[0][e] -= up[e];
             }
             frag_atomic_add<VEC, G, NCH>(a.m.entity.g[0], tn_id, d, gl, tn);
-            touch_row<G>(a.m.entity, cnt + 1, tn_id, step, gl);
+            touch_row_staged<G>(a.m.entity, S, 1, tn_id, step, gl);
           }
         }
       }
       if (nact > 0.f) {
         any_grad = true;
-        const float s = nact * w;
 #pragma unroll
-        for (int e = 0; e < E; ++e) {
-          gh[0][e] += s * up[e];
-          gr[0][e] = gh[0][e];
-          gtp[0][e] = -s * up[e];
-        }
+        for (int e = 0; e < E; ++e) gr[0][e] = gh[0][e];
       }
     } else if (MODEL == KGE_DISTMULT) {
       // pair loss: clamp_min(margin - s+ + s-, 0), s = sum h*r*t
@@ -265,7 +293,7 @@ __global__ void __launch_bounds__(256) train_fwd_kernel(const TrainArgs a) {
               gtn[e] = w * q[e];
             }
             frag_atomic_add<VEC, G, NCH>(a.m.entity.g[0], tn_id, d, gl, gtn);
-            touch_row<G>(a.m.entity, cnt + 1, tn_id, step, gl);
+            touch_row_staged<G>(a.m.entity, S, 1, tn_id, step, gl);
           }
         }
       }
@@ -331,7 +359,7 @@ __global__ void __launch_bounds__(256) train_fwd_kernel(const TrainArgs a) {
           } else {
             frag_atomic_add<VEC, G, NCH>(a.m.entity.g[0], t_id, d, gl, tre);
             frag_atomic_add<VEC, G, NCH>(a.m.entity.g[1], t_id, d, gl, tim);
-            touch_row<G>(a.m.entity, cnt + 1, t_id, step, gl);
+            touch_row_staged<G>(a.m.entity, S, 1, t_id, step, gl);
           }
         }
       }
@@ -388,7 +416,7 @@ __global__ void __launch_bounds__(256) train_fwd_kernel(const TrainArgs a) {
           } else {
             frag_atomic_add<VEC, G, NCH>(a.m.entity.g[0], t_id, d, gl, tre);
             frag_atomic_add<VEC, G, NCH>(a.m.entity.g[1], t_id, d, gl, tim);
-            touch_row<G>(a.m.entity, cnt + 1, t_id, step, gl);
+            touch_row_staged<G>(a.m.entity, S, 1, t_id, step, gl);
           }
         }
       }
@@ -411,8 +439,8 @@ __global__ void __launch_bounds__(256) train_fwd_kernel(const TrainArgs a) {
         frag_atomic_add<VEC, G, NCH>(HT.g[p], h_id, d, gl, gh[p]);
         frag_atomic_add<VEC, G, NCH>(a.m.entity.g[p], tp_id, d, gl, gtp[p]);
       }
-      touch_row<G>(HT, cnt + (is_rec ? 0 : 1), h_id, step, gl);
-      touch_row<G>(a.m.entity, cnt + 1, tp_id, step, gl);
+      touch_row_staged<G>(HT, S, is_rec ? 0 : 1, h_id, step, gl);
+      touch_row_staged<G>(a.m.entity, S, 1, tp_id, step, gl);
       if (is_rec) {
         rec_seen = true;
 #pragma unroll
@@ -422,7 +450,7 @@ __global__ void __launch_bounds__(256) train_fwd_kernel(const TrainArgs a) {
       } else {
 #pragma unroll
         for (int p = 0; p < PR; ++p) frag_atomic_add<VEC, G, NCH>(a.m.relation.g[p], r_id, d, gl, gr[p]);
-        touch_row<G>(a.m.relation, cnt + 2, r_id, step, gl);
+        touch_row_staged<G>(a.m.relation, S, 2, r_id, step, gl);
       }
     }
   }
@@ -445,14 +473,17 @@ __global__ void __launch_bounds__(256) train_fwd_kernel(const TrainArgs a) {
       const int p = i / d, col = i - p * d;
       atomicAdd(a.m.relation.g[p] + (int64_t)a.m.ui_relation * d + col, s_racc[i]);
     }
-    if (threadIdx.x == 0) {
-      const kge_table_t& RT = a.m.relation;
-      const int64_t row = a.m.ui_relation;
-      if (*reinterpret_cast<volatile int32_t*>(RT.touch_step + row) != step) {
-        const int old = atomicExch(RT.touch_step + row, step);
-        if (old != step) RT.uniq[atomicAdd(cnt + 2, 1)] = (int32_t)row;
-      }
-    }
+    if (threadIdx.x == 0) touch_row_staged<1>(a.m.relation, S, 2, a.m.ui_relation, step, 0);
+  }
+  // ---- publish the staged unique-row lists: one returning atomic per table per CTA -----------------
+  __syncthreads();
+  if (threadIdx.x < 3) s_base[threadIdx.x] = s_cnt[threadIdx.x] ? atomicAdd(cnt + threadIdx.x, s_cnt[threadIdx.x]) : 0;
+  __syncthreads();
+  {
+    int32_t* dst[3] = {a.m.user.uniq, a.m.entity.uniq, a.m.relation.uniq};
+#pragma unroll
+    for (int t = 0; t < 3; ++t)
+      for (int i = threadIdx.x; i < s_cnt[t]; i += blockDim.x) dst[t][s_base[t] + i] = S.list[t][i];
   }
   lsum = warp_sum(lsum);
   if ((threadIdx.x & 31) == 0) s_loss[threadIdx.x >> 5] = lsum;
@@ -693,18 +724,41 @@ extern "C" int kge_train_forward(const kge_model_t* model, const kge_batch_t* b,
   RowCfg c;
   kge_pick_rowcfg(model->d, c);
   const int threads = 256;
-  const int grid = grid_for(n_total, threads / c.g, 8);
-  const size_t smem = (size_t)model->relation.parts * model->d * sizeof(float);
+  const int gpc = threads / c.g;
+  int grid = grid_for(n_total, gpc, 8);
+  // per-CTA staged lists must hold every row the CTA can touch; grow the grid until they fit 48 KB
+  const int kmax = b->k_rec > b->k_kg ? b->k_rec : b->k_kg;
+  int64_t inst_per_cta;
+  for (;;) {
+    const int64_t iters = (n_total + (int64_t)grid * gpc - 1) / ((int64_t)grid * gpc);
+    inst_per_cta = iters * gpc;
+    if (inst_per_cta * (3 + kmax) * 4 <= 48 * 1024 || inst_per_cta <= gpc) break;
+    grid *= 2;
+  }
+  a.cap_user = (int)inst_per_cta;
+  a.cap_entity = (int)(inst_per_cta * (2 + kmax));
+  a.cap_relation = (int)inst_per_cta + 1;
+  const size_t smem = (size_t)model->relation.parts * model->d * sizeof(float) +
+                      ((size_t)a.cap_user + a.cap_entity + a.cap_relation) * sizeof(int32_t);
+  KGE_REQUIRE(smem <= 200 * 1024, KGE_E_UNSUPPORTED, "%d negatives per triple need %zu bytes of shared memory", kmax, smem);
   cudaStream_t st = (cudaStream_t)stream;
-#define CALL(V, G, N)                                                                                   \
-  switch (model->model) {                                                                               \
-    case KGE_TRANSE: train_fwd_kernel<KGE_TRANSE, V, G, N><<<grid, threads, smem, st>>>(a); break;      \
-    case KGE_DISTMULT: train_fwd_kernel<KGE_DISTMULT, V, G, N><<<grid, threads, smem, st>>>(a); break;  \
-    case KGE_ROTATE: train_fwd_kernel<KGE_ROTATE, V, G, N><<<grid, threads, smem, st>>>(a); break;      \
-    default: train_fwd_kernel<KGE_COMPLEX, V, G, N><<<grid, threads, smem, st>>>(a); break;             \
+#define LAUNCH_FWD(M, V, G, N)                                                                                  \
+  do {                                                                                                          \
+    if (smem > 48 * 1024)                                                                                       \
+      KGE_CUDA(cudaFuncSetAttribute(train_fwd_kernel<M, V, G, N>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
+                                    (int)smem));                                                                \
+    train_fwd_kernel<M, V, G, N><<<grid, threads, smem, st>>>(a);                                               \
+  } while (0)
+#define CALL(V, G, N)                                                \
+  switch (model->model) {                                            \
+    case KGE_TRANSE: LAUNCH_FWD(KGE_TRANSE, V, G, N); break;         \
+    case KGE_DISTMULT: LAUNCH_FWD(KGE_DISTMULT, V, G, N); break;     \
+    case KGE_ROTATE: LAUNCH_FWD(KGE_ROTATE, V, G, N); break;         \
+    default: LAUNCH_FWD(KGE_COMPLEX, V, G, N); break;                \
   }
   KGE_DISPATCH_ROWCFG(c, CALL);
 #undef CALL
+#undef LAUNCH_FWD
   KGE_LAUNCH_CHECK();
   return 0;
 }

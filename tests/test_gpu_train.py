@@ -10,6 +10,7 @@ import torch
 from conftest import MODELS, load_golden
 from kge_helpers import (
     BATCH_KEYS,
+    assert_weights_close,
     make_oracle_model,
     make_product_model,
     random_batch,
@@ -112,7 +113,7 @@ CASES = [
     ("RotatE", 200, 150, 700, 9, 256, 128, 128, 1, 1, 12),
     ("ComplEx", 300, 200, 900, 12, 64, 512, 512, 1, 1, 25),
     ("TransE", 300, 200, 900, 12, 128, 0, 400, 1, 1, 6),     # KG half only
-    ("ComplEx", 300, 200, 900, 12, 32, 400, 0, 1, 1, 6),     # rec half only
+    ("DistMult", 300, 200, 900, 12, 32, 400, 0, 1, 1, 6),    # rec half only (BCE models give NaN there, as the reference does)
     ("DistMult", 120, 80, 300, 7, 50, 128, 96, 1, 1, 8),     # d % 4 != 0: scalar row path
     ("RotatE", 120, 80, 300, 7, 24, 64, 64, 4, 3, 8),        # K negatives, compact layout
     ("TransE", 120, 80, 300, 7, 36, 64, 64, 5, 2, 8),
@@ -139,7 +140,7 @@ def test_oracle_trajectory(case):
         got = _trainer_step(m, opt, to_device_batch(b))
         np.testing.assert_allclose(got, want, rtol=RTOL, err_msg=f"loss at step {step + 1}")
     for (k, vo), (_, vp) in zip(ora.state_dict().items(), m.state_dict().items()):
-        np.testing.assert_allclose(vp.cpu().numpy(), vo.numpy(), rtol=RTOL, atol=5e-7, err_msg=k)
+        assert_weights_close(vp.cpu().numpy(), vo.numpy(), rtol=RTOL, atol=5e-7, err_msg=k)
 
 
 def test_tiled_and_compact_negatives_agree():
@@ -176,7 +177,7 @@ def test_loss_without_backward_leaves_weights_alone():
     ora = make_oracle_model(name, U, I, E, R, d)
     train_step(ora, make_optimizer(ora), {k: v.cpu() for k, v in b.items()})
     for (k, vo), (_, vp) in zip(ora.state_dict().items(), m.state_dict().items()):
-        np.testing.assert_allclose(vp.cpu().numpy(), vo.numpy(), rtol=RTOL, atol=5e-7, err_msg=k)
+        assert_weights_close(vp.cpu().numpy(), vo.numpy(), rtol=RTOL, atol=5e-7, err_msg=k)
 
 
 def test_grad_output_scale_is_honoured():
@@ -193,7 +194,7 @@ def test_grad_output_scale_is_honoured():
         (ora.calculate_loss(to_cpu_batch(b)) * 0.25).backward()
         opt_o.step()
     for (k, vo), (_, vp) in zip(ora.state_dict().items(), m.state_dict().items()):
-        np.testing.assert_allclose(vp.cpu().numpy(), vo.numpy(), rtol=RTOL, atol=5e-7, err_msg=k)
+        assert_weights_close(vp.cpu().numpy(), vo.numpy(), rtol=RTOL, atol=5e-7, err_msg=k)
 
 
 def test_long_idle_rows_follow_dense_adam():
@@ -213,16 +214,16 @@ def test_long_idle_rows_follow_dense_adam():
 
     first = half_batch(0.5, 1.0, 32)   # upper half of every id range, seen once
     later = half_batch(0.0, 0.5, 32)   # lower half, seen on every later step
-    m = make_product_model(name, U, I, E, R, d, kge_replay_cap=50)
+    m = make_product_model(name, U, I, E, R, d)   # default replay cap: 200 exact steps, then closed form
     ora = make_oracle_model(name, U, I, E, R, d)
     opt_o = make_optimizer(ora)
     opt = torch.optim.Adam(m.parameters(), lr=1e-3)
-    for step in range(120):
+    for step in range(240):
         b = first if step == 0 else later
         train_step(ora, opt_o, to_cpu_batch(b))
         _trainer_step(m, opt, to_device_batch(b))
     for (k, vo), (_, vp) in zip(ora.state_dict().items(), m.state_dict().items()):
-        np.testing.assert_allclose(vp.cpu().numpy(), vo.numpy(), rtol=RTOL, atol=1e-6, err_msg=k)
+        assert_weights_close(vp.cpu().numpy(), vo.numpy(), rtol=RTOL, atol=1e-6, err_msg=k)
 
 
 def test_checkpoint_round_trip_continues_the_trajectory():
