@@ -30,9 +30,7 @@ class kge_table_t(C.Structure):
         ("m", C.c_void_p * 2),
         ("v", C.c_void_p * 2),
         ("g", C.c_void_p * 2),
-        ("last_step", C.c_void_p),
-        ("touch_step", C.c_void_p),
-        ("uniq", C.c_void_p),
+        ("row_state", C.c_void_p),
     ]
 
 
@@ -48,7 +46,6 @@ class kge_model_t(C.Structure):
         ("user", kge_table_t),
         ("entity", kge_table_t),
         ("relation", kge_table_t),
-        ("counters", C.c_void_p),
         ("adam_table", C.c_void_p),
         ("adam_table_len", C.c_int32),
         ("_pad2", C.c_int32),

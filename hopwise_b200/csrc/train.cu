@@ -7,19 +7,22 @@
 //   trainer/trainer.py:261                  (loss.backward(): dense [rows, d] gradients)
 //   trainer/trainer.py:264 + torch.optim.Adam (dense update of every table)
 //
-// Data layout in HBM: the tables stay exactly where torch keeps them (fp32 [rows, d],
-// one matrix per re/im part), so state_dict() is zero-copy.  Next to every table live m, v
-// (Adam moments), g (a gradient accumulator that is all-zero between steps: only touched
-// rows are ever written and the update kernel zeroes them again), last_step[rows] and a
-// per-step unique-row list.  Nothing of size [rows, d] is traversed per step.
+// Data layout in HBM: the tables stay exactly where torch keeps them (fp32 [rows, d], one
+// matrix per re/im part), so state_dict() is zero-copy.  Next to every table live m, v (Adam
+// moments), g (a gradient accumulator that is all-zero between steps: only touched rows are ever
+// written and the update kernel zeroes them again) and row_state[rows] = {last_step, touch_step}
+// (8 bytes per row).  Nothing of size [rows, d] is traversed per step.
 //
-// Kernel A (train_fwd_kernel): a group of G lanes owns one positive triple; rows move as
-// 128-bit loads; gradients leave as RED.ADD.F32x4.  The user->item relation row is shared by
-// every rec triple, so its gradient is accumulated in registers, reduced per CTA in shared
-// memory and flushed once per CTA.
-// Kernel B (adam_apply_kernel): one group per unique touched row: replay the zero-gradient
-// steps the row skipped (dense Adam keeps moving a row after its last gradient), apply the
-// real step, zero g.
+// Kernel A (train_fwd_kernel): a group of G lanes owns one positive triple.  Ids of the whole
+// triple are read first, then the 8-byte row states and the 128-bit row fragments of head,
+// relation, positive and first negative tail are all issued before anything is consumed (one
+// memory latency per triple; further negatives are prefetched one ahead).  Gradients leave as
+// RED.ADD.F32x4; a touched row is marked by a plain store of the step number.  The user->item
+// relation row is shared by every rec triple, so its gradient is accumulated in registers,
+// reduced per CTA in shared memory and flushed once per CTA.
+// Kernel B (adam_apply_kernel): lanes scan row_state (8 B per row, coalesced), ballot the rows
+// marked in this step and a lane group updates each: replay the zero-gradient steps the row
+// skipped (dense Adam keeps moving a row after its last gradient), apply the real step, zero g.
 #include <math.h>
 #include <stdarg.h>
 #include <stdio.h>
@@ -40,11 +43,10 @@ struct TrainArgs {
   kge_model_t m;
   kge_batch_t b;
   AdamDev adam;
-  float w_rec, w_kg;       // weight of one (positive, negative) pair in the scalar loss
-  float wpos_rec, wpos_kg; // BCE models: weight of the positive term (= w * k)
+  float w_rec, w_kg;        // weight of one (positive, negative) pair in the scalar loss
+  float wpos_rec, wpos_kg;  // BCE models: weight of the positive term (= w * k)
   int with_grad;
   float* loss;
-  int cap_user, cap_entity, cap_relation;  // per-CTA capacity of the staged unique-row lists
 };
 
 __device__ __forceinline__ float2 adam_consts(const AdamDev& A, int j) {
@@ -82,11 +84,16 @@ __device__ __forceinline__ void adam_replay(float (&p)[E], float (&m)[E], float 
   }
 }
 
-// Current value (as of step-1) of one part of a row, replaying lazily-skipped steps on the fly.
+// {last_step, touch_step} of a row; tables without optimiser state read as never updated.
+__device__ __forceinline__ int2 row_state(const kge_table_t& T, int64_t row) {
+  if (!T.row_state) return make_int2(-1, -1);
+  return *(reinterpret_cast<const int2*>(T.row_state) + row);
+}
+
+// Bring a fragment that was loaded from w up to step-1 when the row lags behind (rare path).
 template <int VEC, int G, int NCH>
-__device__ __forceinline__ void load_current(const kge_table_t& T, int part, int64_t row, int last, int d, int gl,
-                                             const AdamDev& A, float (&x)[VEC * NCH]) {
-  frag_load<VEC, G, NCH>(T.w[part], row, d, gl, x);
+__device__ __forceinline__ void catch_up(const kge_table_t& T, int part, int64_t row, int last, int d, int gl,
+                                         const AdamDev& A, float (&x)[VEC * NCH]) {
   if (last >= 0 && last < A.step - 1) {
     float m[VEC * NCH], v[VEC * NCH];
     frag_load<VEC, G, NCH>(T.m[part], row, d, gl, m);
@@ -95,62 +102,29 @@ __device__ __forceinline__ void load_current(const kge_table_t& T, int part, int
   }
 }
 
-__device__ __forceinline__ int row_last(const kge_table_t& T, int64_t row) {
-  return T.last_step ? __ldg(T.last_step + row) : -1;
-}
-
-template <int G>
-__device__ __forceinline__ void touch_row(const kge_table_t& T, int32_t* counter, int64_t row, int step, int gl) {
-  if (gl == 0) {
-    if (*reinterpret_cast<volatile int32_t*>(T.touch_step + row) != step) {
-      const int old = atomicExch(T.touch_step + row, step);
-      if (old != step) {
-        const int pos = atomicAdd(counter, 1);
-        T.uniq[pos] = (int32_t)row;
-      }
-    }
-  }
-}
-
-// Same, but the new row goes to a per-CTA list in shared memory (table index t: 0 user, 1 entity,
-// 2 relation); the CTA publishes its lists with one global atomicAdd per table at the end, so
-// the unique-row counters are not hammered by one returning atomic per touched row.
-struct StageLists {
-  int* cnt;      // [3]
-  int32_t* list[3];
-};
-template <int G>
-__device__ __forceinline__ void touch_row_staged(const kge_table_t& T, const StageLists& S, int t, int64_t row,
-                                                 int step, int gl) {
-  if (gl == 0) {
-    if (*reinterpret_cast<volatile int32_t*>(T.touch_step + row) != step) {
-      const int old = atomicExch(T.touch_step + row, step);
-      if (old != step) {
-        const int pos = atomicAdd(&S.cnt[t], 1);
-        S.list[t][pos] = (int32_t)row;
-      }
-    }
-  }
+// Mark a row as touched in `step` (idempotent plain store; skipped when the loaded state shows it).
+__device__ __forceinline__ void mark_row(const kge_table_t& T, int64_t row, int seen_touch, int step, int gl) {
+  if (gl == 0 && seen_touch != step) T.row_state[2 * row + 1] = step;
 }
 
 __device__ __forceinline__ float softplusf(float z) { return fmaxf(z, 0.f) + log1pf(expf(-fabsf(z))); }
 __device__ __forceinline__ float sigmoidf(float z) { return 1.f / (1.f + expf(-z)); }
 
+template <int MODEL, int VEC, int NCH>
+struct FwdBounds {
+  static constexpr int E = VEC * NCH;
+  static constexpr int PH = (MODEL == KGE_ROTATE || MODEL == KGE_COMPLEX) ? 2 : 1;
+  // resident CTAs per SM the register budget is shaped for (more warps = more loads in flight)
+  static constexpr int MIN_CTAS = (E * PH <= 4) ? 4 : (E * PH <= 8 ? 3 : (E * PH <= 16 ? 2 : 1));
+};
+
 template <int MODEL, int VEC, int G, int NCH>
-__global__ void __launch_bounds__(256) train_fwd_kernel(const TrainArgs a) {
+__global__ void __launch_bounds__(256, FwdBounds<MODEL, VEC, NCH>::MIN_CTAS) train_fwd_kernel(const TrainArgs a) {
   constexpr int E = VEC * NCH;
   constexpr int PH = (MODEL == KGE_ROTATE || MODEL == KGE_COMPLEX) ? 2 : 1;  // head / tail parts
   constexpr int PR = (MODEL == KGE_COMPLEX) ? 2 : 1;                          // relation parts
-  extern __shared__ float s_racc[];  // [PR][d] user->item relation gradient of this CTA, then the staged lists
+  extern __shared__ float s_racc[];  // [PR][d] user->item relation gradient of this CTA
   __shared__ float s_loss[8];
-  __shared__ int s_cnt[3];
-  __shared__ int s_base[3];
-  StageLists S;
-  S.cnt = s_cnt;
-  S.list[0] = reinterpret_cast<int32_t*>(s_racc + PR * a.m.d);
-  S.list[1] = S.list[0] + a.cap_user;
-  S.list[2] = S.list[1] + a.cap_entity;
-  if (threadIdx.x < 3) s_cnt[threadIdx.x] = 0;
 
   const int d = a.m.d;
   const int gl = (threadIdx.x & 31) % G;
@@ -158,8 +132,9 @@ __global__ void __launch_bounds__(256) train_fwd_kernel(const TrainArgs a) {
   const int64_t n_groups = (int64_t)gridDim.x * groups_per_cta;
   const int64_t n_rec = a.b.n_rec, n_total = a.b.n_rec + a.b.n_kg;
   const int step = a.adam.step;
-  int32_t* cnt = a.m.counters + (step & 1) * 4;
   const float margin = a.m.margin;
+  const kge_table_t& ET = a.m.entity;
+  const kge_table_t& RT = a.m.relation;
 
   for (int i = threadIdx.x; i < PR * d; i += blockDim.x) s_racc[i] = 0.f;
   __syncthreads();
@@ -178,23 +153,32 @@ __global__ void __launch_bounds__(256) train_fwd_kernel(const TrainArgs a) {
     const int64_t n_seg = is_rec ? a.b.n_rec : a.b.n_kg;
     const int K = is_rec ? a.b.k_rec : a.b.k_kg;
     const kge_table_t& HT = is_rec ? a.m.user : a.m.entity;
-    const int64_t h_id = is_rec ? __ldg(a.b.user + i) : __ldg(a.b.head + i);
-    const int64_t r_id = is_rec ? (int64_t)a.m.ui_relation : __ldg(a.b.relation + i);
-    const int64_t tp_id = is_rec ? __ldg(a.b.item + i) : __ldg(a.b.tail + i);
     const int64_t* negs = is_rec ? a.b.neg_item : a.b.neg_tail;
     const float w = is_rec ? a.w_rec : a.w_kg;
     const float wpos = is_rec ? a.wpos_rec : a.wpos_kg;
 
-    float h[PH][E], r[PR][E], tp[PH][E];
-    {
-      const int lh = row_last(HT, h_id), lr_ = row_last(a.m.relation, r_id), lt = row_last(a.m.entity, tp_id);
+    // ---- one memory latency: ids, then every row state and row fragment of the triple ---------------
+    const int64_t h_id = is_rec ? __ldg(a.b.user + i) : __ldg(a.b.head + i);
+    const int64_t r_id = is_rec ? (int64_t)a.m.ui_relation : __ldg(a.b.relation + i);
+    const int64_t tp_id = is_rec ? __ldg(a.b.item + i) : __ldg(a.b.tail + i);
+    int64_t tn_id = __ldg(negs + i);
+    const int2 sh = row_state(HT, h_id), sr = row_state(RT, r_id), stp = row_state(ET, tp_id);
+    int2 stn = row_state(ET, tn_id);
+    float h[PH][E], r[PR][E], tp[PH][E], tnx[PH][E];
 #pragma unroll
-      for (int p = 0; p < PH; ++p) load_current<VEC, G, NCH>(HT, p, h_id, lh, d, gl, a.adam, h[p]);
+    for (int p = 0; p < PH; ++p) frag_load<VEC, G, NCH>(HT.w[p], h_id, d, gl, h[p]);
 #pragma unroll
-      for (int p = 0; p < PR; ++p) load_current<VEC, G, NCH>(a.m.relation, p, r_id, lr_, d, gl, a.adam, r[p]);
+    for (int p = 0; p < PR; ++p) frag_load<VEC, G, NCH>(RT.w[p], r_id, d, gl, r[p]);
 #pragma unroll
-      for (int p = 0; p < PH; ++p) load_current<VEC, G, NCH>(a.m.entity, p, tp_id, lt, d, gl, a.adam, tp[p]);
-    }
+    for (int p = 0; p < PH; ++p) frag_load<VEC, G, NCH>(ET.w[p], tp_id, d, gl, tp[p]);
+#pragma unroll
+    for (int p = 0; p < PH; ++p) frag_load<VEC, G, NCH>(ET.w[p], tn_id, d, gl, tnx[p]);
+#pragma unroll
+    for (int p = 0; p < PH; ++p) catch_up<VEC, G, NCH>(HT, p, h_id, sh.x, d, gl, a.adam, h[p]);
+#pragma unroll
+    for (int p = 0; p < PR; ++p) catch_up<VEC, G, NCH>(RT, p, r_id, sr.x, d, gl, a.adam, r[p]);
+#pragma unroll
+    for (int p = 0; p < PH; ++p) catch_up<VEC, G, NCH>(ET, p, tp_id, stp.x, d, gl, a.adam, tp[p]);
 
     // gradient fragments of the anchor, relation and positive tail
     float gh[PH][E], gr[PR][E], gtp[PH][E];
@@ -209,37 +193,96 @@ __global__ void __launch_bounds__(256) train_fwd_kernel(const TrainArgs a) {
     bool any_grad = false;
     float inst_loss = 0.f;
 
+    // ---- model-specific precomputation on (h, r, positive tail) -------------------------------------
+    // TransE:   c0 = x = h + r, c1 = w * unit(x - tp + eps), s_pos = ||x - tp + eps||  (transe.py:96)
+    // DistMult: c0 = q = h * r, s_pos = q . tp                                         (distmult.py:90-93)
+    // RotatE:   c0 = cos, c1 = sin of the phases, (c2, c3) = rot(h)                    (rotate.py:118-131)
+    // ComplEx:  c0 = A = hr*rr, c1 = B = hi*rr + hr*ri - hi*ri                          (complex.py:115-128)
+    float c0[E], c1[E], c2[E], c3[E];
+    float acc0[E], acc1[E];  // per-triple accumulators over the tails
+    float s_pos = 0.f;
+#pragma unroll
+    for (int e = 0; e < E; ++e) { c0[e] = c1[e] = c2[e] = c3[e] = 0.f; acc0[e] = acc1[e] = 0.f; }
+    float nact = 0.f;
     if (MODEL == KGE_TRANSE) {
-      // pair loss: clamp_min(margin + ||x - tp + eps|| - ||x - tn + eps||, 0), x = h + r
-      float x[E], up[E];
       float sp = 0.f;
 #pragma unroll
       for (int e = 0; e < E; ++e) {
-        x[e] = h[0][e] + r[0][e];
-        const float dp = frag_valid<VEC, G, NCH>(d, gl, e) ? (x[e] - tp[0][e] + 1e-6f) : 0.f;
-        up[e] = dp;
+        c0[e] = h[0][e] + r[0][e];
+        const float dp = frag_valid<VEC, G, NCH>(d, gl, e) ? (c0[e] - tp[0][e] + 1e-6f) : 0.f;
+        c1[e] = dp;
         sp += dp * dp;
       }
-      const float np_ = sqrtf(group_sum<G>(sp));
-      const float inv_p = np_ > 0.f ? 1.f / np_ : 0.f;
-      // the positive and the negative term are formed by the same operations, so that a pair
-      // whose negative equals its positive cancels exactly, as it does under autograd
+      s_pos = sqrtf(group_sum<G>(sp));
+      const float inv_p = s_pos > 0.f ? 1.f / s_pos : 0.f;
+      // positive and negative terms are formed by the same operations so that a pair whose
+      // negative equals its positive cancels exactly, as it does under autograd
 #pragma unroll
-      for (int e = 0; e < E; ++e) up[e] = w * (up[e] * inv_p);
-      float nact = 0.f;
-      for (int j = 0; j < K; ++j) {
-        const int64_t tn_id = __ldg(negs + (int64_t)j * n_seg + i);
-        float tn[E];
-        load_current<VEC, G, NCH>(a.m.entity, 0, tn_id, row_last(a.m.entity, tn_id), d, gl, a.adam, tn);
+      for (int e = 0; e < E; ++e) c1[e] = w * (c1[e] * inv_p);
+    } else if (MODEL == KGE_DISTMULT) {
+      float sp = 0.f;
+#pragma unroll
+      for (int e = 0; e < E; ++e) {
+        c0[e] = h[0][e] * r[0][e];
+        sp += c0[e] * tp[0][e];
+      }
+      s_pos = group_sum<G>(sp);
+    } else if (MODEL == KGE_ROTATE) {
+#pragma unroll
+      for (int e = 0; e < E; ++e) {
+        sincosf(r[0][e], &c1[e], &c0[e]);
+        c2[e] = c0[e] * h[0][e] - c1[e] * h[PH - 1][e];
+        c3[e] = c0[e] * h[PH - 1][e] + c1[e] * h[0][e];
+      }
+    } else {
+#pragma unroll
+      for (int e = 0; e < E; ++e) {
+        c0[e] = h[0][e] * r[0][e];
+        c1[e] = h[PH - 1][e] * r[0][e] + h[0][e] * r[PR - 1][e] - h[PH - 1][e] * r[PR - 1][e];
+      }
+    }
+
+    // ---- tails: j = -1 is the positive (BCE models only), then K negatives, prefetched one ahead ------
+    const int j0 = (MODEL == KGE_ROTATE || MODEL == KGE_COMPLEX) ? -1 : 0;
+    for (int j = j0; j < K; ++j) {
+      const bool pos = j < 0;
+      float t[PH][E];
+      int64_t t_id;
+      int2 st;
+      if (pos) {
+        t_id = tp_id;
+        st = stp;
+#pragma unroll
+        for (int p = 0; p < PH; ++p)
+#pragma unroll
+          for (int e = 0; e < E; ++e) t[p][e] = tp[p][e];
+      } else {
+        t_id = tn_id;
+        st = stn;
+#pragma unroll
+        for (int p = 0; p < PH; ++p)
+#pragma unroll
+          for (int e = 0; e < E; ++e) t[p][e] = tnx[p][e];
+        if (j + 1 < K) {  // prefetch the next negative while this one is consumed
+          tn_id = __ldg(negs + (int64_t)(j + 1) * n_seg + i);
+          stn = row_state(ET, tn_id);
+#pragma unroll
+          for (int p = 0; p < PH; ++p) frag_load<VEC, G, NCH>(ET.w[p], tn_id, d, gl, tnx[p]);
+        }
+#pragma unroll
+        for (int p = 0; p < PH; ++p) catch_up<VEC, G, NCH>(ET, p, t_id, st.x, d, gl, a.adam, t[p]);
+      }
+
+      if (MODEL == KGE_TRANSE) {
         float sn = 0.f;
 #pragma unroll
         for (int e = 0; e < E; ++e) {
-          const float dn = frag_valid<VEC, G, NCH>(d, gl, e) ? (x[e] - tn[e] + 1e-6f) : 0.f;
-          tn[e] = dn;
+          const float dn = frag_valid<VEC, G, NCH>(d, gl, e) ? (c0[e] - t[0][e] + 1e-6f) : 0.f;
+          t[0][e] = dn;
           sn += dn * dn;
         }
         const float nn_ = sqrtf(group_sum<G>(sn));
-        const float z = margin + np_ - nn_;
+        const float z = margin + s_pos - nn_;
         if (z >= 0.f) {
           inst_loss += z * w;
           if (a.with_grad) {
@@ -247,41 +290,20 @@ __global__ void __launch_bounds__(256) train_fwd_kernel(const TrainArgs a) {
             nact += 1.f;
 #pragma unroll
             for (int e = 0; e < E; ++e) {
-              tn[e] = w * (tn[e] * inv_n);  // gradient of the negative tail
-              gh[0][e] += up[e] - tn[e];
-              gtp[0][e] -= up[e];
+              t[0][e] = w * (t[0][e] * inv_n);  // gradient of the negative tail
+              gh[0][e] += c1[e] - t[0][e];
+              gtp[0][e] -= c1[e];
             }
-            frag_atomic_add<VEC, G, NCH>(a.m.entity.g[0], tn_id, d, gl, tn);
-            touch_row_staged<G>(a.m.entity, S, 1, tn_id, step, gl);
+            frag_atomic_add<VEC, G, NCH>(ET.g[0], t_id, d, gl, t[0]);
+            mark_row(ET, t_id, st.y, step, gl);
           }
         }
-      }
-      if (nact > 0.f) {
-        any_grad = true;
-#pragma unroll
-        for (int e = 0; e < E; ++e) gr[0][e] = gh[0][e];
-      }
-    } else if (MODEL == KGE_DISTMULT) {
-      // pair loss: clamp_min(margin - s+ + s-, 0), s = sum h*r*t
-      float q[E], dacc[E];
-      float sp = 0.f;
-#pragma unroll
-      for (int e = 0; e < E; ++e) {
-        q[e] = h[0][e] * r[0][e];
-        sp += q[e] * tp[0][e];
-        dacc[e] = 0.f;
-      }
-      sp = group_sum<G>(sp);
-      float nact = 0.f;
-      for (int j = 0; j < K; ++j) {
-        const int64_t tn_id = __ldg(negs + (int64_t)j * n_seg + i);
-        float tn[E];
-        load_current<VEC, G, NCH>(a.m.entity, 0, tn_id, row_last(a.m.entity, tn_id), d, gl, a.adam, tn);
+      } else if (MODEL == KGE_DISTMULT) {
         float sn = 0.f;
 #pragma unroll
-        for (int e = 0; e < E; ++e) sn += q[e] * tn[e];
+        for (int e = 0; e < E; ++e) sn += c0[e] * t[0][e];
         sn = group_sum<G>(sn);
-        const float z = margin - sp + sn;
+        const float z = margin - s_pos + sn;
         if (z >= 0.f) {
           inst_loss += z * w;
           if (a.with_grad) {
@@ -289,52 +311,21 @@ __global__ void __launch_bounds__(256) train_fwd_kernel(const TrainArgs a) {
             float gtn[E];
 #pragma unroll
             for (int e = 0; e < E; ++e) {
-              dacc[e] += w * (tn[e] - tp[0][e]);
-              gtn[e] = w * q[e];
+              acc0[e] += w * (t[0][e] - tp[0][e]);
+              gtn[e] = w * c0[e];
             }
-            frag_atomic_add<VEC, G, NCH>(a.m.entity.g[0], tn_id, d, gl, gtn);
-            touch_row_staged<G>(a.m.entity, S, 1, tn_id, step, gl);
+            frag_atomic_add<VEC, G, NCH>(ET.g[0], t_id, d, gl, gtn);
+            mark_row(ET, t_id, st.y, step, gl);
           }
         }
-      }
-      if (nact > 0.f) {
-        any_grad = true;
-#pragma unroll
-        for (int e = 0; e < E; ++e) {
-          gh[0][e] = r[0][e] * dacc[e];
-          gr[0][e] = h[0][e] * dacc[e];
-          gtp[0][e] = -nact * w * q[e];
-        }
-      }
-    } else if (MODEL == KGE_ROTATE) {
-      // score = margin - || (rot(h, theta) - t) ||_2 over the stacked (re, im) vector; BCE with logits
-      float cs[E], sn_[E], rre[E], rim[E], qre[E], qim[E];
-#pragma unroll
-      for (int e = 0; e < E; ++e) {
-        sincosf(r[0][e], &sn_[e], &cs[e]);
-        rre[e] = cs[e] * h[0][e] - sn_[e] * h[1][e];
-        rim[e] = cs[e] * h[1][e] + sn_[e] * h[0][e];
-        qre[e] = 0.f;
-        qim[e] = 0.f;
-      }
-      for (int j = -1; j < K; ++j) {
-        const bool pos = j < 0;
-        const int64_t t_id = pos ? tp_id : __ldg(negs + (int64_t)j * n_seg + i);
-        float tre[E], tim[E];
-        if (pos) {
-#pragma unroll
-          for (int e = 0; e < E; ++e) { tre[e] = tp[0][e]; tim[e] = tp[1][e]; }
-        } else {
-          const int lt = row_last(a.m.entity, t_id);
-          load_current<VEC, G, NCH>(a.m.entity, 0, t_id, lt, d, gl, a.adam, tre);
-          load_current<VEC, G, NCH>(a.m.entity, 1, t_id, lt, d, gl, a.adam, tim);
-        }
+      } else if (MODEL == KGE_ROTATE) {
+        // score = margin - || rot(h, theta) - t ||_2 over the stacked (re, im) vector
         float ss = 0.f;
 #pragma unroll
         for (int e = 0; e < E; ++e) {
-          tre[e] = rre[e] - tre[e];  // residual; padding lanes are 0 - 0
-          tim[e] = rim[e] - tim[e];
-          ss += tre[e] * tre[e] + tim[e] * tim[e];
+          t[0][e] = c2[e] - t[0][e];  // residual; padding lanes are 0 - 0
+          t[PH - 1][e] = c3[e] - t[PH - 1][e];
+          ss += t[0][e] * t[0][e] + t[PH - 1][e] * t[PH - 1][e];
         }
         const float nrm = sqrtf(group_sum<G>(ss));
         const float sc = margin - nrm;
@@ -346,57 +337,29 @@ __global__ void __launch_bounds__(256) train_fwd_kernel(const TrainArgs a) {
           const float f = nrm > 0.f ? -dl / nrm : 0.f;  // dL/d(residual) = dl * (-e / nrm)
 #pragma unroll
           for (int e = 0; e < E; ++e) {
-            tre[e] *= f;
-            tim[e] *= f;
-            qre[e] += tre[e];
-            qim[e] += tim[e];
-            tre[e] = -tre[e];  // gradient of the tail
-            tim[e] = -tim[e];
+            t[0][e] *= f;
+            t[PH - 1][e] *= f;
+            acc0[e] += t[0][e];
+            acc1[e] += t[PH - 1][e];
+            t[0][e] = -t[0][e];  // gradient of the tail
+            t[PH - 1][e] = -t[PH - 1][e];
           }
           if (pos) {
 #pragma unroll
-            for (int e = 0; e < E; ++e) { gtp[0][e] = tre[e]; gtp[1][e] = tim[e]; }
+            for (int p = 0; p < PH; ++p)
+#pragma unroll
+              for (int e = 0; e < E; ++e) gtp[p][e] = t[p][e];
           } else {
-            frag_atomic_add<VEC, G, NCH>(a.m.entity.g[0], t_id, d, gl, tre);
-            frag_atomic_add<VEC, G, NCH>(a.m.entity.g[1], t_id, d, gl, tim);
-            touch_row_staged<G>(a.m.entity, S, 1, t_id, step, gl);
+#pragma unroll
+            for (int p = 0; p < PH; ++p) frag_atomic_add<VEC, G, NCH>(ET.g[p], t_id, d, gl, t[p]);
+            mark_row(ET, t_id, st.y, step, gl);
           }
         }
-      }
-      if (any_grad) {
-#pragma unroll
-        for (int e = 0; e < E; ++e) {
-          gh[0][e] = cs[e] * qre[e] + sn_[e] * qim[e];
-          gh[1][e] = -sn_[e] * qre[e] + cs[e] * qim[e];
-          gr[0][e] = -qre[e] * rim[e] + qim[e] * rre[e];
-        }
-      }
-    } else {
-      // ComplEx as written in the reference: s = sum tr*A + ti*B,
-      // A = hr*rr, B = hi*rr + hr*ri - hi*ri (the 4th term pairs with tail_im)
-      float A_[E], B_[E], Tr[E], Ti[E];
-#pragma unroll
-      for (int e = 0; e < E; ++e) {
-        A_[e] = h[0][e] * r[0][e];
-        B_[e] = h[1][e] * r[0][e] + h[0][e] * r[1][e] - h[1][e] * r[1][e];
-        Tr[e] = 0.f;
-        Ti[e] = 0.f;
-      }
-      for (int j = -1; j < K; ++j) {
-        const bool pos = j < 0;
-        const int64_t t_id = pos ? tp_id : __ldg(negs + (int64_t)j * n_seg + i);
-        float tre[E], tim[E];
-        if (pos) {
-#pragma unroll
-          for (int e = 0; e < E; ++e) { tre[e] = tp[0][e]; tim[e] = tp[1][e]; }
-        } else {
-          const int lt = row_last(a.m.entity, t_id);
-          load_current<VEC, G, NCH>(a.m.entity, 0, t_id, lt, d, gl, a.adam, tre);
-          load_current<VEC, G, NCH>(a.m.entity, 1, t_id, lt, d, gl, a.adam, tim);
-        }
+      } else {
+        // ComplEx as written in the reference: s = sum tr*A + ti*B
         float ss = 0.f;
 #pragma unroll
-        for (int e = 0; e < E; ++e) ss += tre[e] * A_[e] + tim[e] * B_[e];
+        for (int e = 0; e < E; ++e) ss += t[0][e] * c0[e] + t[PH - 1][e] * c1[e];
         const float sc = group_sum<G>(ss);
         float dl;
         if (pos) { inst_loss += wpos * softplusf(-sc); dl = -wpos * sigmoidf(-sc); }
@@ -405,28 +368,59 @@ __global__ void __launch_bounds__(256) train_fwd_kernel(const TrainArgs a) {
           any_grad = true;
 #pragma unroll
           for (int e = 0; e < E; ++e) {
-            Tr[e] += dl * tre[e];
-            Ti[e] += dl * tim[e];
-            tre[e] = dl * A_[e];
-            tim[e] = dl * B_[e];
+            acc0[e] += dl * t[0][e];
+            acc1[e] += dl * t[PH - 1][e];
+            t[0][e] = dl * c0[e];
+            t[PH - 1][e] = dl * c1[e];
           }
           if (pos) {
 #pragma unroll
-            for (int e = 0; e < E; ++e) { gtp[0][e] = tre[e]; gtp[1][e] = tim[e]; }
+            for (int p = 0; p < PH; ++p)
+#pragma unroll
+              for (int e = 0; e < E; ++e) gtp[p][e] = t[p][e];
           } else {
-            frag_atomic_add<VEC, G, NCH>(a.m.entity.g[0], t_id, d, gl, tre);
-            frag_atomic_add<VEC, G, NCH>(a.m.entity.g[1], t_id, d, gl, tim);
-            touch_row_staged<G>(a.m.entity, S, 1, t_id, step, gl);
+#pragma unroll
+            for (int p = 0; p < PH; ++p) frag_atomic_add<VEC, G, NCH>(ET.g[p], t_id, d, gl, t[p]);
+            mark_row(ET, t_id, st.y, step, gl);
           }
         }
       }
+    }
+
+    // ---- gradients of head, relation and positive tail from the accumulators ------------------------
+    if (MODEL == KGE_TRANSE) {
+      if (nact > 0.f) {
+        any_grad = true;
+#pragma unroll
+        for (int e = 0; e < E; ++e) gr[0][e] = gh[0][e];
+      }
+    } else if (MODEL == KGE_DISTMULT) {
+      if (nact > 0.f) {
+        any_grad = true;
+#pragma unroll
+        for (int e = 0; e < E; ++e) {
+          gh[0][e] = r[0][e] * acc0[e];
+          gr[0][e] = h[0][e] * acc0[e];
+          gtp[0][e] = -nact * w * c0[e];
+        }
+      }
+    } else if (MODEL == KGE_ROTATE) {
       if (any_grad) {
 #pragma unroll
         for (int e = 0; e < E; ++e) {
-          gh[0][e] = r[0][e] * Tr[e] + r[1][e] * Ti[e];
-          gh[1][e] = r[0][e] * Ti[e] - r[1][e] * Ti[e];
-          gr[0][e] = h[0][e] * Tr[e] + h[1][e] * Ti[e];
-          gr[1][e] = h[0][e] * Ti[e] - h[1][e] * Ti[e];
+          gh[0][e] = c0[e] * acc0[e] + c1[e] * acc1[e];
+          gh[PH - 1][e] = -c1[e] * acc0[e] + c0[e] * acc1[e];
+          gr[0][e] = -acc0[e] * c3[e] + acc1[e] * c2[e];
+        }
+      }
+    } else {
+      if (any_grad) {
+#pragma unroll
+        for (int e = 0; e < E; ++e) {
+          gh[0][e] = r[0][e] * acc0[e] + r[PR - 1][e] * acc1[e];
+          gh[PH - 1][e] = r[0][e] * acc1[e] - r[PR - 1][e] * acc1[e];
+          gr[0][e] = h[0][e] * acc0[e] + h[PH - 1][e] * acc1[e];
+          gr[PR - 1][e] = h[0][e] * acc1[e] - h[PH - 1][e] * acc1[e];
         }
       }
     }
@@ -437,10 +431,10 @@ __global__ void __launch_bounds__(256) train_fwd_kernel(const TrainArgs a) {
 #pragma unroll
       for (int p = 0; p < PH; ++p) {
         frag_atomic_add<VEC, G, NCH>(HT.g[p], h_id, d, gl, gh[p]);
-        frag_atomic_add<VEC, G, NCH>(a.m.entity.g[p], tp_id, d, gl, gtp[p]);
+        frag_atomic_add<VEC, G, NCH>(ET.g[p], tp_id, d, gl, gtp[p]);
       }
-      touch_row_staged<G>(HT, S, is_rec ? 0 : 1, h_id, step, gl);
-      touch_row_staged<G>(a.m.entity, S, 1, tp_id, step, gl);
+      mark_row(HT, h_id, sh.y, step, gl);
+      mark_row(ET, tp_id, stp.y, step, gl);
       if (is_rec) {
         rec_seen = true;
 #pragma unroll
@@ -449,8 +443,8 @@ __global__ void __launch_bounds__(256) train_fwd_kernel(const TrainArgs a) {
           for (int e = 0; e < E; ++e) racc[p][e] += gr[p][e];
       } else {
 #pragma unroll
-        for (int p = 0; p < PR; ++p) frag_atomic_add<VEC, G, NCH>(a.m.relation.g[p], r_id, d, gl, gr[p]);
-        touch_row_staged<G>(a.m.relation, S, 2, r_id, step, gl);
+        for (int p = 0; p < PR; ++p) frag_atomic_add<VEC, G, NCH>(RT.g[p], r_id, d, gl, gr[p]);
+        mark_row(RT, r_id, sr.y, step, gl);
       }
     }
   }
@@ -471,19 +465,9 @@ __global__ void __launch_bounds__(256) train_fwd_kernel(const TrainArgs a) {
   if (any_rec) {
     for (int i = threadIdx.x; i < PR * d; i += blockDim.x) {
       const int p = i / d, col = i - p * d;
-      atomicAdd(a.m.relation.g[p] + (int64_t)a.m.ui_relation * d + col, s_racc[i]);
+      atomicAdd(RT.g[p] + (int64_t)a.m.ui_relation * d + col, s_racc[i]);
     }
-    if (threadIdx.x == 0) touch_row_staged<1>(a.m.relation, S, 2, a.m.ui_relation, step, 0);
-  }
-  // ---- publish the staged unique-row lists: one returning atomic per table per CTA -----------------
-  __syncthreads();
-  if (threadIdx.x < 3) s_base[threadIdx.x] = s_cnt[threadIdx.x] ? atomicAdd(cnt + threadIdx.x, s_cnt[threadIdx.x]) : 0;
-  __syncthreads();
-  {
-    int32_t* dst[3] = {a.m.user.uniq, a.m.entity.uniq, a.m.relation.uniq};
-#pragma unroll
-    for (int t = 0; t < 3; ++t)
-      for (int i = threadIdx.x; i < s_cnt[t]; i += blockDim.x) dst[t][s_base[t] + i] = S.list[t][i];
+    if (threadIdx.x == 0) RT.row_state[2 * (int64_t)a.m.ui_relation + 1] = step;
   }
   lsum = warp_sum(lsum);
   if ((threadIdx.x & 31) == 0) s_loss[threadIdx.x >> 5] = lsum;
@@ -495,19 +479,49 @@ __global__ void __launch_bounds__(256) train_fwd_kernel(const TrainArgs a) {
   }
 }
 
-// ---- kernel B: exact lazy Adam on the touched rows ------------------------------------------
+// ---- scanning the row states -------------------------------------------------------------------
+// Lanes read the 8-byte states of 32 consecutive rows, ballot the rows selected by `pred` and the
+// lane groups of the warp then work on the selected rows, 32/G at a time.  `body(row, last_step)`
+// runs converged within a group.
+// `win` (4..32) rows per warp window: small windows spread a densely touched small table over
+// more warps, 32 keeps the scan of a large sparse table cheap.
+template <int G, typename Pred, typename Body>
+__device__ __forceinline__ void for_selected_rows(const kge_table_t& T, int win, Pred pred, Body body) {
+  constexpr int NG = 32 / G;
+  const int lane = threadIdx.x & 31;
+  const int grp = lane / G;
+  const int64_t warp_global = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int64_t n_warps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+  for (int64_t base = warp_global * win; base < T.rows; base += n_warps * win) {
+    const int64_t row = base + lane;
+    const bool mine = lane < win && row < T.rows;
+    int2 st = make_int2(-1, -1);
+    if (mine) st = *(reinterpret_cast<const int2*>(T.row_state) + row);
+    unsigned mask = __ballot_sync(0xffffffffu, mine && pred(st));
+    while (mask) {
+      unsigned m = mask;  // group `grp` takes the grp-th set bit
+      for (int q = 0; q < grp; ++q) m &= m - 1;
+      const int bit = m ? (__ffs(m) - 1) : -1;
+      const int last = __shfl_sync(0xffffffffu, st.x, bit < 0 ? 0 : bit);
+      if (bit >= 0) body(base + bit, last);
+      for (int q = 0; q < NG && mask; ++q) mask &= mask - 1;
+      __syncwarp();
+    }
+  }
+}
+
 struct ApplyArgs {
   kge_model_t m;
   AdamDev adam;
   float scale;
   const float* scale_dev;  // optional device-side factor (the incoming grad of the loss)
+  int win[3];              // scan window per table
 };
 
 template <int VEC, int G, int NCH>
-__device__ __forceinline__ void adam_row(const kge_table_t& T, int64_t row, int d, int gl, const AdamDev& A,
+__device__ __forceinline__ void adam_row(const kge_table_t& T, int64_t row, int last, int d, int gl, const AdamDev& A,
                                          float scale) {
   constexpr int E = VEC * NCH;
-  const int last = T.last_step[row];
   const float2 c = adam_consts(A, A.step);
   for (int part = 0; part < T.parts; ++part) {
     float p[E], m[E], v[E], g[E];
@@ -531,82 +545,105 @@ __device__ __forceinline__ void adam_row(const kge_table_t& T, int64_t row, int 
     frag_store<VEC, G, NCH>(T.v[part], row, d, gl, v);
     frag_store<VEC, G, NCH>(T.g[part], row, d, gl, z);
   }
-  __syncwarp(group_mask<G>());  // every lane has read last_step
-  if (gl == 0) T.last_step[row] = A.step;
+  if (gl == 0) T.row_state[2 * row] = A.step;  // last_step; touch_step keeps `step` (stale from step+1 on)
 }
 
 template <int VEC, int G, int NCH>
 __global__ void __launch_bounds__(256) adam_apply_kernel(const ApplyArgs a) {
   const int gl = (threadIdx.x & 31) % G;
-  const int groups_per_cta = blockDim.x / G;
-  const int64_t n_groups = (int64_t)gridDim.x * groups_per_cta;
-  const int32_t* cnt = a.m.counters + (a.adam.step & 1) * 4;
-  const int64_t cu = cnt[0], ce = cnt[1], cr = cnt[2];
-  const int64_t total = cu + ce + cr;
+  const int step = a.adam.step;
   const float scale = a.scale_dev ? a.scale * __ldg(a.scale_dev) : a.scale;
-  for (int64_t idx = (int64_t)blockIdx.x * groups_per_cta + threadIdx.x / G; idx < total; idx += n_groups) {
-    if (idx < cu) adam_row<VEC, G, NCH>(a.m.user, a.m.user.uniq[idx], a.m.d, gl, a.adam, scale);
-    else if (idx < cu + ce) adam_row<VEC, G, NCH>(a.m.entity, a.m.entity.uniq[idx - cu], a.m.d, gl, a.adam, scale);
-    else adam_row<VEC, G, NCH>(a.m.relation, a.m.relation.uniq[idx - cu - ce], a.m.d, gl, a.adam, scale);
-  }
-  // hand the next step a zeroed set of counters (the other parity)
-  if (blockIdx.x == 0 && threadIdx.x < 4) a.m.counters[((a.adam.step + 1) & 1) * 4 + threadIdx.x] = 0;
+  auto marked = [step](int2 st) { return st.y == step; };
+  // (the tables are kernel parameters: index them by name, a pointer array would copy them to local memory)
+  for_selected_rows<G>(a.m.user, a.win[0], marked, [&](int64_t row, int last) {
+    adam_row<VEC, G, NCH>(a.m.user, row, last, a.m.d, gl, a.adam, scale);
+  });
+  for_selected_rows<G>(a.m.entity, a.win[1], marked, [&](int64_t row, int last) {
+    adam_row<VEC, G, NCH>(a.m.entity, row, last, a.m.d, gl, a.adam, scale);
+  });
+  for_selected_rows<G>(a.m.relation, a.win[2], marked, [&](int64_t row, int last) {
+    adam_row<VEC, G, NCH>(a.m.relation, row, last, a.m.d, gl, a.adam, scale);
+  });
 }
 
 // ---- dense catch-up of every row to adam.step (before weights are read by others) ------------
 template <int VEC, int G, int NCH>
-__global__ void __launch_bounds__(256) adam_flush_kernel(const kge_table_t T, int d, const AdamDev A) {
+__global__ void __launch_bounds__(256) adam_flush_kernel(const kge_table_t T, int d, const AdamDev A, int win) {
   constexpr int E = VEC * NCH;
   const int gl = (threadIdx.x & 31) % G;
-  const int groups_per_cta = blockDim.x / G;
-  const int64_t n_groups = (int64_t)gridDim.x * groups_per_cta;
-  for (int64_t row = (int64_t)blockIdx.x * groups_per_cta + threadIdx.x / G; row < T.rows; row += n_groups) {
-    const int last = T.last_step[row];
-    if (last < 0 || last >= A.step) continue;
-    for (int part = 0; part < T.parts; ++part) {
-      float p[E], m[E], v[E];
-      frag_load<VEC, G, NCH>(T.w[part], row, d, gl, p);
-      frag_load<VEC, G, NCH>(T.m[part], row, d, gl, m);
-      frag_load<VEC, G, NCH>(T.v[part], row, d, gl, v);
-      adam_replay<E>(p, m, v, last, A.step, A);
-      frag_store<VEC, G, NCH>(T.w[part], row, d, gl, p);
-      frag_store<VEC, G, NCH>(T.m[part], row, d, gl, m);
-      frag_store<VEC, G, NCH>(T.v[part], row, d, gl, v);
-    }
-    __syncwarp(group_mask<G>());
-    if (gl == 0) T.last_step[row] = A.step;
-  }
+  const int step = A.step;
+  for_selected_rows<G>(
+      T, win, [step](int2 st) { return st.x >= 0 && st.x < step; },
+      [&](int64_t row, int last) {
+        for (int part = 0; part < T.parts; ++part) {
+          float p[E], m[E], v[E];
+          frag_load<VEC, G, NCH>(T.w[part], row, d, gl, p);
+          frag_load<VEC, G, NCH>(T.m[part], row, d, gl, m);
+          frag_load<VEC, G, NCH>(T.v[part], row, d, gl, v);
+          adam_replay<E>(p, m, v, last, A.step, A);
+          frag_store<VEC, G, NCH>(T.w[part], row, d, gl, p);
+          frag_store<VEC, G, NCH>(T.m[part], row, d, gl, m);
+          frag_store<VEC, G, NCH>(T.v[part], row, d, gl, v);
+        }
+        if (gl == 0) T.row_state[2 * row] = A.step;
+      });
 }
 
 // ---- discard / pack / add (row-sparse exchange) --------------------------------------------------
+// take: every row marked in `step` gives up its gradient row (zeroed, mark cleared); with outputs
+// the rows are compacted into ids_out / rows_out (order unspecified) and *count_out is advanced.
 template <int VEC, int G, int NCH>
-__global__ void __launch_bounds__(256) grad_take_kernel(const kge_table_t T, int d, const int32_t* counter,
-                                                        int64_t* ids_out, float* rows_out) {
+__global__ void __launch_bounds__(256) grad_take_kernel(const kge_table_t T, int d, int step, int64_t* ids_out,
+                                                        float* rows_out, int32_t* count_out) {
   constexpr int E = VEC * NCH;
-  const int gl = (threadIdx.x & 31) % G;
-  const int groups_per_cta = blockDim.x / G;
-  const int64_t n_groups = (int64_t)gridDim.x * groups_per_cta;
-  const int64_t total = *counter;
-  for (int64_t idx = (int64_t)blockIdx.x * groups_per_cta + threadIdx.x / G; idx < total; idx += n_groups) {
-    const int64_t row = T.uniq[idx];
-    for (int part = 0; part < T.parts; ++part) {
-      float g[E], z[E];
-      frag_load_cg<VEC, G, NCH>(T.g[part], row, d, gl, g);
-#pragma unroll
-      for (int e = 0; e < E; ++e) z[e] = 0.f;
-      frag_store<VEC, G, NCH>(T.g[part], row, d, gl, z);
-      if (rows_out) frag_store<VEC, G, NCH>(rows_out + (int64_t)part * d, idx * T.parts, d, gl, g);
+  constexpr int NG = 32 / G;
+  const int lane = threadIdx.x & 31, gl = lane % G, grp = lane / G;
+  const int64_t warp_global = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int64_t n_warps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+  for (int64_t base = warp_global * 32; base < T.rows; base += n_warps * 32) {
+    const int64_t row_l = base + lane;
+    int touch = -1;
+    if (row_l < T.rows) touch = T.row_state[2 * row_l + 1];
+    unsigned mask = __ballot_sync(0xffffffffu, touch == step);
+    if (!mask) continue;
+    int slot0 = 0;
+    if (count_out) {  // one returning atomic per 32 scanned rows that hold anything
+      if (lane == 0) slot0 = atomicAdd(count_out, __popc(mask));
+      slot0 = __shfl_sync(0xffffffffu, slot0, 0);
     }
-    if (gl == 0) {
-      T.touch_step[row] = -1;
-      if (ids_out) ids_out[idx] = row;
+    int taken = 0;
+    while (mask) {
+      unsigned m = mask;
+      for (int q = 0; q < grp; ++q) m &= m - 1;
+      const int bit = m ? (__ffs(m) - 1) : -1;
+      if (bit >= 0) {
+        const int64_t row = base + bit;
+        const int64_t idx = slot0 + taken + grp;
+        for (int part = 0; part < T.parts; ++part) {
+          float g[E], z[E];
+          frag_load_cg<VEC, G, NCH>(T.g[part], row, d, gl, g);
+#pragma unroll
+          for (int e = 0; e < E; ++e) z[e] = 0.f;
+          frag_store<VEC, G, NCH>(T.g[part], row, d, gl, z);
+          if (rows_out) frag_store<VEC, G, NCH>(rows_out + (int64_t)part * d, idx * T.parts, d, gl, g);
+        }
+        if (gl == 0) {
+          T.row_state[2 * row + 1] = -1;
+          if (ids_out) ids_out[idx] = row;
+        }
+      }
+      for (int q = 0; q < NG && mask; ++q) {
+        mask &= mask - 1;
+        ++taken;
+      }
+      __syncwarp();
     }
   }
 }
 
 template <int VEC, int G, int NCH>
-__global__ void __launch_bounds__(256) grad_add_kernel(const kge_table_t T, int d, int step, int32_t* counter,
-                                                       const int64_t* ids, const float* rows, const int32_t* count_dev) {
+__global__ void __launch_bounds__(256) grad_add_kernel(const kge_table_t T, int d, int step, const int64_t* ids,
+                                                       const float* rows, const int32_t* count_dev) {
   constexpr int E = VEC * NCH;
   const int gl = (threadIdx.x & 31) % G;
   const int groups_per_cta = blockDim.x / G;
@@ -622,7 +659,7 @@ __global__ void __launch_bounds__(256) grad_add_kernel(const kge_table_t T, int 
       for (int e = 0; e < E; ++e) g[e] += x[e];
       frag_store<VEC, G, NCH>(T.g[part], row, d, gl, g);
     }
-    touch_row<G>(T, counter, row, step, gl);
+    if (gl == 0) T.row_state[2 * row + 1] = step;
   }
 }
 
@@ -649,10 +686,20 @@ int grid_for(int64_t n_groups_needed, int groups_per_cta, int ctas_per_sm) {
   return (int)g;
 }
 
+// scan window: as large as still gives every resident warp (32 per SM) a window of its own
+int scan_window(int64_t rows) {
+  const int64_t warps = (int64_t)kge_num_sms() * 32;
+  int win = 32;
+  while (win > 4 && (rows + win - 1) / win < warps) win >>= 1;
+  return win;
+}
+// grid for a scan over `rows` row states: `win` rows per warp iteration, 8 warps per CTA
+int scan_grid(int64_t rows, int win, int ctas_per_sm) { return grid_for((rows + win - 1) / win, 8, ctas_per_sm); }
+
 bool table_has_state(const kge_table_t& T) {
   for (int p = 0; p < T.parts; ++p)
     if (!T.m[p] || !T.v[p] || !T.g[p]) return false;
-  return T.last_step && T.touch_step && T.uniq;
+  return T.row_state != nullptr;
 }
 
 int check_model(const kge_model_t* m, bool need_state) {
@@ -665,10 +712,11 @@ int check_model(const kge_model_t* m, bool need_state) {
   for (int p = 0; p < ph; ++p) KGE_REQUIRE(m->user.w[p] && m->entity.w[p], KGE_E_ARG, "NULL weight table");
   for (int p = 0; p < pr; ++p) KGE_REQUIRE(m->relation.w[p], KGE_E_ARG, "NULL relation table");
   RowCfg c;
-  KGE_REQUIRE(kge_pick_rowcfg(m->d, c), KGE_E_UNSUPPORTED, "embedding_size %d unsupported (max 512, or 256 when not a multiple of 4)", m->d);
+  KGE_REQUIRE(kge_pick_rowcfg(m->d, c), KGE_E_UNSUPPORTED,
+              "embedding_size %d unsupported (max 512, or 256 when not a multiple of 4)", m->d);
   if (need_state) {
-    KGE_REQUIRE(table_has_state(m->user) && table_has_state(m->entity) && table_has_state(m->relation) && m->counters,
-                KGE_E_STATE, "optimiser state buffers missing");
+    KGE_REQUIRE(table_has_state(m->user) && table_has_state(m->entity) && table_has_state(m->relation), KGE_E_STATE,
+                "optimiser state buffers missing");
   }
   return 0;
 }
@@ -702,8 +750,11 @@ extern "C" int kge_train_forward(const kge_model_t* model, const kge_batch_t* b,
   if (n_total == 0) return 0;
   KGE_REQUIRE(b->n_rec == 0 || (b->user && b->item && b->neg_item), KGE_E_ARG, "NULL rec id array");
   KGE_REQUIRE(b->n_kg == 0 || (b->head && b->relation && b->tail && b->neg_tail), KGE_E_ARG, "NULL KG id array");
-  const bool lazy = model->user.last_step && model->entity.last_step && model->relation.last_step;
-  KGE_REQUIRE(!lazy || (model->user.m[0] && model->entity.m[0]), KGE_E_STATE, "last_step without moments");
+  const bool any_state = model->user.row_state || model->entity.row_state || model->relation.row_state;
+  const bool all_state = model->user.row_state && model->entity.row_state && model->relation.row_state;
+  KGE_REQUIRE(any_state == all_state, KGE_E_STATE, "row_state must be given for all tables or none");
+  KGE_REQUIRE(!all_state || (model->user.m[0] && model->entity.m[0] && model->relation.m[0]), KGE_E_STATE,
+              "row_state without moments");
 
   TrainArgs a;
   a.m = *model;
@@ -724,41 +775,18 @@ extern "C" int kge_train_forward(const kge_model_t* model, const kge_batch_t* b,
   RowCfg c;
   kge_pick_rowcfg(model->d, c);
   const int threads = 256;
-  const int gpc = threads / c.g;
-  int grid = grid_for(n_total, gpc, 8);
-  // per-CTA staged lists must hold every row the CTA can touch; grow the grid until they fit 48 KB
-  const int kmax = b->k_rec > b->k_kg ? b->k_rec : b->k_kg;
-  int64_t inst_per_cta;
-  for (;;) {
-    const int64_t iters = (n_total + (int64_t)grid * gpc - 1) / ((int64_t)grid * gpc);
-    inst_per_cta = iters * gpc;
-    if (inst_per_cta * (3 + kmax) * 4 <= 48 * 1024 || inst_per_cta <= gpc) break;
-    grid *= 2;
-  }
-  a.cap_user = (int)inst_per_cta;
-  a.cap_entity = (int)(inst_per_cta * (2 + kmax));
-  a.cap_relation = (int)inst_per_cta + 1;
-  const size_t smem = (size_t)model->relation.parts * model->d * sizeof(float) +
-                      ((size_t)a.cap_user + a.cap_entity + a.cap_relation) * sizeof(int32_t);
-  KGE_REQUIRE(smem <= 200 * 1024, KGE_E_UNSUPPORTED, "%d negatives per triple need %zu bytes of shared memory", kmax, smem);
+  const int grid = grid_for(n_total, threads / c.g, 8);
+  const size_t smem = (size_t)model->relation.parts * model->d * sizeof(float);
   cudaStream_t st = (cudaStream_t)stream;
-#define LAUNCH_FWD(M, V, G, N)                                                                                  \
-  do {                                                                                                          \
-    if (smem > 48 * 1024)                                                                                       \
-      KGE_CUDA(cudaFuncSetAttribute(train_fwd_kernel<M, V, G, N>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
-                                    (int)smem));                                                                \
-    train_fwd_kernel<M, V, G, N><<<grid, threads, smem, st>>>(a);                                               \
-  } while (0)
-#define CALL(V, G, N)                                                \
-  switch (model->model) {                                            \
-    case KGE_TRANSE: LAUNCH_FWD(KGE_TRANSE, V, G, N); break;         \
-    case KGE_DISTMULT: LAUNCH_FWD(KGE_DISTMULT, V, G, N); break;     \
-    case KGE_ROTATE: LAUNCH_FWD(KGE_ROTATE, V, G, N); break;         \
-    default: LAUNCH_FWD(KGE_COMPLEX, V, G, N); break;                \
+#define CALL(V, G, N)                                                                                   \
+  switch (model->model) {                                                                               \
+    case KGE_TRANSE: train_fwd_kernel<KGE_TRANSE, V, G, N><<<grid, threads, smem, st>>>(a); break;      \
+    case KGE_DISTMULT: train_fwd_kernel<KGE_DISTMULT, V, G, N><<<grid, threads, smem, st>>>(a); break;  \
+    case KGE_ROTATE: train_fwd_kernel<KGE_ROTATE, V, G, N><<<grid, threads, smem, st>>>(a); break;      \
+    default: train_fwd_kernel<KGE_COMPLEX, V, G, N><<<grid, threads, smem, st>>>(a); break;             \
   }
   KGE_DISPATCH_ROWCFG(c, CALL);
 #undef CALL
-#undef LAUNCH_FWD
   KGE_LAUNCH_CHECK();
   return 0;
 }
@@ -775,7 +803,11 @@ extern "C" int kge_adam_apply(const kge_model_t* model, const kge_adam_t* adam, 
   RowCfg c;
   kge_pick_rowcfg(model->d, c);
   const int threads = 256;
-  const int grid = kge_num_sms() * 4;
+  const int64_t max_rows = model->entity.rows > model->user.rows ? model->entity.rows : model->user.rows;
+  a.win[0] = scan_window(model->user.rows);
+  a.win[1] = scan_window(model->entity.rows);
+  a.win[2] = 4;
+  const int grid = scan_grid(max_rows, scan_window(max_rows), 4);
   cudaStream_t st = (cudaStream_t)stream;
 #define CALL(V, G, N) adam_apply_kernel<V, G, N><<<grid, threads, 0, st>>>(a)
   KGE_DISPATCH_ROWCFG(c, CALL);
@@ -795,8 +827,9 @@ extern "C" int kge_adam_flush(const kge_model_t* model, const kge_adam_t* adam, 
   cudaStream_t st = (cudaStream_t)stream;
   const kge_table_t* tabs[3] = {&model->user, &model->entity, &model->relation};
   for (int t = 0; t < 3; ++t) {
-    const int grid = grid_for(tabs[t]->rows, threads / c.g, 8);
-#define CALL(V, G, N) adam_flush_kernel<V, G, N><<<grid, threads, 0, st>>>(*tabs[t], model->d, A)
+    const int win = scan_window(tabs[t]->rows);
+    const int grid = scan_grid(tabs[t]->rows, win, 8);
+#define CALL(V, G, N) adam_flush_kernel<V, G, N><<<grid, threads, 0, st>>>(*tabs[t], model->d, A, win)
     KGE_DISPATCH_ROWCFG(c, CALL);
 #undef CALL
     KGE_LAUNCH_CHECK();
@@ -808,17 +841,16 @@ static int grad_take(const kge_model_t* model, int which, int step, int64_t* ids
                      int32_t* count_out, cudaStream_t st) {
   const kge_table_t* tabs[3] = {&model->user, &model->entity, &model->relation};
   const kge_table_t& T = *tabs[which];
-  int32_t* counter = model->counters + (step & 1) * 4 + which;
   RowCfg c;
   kge_pick_rowcfg(model->d, c);
   const int threads = 256;
-  const int grid = kge_num_sms() * 4;
-  if (count_out) KGE_CUDA(cudaMemcpyAsync(count_out, counter, sizeof(int32_t), cudaMemcpyDeviceToDevice, st));
-#define CALL(V, G, N) grad_take_kernel<V, G, N><<<grid, threads, 0, st>>>(T, model->d, counter, ids_out, rows_out)
+  const int grid = scan_grid(T.rows, 32, 4);
+  if (count_out) KGE_CUDA(cudaMemsetAsync(count_out, 0, sizeof(int32_t), st));
+#define CALL(V, G, N) \
+  grad_take_kernel<V, G, N><<<grid, threads, 0, st>>>(T, model->d, step, ids_out, rows_out, count_out)
   KGE_DISPATCH_ROWCFG(c, CALL);
 #undef CALL
   KGE_LAUNCH_CHECK();
-  KGE_CUDA(cudaMemsetAsync(counter, 0, sizeof(int32_t), st));
   return 0;
 }
 
@@ -842,13 +874,13 @@ extern "C" int kge_grad_add(const kge_model_t* model, int32_t which, int32_t ste
   KGE_REQUIRE(which >= 0 && which < 3 && ids && rows && count_dev && max_count >= 0, KGE_E_ARG, "bad add arguments");
   if (max_count == 0) return 0;
   const kge_table_t* tabs[3] = {&model->user, &model->entity, &model->relation};
-  int32_t* counter = model->counters + (step & 1) * 4 + which;
   RowCfg c;
   kge_pick_rowcfg(model->d, c);
   const int threads = 256;
   const int grid = grid_for(max_count, threads / c.g, 4);
-#define CALL(V, G, N) \
-  grad_add_kernel<V, G, N><<<grid, threads, 0, (cudaStream_t)stream>>>(*tabs[which], model->d, step, counter, ids, rows, count_dev)
+#define CALL(V, G, N)                                                                                            \
+  grad_add_kernel<V, G, N><<<grid, threads, 0, (cudaStream_t)stream>>>(*tabs[which], model->d, step, ids, rows, \
+                                                                         count_dev)
   KGE_DISPATCH_ROWCFG(c, CALL);
 #undef CALL
   KGE_LAUNCH_CHECK();

@@ -213,11 +213,9 @@ class FusedKGEModel(KnowledgeRecommender):
                 "m": [torch.zeros(rows, d, device=device) for _ in names],
                 "v": [torch.zeros(rows, d, device=device) for _ in names],
                 "g": [torch.zeros(rows, d, device=device) for _ in names],
-                "last_step": torch.full((rows,), -1, dtype=torch.int32, device=device),
-                "touch_step": torch.full((rows,), -1, dtype=torch.int32, device=device),
-                "uniq": torch.zeros(rows, dtype=torch.int32, device=device),
+                # [rows, 2] int32: {last_step, touch_step}
+                "row_state": torch.full((rows, 2), -1, dtype=torch.int32, device=device),
             }
-        st["counters"] = torch.zeros(8, dtype=torch.int32, device=device)
         lib = _abi.lib()
         n = lib.kge_adam_table_fill(self.learning_rate, self.betas[0], self.betas[1], None, 0)
         host = (C.c_float * (2 * n))()
@@ -252,11 +250,8 @@ class FusedKGEModel(KnowledgeRecommender):
                     t.v[p] = st[fam]["v"][p].data_ptr()
                     t.g[p] = st[fam]["g"][p].data_ptr()
             if st is not None:
-                t.last_step = st[fam]["last_step"].data_ptr()
-                t.touch_step = st[fam]["touch_step"].data_ptr()
-                t.uniq = st[fam]["uniq"].data_ptr()
+                t.row_state = st[fam]["row_state"].data_ptr()
         if st is not None:
-            m.counters = st["counters"].data_ptr()
             m.adam_table = st["adam_table"].data_ptr()
             m.adam_table_len = st["adam_table_len"]
         return m
@@ -415,7 +410,7 @@ class FusedKGEModel(KnowledgeRecommender):
             out[fam] = {
                 "m": [t.detach().cpu() for t in self._state[fam]["m"]],
                 "v": [t.detach().cpu() for t in self._state[fam]["v"]],
-                "last_step": self._state[fam]["last_step"].detach().cpu(),
+                "row_state": self._state[fam]["row_state"].detach().cpu(),
             }
         return out
 
@@ -431,7 +426,7 @@ class FusedKGEModel(KnowledgeRecommender):
                 dst.copy_(src)
             for dst, src in zip(st[fam]["v"], value[fam]["v"]):
                 dst.copy_(src)
-            st[fam]["last_step"].copy_(value[fam]["last_step"])
+            st[fam]["row_state"].copy_(value[fam]["row_state"])
         self._dirty = False
         self._pending = False
 

@@ -39,18 +39,18 @@ enum kge_error {
 
 /* One family of embedding tables (user / entity / relation): `parts` fp32 matrices
  * [rows, d] (1 = real models, 2 = re/im) plus the row-lazy Adam state that rides with it.
- * m, v, g, last_step, touch_step, uniq may be NULL for an inference-only model. */
+ * m, v, g and row_state may be NULL for an inference-only model. */
 typedef struct {
   int64_t rows;
   int32_t parts;
   int32_t _pad;
-  float* w[2];         /* parameters: nn.Embedding.weight.data_ptr() */
-  float* m[2];         /* Adam exp_avg */
-  float* v[2];         /* Adam exp_avg_sq */
-  float* g[2];         /* gradient accumulators; all-zero between steps (invariant) */
-  int32_t* last_step;  /* [rows] optimiser step the stored (w,m,v) are current for; -1 = never updated */
-  int32_t* touch_step; /* [rows] step whose unique-row list already holds the row */
-  int32_t* uniq;       /* [rows] rows touched by the step being accumulated */
+  float* w[2];        /* parameters: nn.Embedding.weight.data_ptr() */
+  float* m[2];        /* Adam exp_avg */
+  float* v[2];        /* Adam exp_avg_sq */
+  float* g[2];        /* gradient accumulators; all-zero between steps (invariant) */
+  int32_t* row_state; /* [rows][2]: {last_step, touch_step}.  last_step = optimiser step the stored
+                         (w, m, v) are current for (-1 = never updated); touch_step = last step whose
+                         gradient touched the row (-1 = none / taken).  Initialise to -1. */
 } kge_table_t;
 
 typedef struct {
@@ -64,7 +64,6 @@ typedef struct {
   int32_t _pad;
   int64_t n_items;              /* items are entity rows [0, n_items) (kg_dataset.py:556-588) */
   kge_table_t user, entity, relation;
-  int32_t* counters;            /* [8] unique-row counts: [parity*4 + {user,entity,relation}] */
   const float* adam_table;      /* [2*adam_table_len]: {lr/(1-b1^j), 1/sqrt(1-b2^j)} for j = 0..len-1 */
   int32_t adam_table_len;
   int32_t _pad2;
@@ -107,7 +106,7 @@ int kge_adam_table_fill(float lr, float beta1, float beta2, float* out_host, int
  * rotate.py:98-131, complex.py:95-128) AND the autograd backward of it
  * (trainer.py:261): gathers rows (catching lazily-updated rows up to step-1 on the fly),
  * scores, adds the scalar loss into *loss_out (caller zeroes it), and when with_grad != 0
- * accumulates analytic gradients into table.g and records the touched rows. */
+ * accumulates analytic gradients into table.g and marks the touched rows in row_state. */
 int kge_train_forward(const kge_model_t* model, const kge_batch_t* batch, const kge_adam_t* adam,
                       int with_grad, float* loss_out, kge_stream_t stream);
 
@@ -128,10 +127,11 @@ int kge_adam_flush(const kge_model_t* model, const kge_adam_t* adam, kge_stream_
 int kge_grad_discard(const kge_model_t* model, int32_t step, kge_stream_t stream);
 
 /* Row-sparse gradient exchange (replaces DDP's dense all-reduce, trainer.py:82-112).
- * pack: copy this rank's touched rows of table `which` (0 user, 1 entity, 2 relation) into
- *       ids_out[count] / rows_out[count, parts*d], zero them in g and clear their touch
- *       marks; *count_out (device) receives the count.
- * add:  add a (possibly remote) packed list into g and the unique-row list. */
+ * pack: compact this rank's touched rows of table `which` (0 user, 1 entity, 2 relation) into
+ *       ids_out[count] / rows_out[count, parts*d] (order unspecified), zero them in g and clear
+ *       their touch marks; *count_out (device) receives the count.  The outputs must hold
+ *       min(rows, rows the batch can touch) entries.
+ * add:  add a (possibly remote) packed list (unique ids) into g and mark the rows touched. */
 int kge_grad_pack(const kge_model_t* model, int32_t which, int32_t step, int64_t* ids_out, float* rows_out,
                   int32_t* count_out, kge_stream_t stream);
 int kge_grad_add(const kge_model_t* model, int32_t which, int32_t step, const int64_t* ids, const float* rows,

@@ -79,11 +79,12 @@ def test_golden_gradients(name):
             got = m._state[fam]["g"][p].cpu().numpy()
             want = g[f"grad1/{tname}.weight"]
             np.testing.assert_allclose(got, want, rtol=1e-4, atol=1e-8, err_msg=f"{name} {tname}")
-        # the unique-row list holds exactly the rows with a non-zero gradient row
-        cnt = int(m._state["counters"][4 + ("user", "entity", "relation").index(fam)].item())
-        touched = np.sort(m._state[fam]["uniq"][:cnt].cpu().numpy())
+        # every row with a non-zero gradient is marked as touched in step 1, and nothing untouched is
+        touched = np.flatnonzero(m._state[fam]["row_state"][:, 1].cpu().numpy() == 1)
         nz = np.flatnonzero(np.any(np.stack([g[f"grad1/{t}.weight"] for t in names]) != 0, axis=(0, 2)))
         assert set(nz) <= set(touched)
+        got_all = np.stack([m._state[fam]["g"][p].cpu().numpy() for p in range(len(names))])
+        assert not np.any(got_all[:, np.setdiff1d(np.arange(got_all.shape[1]), touched)])
     m.flush()
 
 
