@@ -210,7 +210,7 @@ def time_train_e2e(model, host_batches, steps, warmup, world, device):
     return e0.elapsed_time(e1)
 
 
-def time_fullsort(fs, device, n_users_step, steps, warmup, world, rank):
+def time_fullsort(fs, device, n_users_step, steps, warmup, world, rank, path="auto"):
     """users/s of fused full-sort + mask + top-k on a block of users per step."""
     from kge_helpers import make_product_model
 
@@ -224,18 +224,19 @@ def time_fullsort(fs, device, n_users_step, steps, warmup, world, rank):
         blocks.append((users, off, torch.from_numpy(hist.reshape(-1)).to(device)))
     for i in range(warmup):
         u, o, h = blocks[i % len(blocks)]
-        m.full_sort_topk(u, fs["k"], o, h, return_scores=False)
+        m.full_sort_topk(u, fs["k"], o, h, return_scores=False, path=path)
     barrier(world)
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
     for i in range(steps):
         u, o, h = blocks[(warmup + i) % len(blocks)]
-        ids, _ = m.full_sort_topk(u, fs["k"], o, h, return_scores=False)
+        ids, _ = m.full_sort_topk(u, fs["k"], o, h, return_scores=False, path=path)
     e1.record()
     barrier(world)
     ms = e0.elapsed_time(e1)
+    fallback = m._mma_last_fallback_rows
     del m
-    return ms
+    return ms, fallback
 
 
 def cpu_reference_steps(w, steps, warmup, budget_s=None, threads=None):
@@ -379,16 +380,21 @@ def main():
         # second headline metric: users/s of full-sort top-k (user blocks sharded across ranks)
         for name, fs in FULLSORT.items():
             try:
-                n_users_step = 32768
-                ms = time_fullsort(fs, device, n_users_step, max(3, args.steps // 4), 3, world, rank)
-                ms = max_over_ranks(ms / max(3, args.steps // 4), device, world)
-                ups = world * n_users_step / (ms * 1e-3)
+                n_users_step = 148 * 256   # one CTA (256 users) per SM
+                reps = max(3, args.steps // 4)
                 flops = 2.0 * fs["I"] * fs["d"] * PARTS[fs["model"]]
-                extras[name] = {"metric": "users/sec (full-sort top-20)", "users_per_s": ups, "ms_per_block": ms,
-                                "users_per_block_per_gpu": n_users_step, "path": "cuda-core fp32 tile kernel",
-                                "algorithmic_tflops": ups * flops / 1e12,
-                                "tensor_frac_of_bf16_peak": ups / world * flops / 1e12 / peaks["bf16_tflops"]}
-                torch.cuda.empty_cache()
+                entry = {"metric": "users/sec (full-sort top-20)", "users_per_block_per_gpu": n_users_step}
+                for path in ("mma", "cuda"):
+                    ms, fb = time_fullsort(fs, device, n_users_step, reps, 3, world, rank, path=path)
+                    ms = max_over_ranks(ms / reps, device, world)
+                    ups = world * n_users_step / (ms * 1e-3)
+                    entry[path] = {"users_per_s": ups, "ms_per_block": ms, "algorithmic_tflops": ups * flops / 1e12,
+                                   "tensor_frac_of_bf16_peak": ups / world * flops / 1e12 / peaks["bf16_tflops"],
+                                   "rows_recomputed_exactly": fb}
+                    torch.cuda.empty_cache()
+                entry["paths"] = {"mma": "tcgen05 bf16 filter + exact fp32 re-score (same ids/scores)",
+                                  "cuda": "fp32 CUDA-core tile kernel"}
+                extras[name] = entry
             except Exception as exc:
                 extras[name] = {"error": repr(exc)}
         line["extras"] = extras

@@ -22,6 +22,7 @@
 #include <math.h>
 
 #include "common.cuh"
+#include "score_common.cuh"
 
 namespace {
 
@@ -30,56 +31,6 @@ constexpr int BT = 128;   // target rows per tile
 constexpr int KC = 32;    // K chunk (floats)
 constexpr int TS = KC + 4;  // padded row stride of the target tile: conflict-free LDS.128
 constexpr int TILE_THREADS = 256;
-constexpr int KMAX = 128;  // largest supported k
-
-__device__ __forceinline__ uint64_t make_key(float score, uint32_t id) {
-  uint32_t b = __float_as_uint(score);
-  b = (b & 0x80000000u) ? ~b : (b | 0x80000000u);  // order-preserving map of fp32 to uint32
-  return ((uint64_t)b << 32) | (uint64_t)(0xFFFFFFFFu - id);  // larger key = better (score desc, id asc)
-}
-__device__ __forceinline__ float key_score(uint64_t key) {
-  uint32_t b = (uint32_t)(key >> 32);
-  b = (b & 0x80000000u) ? (b & 0x7FFFFFFFu) : ~b;
-  return __uint_as_float(b);
-}
-__device__ __forceinline__ int64_t key_id(uint64_t key) { return (int64_t)(0xFFFFFFFFu - (uint32_t)key); }
-
-// Insert `c` into the descending list (capacity k) cooperatively by one warp.  `len` is warp-uniform.
-__device__ __forceinline__ void warp_insert(uint64_t* list, int& len, int k, uint64_t c, int lane) {
-  if (len == k && c <= list[k - 1]) return;
-  int pos = 0;
-  for (int base = 0; base < len; base += 32) {
-    const int i = base + lane;
-    const bool gt = (i < len) && (list[i] > c);
-    pos += __popc(__ballot_sync(0xffffffffu, gt));
-  }
-  const int newlen = len < k ? len + 1 : k;
-  uint64_t moved[KMAX / 32];
-#pragma unroll
-  for (int q = 0; q < KMAX / 32; ++q) {
-    const int i = q * 32 + lane;
-    moved[q] = (i > pos && i < newlen) ? list[i - 1] : 0ull;
-  }
-  __syncwarp();
-#pragma unroll
-  for (int q = 0; q < KMAX / 32; ++q) {
-    const int i = q * 32 + lane;
-    if (i > pos && i < newlen) list[i] = moved[q];
-  }
-  if (lane == 0) list[pos] = c;
-  len = newlen;
-  __syncwarp();
-}
-
-struct ScoreArgs {
-  kge_model_t m;
-  const int64_t* heads;
-  const int64_t* rels;   // NULL: the user->item relation row
-  const int64_t* tails;  // predict only
-  int64_t n;
-  int head_is_user;
-  int rel_row;  // row used when rels == NULL
-};
 
 // ---- predict: one lane group per (head, relation, tail) -------------------------------------
 template <int MODEL, int VEC, int G, int NCH>
@@ -158,35 +109,12 @@ struct TileArgs {
 
 __device__ __forceinline__ void build_queries(const ScoreArgs& a, int64_t row0, int nrows, int kpad, float* Qs) {
   const int d = a.m.d;
-  const int model = a.m.model;
-  const int parts = (model == KGE_ROTATE || model == KGE_COMPLEX) ? 2 : 1;
+  const int parts = (a.m.model == KGE_ROTATE || a.m.model == KGE_COMPLEX) ? 2 : 1;
   const int qstride = parts * kpad;
-  const kge_table_t& HT = a.head_is_user ? a.m.user : a.m.entity;
   for (int idx = threadIdx.x; idx < BU * kpad; idx += blockDim.x) {
     const int u = idx / kpad, c = idx - u * kpad;
     float q0 = 0.f, q1 = 0.f;
-    if (u < nrows && c < d) {
-      const int64_t h_id = __ldg(a.heads + row0 + u);
-      const int64_t r_id = a.rels ? __ldg(a.rels + row0 + u) : (int64_t)a.rel_row;
-      const float h0 = __ldg(HT.w[0] + h_id * d + c);
-      const float r0 = __ldg(a.m.relation.w[0] + r_id * d + c);
-      if (model == KGE_TRANSE) {
-        q0 = h0 + r0;
-      } else if (model == KGE_DISTMULT) {
-        q0 = h0 * r0;
-      } else if (model == KGE_ROTATE) {
-        const float h1 = __ldg(HT.w[1] + h_id * d + c);
-        float sn, cs;
-        sincosf(r0, &sn, &cs);
-        q0 = cs * h0 - sn * h1;
-        q1 = cs * h1 + sn * h0;
-      } else {
-        const float h1 = __ldg(HT.w[1] + h_id * d + c);
-        const float r1 = __ldg(a.m.relation.w[1] + r_id * d + c);
-        q0 = h0 * r0;
-        q1 = h1 * r0 + h0 * r1 - h1 * r1;
-      }
-    }
+    if (u < nrows && c < d) query_value(a, row0 + u, c, q0, q1);
     Qs[u * qstride + c] = q0;
     if (parts == 2) Qs[u * qstride + kpad + c] = q1;
   }

@@ -177,6 +177,8 @@ class FusedKGEModel(KnowledgeRecommender):
         self._grad_scale = 1.0  # 1 / world_size under data parallelism (DDP averages gradients)
         self._keepalive = None
         self._touch_bounds = (0, 0, 0)
+        self._mma_cache = None
+        self._mma_last_fallback_rows = 0
 
     # ------------------------------------------------------------------ tables
     def _tables(self, names):
@@ -478,13 +480,52 @@ class FusedKGEModel(KnowledgeRecommender):
     def full_sort_predict_kg(self, interaction):
         return self._full_sort(interaction[self.HEAD_ENTITY_ID], interaction[self.RELATION_ID], False, self.n_entities)
 
+    # ------------------------------------------------------------------ fused full-sort top-k
+    def _topk_exact(self, m, users, k, hist_off, hist_items, mask_pad, ids, scores):
+        lib = _abi.lib()
+        n = users.numel()
+        need = lib.kge_full_sort_topk_workspace_bytes(C.byref(m), n, self.n_items, k)
+        if need < 0:
+            raise _abi.KgeError(f"kge_full_sort_topk: unsupported shape (k={k}, d={self.embedding_size})")
+        ws = torch.empty(max(need, 8), dtype=torch.uint8, device=users.device)
+        _abi.check(
+            lib.kge_full_sort_topk(
+                C.byref(m), users.data_ptr(), None, n, 1, self.n_items, _abi.ptr(hist_off), _abi.ptr(hist_items),
+                1 if mask_pad else 0, k, ids.data_ptr(), _abi.ptr(scores), ws.data_ptr(), ws.numel(),
+                _abi.stream_ptr(),
+            ),
+            "kge_full_sort_topk",
+        )
+
+    def _mma_supported(self, k: int) -> bool:
+        m = self._model_struct(False)
+        return _abi.lib().kge_full_sort_topk_mma_workspace_bytes(C.byref(m), 1, self.n_items, k) >= 0
+
+    def _mma_image(self, m, device):
+        """bf16 operand image of the item rows, cached until the entity table changes."""
+        tabs = self._tables(self.ENTITY_TABLES)
+        key = (self._step, self.n_items, tuple(t.data_ptr() for t in tabs), tuple(t._version for t in tabs))
+        if self._mma_cache is not None and self._mma_cache[0] == key:
+            return self._mma_cache[1]
+        lib = _abi.lib()
+        nbytes = lib.kge_mma_image_bytes(C.byref(m), self.n_items)
+        image = torch.empty(nbytes, dtype=torch.uint8, device=device)
+        _abi.check(
+            lib.kge_mma_prepare_targets(C.byref(m), self.n_items, image.data_ptr(), nbytes, _abi.stream_ptr()),
+            "kge_mma_prepare_targets",
+        )
+        self._mma_cache = (key, image)
+        return image
+
     def full_sort_topk(self, user_ids, k: int, hist_off=None, hist_items=None, mask_pad: bool = True,
-                       return_scores: bool = True):
+                       return_scores: bool = True, path: str = "auto", _debug_scores: bool = False):
         """Fused full_sort_predict + trainer masking + top-k (trainer.py:716-735, collector.py:176-177).
 
         ``hist_off`` [n+1] / ``hist_items`` (sorted ascending per user) is the CSR of the items to
         mask for each of the ``user_ids``.  Returns (ids [n,k] int64, scores [n,k] fp32 or None),
-        ordered by (score desc, id asc).
+        ordered by (score desc, id asc).  ``path``: "cuda" = fp32 CUDA-core kernel, "mma" = tcgen05
+        filter + exact fp32 re-score (same results), "auto" = "mma" where it is supported and the
+        item set is large enough to pay for the operand image.
         """
         device = self._check_ready()
         self.flush()
@@ -497,19 +538,50 @@ class FusedKGEModel(KnowledgeRecommender):
         ids = torch.empty(n, k, dtype=torch.int64, device=device)
         scores = torch.empty(n, k, dtype=torch.float32, device=device) if return_scores else None
         m = self._model_struct(False)
+        if path not in ("auto", "mma", "cuda"):
+            raise ValueError(path)
+        use_mma = path == "mma" or (path == "auto" and self.n_items >= 8192 and n >= 64 and self._mma_supported(k))
+        if not use_mma or n == 0:
+            self._topk_exact(m, users, k, hist_off, hist_items, mask_pad, ids, scores)
+            return ids, scores
         lib = _abi.lib()
-        need = lib.kge_full_sort_topk_workspace_bytes(C.byref(m), n, self.n_items, k)
+        need = lib.kge_full_sort_topk_mma_workspace_bytes(C.byref(m), n, self.n_items, k)
         if need < 0:
-            raise _abi.KgeError(f"kge_full_sort_topk: unsupported shape (k={k}, d={self.embedding_size})")
-        ws = torch.empty(max(need, 8), dtype=torch.uint8, device=device)
+            raise _abi.KgeError(f"tensor-core top-k: {lib.kge_last_error().decode()}")
+        image = self._mma_image(m, device)
+        ws = torch.empty(need, dtype=torch.uint8, device=device)
+        flags = torch.empty(n, dtype=torch.int32, device=device)
+        dbg = None
+        if _debug_scores:
+            dbg = torch.zeros(n, (self.n_items + 127) // 128 * 128, dtype=torch.float32, device=device)
         _abi.check(
-            lib.kge_full_sort_topk(
-                C.byref(m), users.data_ptr(), None, n, 1, self.n_items, _abi.ptr(hist_off), _abi.ptr(hist_items),
-                1 if mask_pad else 0, k, ids.data_ptr(), _abi.ptr(scores), ws.data_ptr(), ws.numel(),
-                _abi.stream_ptr(),
+            lib.kge_full_sort_topk_mma(
+                C.byref(m), users.data_ptr(), None, n, 1, self.n_items, image.data_ptr(), _abi.ptr(hist_off),
+                _abi.ptr(hist_items), 1 if mask_pad else 0, k, ids.data_ptr(), _abi.ptr(scores), flags.data_ptr(),
+                ws.data_ptr(), ws.numel(), _abi.ptr(dbg), _abi.stream_ptr(),
             ),
-            "kge_full_sort_topk",
+            "kge_full_sort_topk_mma",
         )
+        bad = torch.nonzero(flags, as_tuple=False).flatten()  # rows the filter could not bound (host sync)
+        self._mma_last_fallback_rows = int(bad.numel())
+        if bad.numel():
+            sub_off = sub_items = None
+            if hist_off is not None:
+                lens = (hist_off[1:] - hist_off[:-1])[bad]
+                sub_off = torch.zeros(bad.numel() + 1, dtype=torch.int64, device=device)
+                torch.cumsum(lens, 0, out=sub_off[1:])
+                total = int(sub_off[-1].item())
+                seg = torch.repeat_interleave(torch.arange(bad.numel(), device=device), lens)
+                pos = torch.arange(total, device=device) - sub_off[seg] + hist_off[bad][seg]
+                sub_items = hist_items[pos].contiguous()
+            sub_ids = torch.empty(bad.numel(), k, dtype=torch.int64, device=device)
+            sub_scores = torch.empty(bad.numel(), k, dtype=torch.float32, device=device) if return_scores else None
+            self._topk_exact(m, users[bad].contiguous(), k, sub_off, sub_items, mask_pad, sub_ids, sub_scores)
+            ids[bad] = sub_ids
+            if return_scores:
+                scores[bad] = sub_scores
+        if _debug_scores:
+            return ids, scores, dbg
         return ids, scores
 
     def forward(self, *args, **kwargs):  # the reference's forward is the scorer on gathered rows

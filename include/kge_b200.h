@@ -163,6 +163,26 @@ int kge_full_sort_topk(const kge_model_t* model, const int64_t* heads, const int
                        int mask_first, int32_t k, int64_t* ids_out, float* scores_out, void* workspace,
                        int64_t workspace_bytes, kge_stream_t stream);
 
+/* ---- tensor-core full-sort top-k (tcgen05) -------------------------------------------------------
+ * Same contract and same results as kge_full_sort_topk (ids and scores are bit-identical: the
+ * bf16 tensor-core pass only filters, every reported score comes from the fp32 chain), for
+ * k <= 32 and parts*d (+3 for the L2 models) <= 256.
+ * kge_mma_prepare_targets converts entity rows [0, n_targets) into the tiled bf16 operand image
+ * (128-byte aligned buffer of kge_mma_image_bytes bytes); rebuild it whenever the entity table
+ * changes.  row_flags[n] (int32, device): 0 = row done, 1 = the row must be recomputed with
+ * kge_full_sort_topk (its candidate list could not be bounded, or it has fewer than k unmasked
+ * targets); ids/scores of flagged rows are not written.  debug_scores: NULL, or [n, ceil(n_targets
+ * /128)*128] fp32 receiving the raw tensor-core scores (tests only). */
+int64_t kge_mma_image_bytes(const kge_model_t* model, int64_t n_targets);
+int kge_mma_prepare_targets(const kge_model_t* model, int64_t n_targets, void* image, int64_t image_bytes,
+                            kge_stream_t stream);
+int64_t kge_full_sort_topk_mma_workspace_bytes(const kge_model_t* model, int64_t n, int64_t n_targets, int32_t k);
+int kge_full_sort_topk_mma(const kge_model_t* model, const int64_t* heads, const int64_t* rels, int64_t n,
+                           int head_is_user, int64_t n_targets, const void* image, const int64_t* hist_off,
+                           const int64_t* hist_items, int mask_first, int32_t k, int64_t* ids_out, float* scores_out,
+                           int32_t* row_flags, void* workspace, int64_t workspace_bytes, float* debug_scores,
+                           kge_stream_t stream);
+
 /* kge_topk_hits: collector.py:178-183 without the [n, I] pos_matrix: out[n, k+1] int32 =
  * hit flags of ids[n,k] against the positives CSR (pos_off[n+1], pos_items sorted) then pos_len. */
 int kge_topk_hits(const int64_t* ids, int64_t n, int32_t k, const int64_t* pos_off, const int64_t* pos_items,

@@ -233,3 +233,85 @@ def test_full_size_topk_properties():
         masked[r, hist[r]] = -np.inf
         assert (masked[r] > sc_c[r, -1]).sum() == k - 1
         np.testing.assert_array_equal(ids_c[r], ofs.topk_canonical(masked[r : r + 1], k)[0][0])
+
+
+# ---- tensor-core (tcgen05) path: identical results to the fp32 CUDA-core path -----------------------
+def _bf16_round(x):
+    return torch.from_numpy(np.ascontiguousarray(x)).to(torch.bfloat16).to(torch.float32).numpy()
+
+
+@pytest.mark.parametrize("name,d", [("DistMult", 64), ("ComplEx", 32), ("TransE", 100), ("RotatE", 24)])
+def test_mma_raw_scores_match_bf16_emulation(name, d):
+    """The raw tensor-core scores equal q^ . t^ (bf16-rounded operands, fp32 accumulation): checks the
+    operand layouts, descriptors and the TMEM read-back independently of the top-k logic."""
+    U, I, E, R, k = 400, 1000, 1300, 7, 10
+    ora = make_oracle_model(name, U, I, E, R, d)
+    m = make_product_model(name, U, I, E, R, d)
+    users = torch.arange(1, 301)
+    ids, sc, raw = m.full_sort_topk(users.cuda(), k, path="mma", _debug_scores=True)
+    raw = raw.cpu().numpy()[:, :I]
+    sd = {k_: v.numpy().astype(np.float64) for k_, v in ora.state_dict().items()}
+    un, en, rn = [[sd[t + ".weight"] for t in names] for names in
+                  (type(m).USER_TABLES, type(m).ENTITY_TABLES, type(m).RELATION_TABLES)]
+    u = [t[users.numpy()].astype(np.float32) for t in un]
+    r = [t[m._ui_row(True)].astype(np.float32) for t in rn]
+    if name == "TransE":
+        q = [u[0] + r[0]]
+    elif name == "DistMult":
+        q = [u[0] * r[0]]
+    elif name == "RotatE":
+        c, s = np.cos(r[0]), np.sin(r[0])
+        q = [c * u[0] - s * u[1], c * u[1] + s * u[0]]
+    else:
+        q = [u[0] * r[0], u[1] * r[0] + u[0] * r[1] - u[1] * r[1]]
+    qc = np.concatenate(q, axis=1)
+    tc = np.concatenate([t[:I].astype(np.float32) for t in en], axis=1)
+    want = _bf16_round(qc).astype(np.float64) @ _bf16_round(tc).astype(np.float64).T
+    if name in ("TransE", "RotatE"):
+        want = want - 0.5 * (tc.astype(np.float64) ** 2).sum(1)[None, :]
+    scale = np.abs(want).max()
+    np.testing.assert_allclose(raw, want, rtol=0, atol=2e-3 * scale)   # q of RotatE differs by sincos ulps
+    assert np.abs(raw - want).mean() < 2e-4 * scale
+
+
+@pytest.mark.parametrize("name,d,I,k", [("DistMult", 64, 20000, 20), ("ComplEx", 64, 9000, 20), ("TransE", 100, 12000, 10),
+                                        ("RotatE", 32, 8200, 32), ("DistMult", 50, 4099, 5)])
+def test_mma_topk_equals_cuda_core_topk(name, d, I, k):
+    U, E, R = 900, I + 100, 6
+    m = make_product_model(name, U, I, E, R, d)
+    rng = np.random.default_rng(8)
+    n = 700
+    users = torch.from_numpy(rng.integers(1, U, n)).cuda()
+    lens = rng.integers(0, 80, n)
+    lens[7] = I - 1 - 3              # fewer than k unmasked items -> must be recomputed exactly
+    hist = [np.sort(rng.choice(np.arange(1, I), size=int(l), replace=False)) for l in lens]
+    off = torch.from_numpy(np.concatenate([[0], np.cumsum(lens)])).cuda()
+    items = torch.from_numpy(np.concatenate(hist)).cuda()
+    ids_c, sc_c = m.full_sort_topk(users, k, off, items, path="cuda")
+    ids_m, sc_m = m.full_sort_topk(users, k, off, items, path="mma")
+    assert m._mma_last_fallback_rows >= 1
+    assert m._mma_last_fallback_rows < 0.1 * n   # flagged rows are rare (k = 32 is the tightest case)
+    np.testing.assert_array_equal(ids_m.cpu().numpy(), ids_c.cpu().numpy())
+    np.testing.assert_array_equal(sc_m.cpu().numpy(), sc_c.cpu().numpy())
+    # no history, no pad masking, a user count that is not a multiple of the CTA tile
+    ids_c, sc_c = m.full_sort_topk(users[:300], k, mask_pad=False, path="cuda")
+    ids_m, sc_m = m.full_sort_topk(users[:300], k, mask_pad=False, path="mma")
+    np.testing.assert_array_equal(ids_m.cpu().numpy(), ids_c.cpu().numpy())
+    np.testing.assert_array_equal(sc_m.cpu().numpy(), sc_c.cpu().numpy())
+
+
+def test_mma_topk_trained_like_weights_and_cache_invalidation():
+    """Heavy-tailed item norms (a few items dominate) and a weight update between calls."""
+    name, U, I, E, R, d, k = "DistMult", 600, 30000, 30000, 4, 64, 20
+    m = make_product_model(name, U, I, E, R, d)
+    with torch.no_grad():
+        m.entity_embedding.weight[100:130] *= 25.0
+        m.entity_embedding.weight[5000:5010] *= -40.0
+    users = torch.arange(1, 513).cuda()
+    for _ in range(2):
+        ids_c, sc_c = m.full_sort_topk(users, k, path="cuda")
+        ids_m, sc_m = m.full_sort_topk(users, k, path="mma")
+        np.testing.assert_array_equal(ids_m.cpu().numpy(), ids_c.cpu().numpy())
+        np.testing.assert_array_equal(sc_m.cpu().numpy(), sc_c.cpu().numpy())
+        with torch.no_grad():
+            m.entity_embedding.weight.mul_(-1.0)   # the cached operand image must be rebuilt
