@@ -10,38 +10,46 @@
 // The tensor cores only FILTER; the answer is exact:
 //   1. bf16 GEMM  a^_ij ~ q_i . t_j  with fp32 accumulation in TMEM.  |a^ - a| <= eps_i =
 //      1.02 * 2^-8 * ||q_i|| * max_j ||t_j||   (two bf16 roundings per product, Cauchy-Schwarz).
-//   2. epilogue, one thread per query row: maxima of groups of 8 adjacent targets are compared with
-//      a running threshold thr_i = tau_i - 2 eps_i, where tau_i is the k-th largest group maximum
-//      among groups without masked targets seen so far (a lower bound of the k-th largest
+//   2. sweep epilogue, one thread per query row: maxima of groups of 8 adjacent targets are compared
+//      with a running threshold thr_i = tau_i - 2 eps_i, where tau_i is the k-th largest group
+//      maximum among groups without masked targets seen so far (a lower bound of the k-th largest
 //      unmasked approximate score).  Every member of the exact top-k has a^ >= tau_final - 2 eps,
-//      so its group survives.  Surviving group ids go to a 64-entry list per row (warp-cooperative
-//      compaction when it fills; a row whose list cannot be compacted is flagged).
-//   3. rescore kernel: the <= 512 targets of a row's surviving groups are scored in fp32 with the
-//      same sequential FMA chain as the CUDA-core kernel (bit-identical scores), masked, and the
-//      top-k is selected under (score desc, id asc).  Rows flagged in 2 or with fewer than k valid
-//      candidates are reported to the caller, which runs them through kge_full_sort_topk.
+//      so its group survives.  Surviving groups are appended to a list of CAND entries per row in
+//      global memory (L2); when a list fills, its warp compacts it (radix select of tau, keep the
+//      entries >= tau - 2 eps); a list that cannot be compacted flags the row.
+//   3. rescore kernel (one warp per row): final tau over the row's lists, then only the targets of
+//      the groups >= tau - 2 eps are scored in fp32 with the same sequential FMA chain as the
+//      CUDA-core kernel (bit-identical scores), masked, pre-filtered by score >= tau - eps (the k
+//      targets behind tau have exact scores above that) and selected under (score desc, id asc).
+//      Flagged rows and rows with fewer than k valid candidates are reported to the caller, which
+//      runs them through kge_full_sort_topk.
 //
-// Kernel shape: CTA = 256 query rows = two M=128 accumulators against a target tile of N=128
-// (so every B tile feeds two MMAs and halves the L2 traffic per flop); TMEM holds 2 x 2
-// accumulators of 128 columns, double-buffered so the epilogue of tile i overlaps the MMAs of tile
-// i+1.  Warp 0 streams pre-tiled bf16 target images with cp.async.bulk into a ring of
-// shared-memory stages (mbarrier expect_tx), warp 1 issues tcgen05.mma (one thread), warps 4..11
-// run the epilogue from tcgen05.ld.  Operands use the no-swizzle K-major canonical layout
-// [K/8][rows][8 bf16]: 8x16-byte core matrices, SBO = 128 B, LBO = rows * 16 B.
+// Sweep kernel shape: CTA = 256 query rows = two M=128 accumulators against target tiles of TN rows
+// (every B tile feeds two MMAs); the accumulators are double-buffered in TMEM (4 x TN columns) and
+// the epilogue releases a buffer as soon as its values sit in registers, so the MMAs of tile i+1
+// run under the epilogue of tile i.  TN = 64 keeps the CTA at 256 TMEM columns and <= 113 KB of
+// shared memory so that two CTAs share an SM: 16 epilogue warps hide the TMEM-load and issue
+// latencies of each other.  Warp 0 streams pre-tiled bf16 target images with cp.async.bulk into a
+// ring of shared-memory stages (mbarrier expect_tx), warp 1 issues tcgen05.mma (one thread), warps
+// 2..9 are the epilogue (warp % 4 = the TMEM lane quadrant a warp may read).  A grid of
+// (row blocks) x (target splits) fills the GPU when few users are evaluated; every (row, split)
+// owns a list.  Operands use the no-swizzle K-major canonical layout [K/8][rows][8 bf16]:
+// 8x16-byte core matrices, SBO = 128 B, LBO = rows * 16 B.
 #include <cuda_bf16.h>
 #include <math.h>
+#include <stdlib.h>
 
 #include "common.cuh"
 #include "score_common.cuh"
 
 namespace {
 
-constexpr int MM = 256;   // query rows per CTA
-constexpr int TN = 128;   // targets per tile (UMMA N)
-constexpr int GRP = 8;    // targets per candidate group
-constexpr int CAND = 64;  // candidate groups kept per row
-constexpr int MMA_THREADS = 384;
-constexpr int EPI_WARP0 = 4;
+constexpr int MM = 256;    // query rows per CTA
+constexpr int GRP = 4;     // targets per candidate group (what the rescore kernel reads per mask bit)
+constexpr int CAND = 128;  // candidate groups kept per (row, split)
+constexpr int MAX_SPLITS = 4;
+constexpr int SWEEP_THREADS = 320;  // warp 0 producer, warp 1 MMA issuer, warps 2..9 epilogue
+constexpr int EPI_WARP0 = 2;
 constexpr int IMG_HEADER = 128;  // bytes before the first tile image: {float tmax}
 constexpr uint32_t SPIN_LIMIT = 1u << 26;
 
@@ -107,22 +115,6 @@ __device__ __forceinline__ void umma_f16(uint32_t tmem_d, uint64_t adesc, uint64
 __device__ __forceinline__ void umma_commit(uint32_t bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
 }
-__device__ __forceinline__ void tmem_ld32(uint32_t taddr, float (&v)[32]) {
-  uint32_t r[32];
-  asm volatile(
-      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
-      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
-      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
-      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
-        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
-        "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
-        "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
-      : "r"(taddr)
-      : "memory");
-  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-#pragma unroll
-  for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
-}
 #define KGE_TMEM_LD32_ASM(R, ADDR)                                                                                  \
   asm volatile(                                                                                                    \
       "tcgen05.ld.sync.aligned.32x32b.x32.b32 "                                                                    \
@@ -152,6 +144,17 @@ __device__ __forceinline__ float max3f(float a, float b, float c) {
   return r;
 }
 
+// One lane of the (converged) warp; the choice is stable across calls.
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "elect.sync _|p, 0xffffffff;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(pred));
+  return pred != 0;
+}
+
 // No-swizzle K-major shared-memory matrix descriptor (bits: start>>4 [0,14), LBO>>4 [16,30),
 // SBO>>4 [32,46), version=1 [46,48), layout type 0 = SWIZZLE_NONE [61,64)).
 __device__ __forceinline__ uint64_t make_smem_desc(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
@@ -162,8 +165,10 @@ __device__ __forceinline__ uint64_t make_smem_desc(uint32_t saddr, uint32_t lbo_
   d |= (uint64_t)1 << 46;
   return d;
 }
-// kind::f16 instruction descriptor: D fp32, A/B bf16, both K-major, N = 128, M = 128.
-constexpr uint32_t IDESC = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(TN >> 3) << 17) | ((128u >> 4) << 24);
+// kind::f16 instruction descriptor: D fp32, A/B bf16, both K-major, N = tn, M = 128.
+__host__ __device__ constexpr uint32_t make_idesc(int tn) {
+  return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(tn >> 3) << 17) | ((128u >> 4) << 24);
+}
 
 __device__ __forceinline__ uint16_t bf16_bits(float x) { return __bfloat16_as_ushort(__float2bfloat16_rn(x)); }
 __device__ __forceinline__ float bf16_back(uint16_t b) { return __uint_as_float((uint32_t)b << 16); }
@@ -172,10 +177,10 @@ __device__ __forceinline__ float bf16_back(uint16_t b) { return __uint_as_float(
 struct PrepArgs {
   kge_model_t m;
   int64_t n_targets;
-  int parts, kp, dist;
+  int parts, kp, dist, tn;
   float* tn2;        // [n_targets] squared norms (scratch inside the image buffer's tail)
   float* header;     // {tmax}
-  uint16_t* tiles;   // [n_tiles][kp/8][TN][8]
+  uint16_t* tiles;   // [n_tiles][kp/8][tn][8]
 };
 
 __global__ void __launch_bounds__(256) target_norm_kernel(const PrepArgs a) {
@@ -200,16 +205,17 @@ __global__ void __launch_bounds__(256) target_norm_kernel(const PrepArgs a) {
 
 __global__ void __launch_bounds__(256) target_image_kernel(const PrepArgs a) {
   const int d = a.m.d;
+  const int tn = a.tn;
   const int kchunks = a.kp / 8;
-  const int64_t n_tiles = (a.n_targets + TN - 1) / TN;
-  const int64_t total = n_tiles * kchunks * TN;
+  const int64_t n_tiles = (a.n_targets + tn - 1) / tn;
+  const int64_t total = n_tiles * kchunks * tn;
   const int kd = a.parts * d;
   for (int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total;
        idx += (int64_t)gridDim.x * blockDim.x) {
-    const int r = (int)(idx % TN);
-    const int kc = (int)((idx / TN) % kchunks);
-    const int64_t tile = idx / ((int64_t)TN * kchunks);
-    const int64_t j = tile * TN + r;
+    const int r = (int)(idx % tn);
+    const int kc = (int)((idx / tn) % kchunks);
+    const int64_t tile = idx / ((int64_t)tn * kchunks);
+    const int64_t j = tile * tn + r;
     uint16_t out[8];
 #pragma unroll
     for (int e = 0; e < 8; ++e) {
@@ -240,11 +246,13 @@ __global__ void __launch_bounds__(256) target_image_kernel(const PrepArgs a) {
   }
 }
 
-// ---- main kernel -------------------------------------------------------------------------------------
+// ---- sweep kernel ------------------------------------------------------------------------------------
 struct MmaArgs {
   ScoreArgs s;
   int64_t n_targets;
   int64_t n_tiles;
+  int64_t rows_pad;       // n rounded up to MM: stride of the per-split arrays
+  int tiles_per_split;
   int parts, kp, dist, stages;
   const float* header;
   const uint16_t* tiles;
@@ -252,16 +260,21 @@ struct MmaArgs {
   const int64_t* hist_items;
   int mask_first;
   int k;
-  uint2* cand;        // [n][CAND]: {approx value bits, group id | unsafe << 31}
-  int32_t* cand_cnt;  // [n]: entries, or -1 when the list could not be compacted
-  float* dbg_out;     // optional dense approximate scores [n, n_tiles * TN]
+  uint2* cand;        // [splits][rows_pad][CAND]: {group maximum bits, group id | flags}
+  int32_t* cand_cnt;  // [splits][rows_pad]: entries, or -1 when the list could not be compacted
+  float* cand_thr;    // [splits][rows_pad]: threshold the list was last compacted with (-inf: never)
+  float* eps_out;     // [rows_pad]
+  float* dbg_out;     // optional dense approximate scores [n, dbg_stride]
+  int64_t dbg_stride;
 };
 
-// Entry of a row's candidate list: x = group maximum (fp32 bits); y = group id (bits 0..28),
-// bit 30 = "safety known", bit 31 = "unsafe" (the group holds a masked / out-of-range target, so
-// its maximum must not feed the threshold).  Safety is resolved lazily, at compaction time, by the
-// whole warp (one binary search per lane instead of one per push).
-constexpr uint32_t GID_MASK = 0x1FFFFFFFu, F_KNOWN = 0x40000000u, F_UNSAFE = 0x80000000u;
+// Entry of a row's candidate list = one 32-target chunk of the sweep: x = maximum of the chunk's
+// groups that cleared the threshold (fp32 bits) = the chunk maximum; y = mask of those groups (bits
+// 0..7), chunk id (bits 8..28), bit 30 = "safety known", bit 31 = "unsafe" (the chunk holds a masked
+// or out-of-range target, so its maximum must not feed the threshold).  Safety is resolved lazily, at
+// compaction time, by the whole warp (one binary search per lane instead of one per push).
+constexpr int CH = 32;  // targets per chunk = one tcgen05.ld.x32 = 8 groups
+constexpr uint32_t CID_SHIFT = 8, CID_MASK = 0x1FFFFFu, F_KNOWN = 0x40000000u, F_UNSAFE = 0x80000000u;
 
 __device__ __forceinline__ uint32_t orderable(float x) {
   const uint32_t b = __float_as_uint(x);
@@ -278,22 +291,58 @@ struct MaskInfo {
   int mask_first;
 };
 
-__device__ __forceinline__ bool group_unsafe(const MaskInfo& mi, uint32_t gid) {
-  const int64_t j0 = (int64_t)gid * GRP;
-  if (j0 + GRP > mi.n_targets || (mi.mask_first && gid == 0)) return true;
+__device__ __forceinline__ bool chunk_unsafe(const MaskInfo& mi, uint32_t cid) {
+  const int64_t j0 = (int64_t)cid * CH;
+  if (j0 + CH > mi.n_targets || (mi.mask_first && cid == 0)) return true;
   int64_t lo = mi.h_lo, hi = mi.h_hi;
   while (lo < hi) {
     const int64_t mid = (lo + hi) >> 1;
     if (mi.hist_items[mid] < j0) lo = mid + 1; else hi = mid;
   }
-  return lo < mi.h_hi && mi.hist_items[lo] < j0 + GRP;
+  return lo < mi.h_hi && mi.hist_items[lo] < j0 + CH;
+}
+
+// k-th largest of the warp's keys (NQ per lane, 0 = absent; all present keys are > 0), or 0 when fewer
+// than k are present.  Radix descent on the order-preserving bit pattern that stops as soon as
+// exactly k keys remain above the prefix (their minimum is the answer).
+template <int NQ>
+__device__ __forceinline__ uint32_t warp_kth_largest(const uint32_t (&key)[NQ], int k) {
+  int n_t = 0;
+#pragma unroll
+  for (int q = 0; q < NQ; ++q) n_t += __popc(__ballot_sync(0xffffffffu, key[q] != 0u));
+  if (n_t < k) return 0u;
+  uint32_t P = 0u;  // invariant: #(key >= max(P, 1)) = n_t >= k
+  for (int bit = 31; bit >= 0 && n_t > k; --bit) {
+    const uint32_t c = P | (1u << bit);
+    int n = 0;
+#pragma unroll
+    for (int q = 0; q < NQ; ++q) n += __popc(__ballot_sync(0xffffffffu, key[q] >= c));
+    if (n >= k) {
+      P = c;
+      n_t = n;
+    }
+  }
+  const uint32_t T = P ? P : 1u;
+  uint32_t mn = 0xFFFFFFFFu;
+#pragma unroll
+  for (int q = 0; q < NQ; ++q)
+    if (key[q] >= T) mn = min(mn, key[q]);
+  return __reduce_min_sync(0xffffffffu, mn);
 }
 
 // Warp-cooperative compaction of one row's candidate list: tau = k-th largest maximum among the
-// safe groups (radix select on the order-preserving bit pattern), keep every entry >= tau - 2 eps.
-// Returns the new count (lane-uniform), -1 when the list cannot be shrunk; thr_out = new threshold.
-__device__ __forceinline__ int compact_row(uint2* buf, int cnt, int k, float eps, const MaskInfo& mi, int lane,
-                                           float& thr_out) {
+// safe chunks, keep every entry >= tau - 2 eps.  Returns the new count (lane-uniform), -1 when the
+// list cannot be shrunk enough to take `room` more entries; thr_out = new threshold.
+__device__ __noinline__ int compact_row(uint2* buf, int cnt, int k, float eps, const int64_t* hist_items,
+                                        int64_t h_lo, int64_t h_hi, int64_t n_targets, int mask_first, int room,
+                                        float* thr_out) {
+  const int lane = threadIdx.x & 31;
+  MaskInfo mi;
+  mi.hist_items = hist_items;
+  mi.h_lo = h_lo;
+  mi.h_hi = h_hi;
+  mi.n_targets = n_targets;
+  mi.mask_first = mask_first;
   uint2 e[CAND / 32];
   bool valid[CAND / 32];
   uint32_t key[CAND / 32];
@@ -302,19 +351,10 @@ __device__ __forceinline__ int compact_row(uint2* buf, int cnt, int k, float eps
     const int i = q * 32 + lane;
     valid[q] = i < cnt;
     e[q] = valid[q] ? buf[i] : make_uint2(0u, 0u);
-    if (valid[q] && !(e[q].y & F_KNOWN)) e[q].y |= F_KNOWN | (group_unsafe(mi, e[q].y & GID_MASK) ? F_UNSAFE : 0u);
+    if (valid[q] && !(e[q].y & F_KNOWN)) e[q].y |= F_KNOWN | (chunk_unsafe(mi, (e[q].y >> CID_SHIFT) & CID_MASK) ? F_UNSAFE : 0u);
     key[q] = (valid[q] && !(e[q].y & F_UNSAFE)) ? orderable(__uint_as_float(e[q].x)) : 0u;  // orderable() > 0
   }
-  // largest T with #(key >= T) >= k  ==  the k-th largest safe key (0 when fewer than k are safe)
-  uint32_t T = 0u;
-#pragma unroll 4
-  for (int bit = 31; bit >= 0; --bit) {
-    const uint32_t c = T | (1u << bit);
-    int n = 0;
-#pragma unroll
-    for (int q = 0; q < CAND / 32; ++q) n += __popc(__ballot_sync(0xffffffffu, key[q] >= c));
-    if (n >= k) T = c;
-  }
+  const uint32_t T = warp_kth_largest<CAND / 32>(key, k);
   const float tau = T ? from_orderable(T) : -INFINITY;
   const float thr = tau - 2.f * eps;
   __syncwarp();
@@ -327,14 +367,43 @@ __device__ __forceinline__ int compact_row(uint2* buf, int cnt, int k, float eps
     base += __popc(b);
   }
   __syncwarp();
-  thr_out = thr;
-  return (base > CAND - 12) ? -1 : base;
+  *thr_out = thr;
+  return (base > CAND - room) ? -1 : base;
 }
 
-__global__ void __launch_bounds__(MMA_THREADS, 1) fullsort_mma_kernel(const MmaArgs a) {
+struct EpiState {
+  float thr, thr_pub;
+  int cnt;
+  bool overflow;
+  uint2* buf;
+};
+
+// One chunk (32 columns = 8 groups of 4) of one row: group maxima, chunk maximum, and (rarely) one list entry.
+template <bool TAIL>
+__device__ __forceinline__ void epi_chunk(const float* v, EpiState& st, uint32_t cid, int g_valid) {
+  float gm[8];
+#pragma unroll
+  for (int g = 0; g < 8; ++g) {
+    gm[g] = fmaxf(max3f(v[4 * g], v[4 * g + 1], v[4 * g + 2]), v[4 * g + 3]);
+    if (TAIL && g >= g_valid) gm[g] = -INFINITY;
+  }
+  const float tm = fmaxf(max3f(gm[0], gm[1], gm[2]), max3f(max3f(gm[3], gm[4], gm[5]), gm[6], gm[7]));
+  if (tm >= st.thr && (!TAIL || g_valid > 0)) {  // rare after the first tiles
+    uint32_t mask = 0u;
+#pragma unroll
+    for (int g = 0; g < 8; ++g) mask |= (gm[g] >= st.thr) ? (1u << g) : 0u;
+    if (TAIL) mask &= (1u << g_valid) - 1u;
+    st.buf[st.cnt] = make_uint2(__float_as_uint(tm), (cid << CID_SHIFT) | mask);
+    ++st.cnt;
+  }
+}
+
+template <int TN>
+__global__ void __launch_bounds__(SWEEP_THREADS, (TN == 64) ? 2 : 1) fullsort_mma_kernel(const MmaArgs a) {
+  constexpr int ROOM = 16;              // list room demanded after a compaction
+  constexpr uint32_t IDESC = make_idesc(TN);
   extern __shared__ __align__(128) unsigned char smem[];
   const int kp = a.kp;
-  const int kchunks = kp / 8;
   const uint32_t a_bytes = (uint32_t)MM * kp * 2;
   const uint32_t b_bytes = (uint32_t)TN * kp * 2;
   uint16_t* As = reinterpret_cast<uint16_t*>(smem);
@@ -347,6 +416,10 @@ __global__ void __launch_bounds__(MMA_THREADS, 1) fullsort_mma_kernel(const MmaA
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int64_t row0 = (int64_t)blockIdx.x * MM;
   const int nrows = (int)min((int64_t)MM, a.s.n - row0);
+  const int split = blockIdx.y;
+  const int64_t t0 = (int64_t)split * a.tiles_per_split;
+  const int64_t t1 = min(a.n_tiles, t0 + a.tiles_per_split);
+  const int64_t nt = t1 - t0;
   const int d = a.s.m.d;
   const int kd = a.parts * d;
 
@@ -354,7 +427,7 @@ __global__ void __launch_bounds__(MMA_THREADS, 1) fullsort_mma_kernel(const MmaA
   for (uint32_t i = threadIdx.x; i < a_bytes / 16; i += blockDim.x) reinterpret_cast<uint4*>(As)[i] = make_uint4(0, 0, 0, 0);
   __syncthreads();
   const float tmax = a.header[0];
-  for (int u = warp; u < MM; u += MMA_THREADS / 32) {
+  for (int u = warp; u < MM; u += SWEEP_THREADS / 32) {
     float nq = 0.f;
     if (u < nrows) {
       for (int c = lane; c < d; c += 32) {
@@ -378,6 +451,7 @@ __global__ void __launch_bounds__(MMA_THREADS, 1) fullsort_mma_kernel(const MmaA
       float eps = 1.02f * 0.00390625f * sqrtf(nq) * tmax;                // 2^-8 ||q|| max||t||
       if (a.dist) eps += 9.5367431640625e-7f * 0.5f * tmax * tmax;        // 2^-20 * ||t||^2 / 2 (split remainder)
       eps_row[u] = eps;
+      if (split == 0) a.eps_out[row0 + u] = eps;
     }
   }
   if (threadIdx.x == 0) {
@@ -391,8 +465,8 @@ __global__ void __launch_bounds__(MMA_THREADS, 1) fullsort_mma_kernel(const MmaA
     mbar_init(smem_u32(&bars[2 * a.stages + 3]), 8);
     fence_mbar_init();
   }
-  if (warp == 2) {
-    tmem_alloc(smem_u32(tmem_slot), 512);
+  if (warp == 1) {
+    tmem_alloc(smem_u32(tmem_slot), 4 * TN);
     tmem_relinquish();
   }
   fence_proxy_async();  // the generic-proxy writes of A must be visible to the tensor core (async proxy)
@@ -404,259 +478,482 @@ __global__ void __launch_bounds__(MMA_THREADS, 1) fullsort_mma_kernel(const MmaA
   const uint32_t tfull0 = smem_u32(&bars[2 * a.stages]), tempty0 = smem_u32(&bars[2 * a.stages + 2]);
 
   if (warp == 0) {
-    // ===== producer: stream target tiles into the ring =====
-    if (lane == 0) {
-      for (int64_t t = 0; t < a.n_tiles; ++t) {
-        const int s = (int)(t % a.stages);
-        const uint32_t ph = (uint32_t)((t / a.stages) & 1);
-        mbar_wait(empty0 + 8 * s, ph ^ 1u);
+    // ===== producer: stream target tiles into the ring (uniform control flow, one elected lane issues) =====
+    const bool leader = elect_one();
+    int s = 0;
+    uint32_t ph = 0;
+    const unsigned char* src = reinterpret_cast<const unsigned char*>(a.tiles) + (size_t)t0 * b_bytes;
+    const uint32_t bs0 = smem_u32(Bs);
+    for (int64_t i = 0; i < nt; ++i) {
+      mbar_wait(empty0 + 8 * s, ph ^ 1u);
+      if (leader) {
         mbar_arrive_expect_tx(full0 + 8 * s, b_bytes);
-        bulk_g2s(smem_u32(Bs + (size_t)s * b_bytes), reinterpret_cast<const unsigned char*>(a.tiles) + (size_t)t * b_bytes,
-                 b_bytes, full0 + 8 * s);
+        bulk_g2s(bs0 + (uint32_t)s * b_bytes, src + (size_t)i * b_bytes, b_bytes, full0 + 8 * s);
+      }
+      __syncwarp();
+      if (++s == a.stages) {
+        s = 0;
+        ph ^= 1u;
       }
     }
   } else if (warp == 1) {
-    // ===== MMA issuer: one thread =====
-    if (lane == 0) {
-      const uint32_t a_lbo = MM * 16, b_lbo = TN * 16, sbo = 128;
-      const uint32_t a_addr = smem_u32(As);
-      for (int64_t t = 0; t < a.n_tiles; ++t) {
-        const int s = (int)(t % a.stages);
-        const uint32_t ph = (uint32_t)((t / a.stages) & 1);
-        const int buf = (int)(t & 1);
-        const uint32_t tph = (uint32_t)((t >> 1) & 1);
-        mbar_wait(tempty0 + 8 * buf, tph ^ 1u);  // epilogue has drained this accumulator pair
-        mbar_wait(full0 + 8 * s, ph);            // tile landed
-        tc_fence_after();
-        const uint32_t b_addr = smem_u32(Bs + (size_t)s * b_bytes);
+    // ===== MMA issuer: the warp runs the loop with uniform control flow (descriptors live in uniform
+    // registers), one elected lane issues.  Only the 14-bit start-address field of a descriptor changes.
+    const bool leader = elect_one();
+    const uint32_t a_lbo = MM * 16, b_lbo = TN * 16;
+    const uint32_t desc_hi = (128u >> 4) | (1u << 14);   // SBO = 128 B, descriptor version 1
+    const uint32_t a_lo0 = ((smem_u32(As) >> 4) & 0x3FFFu) | ((a_lbo >> 4) << 16);
+    const uint32_t b_lo0 = ((smem_u32(Bs) >> 4) & 0x3FFFu) | ((b_lbo >> 4) << 16);
+    const uint32_t a_kstep = (2 * a_lbo) >> 4, b_kstep = (2 * b_lbo) >> 4, a_hstep = (128 * 16) >> 4;
+    const uint32_t b_sstep = b_bytes >> 4;
+    const int ksteps = kp / 16;
+    int s = 0;
+    uint32_t ph = 0;
+    for (int64_t i = 0; i < nt; ++i) {
+      const uint32_t buf = (uint32_t)(i & 1);
+      const uint32_t tph = (uint32_t)((i >> 1) & 1);
+      mbar_wait(tempty0 + 8 * buf, tph ^ 1u);  // epilogue has drained this accumulator pair
+      mbar_wait(full0 + 8 * s, ph);            // tile landed
+      tc_fence_after();
+      if (leader) {
+        const uint32_t b_lo = b_lo0 + (uint32_t)s * b_sstep;
+#pragma unroll
         for (int h = 0; h < 2; ++h) {
-          const uint32_t dcol = tmem_base + (uint32_t)(buf * 2 + h) * TN;
-          for (int ks = 0; ks < kp / 16; ++ks) {
-            const uint64_t adesc = make_smem_desc(a_addr + (uint32_t)h * 128 * 16 + (uint32_t)ks * 2 * a_lbo, a_lbo, sbo);
-            const uint64_t bdesc = make_smem_desc(b_addr + (uint32_t)ks * 2 * b_lbo, b_lbo, sbo);
+          const uint32_t dcol = tmem_base + (buf * 2 + h) * TN;
+          const uint32_t a_lo = a_lo0 + (uint32_t)h * a_hstep;
+          for (int ks = 0; ks < ksteps; ++ks) {
+            const uint64_t adesc = ((uint64_t)desc_hi << 32) | (a_lo + (uint32_t)ks * a_kstep);
+            const uint64_t bdesc = ((uint64_t)desc_hi << 32) | (b_lo + (uint32_t)ks * b_kstep);
             umma_f16(dcol, adesc, bdesc, IDESC, ks > 0 ? 1u : 0u);
           }
         }
         umma_commit(empty0 + 8 * s);       // smem stage reusable once these MMAs have read it
         umma_commit(tfull0 + 8 * buf);     // accumulators ready
       }
+      __syncwarp();
+      if (++s == a.stages) {
+        s = 0;
+        ph ^= 1u;
+      }
     }
-  } else if (warp >= EPI_WARP0) {
+  } else {
     // ===== epilogue: one thread per query row =====
     const int e = warp - EPI_WARP0;
-    const int h = e >> 2, quad = e & 3;   // quad == warp % 4: the TMEM lane quadrant this warp may read
+    const int h = e >> 2, quad = warp & 3;   // quad == warp % 4: the TMEM lane quadrant this warp may read
     const int u = h * 128 + quad * 32 + lane;
     const bool active = u < nrows;
     const int64_t qrow = row0 + u;
+    const int64_t lrow = (int64_t)split * a.rows_pad + qrow;   // list index of (row, split)
+    EpiState st;
+    st.thr = active ? -INFINITY : INFINITY;
+    st.thr_pub = -INFINITY;
+    st.cnt = 0;
+    st.overflow = false;
+    st.buf = a.cand + lrow * CAND;
     const float eps = eps_row[u];
-    float thr = active ? -INFINITY : INFINITY;
-    int cnt = 0;
-    bool overflow = false;
-    uint2* mybuf = a.cand + (active ? qrow : row0) * CAND;
-    int64_t h_lo = 0, h_hi = 0;
-    if (active && a.hist_off) {
-      h_lo = a.hist_off[qrow];
-      h_hi = a.hist_off[qrow + 1];
-    }
-    for (int64_t t = 0; t < a.n_tiles; ++t) {
-      const int buf = (int)(t & 1);
-      const uint32_t tph = (uint32_t)((t >> 1) & 1);
+    uint32_t tlane = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(h * TN);
+    asm volatile("" : "+r"(tlane));   // keep the address in a register (ptxas would rebuild it from tid every tile)
+    const int64_t wrow0 = row0 + h * 128 + quad * 32;   // first row of this warp
+    for (int64_t i = 0; i < nt; ++i) {
+      const int64_t t = t0 + i;
+      const int buf = (int)(i & 1);
+      const uint32_t tph = (uint32_t)((i >> 1) & 1);
       mbar_wait(tfull0 + 8 * buf, tph);
       tc_fence_after();
-#pragma unroll 1
+#pragma unroll
       for (int c0 = 0; c0 < TN; c0 += 64) {
         float v[64];
-        const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(buf * 2 + h) * TN + (uint32_t)c0;
-        tmem_ld32x2(taddr, v);  // two 32-column loads in flight, one wait
-        if (a.dbg_out && active) {
-          float* o = a.dbg_out + qrow * (a.n_tiles * TN) + t * TN + c0;
-#pragma unroll
-          for (int i = 0; i < 64; ++i) o[i] = v[i];
+        tmem_ld32x2(tlane + (uint32_t)(buf * 2 * TN + c0), v);  // two 32-column loads in flight, one wait
+        if (c0 + 64 == TN) {  // values are in registers: hand the accumulators back before working on them
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(tempty0 + 8 * buf);
         }
-        const uint32_t g0 = (uint32_t)((t * TN + c0) / GRP);
+        const int64_t col0 = t * TN + c0;
+        if (a.dbg_out && active) {
+          float* o = a.dbg_out + qrow * a.dbg_stride + col0;
 #pragma unroll
-        for (int g = 0; g < 8; ++g) {
-          const float m = fmaxf(max3f(v[8 * g], v[8 * g + 1], v[8 * g + 2]),
-                                max3f(max3f(v[8 * g + 3], v[8 * g + 4], v[8 * g + 5]), v[8 * g + 6], v[8 * g + 7]));
-          if (m >= thr && (int64_t)(g0 + g) * GRP < a.n_targets) {  // rare after the first tiles
-            mybuf[cnt] = make_uint2(__float_as_uint(m), g0 + g);
-            ++cnt;
+          for (int j = 0; j < 64; ++j) o[j] = v[j];
+        }
+        const uint32_t cid = (uint32_t)(col0 / CH);
+        // groups beyond the table exist only in the last tile (the image pads it with zero rows)
+        if (t + 1 < a.n_tiles) {
+          epi_chunk<false>(v, st, cid, 8);
+          epi_chunk<false>(v + CH, st, cid + 1, 8);
+        } else {
+#pragma unroll
+          for (int x = 0; x < 2; ++x) {
+            const int64_t left = a.n_targets - (col0 + x * CH);
+            const int gv = left <= 0 ? 0 : (left >= CH ? 8 : (int)((left + GRP - 1) / GRP));
+            epi_chunk<true>(v + x * CH, st, cid + x, gv);
           }
         }
-        unsigned full = __ballot_sync(0xffffffffu, cnt > CAND - 8);
+        unsigned full = __ballot_sync(0xffffffffu, st.cnt > CAND - 3);
         while (full) {
           const int r = __ffs(full) - 1;
           full &= full - 1;
-          const int cnt_r = __shfl_sync(0xffffffffu, cnt, r);
+          const int cnt_r = __shfl_sync(0xffffffffu, st.cnt, r);
           const float eps_r = __shfl_sync(0xffffffffu, eps, r);
-          MaskInfo mi;
-          mi.hist_items = a.hist_items;
-          mi.h_lo = __shfl_sync(0xffffffffu, h_lo, r);
-          mi.h_hi = __shfl_sync(0xffffffffu, h_hi, r);
-          mi.n_targets = a.n_targets;
-          mi.mask_first = a.mask_first;
-          uint2* buf_r = a.cand + (row0 + h * 128 + quad * 32 + r) * CAND;
+          const int64_t qrow_r = wrow0 + r;
+          int64_t h_lo = 0, h_hi = 0;
+          if (a.hist_off) {
+            h_lo = a.hist_off[qrow_r];
+            h_hi = a.hist_off[qrow_r + 1];
+          }
+          uint2* buf_r = a.cand + ((int64_t)split * a.rows_pad + qrow_r) * CAND;
           __syncwarp();
           float thr_new;
-          const int n_new = compact_row(buf_r, cnt_r, a.k, eps_r, mi, lane, thr_new);
+          const int n_new = compact_row(buf_r, cnt_r, a.k, eps_r, a.hist_items, h_lo, h_hi, a.n_targets, a.mask_first,
+                                        ROOM, &thr_new);
           if (lane == r) {
             if (n_new < 0) {
-              overflow = true;
-              thr = INFINITY;  // stop collecting: the row goes to the exact path
-              cnt = 0;
+              st.overflow = true;
+              st.thr = INFINITY;  // stop collecting: the row goes to the exact path
+              st.cnt = 0;
             } else {
-              cnt = n_new;
-              thr = thr_new;
+              st.cnt = n_new;
+              st.thr = thr_new;
+              st.thr_pub = thr_new;
             }
           }
         }
       }
-      tc_fence_before();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(tempty0 + 8 * buf);
     }
-    if (active) a.cand_cnt[qrow] = overflow ? -1 : cnt;
+    if (active) {
+      a.cand_cnt[lrow] = st.overflow ? -1 : st.cnt;
+      a.cand_thr[lrow] = st.thr_pub;
+    }
   }
 
   // ---- teardown ------------------------------------------------------------------------------------
   tc_fence_before();
   __syncthreads();
-  if (warp == 2) tmem_dealloc(tmem_base, 512);
+  if (warp == 1) tmem_dealloc(tmem_base, 4 * TN);
 }
 
 // ---- exact re-score + top-k ------------------------------------------------------------------------------
 struct RescoreArgs {
   ScoreArgs s;
   int64_t n_targets;
-  int parts, dist;
+  int64_t rows_pad;
+  int splits, nent;
+  int parts;
   const int64_t* hist_off;
   const int64_t* hist_items;
   int mask_first;
   int k;
   const uint2* cand;
   const int32_t* cand_cnt;
+  const float* cand_thr;
+  const float* eps;
   int64_t* ids_out;
   float* scores_out;
   int32_t* row_flags;
 };
 
-constexpr int RS_WARPS = 4;
+constexpr int RS_WARPS = 8;
+constexpr int RS_GIDS = 256;               // group ids expanded per batch of 32 entries
+constexpr int RS_HIST = 256;               // history items staged in shared memory (longer ones stay in global)
+constexpr int RS_KEYS = 64;                // exact keys staged before they are ordered
 
+// nent = entries a row can bring (splits * CAND, at least RS_GIDS so that kbuf also holds a batch of group ids)
+__host__ __device__ inline size_t rescore_smem_per_warp(int kd, int nent) {
+  return ((size_t)kd * 4 + 15) / 16 * 16 + (size_t)nent * 8 + (size_t)nent * 4 + (size_t)RS_HIST * 4 +
+         (size_t)RS_KEYS * 8 + (size_t)32 * 8;
+}
+
+// 32 keys, one per lane, sorted descending across the warp (bitonic network).
+__device__ __forceinline__ uint64_t warp_sort_desc(uint64_t key, int lane) {
+#pragma unroll
+  for (int k2 = 2; k2 <= 32; k2 <<= 1) {
+#pragma unroll
+    for (int j = k2 >> 1; j > 0; j >>= 1) {
+      const uint64_t other = __shfl_xor_sync(0xffffffffu, key, j);
+      const bool desc_block = (lane & k2) == 0;
+      const bool lower = (lane & j) == 0;
+      const bool take_max = lower == desc_block;
+      key = take_max ? (key > other ? key : other) : (key < other ? key : other);
+    }
+  }
+  return key;
+}
+
+template <bool DIST>
 __global__ void __launch_bounds__(RS_WARPS * 32) rescore_topk_kernel(const RescoreArgs a) {
-  extern __shared__ __align__(16) unsigned char smem[];
+  extern __shared__ __align__(128) unsigned char smem[];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int d = a.s.m.d;
   const int kd = a.parts * d;
   const int k = a.k;
-  // per warp: q[kd] floats | keys[CAND * GRP] | list[k]
-  const size_t per_warp = ((size_t)kd * 4 + 15) / 16 * 16 + (size_t)CAND * GRP * 8 + (size_t)k * 8;
-  unsigned char* base = smem + warp * per_warp;
+  // per warp: q[kd] | ent[nent] {value, chunk|mask|flags} | kbuf[nent] keys / group ids | hist | keys | list
+  unsigned char* base = smem + warp * rescore_smem_per_warp(kd, a.nent);
   float* q = reinterpret_cast<float*>(base);
-  uint64_t* keys = reinterpret_cast<uint64_t*>(base + ((size_t)kd * 4 + 15) / 16 * 16);
-  uint64_t* list = keys + CAND * GRP;
+  uint2* ent = reinterpret_cast<uint2*>(base + ((size_t)kd * 4 + 15) / 16 * 16);
+  uint32_t* kbuf = reinterpret_cast<uint32_t*>(ent + a.nent);
+  uint32_t* hist = kbuf + a.nent;
+  uint64_t* keys = reinterpret_cast<uint64_t*>(hist + RS_HIST);
+  uint64_t* list = keys + RS_KEYS;
   const float margin = (a.s.m.model == KGE_ROTATE) ? a.s.m.margin : 0.f;
 
   for (int64_t row = (int64_t)blockIdx.x * RS_WARPS + warp; row < a.s.n; row += (int64_t)gridDim.x * RS_WARPS) {
-    const int cnt = a.cand_cnt[row];
-    if (cnt < 0) {
+    // ---- gather the row's lists ------------------------------------------------------------------------
+    int E = 0;
+    float thr0 = -INFINITY;
+    bool bad = false;
+    for (int s = 0; s < a.splits; ++s) {
+      const int64_t lrow = (int64_t)s * a.rows_pad + row;
+      const int c = a.cand_cnt[lrow];
+      if (c < 0) {
+        bad = true;
+        break;
+      }
+      thr0 = fmaxf(thr0, a.cand_thr[lrow]);
+      for (int i = lane; i < c; i += 32) ent[E + i] = a.cand[lrow * CAND + i];
+      E += c;
+    }
+    if (bad) {
       if (lane == 0) a.row_flags[row] = 1;
       continue;
     }
+    float nq2 = 0.f;
     for (int c = lane; c < d; c += 32) {
       float q0, q1;
       query_value(a.s, row, c, q0, q1);
       q[c] = q0;
-      if (a.parts == 2) q[d + c] = q1;
-    }
-    __syncwarp();
-    int64_t h_lo = 0, h_hi = 0;
-    if (a.hist_off) {
-      h_lo = a.hist_off[row];
-      h_hi = a.hist_off[row + 1];
-    }
-    const int total = cnt * GRP;
-    int n_valid = 0;
-    for (int idx = lane; idx < total; idx += 32) {
-      const uint32_t gid = a.cand[row * CAND + idx / GRP].y & GID_MASK;
-      const int64_t j = (int64_t)gid * GRP + (idx % GRP);
-      uint64_t key = 0ull;
-      bool ok = j < a.n_targets && !(a.mask_first && j == 0);
-      if (ok && h_hi > h_lo) {
-        int64_t lo = h_lo, hi = h_hi;
-        while (lo < hi) {
-          const int64_t mid = (lo + hi) >> 1;
-          if (a.hist_items[mid] < j) lo = mid + 1; else hi = mid;
-        }
-        ok = !(lo < h_hi && a.hist_items[lo] == j);
+      nq2 = fmaf(q0, q0, nq2);
+      if (a.parts == 2) {
+        q[d + c] = q1;
+        nq2 = fmaf(q1, q1, nq2);
       }
-      if (ok) {
-        // the CUDA-core kernel's chain: parts in order, columns ascending, one fmaf per column
-        float acc = 0.f;
-        for (int p = 0; p < a.parts; ++p) {
-          const float* t = a.s.m.entity.w[p] + j * d;
-          const float* qp = q + p * d;
-          if ((d & 3) == 0) {
-            for (int c = 0; c < d; c += 4) {
-              const float4 tv = __ldg(reinterpret_cast<const float4*>(t + c));
-              if (a.dist) {
-                const float e0 = qp[c] - tv.x, e1 = qp[c + 1] - tv.y, e2 = qp[c + 2] - tv.z, e3 = qp[c + 3] - tv.w;
-                acc = fmaf(e0, e0, acc);
-                acc = fmaf(e1, e1, acc);
-                acc = fmaf(e2, e2, acc);
-                acc = fmaf(e3, e3, acc);
-              } else {
-                acc = fmaf(qp[c], tv.x, acc);
-                acc = fmaf(qp[c + 1], tv.y, acc);
-                acc = fmaf(qp[c + 2], tv.z, acc);
-                acc = fmaf(qp[c + 3], tv.w, acc);
-              }
+    }
+    nq2 = warp_sum(nq2);
+    MaskInfo mi;
+    mi.hist_items = a.hist_items;
+    mi.h_lo = mi.h_hi = 0;
+    if (a.hist_off) {
+      mi.h_lo = a.hist_off[row];
+      mi.h_hi = a.hist_off[row + 1];
+    }
+    mi.n_targets = a.n_targets;
+    mi.mask_first = a.mask_first;
+    const int hlen = (int)(mi.h_hi - mi.h_lo);
+    const bool hist_sm = hlen <= RS_HIST;
+    if (hist_sm)
+      for (int i = lane; i < hlen; i += 32) hist[i] = (uint32_t)a.hist_items[mi.h_lo + i];
+    const float eps = a.eps[row];
+    __syncwarp();
+    // ---- final tau: k-th largest maximum among the safe chunks that clear every split's threshold ------
+    for (int i = lane; i < E; i += 32) {
+      const uint2 e = ent[i];
+      uint32_t key = 0u;
+      if (__uint_as_float(e.x) >= thr0) {
+        bool unsafe = (e.y & F_UNSAFE) != 0;
+        if (!(e.y & F_KNOWN)) {
+          const uint32_t cid = (e.y >> CID_SHIFT) & CID_MASK;
+          const int64_t j0 = (int64_t)cid * CH;
+          if (j0 + CH > mi.n_targets || (mi.mask_first && cid == 0)) {
+            unsafe = true;
+          } else if (hist_sm) {
+            int lo = 0, hi = hlen;
+            while (lo < hi) {
+              const int mid = (lo + hi) >> 1;
+              if ((int64_t)hist[mid] < j0) lo = mid + 1; else hi = mid;
             }
+            unsafe = lo < hlen && (int64_t)hist[lo] < j0 + CH;
           } else {
-            for (int c = 0; c < d; ++c) {
-              const float tv = __ldg(t + c);
-              if (a.dist) {
-                const float e0 = qp[c] - tv;
-                acc = fmaf(e0, e0, acc);
-              } else {
-                acc = fmaf(qp[c], tv, acc);
-              }
-            }
+            unsafe = chunk_unsafe(mi, cid);
           }
         }
-        const float sc = a.dist ? (margin - sqrtf(acc)) : acc;
-        key = make_key(sc, (uint32_t)j);
-        ++n_valid;
+        if (!unsafe) key = orderable(__uint_as_float(e.x));
       }
-      keys[idx] = key;
+      kbuf[i] = key;
     }
-    n_valid = (int)warp_sum((float)n_valid);
     __syncwarp();
-    int len = 0;
-    for (int idx = 0; idx < total; ++idx) {
-      const uint64_t key = keys[idx];
-      if (key != 0ull) warp_insert(list, len, k, key, lane);
+    uint32_t T = 0u;
+    {
+      int n_t = 0;
+      for (int i = lane; i < E; i += 32) n_t += kbuf[i] != 0u;
+      n_t = __reduce_add_sync(0xffffffffu, n_t);
+      if (n_t >= k) {
+        uint32_t P = 0u;
+        for (int bit = 31; bit >= 0 && n_t > k; --bit) {
+          const uint32_t c = P | (1u << bit);
+          int n = 0;
+          for (int i = lane; i < E; i += 32) n += kbuf[i] >= c;
+          n = __reduce_add_sync(0xffffffffu, n);
+          if (n >= k) {
+            P = c;
+            n_t = n;
+          }
+        }
+        const uint32_t Tm = P ? P : 1u;
+        uint32_t mn = 0xFFFFFFFFu;
+        for (int i = lane; i < E; i += 32)
+          if (kbuf[i] >= Tm) mn = min(mn, kbuf[i]);
+        T = __reduce_min_sync(0xffffffffu, mn);
+      }
     }
-    if (n_valid < k) {
+    const float tau = T ? from_orderable(T) : -INFINITY;
+    const float thr = fmaxf(thr0, tau - 2.f * eps);
+    // The k targets behind tau have exact a >= tau - eps (a = q.t, or q.t - |t|^2/2 for the L2 models, where
+    // the squared distance is |q|^2 - 2a): nothing that scores below them can enter the top-k.
+    const float lo_a = tau - 1.25f * eps;
+    const float hi_acc = (nq2 - 2.f * lo_a) * 1.00001f + 4e-6f * nq2;   // only used when tau is finite
+    const bool have_tau = T != 0u;
+    __syncwarp();
+    // ---- survivors: the masked groups of the chunks >= thr, 32 chunks at a time ---------------------------
+    int n_pass = 0, nk = 0, len = 0;
+    for (int b0 = 0; b0 < E; b0 += 32) {
+      const int i = b0 + lane;
+      uint32_t gmask = 0u, cid = 0u;
+      if (i < E && __uint_as_float(ent[i].x) >= thr) {
+        gmask = ent[i].y & 0xFFu;
+        cid = (ent[i].y >> CID_SHIFT) & CID_MASK;
+      }
+      int pos = __popc(gmask);   // exclusive prefix over the lanes -> slot of this lane's first group
+      int incl = pos;
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) {
+        const int y = __shfl_up_sync(0xffffffffu, incl, o);
+        if (lane >= o) incl += y;
+      }
+      const int ng = __shfl_sync(0xffffffffu, incl, 31);
+      pos = incl - pos;
+      __syncwarp();
+      while (gmask) {
+        const int g = __ffs(gmask) - 1;
+        gmask &= gmask - 1;
+        kbuf[pos++] = cid * 8u + (uint32_t)g;
+      }
+      __syncwarp();
+      // exact scores of the members
+      const int total = ng * GRP;
+      for (int m0 = 0; m0 < total; m0 += 32) {
+        const int idx = m0 + lane;
+        uint64_t key = 0ull;
+        if (idx < total) {
+          const int64_t j = (int64_t)kbuf[idx / GRP] * GRP + (idx % GRP);
+          bool ok = j < a.n_targets && !(a.mask_first && j == 0);
+          if (ok && hlen > 0) {
+            if (hist_sm) {
+              int lo = 0, hi = hlen;
+              while (lo < hi) {
+                const int mid = (lo + hi) >> 1;
+                if ((int64_t)hist[mid] < j) lo = mid + 1; else hi = mid;
+              }
+              ok = !(lo < hlen && (int64_t)hist[lo] == j);
+            } else {
+              int64_t lo = mi.h_lo, hi = mi.h_hi;
+              while (lo < hi) {
+                const int64_t mid = (lo + hi) >> 1;
+                if (a.hist_items[mid] < j) lo = mid + 1; else hi = mid;
+              }
+              ok = !(lo < mi.h_hi && a.hist_items[lo] == j);
+            }
+          }
+          if (ok) {
+            // the CUDA-core kernel's chain: parts in order, columns ascending, one fmaf per column; the
+            // loads of a 64-column block are all issued before the chain consumes them
+            float acc = 0.f;
+            for (int p = 0; p < a.parts; ++p) {
+              const float* t = a.s.m.entity.w[p] + j * d;
+              const float* qp = q + p * d;
+              if ((d & 3) == 0) {
+                for (int c0 = 0; c0 < d; c0 += 64) {
+                  float4 tv[16];
+#pragma unroll
+                  for (int x = 0; x < 16; ++x)
+                    if (c0 + 4 * x < d) tv[x] = __ldg(reinterpret_cast<const float4*>(t + c0) + x);
+#pragma unroll
+                  for (int x = 0; x < 16; ++x) {
+                    if (c0 + 4 * x < d) {
+                      const float4 qv = *reinterpret_cast<const float4*>(qp + c0 + 4 * x);
+                      if (DIST) {
+                        const float e0 = qv.x - tv[x].x, e1 = qv.y - tv[x].y, e2 = qv.z - tv[x].z, e3 = qv.w - tv[x].w;
+                        acc = fmaf(e0, e0, acc);
+                        acc = fmaf(e1, e1, acc);
+                        acc = fmaf(e2, e2, acc);
+                        acc = fmaf(e3, e3, acc);
+                      } else {
+                        acc = fmaf(qv.x, tv[x].x, acc);
+                        acc = fmaf(qv.y, tv[x].y, acc);
+                        acc = fmaf(qv.z, tv[x].z, acc);
+                        acc = fmaf(qv.w, tv[x].w, acc);
+                      }
+                    }
+                  }
+                }
+              } else {
+#pragma unroll 8
+                for (int c = 0; c < d; ++c) {
+                  const float tv = __ldg(t + c);
+                  if (DIST) {
+                    const float e0 = qp[c] - tv;
+                    acc = fmaf(e0, e0, acc);
+                  } else {
+                    acc = fmaf(qp[c], tv, acc);
+                  }
+                }
+              }
+            }
+            const bool in = !have_tau || (DIST ? (acc <= hi_acc) : (acc >= lo_a));
+            if (in) key = make_key(DIST ? (margin - sqrtf(acc)) : acc, (uint32_t)j);
+          }
+        }
+        // stage the keys that can still matter (warp-uniform order: lane ascending)
+        const unsigned bal = __ballot_sync(0xffffffffu, key != 0ull);
+        const int nb = __popc(bal);
+        if (nb) {
+          if (nk + nb > RS_KEYS) {   // rare: fold the staged keys into the sorted list first
+            for (int x = 0; x < nk; ++x) warp_insert(list, len, k, keys[x], lane);
+            nk = 0;
+          }
+          if (key != 0ull) keys[nk + __popc(bal & ((1u << lane) - 1u))] = key;
+          nk += nb;
+          n_pass += nb;
+          __syncwarp();
+        }
+      }
+      __syncwarp();
+    }
+    // ---- order the keys: (score desc, id asc) ------------------------------------------------------------------
+    if (n_pass < k) {
       if (lane == 0) a.row_flags[row] = 1;
     } else {
+      uint64_t out;
+      if (len == 0 && nk <= 32) {
+        out = warp_sort_desc(lane < nk ? keys[lane] : 0ull, lane);
+      } else {
+        for (int x = 0; x < nk; ++x) warp_insert(list, len, k, keys[x], lane);
+        out = lane < k ? list[lane] : 0ull;
+      }
       if (lane == 0) a.row_flags[row] = 0;
-      for (int i = lane; i < k; i += 32) {
-        const uint64_t key = list[i];
-        a.ids_out[row * k + i] = key_id(key);
-        if (a.scores_out) a.scores_out[row * k + i] = key_score(key);
+      if (lane < k) {
+        a.ids_out[row * k + lane] = key_id(out);
+        if (a.scores_out) a.scores_out[row * k + lane] = key_score(out);
       }
     }
     __syncwarp();
   }
 }
 
+// Tile width of the sweep (64: two CTAs per SM; 128: one).  KGE_MMA_TN overrides it for experiments.
+int mma_tn() {
+  static int tn = 0;
+  if (!tn) {
+    const char* e = getenv("KGE_MMA_TN");
+    tn = (e && atoi(e) == 128) ? 128 : 64;
+  }
+  return tn;
+}
+
 struct MmaPlan {
-  int parts, dist, kp, stages;
+  int parts, dist, kp, stages, tn, splits, tiles_per_split;
   size_t smem;
-  int64_t n_tiles;
+  int64_t n_tiles, rows_pad;
 };
 
-int plan_mma(const kge_model_t* m, int64_t n_targets, int k, MmaPlan& pl) {
+int plan_mma(const kge_model_t* m, int64_t n, int64_t n_targets, int k, MmaPlan& pl) {
   KGE_REQUIRE(m && m->model >= KGE_TRANSE && m->model <= KGE_COMPLEX, KGE_E_ARG, "bad model");
   pl.parts = (m->model == KGE_ROTATE || m->model == KGE_COMPLEX) ? 2 : 1;
   pl.dist = (m->model == KGE_TRANSE || m->model == KGE_ROTATE) ? 1 : 0;
@@ -664,15 +961,29 @@ int plan_mma(const kge_model_t* m, int64_t n_targets, int k, MmaPlan& pl) {
   pl.kp = (kd + 15) / 16 * 16;
   KGE_REQUIRE(pl.kp <= 256, KGE_E_UNSUPPORTED, "K = %d too large for the tensor-core path", pl.kp);
   KGE_REQUIRE(k >= 1 && k <= 32, KGE_E_UNSUPPORTED, "k = %d too large for the tensor-core path (max 32)", k);
-  KGE_REQUIRE(n_targets >= 1 && n_targets < (int64_t)0x1FFFFFFF * GRP, KGE_E_UNSUPPORTED, "bad n_targets");
-  const size_t a_bytes = (size_t)MM * pl.kp * 2, b_bytes = (size_t)TN * pl.kp * 2;
-  const size_t fixed = a_bytes + 64 * 8 + MM * 4 + 64;
-  int stages = (int)((200 * 1024 - fixed) / b_bytes);
-  if (stages > 6) stages = 6;
-  KGE_REQUIRE(stages >= 2, KGE_E_UNSUPPORTED, "K = %d leaves no room for a pipeline", pl.kp);
+  KGE_REQUIRE(n_targets >= 1 && n_targets < (int64_t)CID_MASK * CH, KGE_E_UNSUPPORTED, "bad n_targets");
+  pl.tn = mma_tn();
+  const size_t a_bytes = (size_t)MM * pl.kp * 2, b_bytes = (size_t)pl.tn * pl.kp * 2;
+  const size_t fixed = a_bytes + 32 * 8 + MM * 4 + 64;
+  // two CTAs per SM when the operands allow it (227 KB per SM, 1 KB reserved per CTA)
+  size_t budget = 112 * 1024;
+  if (pl.tn != 64 || fixed + 4 * b_bytes > budget) budget = 200 * 1024;
+  KGE_REQUIRE(fixed + 2 * b_bytes <= budget, KGE_E_UNSUPPORTED, "K = %d leaves no room for a pipeline", pl.kp);
+  int stages = (int)((budget - fixed) / b_bytes);
+  if (stages > 8) stages = 8;
   pl.stages = stages;
   pl.smem = a_bytes + (size_t)stages * b_bytes + (size_t)(2 * stages + 4) * 8 + MM * 4 + 64;
-  pl.n_tiles = (n_targets + TN - 1) / TN;
+  pl.n_tiles = (n_targets + pl.tn - 1) / pl.tn;
+  pl.rows_pad = (n + MM - 1) / MM * MM;
+  // target splits: fill the resident CTA slots (2 per SM) when there are few row blocks
+  const int64_t row_blocks = pl.rows_pad / MM > 0 ? pl.rows_pad / MM : 1;
+  const int64_t slots = (int64_t)kge_num_sms() * (budget == 112 * 1024 ? 2 : 1);
+  int64_t s = slots / row_blocks;
+  if (s > MAX_SPLITS) s = MAX_SPLITS;
+  if (s > pl.n_tiles / 16) s = pl.n_tiles / 16;
+  if (s < 1) s = 1;
+  pl.tiles_per_split = (int)((pl.n_tiles + s - 1) / s);
+  pl.splits = (int)((pl.n_tiles + pl.tiles_per_split - 1) / pl.tiles_per_split);
   return 0;
 }
 
@@ -680,14 +991,14 @@ int plan_mma(const kge_model_t* m, int64_t n_targets, int k, MmaPlan& pl) {
 
 extern "C" int64_t kge_mma_image_bytes(const kge_model_t* model, int64_t n_targets) {
   MmaPlan pl;
-  if (!model || plan_mma(model, n_targets, 1, pl)) return -1;
-  return IMG_HEADER + pl.n_tiles * TN * (int64_t)pl.kp * 2 + ((n_targets * 4 + 127) / 128) * 128;
+  if (!model || plan_mma(model, 1, n_targets, 1, pl)) return -1;
+  return IMG_HEADER + pl.n_tiles * pl.tn * (int64_t)pl.kp * 2 + ((n_targets * 4 + 127) / 128) * 128;
 }
 
 extern "C" int kge_mma_prepare_targets(const kge_model_t* model, int64_t n_targets, void* image, int64_t image_bytes,
                                        kge_stream_t stream) {
   MmaPlan pl;
-  if (int e = plan_mma(model, n_targets, 1, pl)) return e;
+  if (int e = plan_mma(model, 1, n_targets, 1, pl)) return e;
   KGE_REQUIRE(n_targets <= model->entity.rows, KGE_E_ARG, "n_targets beyond the entity table");
   const int64_t need = kge_mma_image_bytes(model, n_targets);
   KGE_REQUIRE(image && image_bytes >= need, KGE_E_ARG, "image buffer too small: need %lld bytes", (long long)need);
@@ -699,9 +1010,10 @@ extern "C" int kge_mma_prepare_targets(const kge_model_t* model, int64_t n_targe
   a.parts = pl.parts;
   a.kp = pl.kp;
   a.dist = pl.dist;
+  a.tn = pl.tn;
   a.header = reinterpret_cast<float*>(image);
   a.tiles = reinterpret_cast<uint16_t*>(reinterpret_cast<unsigned char*>(image) + IMG_HEADER);
-  a.tn2 = reinterpret_cast<float*>(reinterpret_cast<unsigned char*>(image) + IMG_HEADER + pl.n_tiles * TN * (int64_t)pl.kp * 2);
+  a.tn2 = reinterpret_cast<float*>(reinterpret_cast<unsigned char*>(image) + IMG_HEADER + pl.n_tiles * pl.tn * (int64_t)pl.kp * 2);
   KGE_CUDA(cudaMemsetAsync(image, 0, IMG_HEADER, st));
   const int sms = kge_num_sms();
   target_norm_kernel<<<sms * 4, 256, 0, st>>>(a);
@@ -714,9 +1026,8 @@ extern "C" int kge_mma_prepare_targets(const kge_model_t* model, int64_t n_targe
 extern "C" int64_t kge_full_sort_topk_mma_workspace_bytes(const kge_model_t* model, int64_t n, int64_t n_targets,
                                                           int32_t k) {
   MmaPlan pl;
-  if (!model || n < 0 || plan_mma(model, n_targets, k, pl)) return -1;
-  const int64_t rows = (n + MM - 1) / MM * MM;
-  return rows * CAND * 8 + rows * 4;
+  if (!model || n < 0 || plan_mma(model, n, n_targets, k, pl)) return -1;
+  return (int64_t)pl.splits * pl.rows_pad * (CAND * 8 + 4 + 4) + pl.rows_pad * 4;
 }
 
 extern "C" int kge_full_sort_topk_mma(const kge_model_t* model, const int64_t* heads, const int64_t* rels, int64_t n,
@@ -725,7 +1036,7 @@ extern "C" int kge_full_sort_topk_mma(const kge_model_t* model, const int64_t* h
                                       float* scores_out, int32_t* row_flags, void* workspace, int64_t workspace_bytes,
                                       float* debug_scores, kge_stream_t stream) {
   MmaPlan pl;
-  if (int e = plan_mma(model, n_targets, k, pl)) return e;
+  if (int e = plan_mma(model, n, n_targets, k, pl)) return e;
   KGE_REQUIRE(n >= 0 && n_targets <= model->entity.rows && k <= n_targets, KGE_E_ARG, "bad n / n_targets / k");
   if (n == 0) return 0;
   KGE_REQUIRE(heads && image && ids_out && row_flags && workspace, KGE_E_ARG, "NULL argument");
@@ -733,7 +1044,7 @@ extern "C" int kge_full_sort_topk_mma(const kge_model_t* model, const int64_t* h
   const int64_t need = kge_full_sort_topk_mma_workspace_bytes(model, n, n_targets, k);
   KGE_REQUIRE(workspace_bytes >= need, KGE_E_ARG, "workspace too small: need %lld bytes", (long long)need);
   cudaStream_t st = (cudaStream_t)stream;
-  const int64_t rows = (n + MM - 1) / MM * MM;
+  const int64_t lists = (int64_t)pl.splits * pl.rows_pad;
 
   MmaArgs a = {};
   a.s.m = *model;
@@ -745,6 +1056,8 @@ extern "C" int kge_full_sort_topk_mma(const kge_model_t* model, const int64_t* h
   a.s.rel_row = model->ui_relation_fullsort;
   a.n_targets = n_targets;
   a.n_tiles = pl.n_tiles;
+  a.rows_pad = pl.rows_pad;
+  a.tiles_per_split = pl.tiles_per_split;
   a.parts = pl.parts;
   a.kp = pl.kp;
   a.dist = pl.dist;
@@ -755,35 +1068,52 @@ extern "C" int kge_full_sort_topk_mma(const kge_model_t* model, const int64_t* h
   a.hist_items = hist_items;
   a.mask_first = mask_first;
   a.k = k;
-  a.cand = reinterpret_cast<uint2*>(workspace);
-  a.cand_cnt = reinterpret_cast<int32_t*>(reinterpret_cast<unsigned char*>(workspace) + rows * CAND * 8);
+  unsigned char* ws = reinterpret_cast<unsigned char*>(workspace);
+  a.cand = reinterpret_cast<uint2*>(ws);
+  a.cand_cnt = reinterpret_cast<int32_t*>(ws + lists * CAND * 8);
+  a.cand_thr = reinterpret_cast<float*>(ws + lists * (CAND * 8 + 4));
+  a.eps_out = reinterpret_cast<float*>(ws + lists * (CAND * 8 + 8));
   a.dbg_out = debug_scores;
-  KGE_CUDA(cudaFuncSetAttribute(fullsort_mma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pl.smem));
-  fullsort_mma_kernel<<<(unsigned)(rows / MM), MMA_THREADS, pl.smem, st>>>(a);
+  a.dbg_stride = (n_targets + 127) / 128 * 128;
+  const dim3 grid((unsigned)(pl.rows_pad / MM), (unsigned)pl.splits);
+  if (pl.tn == 64) {
+    KGE_CUDA(cudaFuncSetAttribute(fullsort_mma_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pl.smem));
+    fullsort_mma_kernel<64><<<grid, SWEEP_THREADS, pl.smem, st>>>(a);
+  } else {
+    KGE_CUDA(cudaFuncSetAttribute(fullsort_mma_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pl.smem));
+    fullsort_mma_kernel<128><<<grid, SWEEP_THREADS, pl.smem, st>>>(a);
+  }
   KGE_LAUNCH_CHECK();
 
   RescoreArgs r = {};
   r.s = a.s;
   r.n_targets = n_targets;
+  r.rows_pad = pl.rows_pad;
+  r.splits = pl.splits;
   r.parts = pl.parts;
-  r.dist = pl.dist;
   r.hist_off = hist_off;
   r.hist_items = hist_items;
   r.mask_first = mask_first;
   r.k = k;
   r.cand = a.cand;
   r.cand_cnt = a.cand_cnt;
+  r.cand_thr = a.cand_thr;
+  r.eps = a.eps_out;
   r.ids_out = ids_out;
   r.scores_out = scores_out;
   r.row_flags = row_flags;
-  const int kd = pl.parts * model->d;
-  const size_t per_warp = ((size_t)kd * 4 + 15) / 16 * 16 + (size_t)CAND * GRP * 8 + (size_t)k * 8;
-  const size_t rs_smem = per_warp * RS_WARPS;
-  if (rs_smem > 48 * 1024)
-    KGE_CUDA(cudaFuncSetAttribute(rescore_topk_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)rs_smem));
+  r.nent = pl.splits * CAND > RS_GIDS ? pl.splits * CAND : RS_GIDS;
+  const size_t rs_smem = rescore_smem_per_warp(pl.parts * model->d, r.nent) * RS_WARPS;
   int64_t g = (n + RS_WARPS - 1) / RS_WARPS;
-  const int64_t cap = (int64_t)kge_num_sms() * 16;
-  rescore_topk_kernel<<<(unsigned)(g < cap ? g : cap), RS_WARPS * 32, rs_smem, st>>>(r);
+  const int64_t cap = (int64_t)kge_num_sms() * 8;
+  const unsigned rs_grid = (unsigned)(g < cap ? g : cap);
+  if (pl.dist) {
+    KGE_CUDA(cudaFuncSetAttribute(rescore_topk_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)rs_smem));
+    rescore_topk_kernel<true><<<rs_grid, RS_WARPS * 32, rs_smem, st>>>(r);
+  } else {
+    KGE_CUDA(cudaFuncSetAttribute(rescore_topk_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)rs_smem));
+    rescore_topk_kernel<false><<<rs_grid, RS_WARPS * 32, rs_smem, st>>>(r);
+  }
   KGE_LAUNCH_CHECK();
   return 0;
 }
