@@ -380,7 +380,7 @@ def main():
         # second headline metric: users/s of full-sort top-k (user blocks sharded across ranks)
         for name, fs in FULLSORT.items():
             try:
-                n_users_step = 148 * 256   # one CTA (256 users) per SM
+                n_users_step = 148 * 512   # two CTAs of 256 users per SM: one full wave of the tcgen05 sweep
                 reps = max(3, args.steps // 4)
                 flops = 2.0 * fs["I"] * fs["d"] * PARTS[fs["model"]]
                 entry = {"metric": "users/sec (full-sort top-20)", "users_per_block_per_gpu": n_users_step}

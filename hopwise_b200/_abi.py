@@ -127,7 +127,7 @@ def lib():
     global _lib
     if _lib is not None:
         return _lib
-    path = _build.LIB_PATH
+    path = os.environ.get("KGE_B200_LIB") or _build.LIB_PATH   # KGE_B200_LIB: an experimental build (scripts/build_variant.sh)
     if not os.path.exists(path):
         path = _build.build()  # raises when nvcc is missing: no fallback
     handle = C.CDLL(path)

@@ -46,7 +46,10 @@ namespace {
 
 constexpr int MM = 256;    // query rows per CTA
 constexpr int GRP = 4;     // targets per candidate group (what the rescore kernel reads per mask bit)
-constexpr int CAND = 128;  // candidate groups kept per (row, split)
+#ifndef KGE_MMA_CAND
+#define KGE_MMA_CAND 128
+#endif
+constexpr int CAND = KGE_MMA_CAND;  // candidate chunks kept per (row, split)
 constexpr int MAX_SPLITS = 4;
 constexpr int SWEEP_THREADS = 320;  // warps 0..7 epilogue, warp 8 producer, warp 9 MMA issuer: the issue
                                     // arbiter favours high warp ids, and the MMA issuer must never starve
@@ -64,10 +67,10 @@ __device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity) {
   uint32_t ok;
   asm volatile(
       "{\n\t.reg .pred p;\n\t"
-      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\t"
       "selp.u32 %0, 1, 0, p;\n\t}"
       : "=r"(ok)
-      : "r"(bar), "r"(parity)
+      : "r"(bar), "r"(parity), "r"(0x989680u)   // suspend-time hint: sleep in hardware instead of polling
       : "memory");
   return ok != 0;
 }
@@ -269,7 +272,6 @@ struct MmaArgs {
   int64_t unsafe_wpr;
   float* dbg_out;     // optional dense approximate scores [n, dbg_stride]
   int64_t dbg_stride;
-  int dbg_flags;      // experiments only (KGE_MMA_DEBUG): 1 = skip the epilogue arithmetic, 2 = skip the MMAs
 };
 
 // Entry of a row's candidate list = one 32-target chunk of the sweep: x = maximum of the chunk's
@@ -433,7 +435,7 @@ __device__ __forceinline__ void epi_chunk(const uint32_t (&r)[32], EpiState& st,
   }
 }
 
-template <int TN>
+template <int TN, bool DBG>
 __global__ void __launch_bounds__(SWEEP_THREADS, 2) fullsort_mma_kernel(const MmaArgs a) {
   constexpr int ROOM = 16;              // list room demanded after a compaction
   constexpr uint32_t IDESC = make_idesc(TN);
@@ -556,7 +558,7 @@ __global__ void __launch_bounds__(SWEEP_THREADS, 2) fullsort_mma_kernel(const Mm
         if (leader) {
           const uint32_t dcol = tmem_base + (buf * 2 + h) * TN;
           const uint32_t a_lo = a_lo0 + (uint32_t)h * a_hstep;
-          for (int ks = 0; ks < ((a.dbg_flags & 2) ? 0 : ksteps); ++ks) {
+          for (int ks = 0; ks < ksteps; ++ks) {
             const uint64_t adesc = ((uint64_t)desc_hi << 32) | (a_lo + (uint32_t)ks * a_kstep);
             const uint64_t bdesc = ((uint64_t)desc_hi << 32) | (b_lo + (uint32_t)ks * b_kstep);
             umma_f16(dcol, adesc, bdesc, IDESC, ks > 0 ? 1u : 0u);
@@ -591,18 +593,19 @@ __global__ void __launch_bounds__(SWEEP_THREADS, 2) fullsort_mma_kernel(const Mm
     const uint32_t my_tfull = tfull0 + 8 * h, my_tempty = tempty0 + 8 * h;   // + 16 * buf
 
     // One chunk of 32 columns: optional debug dump, then the filter.
-    auto process = [&](const uint32_t (&r)[32], int64_t t, int64_t col0) {
-      if (a.dbg_out && active) {
-        float* o = a.dbg_out + qrow * a.dbg_stride + col0;
+    const int tail_i = (t1 == a.n_tiles) ? (int)nt - 1 : -1;   // groups beyond the table exist only in the last tile
+    auto process = [&](const uint32_t (&r)[32], int i, uint32_t cid) {
+      if (DBG) {
+        if (active) {
+          float* o = a.dbg_out + qrow * a.dbg_stride + (int64_t)cid * CH;
 #pragma unroll
-        for (int j = 0; j < CH; ++j) o[j] = __uint_as_float(r[j]);
+          for (int j = 0; j < CH; ++j) o[j] = __uint_as_float(r[j]);
+        }
       }
-      const uint32_t cid = (uint32_t)(col0 / CH);
-      if (a.dbg_flags & 1) {
-      } else if (t + 1 < a.n_tiles) {
+      if (i != tail_i) {
         epi_chunk<false>(r, st, cid, 8);
-      } else {  // groups beyond the table exist only in the last tile (the image pads it with zero rows)
-        const int64_t left = a.n_targets - col0;
+      } else {  // (the image pads the last tile with zero rows)
+        const int64_t left = a.n_targets - (int64_t)cid * CH;
         epi_chunk<true>(r, st, cid, left <= 0 ? 0 : (left >= CH ? 8 : (int)((left + GRP - 1) / GRP)));
       }
     };
@@ -615,23 +618,24 @@ __global__ void __launch_bounds__(SWEEP_THREADS, 2) fullsort_mma_kernel(const Mm
     tc_fence_after();
     tmem_ld32_issue(tlane, va);
     tmem_ld_wait(va);
-    for (int64_t i = 0; i < nt; ++i) {
-      const int64_t t = t0 + i;
+    const int nti = (int)nt;
+    uint32_t cid = (uint32_t)(t0 * (TN / CH));
+    for (int i = 0; i < nti; ++i, cid += 2) {
       const uint32_t buf = (uint32_t)(i & 1);
       tmem_ld32_issue(tlane + buf * 2 * TN + CH, vb);
-      process(va, t, t * TN);
+      process(va, i, cid);
       tmem_ld_wait(vb);
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(my_tempty + 16 * buf);   // both chunks are in registers: release the accumulator
-      if (i + 1 < nt) {
+      if (i + 1 < nti) {
         const uint32_t nbuf = buf ^ 1u;
         mbar_wait(my_tfull + 16 * nbuf, (uint32_t)(((i + 1) >> 1) & 1));
         tc_fence_after();
         tmem_ld32_issue(tlane + nbuf * 2 * TN, va);
       }
-      process(vb, t, t * TN + CH);
-      if (i + 1 < nt) tmem_ld_wait(va);
+      process(vb, i, cid + 1);
+      if (i + 1 < nti) tmem_ld_wait(va);
       unsigned full = __ballot_sync(0xffffffffu, st.cnt > CAND - 3);
       while (full) {
         const int r = __ffs(full) - 1;
@@ -1108,10 +1112,7 @@ extern "C" int kge_full_sort_topk_mma(const kge_model_t* model, const int64_t* h
   a.unsafe_wpr = pl.unsafe_wpr;
   a.dbg_out = debug_scores;
   a.dbg_stride = (n_targets + 127) / 128 * 128;
-  {
-    const char* e = getenv("KGE_MMA_DEBUG");
-    a.dbg_flags = e ? atoi(e) : 0;
-  }
+
   KGE_CUDA(cudaMemsetAsync(unsafe_bits, 0, (size_t)pl.rows_pad * pl.unsafe_wpr * 4, st));
   {
     int64_t g = (n + 7) / 8;
@@ -1121,8 +1122,13 @@ extern "C" int kge_full_sort_topk_mma(const kge_model_t* model, const int64_t* h
     KGE_LAUNCH_CHECK();
   }
   const dim3 grid((unsigned)(pl.rows_pad / MM), (unsigned)pl.splits);
-  KGE_CUDA(cudaFuncSetAttribute(fullsort_mma_kernel<SWEEP_TN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pl.smem));
-  fullsort_mma_kernel<SWEEP_TN><<<grid, SWEEP_THREADS, pl.smem, st>>>(a);
+  if (debug_scores) {
+    KGE_CUDA(cudaFuncSetAttribute(fullsort_mma_kernel<SWEEP_TN, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pl.smem));
+    fullsort_mma_kernel<SWEEP_TN, true><<<grid, SWEEP_THREADS, pl.smem, st>>>(a);
+  } else {
+    KGE_CUDA(cudaFuncSetAttribute(fullsort_mma_kernel<SWEEP_TN, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pl.smem));
+    fullsort_mma_kernel<SWEEP_TN, false><<<grid, SWEEP_THREADS, pl.smem, st>>>(a);
+  }
   KGE_LAUNCH_CHECK();
 
   RescoreArgs r = {};
