@@ -37,7 +37,7 @@ def shard_bounds(n: int, rank: int, world: int):
 
 class FlatLayout:
     """Byte layout of one rank's packed gradient message: per table
-    [count int32 (padded to 8 B) | ids int64[cap] | rows fp32[cap, parts*d]]."""
+    [count int32 (padded to 16 B) | ids int64[cap] | rows fp32[cap, parts*d], 16-byte aligned]."""
 
     def __init__(self, caps, parts, d):
         self.caps, self.parts, self.d = list(caps), list(parts), int(d)
@@ -45,8 +45,8 @@ class FlatLayout:
         off = 0
         for cap, p in zip(self.caps, self.parts):
             cnt = off
-            ids = cnt + 8
-            rows = ids + 8 * cap
+            ids = cnt + 16
+            rows = (ids + 8 * cap + 15) // 16 * 16   # rows are read and written as float4
             off = rows + 4 * cap * p * self.d
             off = (off + 15) // 16 * 16
             self.offsets.append((cnt, ids, rows))

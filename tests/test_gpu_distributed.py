@@ -1,0 +1,93 @@
+"""Two-GPU NCCL test of the row-sparse data-parallel train step (skipped with fewer than 2 GPUs):
+replicas stay bit-identical, and equal the single-GPU step on the concatenated batch (DDP averages
+the gradients of per-rank mean losses = the global-batch mean for equal shards, trainer.py:82-112)."""
+
+import os
+import socket
+
+import numpy as np
+import pytest
+import torch
+
+from kge_helpers import assert_weights_close, make_product_model, random_batch, to_device_batch
+
+pytestmark = pytest.mark.gpu
+
+SHAPE = dict(U=300, I=200, E=700, R=9, d=64)
+N_REC, N_KG, STEPS = 192, 160, 4
+
+
+def _free_port():
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        return s.getsockname()[1]
+
+
+def _batches(name):
+    rng = np.random.default_rng(5)
+    k = 3 if name in ("RotatE", "ComplEx") else 1
+    return [random_batch(rng, SHAPE["U"], SHAPE["I"], SHAPE["E"], SHAPE["R"], 2 * N_REC, 2 * N_KG, k, k) for _ in range(STEPS)], k
+
+
+def _shard(b, rank, k):
+    """Rank's half of a global batch; negatives are j-major [k, n] (sampler.py:146-153)."""
+    out = {}
+    for key, v in b.items():
+        if key.startswith("neg_"):
+            n = v.shape[0] // k
+            half = n // 2
+            out[key] = v.reshape(k, n)[:, rank * half:(rank + 1) * half].reshape(-1)
+        else:
+            half = v.shape[0] // 2
+            out[key] = v[rank * half:(rank + 1) * half]
+    return out
+
+
+def _worker(rank, world, port, name, out_dir):
+    import torch.distributed as dist
+
+    from hopwise_b200.distributed import broadcast_weights, enable_row_sparse_data_parallel
+
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    torch.cuda.set_device(rank)
+    dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", rank))
+    try:
+        dev = f"cuda:{rank}"
+        m = make_product_model(name, device=dev, seed=2024 + rank, **SHAPE)   # different init: broadcast must fix it
+        broadcast_weights(m)
+        ex = enable_row_sparse_data_parallel(m)
+        batches, k = _batches(name)
+        losses = []
+        for b in batches:
+            loss = m.calculate_loss(to_device_batch(_shard(b, rank, k), dev))
+            loss.backward()
+            losses.append(float(loss.item()))
+        assert ex.bytes_per_step > 0
+        sd = {key: v.cpu().numpy() for key, v in m.state_dict().items()}
+        np.savez(os.path.join(out_dir, f"rank{rank}.npz"), losses=np.array(losses), **sd)
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("name", ["TransE", "ComplEx"])
+def test_two_rank_row_sparse_step_matches_single_gpu(name, tmp_path):
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    import torch.multiprocessing as mp
+
+    mp.spawn(_worker, args=(2, _free_port(), name, str(tmp_path)), nprocs=2, join=True)
+    r0, r1 = np.load(tmp_path / "rank0.npz"), np.load(tmp_path / "rank1.npz")
+    keys = [k_ for k_ in r0.files if k_ != "losses"]
+    for key in keys:   # same values added in the same order on every rank
+        np.testing.assert_array_equal(r0[key], r1[key], err_msg=key)
+    # single GPU, whole batch, weights as rank 0 initialised them
+    m = make_product_model(name, device="cuda:0", seed=2024, **SHAPE)
+    batches, k = _batches(name)
+    losses = []
+    for b in batches:
+        loss = m.calculate_loss(to_device_batch(b, "cuda:0"))
+        loss.backward()
+        losses.append(float(loss.item()))
+    np.testing.assert_allclose(0.5 * (r0["losses"] + r1["losses"]), losses, rtol=1e-5)
+    for key, v in m.state_dict().items():
+        assert_weights_close(r0[key], v.cpu().numpy(), rtol=1e-5, atol=5e-7, err_msg=f"{name} {key}")
