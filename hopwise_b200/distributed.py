@@ -14,6 +14,12 @@ gradient scaled by 1/world_size (DDP's mean).  The adds see the same values in t
 order on every rank, so the replicas stay bit-identical without ever moving a dense table.
 Bytes per rank per step: sum over tables of min(rows, touched) * (8 + parts*d*4), instead of
 4 bytes * every parameter.
+
+A table whose batch can touch at least half of its rows (small tables, or the roofline batches of
+bench.py) takes the dense route instead: its gradient accumulator is all-reduced (sum) and its
+row states are all-reduced (max = union of the touch marks); both live in flat buffers so that
+one collective covers every dense table.  NCCL delivers the same sums to every rank, so the
+replicas stay bit-identical on this route too.
 """
 
 from __future__ import annotations
@@ -97,31 +103,57 @@ class RowSparseExchange:
         self._caps_for = None
         self.device = device
         self.send = self.recv = None
+        self.dense = [False, False, False]
         self.bytes_per_step = 0
 
     def _plan(self, model, batch_rows):
-        """Tighten the per-table capacity to what this batch shape can touch."""
+        """Tighten the per-table capacity to what this batch shape can touch; pick the route per table."""
         rows = (model.n_users, model.n_entities, model.n_relations)
         parts = self.layout.parts
         caps = [max(1, min(r, b)) for r, b in zip(rows, batch_rows)]
+        self.dense = [2 * c >= r for c, r in zip(caps, rows)]
+        caps = [1 if dn else c for c, dn in zip(caps, self.dense)]   # dense tables send nothing through the lists
         if self.send is None or caps != self.layout.caps:
             self.layout = FlatLayout(caps, parts, model.embedding_size)
             device = self.device or next(model.parameters()).device
             self.send = torch.zeros(self.layout.nbytes, dtype=torch.uint8, device=device)
             self.recv = torch.zeros(self.world * self.layout.nbytes, dtype=torch.uint8, device=device)
-            self.bytes_per_step = self.layout.nbytes
+        st = model._state
+        dense_bytes = sum((st[f]["g_span"][1] - st[f]["g_span"][0]) * 4 + (st[f]["rs_span"][1] - st[f]["rs_span"][0]) * 8
+                          for f, dn in zip(FAMILIES, self.dense) if dn)
+        self.bytes_per_step = (0 if all(self.dense) else self.layout.nbytes) + dense_bytes
+
+    def _dense_spans(self, model):
+        """Maximal runs of adjacent dense tables in the flat buffers: [(g_lo, g_hi, rs_lo, rs_hi)]."""
+        st, runs = model._state, []
+        for fam, dn in zip(FAMILIES, self.dense):
+            if not dn:
+                continue
+            (g0, g1), (r0, r1) = st[fam]["g_span"], st[fam]["rs_span"]
+            if runs and runs[-1][1] == g0 and runs[-1][3] == r0:
+                runs[-1] = (runs[-1][0], g1, runs[-1][2], r1)
+            else:
+                runs.append((g0, g1, r0, r1))
+        return runs
 
     def __call__(self, model):
         step = model._step + 1
         self._plan(model, model._touch_bounds)
-        for which in range(3):
+        sparse = [w for w in range(3) if not self.dense[w]]
+        for which in sparse:
             count, ids, rows = self.layout.views(self.send, which)
             self.pack_fn(model, which, step, count, ids, rows)
+        st = model._state
+        for g0, g1, r0, r1 in self._dense_spans(model):
+            dist.all_reduce(st["g_flat"][g0:g1], op=dist.ReduceOp.SUM, group=self.group)
+            dist.all_reduce(st["row_state_flat"][r0:r1], op=dist.ReduceOp.MAX, group=self.group)
+        if not sparse:
+            return
         dist.all_gather_into_tensor(self.recv, self.send, group=self.group)
         n = self.layout.nbytes
         for r in range(self.world):  # fixed order on every rank => identical fp32 sums
             chunk = self.recv[r * n : (r + 1) * n]
-            for which in range(3):
+            for which in sparse:
                 count, ids, rows = self.layout.views(chunk, which)
                 self.add_fn(model, which, step, count, ids, rows)
 

@@ -205,19 +205,32 @@ class FusedKGEModel(KnowledgeRecommender):
         if self._state is not None and self._state["device"] == device:
             return self._state
         st = {"device": device}
-        for fam, names, rows in (
+        fams = (
             ("user", self.USER_TABLES, self.n_users),
             ("entity", self.ENTITY_TABLES, self.n_entities),
             ("relation", self.RELATION_TABLES, self.n_relations),
-        ):
-            d = self.embedding_size
+        )
+        d = self.embedding_size
+        # gradient accumulators and row states of all tables live in two flat buffers, so that the dense
+        # data-parallel path reduces them with one collective each (hopwise_b200/distributed.py)
+        st["g_flat"] = torch.zeros(sum(rows * len(names) for _, names, rows in fams) * d, device=device)
+        st["row_state_flat"] = torch.full((sum(rows for _, _, rows in fams), 2), -1, dtype=torch.int32, device=device)
+        g_off = rs_off = 0
+        for fam, names, rows in fams:
+            g_views = []
+            for _ in names:
+                g_views.append(st["g_flat"][g_off : g_off + rows * d].view(rows, d))
+                g_off += rows * d
             st[fam] = {
                 "m": [torch.zeros(rows, d, device=device) for _ in names],
                 "v": [torch.zeros(rows, d, device=device) for _ in names],
-                "g": [torch.zeros(rows, d, device=device) for _ in names],
+                "g": g_views,
                 # [rows, 2] int32: {last_step, touch_step}
-                "row_state": torch.full((rows, 2), -1, dtype=torch.int32, device=device),
+                "row_state": st["row_state_flat"][rs_off : rs_off + rows],
             }
+            st[fam]["g_span"] = (g_off - rows * d * len(names), g_off)
+            st[fam]["rs_span"] = (rs_off, rs_off + rows)
+            rs_off += rows
         lib = _abi.lib()
         n = lib.kge_adam_table_fill(self.learning_rate, self.betas[0], self.betas[1], None, 0)
         host = (C.c_float * (2 * n))()

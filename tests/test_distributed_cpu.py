@@ -26,19 +26,30 @@ class _FakeModel:
     ENTITY_TABLES = ("e_re", "e_im")
     RELATION_TABLES = ("r",)
 
-    def __init__(self, rank, d=6):
-        self.n_users, self.n_entities, self.n_relations, self.embedding_size = 11, 17, 4, d
+    def __init__(self, rank, d=6, rows=(11, 17, 4)):
+        self.n_users, self.n_entities, self.n_relations, self.embedding_size = *rows, d
         self._step = 3
         self._touch_bounds = (5, 40, 3)   # entity bound above the table size: capacity clamps to the rows
         rng = np.random.default_rng(100 + rank)
         self.g = []
         self.touched = []
-        for rows, parts, n_touch in ((11, 1, 5), (17, 2, 9), (4, 1, 2)):
-            g = np.zeros((rows, parts * d), dtype=np.float32)
-            ids = np.sort(rng.choice(rows, size=n_touch, replace=False))
+        for nrow, parts, n_touch in ((rows[0], 1, 5), (rows[1], 2, 9), (rows[2], 1, 2)):
+            g = np.zeros((nrow, parts * d), dtype=np.float32)
+            ids = np.sort(rng.choice(nrow, size=n_touch, replace=False))
             g[ids] = rng.standard_normal((n_touch, parts * d)).astype(np.float32)
             self.g.append(torch.from_numpy(g))
             self.touched.append(torch.from_numpy(ids))
+        # the flat buffers of the dense route (recommender.py::_ensure_state)
+        self._state = {"g_flat": torch.cat([g.reshape(-1) for g in self.g]),
+                       "row_state_flat": torch.full((sum(rows), 2), -1, dtype=torch.int32)}
+        g_off = rs_off = 0
+        for fam, g, ids in zip(("user", "entity", "relation"), self.g, self.touched):
+            self._state[fam] = {"g_span": (g_off, g_off + g.numel()), "rs_span": (rs_off, rs_off + g.shape[0])}
+            self._state["row_state_flat"][rs_off + ids, 1] = self._step + 1
+            g_off += g.numel()
+            rs_off += g.shape[0]
+        self.g = [self._state["g_flat"][self._state[f]["g_span"][0]:self._state[f]["g_span"][1]].view_as(g)
+                  for f, g in zip(("user", "entity", "relation"), self.g)]
 
     def parameters(self):
         return iter([torch.zeros(1)])
@@ -67,15 +78,18 @@ def _worker(rank, world, port, out_dir):
         before = [g.clone() for g in model.g]
         ex = RowSparseExchange(model, pack_fn=_cpu_pack, add_fn=_cpu_add, device=torch.device("cpu"))
         ex(model)
-        assert ex.layout.caps == [5, 17, 3]
-        assert ex.bytes_per_step == ex.layout.nbytes
+        # user: 5 of 11 rows can be touched -> sparse lists; entity (bound above the table) and relation -> dense
+        assert ex.dense == [False, True, True] and ex.layout.caps == [5, 1, 1]
+        assert ex.bytes_per_step == ex.layout.nbytes + (17 * 2 * 6 + 4 * 6) * 4 + (17 + 4) * 8
+        marks = model._state["row_state_flat"][11:, 1]
+        np.save(os.path.join(out_dir, f"marks_{rank}.npy"), marks.numpy())
         np.save(os.path.join(out_dir, f"before_{rank}.npy"), np.concatenate([b.numpy().ravel() for b in before]))
         np.save(os.path.join(out_dir, f"after_{rank}.npy"), np.concatenate([g.numpy().ravel() for g in model.g]))
         # a second step with another batch shape re-plans the buffers
-        model2 = _FakeModel(rank + 10)
-        model2._touch_bounds = (7, 12, 2)
+        model2 = _FakeModel(rank + 10, rows=(44, 68, 16))
+        model2._touch_bounds = (5, 9, 2)
         ex(model2)
-        assert ex.layout.caps == [7, 12, 2]
+        assert ex.dense == [False, False, False] and ex.layout.caps == [5, 9, 2]
         # exact metric means from per-rank sums
         sums = torch.tensor([[1.0 + rank, 2.0], [3.0, 4.0 * (rank + 1)]], dtype=torch.float64)
         tot, n = reduce_metric_sums(sums, n_users=10 + rank)
@@ -94,6 +108,10 @@ def test_row_sparse_exchange_two_ranks_gloo(tmp_path):
     want = before[0] + before[1]
     np.testing.assert_array_equal(after[0], after[1])
     np.testing.assert_array_equal(after[0], want)
+    # dense route: the touch marks are the union over the ranks
+    m0, m1 = np.load(tmp_path / "marks_0.npy"), np.load(tmp_path / "marks_1.npy")
+    np.testing.assert_array_equal(m0, m1)
+    assert (m0 == 4).sum() >= 9
 
 
 def test_flat_layout_views_do_not_overlap():

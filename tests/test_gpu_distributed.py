@@ -13,7 +13,8 @@ from kge_helpers import assert_weights_close, make_product_model, random_batch, 
 
 pytestmark = pytest.mark.gpu
 
-SHAPE = dict(U=300, I=200, E=700, R=9, d=64)
+# small tables: every table takes the dense all-reduce route; large ones: user / entity lists are exchanged
+SHAPES = {"dense": dict(U=300, I=200, E=700, R=9, d=64), "sparse": dict(U=3000, I=2500, E=9000, R=9, d=64)}
 N_REC, N_KG, STEPS = 192, 160, 4
 
 
@@ -23,7 +24,7 @@ def _free_port():
         return s.getsockname()[1]
 
 
-def _batches(name):
+def _batches(name, SHAPE):
     rng = np.random.default_rng(5)
     k = 3 if name in ("RotatE", "ComplEx") else 1
     return [random_batch(rng, SHAPE["U"], SHAPE["I"], SHAPE["E"], SHAPE["R"], 2 * N_REC, 2 * N_KG, k, k) for _ in range(STEPS)], k
@@ -43,7 +44,7 @@ def _shard(b, rank, k):
     return out
 
 
-def _worker(rank, world, port, name, out_dir):
+def _worker(rank, world, port, name, route, out_dir):
     import torch.distributed as dist
 
     from hopwise_b200.distributed import broadcast_weights, enable_row_sparse_data_parallel
@@ -53,36 +54,39 @@ def _worker(rank, world, port, name, out_dir):
     dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", rank))
     try:
         dev = f"cuda:{rank}"
+        SHAPE = SHAPES[route]
         m = make_product_model(name, device=dev, seed=2024 + rank, **SHAPE)   # different init: broadcast must fix it
         broadcast_weights(m)
         ex = enable_row_sparse_data_parallel(m)
-        batches, k = _batches(name)
+        batches, k = _batches(name, SHAPE)
         losses = []
         for b in batches:
             loss = m.calculate_loss(to_device_batch(_shard(b, rank, k), dev))
             loss.backward()
             losses.append(float(loss.item()))
         assert ex.bytes_per_step > 0
+        assert ex.dense == ([True, True, True] if route == "dense" else [False, False, True])
         sd = {key: v.cpu().numpy() for key, v in m.state_dict().items()}
         np.savez(os.path.join(out_dir, f"rank{rank}.npz"), losses=np.array(losses), **sd)
     finally:
         dist.destroy_process_group()
 
 
-@pytest.mark.parametrize("name", ["TransE", "ComplEx"])
-def test_two_rank_row_sparse_step_matches_single_gpu(name, tmp_path):
+@pytest.mark.parametrize("name,route", [("TransE", "dense"), ("ComplEx", "dense"), ("TransE", "sparse"), ("RotatE", "sparse")])
+def test_two_rank_row_sparse_step_matches_single_gpu(name, route, tmp_path):
     if torch.cuda.device_count() < 2:
         pytest.skip("needs 2 GPUs")
     import torch.multiprocessing as mp
 
-    mp.spawn(_worker, args=(2, _free_port(), name, str(tmp_path)), nprocs=2, join=True)
+    SHAPE = SHAPES[route]
+    mp.spawn(_worker, args=(2, _free_port(), name, route, str(tmp_path)), nprocs=2, join=True)
     r0, r1 = np.load(tmp_path / "rank0.npz"), np.load(tmp_path / "rank1.npz")
     keys = [k_ for k_ in r0.files if k_ != "losses"]
     for key in keys:   # same values added in the same order on every rank
         np.testing.assert_array_equal(r0[key], r1[key], err_msg=key)
     # single GPU, whole batch, weights as rank 0 initialised them
     m = make_product_model(name, device="cuda:0", seed=2024, **SHAPE)
-    batches, k = _batches(name)
+    batches, k = _batches(name, SHAPE)
     losses = []
     for b in batches:
         loss = m.calculate_loss(to_device_batch(b, "cuda:0"))
