@@ -187,24 +187,30 @@ def time_train_device(model, dev_batches, steps, warmup, flush_buf, world):
 
 
 def time_train_e2e(model, host_batches, steps, warmup, world, device):
-    """The trainer's loop body from pinned host ids: H2D, loss, backward, loss.item() (D2H)."""
+    """The trainer's loop body from pinned host ids: H2D of the step's 7 id vectors, loss, loss.item()
+    (D2H, trainer.py:259), backward.  The copies run one batch ahead on a side stream
+    (hopwise_b200.loader.DevicePrefetcher); every step's copy is inside the timed region."""
+    from hopwise_b200.loader import DevicePrefetcher, pack_batch
+
+    host_batches = [pack_batch(b) for b in host_batches]   # the loader's side: one pinned buffer per batch
     nb = len(host_batches)
     stream = torch.cuda.current_stream()
 
-    def one(b):
-        db = {k: v.to(device, non_blocking=True) for k, v in b.items()}
+    def one(db):
         loss = model.calculate_loss(db)
         val = loss.item()   # trainer.py:259 -- the per-step device->host sync of the reference loop
         loss.backward()
         return val
 
-    for i in range(warmup):
-        one(host_batches[i % nb])
+    loader = DevicePrefetcher([host_batches[i % nb] for i in range(warmup)], device)
+    for db in loader:
+        one(db)
+    loader.batches = [host_batches[(warmup + i) % nb] for i in range(steps)]
     barrier(world)
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record(stream)
-    for i in range(steps):
-        one(host_batches[(warmup + i) % nb])
+    for db in loader:
+        one(db)
     e1.record(stream)
     barrier(world)
     return e0.elapsed_time(e1)

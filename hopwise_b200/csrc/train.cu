@@ -115,7 +115,11 @@ struct FwdBounds {
   static constexpr int E = VEC * NCH;
   static constexpr int PH = (MODEL == KGE_ROTATE || MODEL == KGE_COMPLEX) ? 2 : 1;
   // resident CTAs per SM the register budget is shaped for (more warps = more loads in flight)
+#ifdef KGE_FWD_MIN_CTAS
+  static constexpr int MIN_CTAS = KGE_FWD_MIN_CTAS;   // experiment knob (scripts/build_variant.sh)
+#else
   static constexpr int MIN_CTAS = (E * PH <= 4) ? 4 : (E * PH <= 8 ? 3 : (E * PH <= 16 ? 2 : 1));
+#endif
 };
 
 template <int MODEL, int VEC, int G, int NCH>

@@ -116,7 +116,7 @@ class _FusedStep(torch.autograd.Function):
     @staticmethod
     def backward(ctx, grad_out):
         ctx.model._launch_apply(grad_out)
-        return torch.zeros_like(grad_out).reshape(1), None, None
+        return None, None, None   # the anchor only exists to give the loss a grad_fn
 
 
 class FusedKGEModel(KnowledgeRecommender):
@@ -179,6 +179,8 @@ class FusedKGEModel(KnowledgeRecommender):
         self._touch_bounds = (0, 0, 0)
         self._mma_cache = None
         self._mma_last_fallback_rows = 0
+        self._ready_key = None
+        self._struct_cache = {}
 
     # ------------------------------------------------------------------ tables
     def _tables(self, names):
@@ -186,6 +188,10 @@ class FusedKGEModel(KnowledgeRecommender):
 
     def _check_ready(self):
         w = self._tables(self.ENTITY_TABLES)[0]
+        key = tuple(t.data_ptr() for names in (self.USER_TABLES, self.ENTITY_TABLES, self.RELATION_TABLES)
+                    for t in self._tables(names))
+        if key == self._ready_key:   # same storages as the last (successful) check: nothing can have changed
+            return w.device
         if not w.is_cuda:
             raise RuntimeError(
                 f"{type(self).__name__}: the fused KGE path runs on CUDA only (weights are on {w.device}); "
@@ -195,6 +201,8 @@ class FusedKGEModel(KnowledgeRecommender):
             for t in self._tables(names):
                 if t.dtype != torch.float32 or not t.is_contiguous():
                     raise RuntimeError("the fused KGE kernels need contiguous float32 tables (weight_precision float32)")
+        self._ready_key = key
+        self._struct_cache = {}
         return w.device
 
     def _ui_row(self, full_sort: bool) -> int:
@@ -242,6 +250,17 @@ class FusedKGEModel(KnowledgeRecommender):
         return st
 
     def _model_struct(self, with_state: bool) -> _abi.kge_model_t:
+        # the struct only holds pointers and shapes: rebuilt when a table or the optimiser state moves
+        ckey = (bool(with_state) and self._state is not None, self._ready_key, id(self._state))
+        hit = self._struct_cache.get(ckey[0])
+        if hit is not None and hit[0] == ckey:
+            return hit[1]
+        m = self._build_model_struct(with_state)
+        if self._ready_key is not None:
+            self._struct_cache[ckey[0]] = (ckey, m)
+        return m
+
+    def _build_model_struct(self, with_state: bool) -> _abi.kge_model_t:
         m = _abi.kge_model_t()
         m.model = _abi.MODEL_KINDS[self.KIND]
         m.d = self.embedding_size
@@ -494,45 +513,60 @@ class FusedKGEModel(KnowledgeRecommender):
         return self._full_sort(interaction[self.HEAD_ENTITY_ID], interaction[self.RELATION_ID], False, self.n_entities)
 
     # ------------------------------------------------------------------ fused full-sort top-k
-    def _topk_exact(self, m, users, k, hist_off, hist_items, mask_pad, ids, scores):
+    def _topk_exact(self, m, users, k, hist_off, hist_items, mask_pad, ids, scores, rels=None, n_targets=None):
         lib = _abi.lib()
         n = users.numel()
-        need = lib.kge_full_sort_topk_workspace_bytes(C.byref(m), n, self.n_items, k)
+        n_targets = self.n_items if n_targets is None else n_targets
+        head_is_user = 1 if rels is None else 0
+        need = lib.kge_full_sort_topk_workspace_bytes(C.byref(m), n, n_targets, k)
         if need < 0:
             raise _abi.KgeError(f"kge_full_sort_topk: unsupported shape (k={k}, d={self.embedding_size})")
         ws = torch.empty(max(need, 8), dtype=torch.uint8, device=users.device)
         _abi.check(
             lib.kge_full_sort_topk(
-                C.byref(m), users.data_ptr(), None, n, 1, self.n_items, _abi.ptr(hist_off), _abi.ptr(hist_items),
-                1 if mask_pad else 0, k, ids.data_ptr(), _abi.ptr(scores), ws.data_ptr(), ws.numel(),
+                C.byref(m), users.data_ptr(), _abi.ptr(rels), n, head_is_user, n_targets, _abi.ptr(hist_off),
+                _abi.ptr(hist_items), 1 if mask_pad else 0, k, ids.data_ptr(), _abi.ptr(scores), ws.data_ptr(), ws.numel(),
                 _abi.stream_ptr(),
             ),
             "kge_full_sort_topk",
         )
 
-    def _mma_supported(self, k: int) -> bool:
+    def _mma_supported(self, k: int, n_targets=None) -> bool:
         m = self._model_struct(False)
-        return _abi.lib().kge_full_sort_topk_mma_workspace_bytes(C.byref(m), 1, self.n_items, k) >= 0
+        n_targets = self.n_items if n_targets is None else n_targets
+        return _abi.lib().kge_full_sort_topk_mma_workspace_bytes(C.byref(m), 1, n_targets, k) >= 0
 
-    def _mma_image(self, m, device):
-        """bf16 operand image of the item rows, cached until the entity table changes."""
+    def _mma_image(self, m, device, n_targets=None):
+        """bf16 operand image of the target rows, cached until the entity table changes."""
+        n_targets = self.n_items if n_targets is None else n_targets
         tabs = self._tables(self.ENTITY_TABLES)
-        key = (self._step, self.n_items, tuple(t.data_ptr() for t in tabs), tuple(t._version for t in tabs))
+        key = (self._step, n_targets, tuple(t.data_ptr() for t in tabs), tuple(t._version for t in tabs))
         if self._mma_cache is not None and self._mma_cache[0] == key:
             return self._mma_cache[1]
         lib = _abi.lib()
-        nbytes = lib.kge_mma_image_bytes(C.byref(m), self.n_items)
+        nbytes = lib.kge_mma_image_bytes(C.byref(m), n_targets)
         image = torch.empty(nbytes, dtype=torch.uint8, device=device)
         _abi.check(
-            lib.kge_mma_prepare_targets(C.byref(m), self.n_items, image.data_ptr(), nbytes, _abi.stream_ptr()),
+            lib.kge_mma_prepare_targets(C.byref(m), n_targets, image.data_ptr(), nbytes, _abi.stream_ptr()),
             "kge_mma_prepare_targets",
         )
         self._mma_cache = (key, image)
         return image
 
+    def full_sort_topk_kg(self, head_ids, relation_ids, k: int, hist_off=None, hist_items=None, mask_pad: bool = True,
+                          return_scores: bool = True, path: str = "auto"):
+        """Link-prediction twin of full_sort_topk: full_sort_predict_kg (transe.py:139-154, distmult.py:135-146,
+        rotate.py:192-220, complex.py:192-219) over all entities with a relation per row, the same masking
+        (trainer.py:731-734: entity 0 and the known tails in `hist`) and top-k (Collector_KG, collector.py:252-261)."""
+        return self.full_sort_topk(head_ids, k, hist_off, hist_items, mask_pad, return_scores, path,
+                                   relation_ids=relation_ids)
+
     def full_sort_topk(self, user_ids, k: int, hist_off=None, hist_items=None, mask_pad: bool = True,
-                       return_scores: bool = True, path: str = "auto", _debug_scores: bool = False):
+                       return_scores: bool = True, path: str = "auto", _debug_scores: bool = False, relation_ids=None):
         """Fused full_sort_predict + trainer masking + top-k (trainer.py:716-735, collector.py:176-177).
+
+        With ``relation_ids`` the rows are (head entity, relation) queries scored against every entity
+        (the link-prediction evaluation); without, users against the items with the user->item relation.
 
         ``hist_off`` [n+1] / ``hist_items`` (sorted ascending per user) is the CSR of the items to
         mask for each of the ``user_ids``.  Returns (ids [n,k] int64, scores [n,k] fp32 or None),
@@ -544,6 +578,11 @@ class FusedKGEModel(KnowledgeRecommender):
         self.flush()
         users = self._ids(user_ids, device)
         n = users.numel()
+        rels = None if relation_ids is None else self._ids(relation_ids, device)
+        if rels is not None and rels.numel() != n:
+            raise ValueError("relation_ids must have one entry per head")
+        n_targets = self.n_items if rels is None else self.n_entities
+        head_is_user = 1 if rels is None else 0
         if hist_off is not None:
             hist_off, hist_items = self._ids(hist_off, device), self._ids(hist_items, device)
             if hist_off.numel() != n + 1:
@@ -553,23 +592,23 @@ class FusedKGEModel(KnowledgeRecommender):
         m = self._model_struct(False)
         if path not in ("auto", "mma", "cuda"):
             raise ValueError(path)
-        use_mma = path == "mma" or (path == "auto" and self.n_items >= 8192 and n >= 64 and self._mma_supported(k))
+        use_mma = path == "mma" or (path == "auto" and n_targets >= 8192 and n >= 64 and self._mma_supported(k, n_targets))
         if not use_mma or n == 0:
-            self._topk_exact(m, users, k, hist_off, hist_items, mask_pad, ids, scores)
+            self._topk_exact(m, users, k, hist_off, hist_items, mask_pad, ids, scores, rels, n_targets)
             return ids, scores
         lib = _abi.lib()
-        need = lib.kge_full_sort_topk_mma_workspace_bytes(C.byref(m), n, self.n_items, k)
+        need = lib.kge_full_sort_topk_mma_workspace_bytes(C.byref(m), n, n_targets, k)
         if need < 0:
             raise _abi.KgeError(f"tensor-core top-k: {lib.kge_last_error().decode()}")
-        image = self._mma_image(m, device)
+        image = self._mma_image(m, device, n_targets)
         ws = torch.empty(need, dtype=torch.uint8, device=device)
         flags = torch.empty(n, dtype=torch.int32, device=device)
         dbg = None
         if _debug_scores:
-            dbg = torch.zeros(n, (self.n_items + 127) // 128 * 128, dtype=torch.float32, device=device)
+            dbg = torch.zeros(n, (n_targets + 127) // 128 * 128, dtype=torch.float32, device=device)
         _abi.check(
             lib.kge_full_sort_topk_mma(
-                C.byref(m), users.data_ptr(), None, n, 1, self.n_items, image.data_ptr(), _abi.ptr(hist_off),
+                C.byref(m), users.data_ptr(), _abi.ptr(rels), n, head_is_user, n_targets, image.data_ptr(), _abi.ptr(hist_off),
                 _abi.ptr(hist_items), 1 if mask_pad else 0, k, ids.data_ptr(), _abi.ptr(scores), flags.data_ptr(),
                 ws.data_ptr(), ws.numel(), _abi.ptr(dbg), _abi.stream_ptr(),
             ),
@@ -589,7 +628,8 @@ class FusedKGEModel(KnowledgeRecommender):
                 sub_items = hist_items[pos].contiguous()
             sub_ids = torch.empty(bad.numel(), k, dtype=torch.int64, device=device)
             sub_scores = torch.empty(bad.numel(), k, dtype=torch.float32, device=device) if return_scores else None
-            self._topk_exact(m, users[bad].contiguous(), k, sub_off, sub_items, mask_pad, sub_ids, sub_scores)
+            self._topk_exact(m, users[bad].contiguous(), k, sub_off, sub_items, mask_pad, sub_ids, sub_scores,
+                             None if rels is None else rels[bad].contiguous(), n_targets)
             ids[bad] = sub_ids
             if return_scores:
                 scores[bad] = sub_scores

@@ -315,3 +315,41 @@ def test_mma_topk_trained_like_weights_and_cache_invalidation():
         np.testing.assert_array_equal(sc_m.cpu().numpy(), sc_c.cpu().numpy())
         with torch.no_grad():
             m.entity_embedding.weight.mul_(-1.0)   # the cached operand image must be rebuilt
+
+
+# ---- link-prediction twin: (head entity, relation) rows against every entity -------------------------------
+@pytest.mark.parametrize("name,d,E,k,path", [("TransE", 64, 9000, 10, "mma"), ("DistMult", 32, 2000, 10, "cuda"),
+                                             ("RotatE", 32, 8500, 20, "mma"), ("ComplEx", 64, 8300, 5, "mma"),
+                                             ("ComplEx", 16, 700, 10, "auto")])
+def test_topk_kg_against_dense_and_oracle(name, d, E, k, path):
+    """full_sort_topk_kg = canonical top-k of the product's own full_sort_predict_kg after the trainer's
+    masking (trainer.py:731-734), and of the oracle's up to fp32 ties; CUDA-core and tensor-core paths."""
+    U, I, R = 50, 40, 11
+    ora = make_oracle_model(name, U, I, E, R, d)
+    m = make_product_model(name, U, I, E, R, d)
+    rng = np.random.default_rng(11)
+    n = 260
+    heads = rng.integers(1, E, n)
+    rels = rng.integers(1, R - 1, n)
+    hist_u, hist_i = [], []
+    for row in range(n):
+        tails = rng.choice(np.arange(1, E), size=int(rng.integers(0, 40)), replace=False)
+        hist_u += [row] * len(tails)
+        hist_i += list(tails)
+    from hopwise_b200 import evaluator as ev
+
+    hist_off, hist_items = ev.csr_from_pairs(np.array(hist_u), np.array(hist_i), n, "cuda")
+    ids, sc = m.full_sort_topk_kg(torch.from_numpy(heads).cuda(), torch.from_numpy(rels).cuda(), k, hist_off, hist_items,
+                                  path=path)
+    ids, sc = ids.cpu().numpy(), sc.cpu().numpy()
+    batch = {"head_id": torch.from_numpy(heads).cuda(), "relation_id": torch.from_numpy(rels).cuda()}
+    dense = m.full_sort_predict_kg(batch).cpu().numpy().reshape(n, E)
+    masked = ofs.mask_scores(dense, np.array(hist_u), np.array(hist_i))
+    want_ids, want_sc = ofs.topk_canonical(masked, k)
+    np.testing.assert_array_equal(ids, want_ids)
+    np.testing.assert_array_equal(sc, want_sc)
+    with torch.no_grad():
+        o_dense = ora.full_sort_predict_kg({"head_id": torch.from_numpy(heads), "relation_id": torch.from_numpy(rels)}).numpy()
+    np.testing.assert_allclose(dense, o_dense, rtol=RTOL, atol=_score_atol(o_dense))
+    o_ids, o_sc = ofs.topk_canonical(ofs.mask_scores(o_dense, np.array(hist_u), np.array(hist_i)), k)
+    assert (ids != o_ids).mean() < 0.01

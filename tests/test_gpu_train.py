@@ -289,3 +289,34 @@ def test_full_size_step_properties():
     with torch.no_grad():
         want = ora.calculate_loss(to_cpu_batch(b)).item()
     np.testing.assert_allclose(losses[0], want, rtol=RTOL)
+
+
+def test_device_prefetcher_preserves_batches_and_training_result():
+    """Staging batches one step ahead on a copy stream changes nothing but the timing."""
+    from hopwise_b200.loader import DevicePrefetcher
+
+    U, I, E, R, d = 300, 200, 900, 7, 32
+    rng = np.random.default_rng(3)
+    host = [{k: torch.from_numpy(np.asarray(v)).pin_memory() for k, v in random_batch(rng, U, I, E, R, 128, 96).items()}
+            for _ in range(5)]
+    seen = []
+    for db in DevicePrefetcher(host, "cuda"):
+        assert all(t.is_cuda for t in db.values())
+        seen.append({k: v.cpu() for k, v in db.items()})
+    assert len(seen) == len(host)
+    for a, b in zip(seen, host):
+        for k in b:
+            assert torch.equal(a[k], b[k])
+    m1 = make_product_model("TransE", U, I, E, R, d)
+    m2 = make_product_model("TransE", U, I, E, R, d)
+    for b in host:
+        m1.calculate_loss({k: v.cuda() for k, v in b.items()}).backward()
+    from hopwise_b200.loader import pack_batch
+
+    packed = [pack_batch(b) for b in host]   # one copy per step instead of seven
+    assert packed[0].base.is_pinned() and packed[0].base.numel() == sum(v.numel() for v in host[0].values())
+    for db in DevicePrefetcher(packed, "cuda", depth=3):
+        assert set(db) == set(host[0]) and all(t.is_cuda for t in db.values())
+        m2.calculate_loss(db).backward()
+    for (k1, v1), (_, v2) in zip(m1.state_dict().items(), m2.state_dict().items()):
+        assert_weights_close(v2.cpu().numpy(), v1.cpu().numpy(), rtol=1e-5, atol=5e-7, err_msg=k1)
