@@ -153,3 +153,107 @@ class DevicePrefetcher:
             issue()
             prev = idx
             yield db
+
+
+# ---- device-resident training loader ---------------------------------------------------------------------
+class EpochOrder:
+    """The index stream of one reference DataLoader, draw for draw.
+
+    abstract_dataloader.py:47-73 builds ``DataLoader(list(range(n)), batch_size=step, shuffle=True,
+    generator=torch.Generator().manual_seed(seed))``.  Every ``__iter__`` of it draws one int64
+    ``random_()`` (the iterator's base seed) from that generator; the first ``next`` draws the epoch's
+    ``randperm(n)``; and an iterator that is advanced past its last batch draws one more, discarded,
+    ``randperm(n)`` (RandomSampler's trailing ``[: num_samples % n]`` slice).  Unshuffled loaders still
+    draw the base seed.  The generator lives on the CPU, exactly like the reference's.
+    """
+
+    def __init__(self, n: int, step: int, seed: int, shuffle: bool = True):
+        self.n, self.step, self.shuffle = int(n), int(step), bool(shuffle)
+        self.generator = torch.Generator()
+        self.generator.manual_seed(int(seed))
+        self._perm = None
+        self._pos = 0
+        self._live = False
+
+    def __len__(self):
+        return (self.n + self.step - 1) // self.step
+
+    def start(self):
+        """DataLoader.__iter__()."""
+        torch.empty((), dtype=torch.int64).random_(generator=self.generator)
+        self._perm, self._pos, self._live = None, 0, True
+
+    def next_indices(self):
+        """Indices of the next batch (int64 CPU tensor), or None once the iterator is exhausted."""
+        if not self._live:
+            raise RuntimeError("EpochOrder.start() must be called first")
+        if self._perm is None:
+            self._perm = torch.randperm(self.n, generator=self.generator) if self.shuffle else torch.arange(self.n)
+        if self._pos >= self.n:
+            if self.shuffle:
+                torch.randperm(self.n, generator=self.generator)   # the discarded trailing draw
+            self._live = False
+            return None
+        idx = self._perm[self._pos : self._pos + self.step]
+        self._pos += self.step
+        return idx
+
+
+class DeviceKGLoader:
+    """KnowledgeBasedDataLoader in RSKG mode with the data, the gathers and both samplers on the GPU.
+
+    Mirrors knowledge_dataloader.py:78-178 + general_dataloader.py:66-70 + abstract_dataloader.py:165-198:
+    per step the KG batch is drawn first (``kg_feat[index]`` -> heads -> ``sample_by_entity_ids``), then the
+    recommendation batch (``inter_feat[index]`` -> ``sample_by_user_ids``), and the two dicts are merged;
+    an epoch is as long as the recommendation loader; the KG iterator restarts with a fresh permutation
+    every epoch and wraps around if it runs out.  The batch order comes from the reference's CPU torch
+    generators (``EpochOrder``); the interaction / triple arrays live on the device, so per step only the
+    two index vectors (2 x batch x 8 B) cross PCIe instead of the 7 id vectors, and the negatives are
+    drawn by the MT19937 kernel from the stream the two samplers share (KG draws before rec draws, H3).
+
+    ``sample(kind, ids, num)`` is the sampling hook (tests substitute the CPU oracle for it).
+    """
+
+    KEYS = ("user_id", "item_id", "neg_item_id", "head_id", "relation_id", "tail_id", "neg_tail_id")
+
+    def __init__(self, inter_user, inter_item, kg_head, kg_rel, kg_tail, rec_sampler, kg_sampler, batch_size: int,
+                 seed: int, device="cuda", shuffle: bool = True, neg_sample_num: int = 1, gather=None):
+        self.device = torch.device(device)
+        as_dev = lambda x: torch.as_tensor(np.asarray(x), dtype=torch.int64).to(self.device)  # noqa: E731
+        self.inter_user, self.inter_item = as_dev(inter_user), as_dev(inter_item)
+        self.kg_head, self.kg_rel, self.kg_tail = as_dev(kg_head), as_dev(kg_rel), as_dev(kg_tail)
+        self.rec_sampler, self.kg_sampler = rec_sampler, kg_sampler
+        self.rec_order = EpochOrder(self.inter_user.numel(), batch_size, seed, shuffle)
+        self.kg_order = EpochOrder(self.kg_head.numel(), batch_size, seed, True)   # "kg based dataloader must shuffle"
+        self.neg_sample_num = int(neg_sample_num)
+        self._gather = gather or (lambda table, idx: table.index_select(0, idx))
+
+    def __len__(self):
+        return len(self.rec_order)
+
+    def _index(self, idx):
+        if self.device.type == "cuda":
+            idx = idx.pin_memory()
+        return idx.to(self.device, non_blocking=True)
+
+    def __iter__(self):
+        self.kg_order.start()    # knowledge_dataloader.py:131-135: kg iterator first, then the general one
+        self.rec_order.start()
+        while True:
+            kidx = self.kg_order.next_indices()
+            if kidx is None:     # :137-142 wraps a KG loader that ran out
+                self.kg_order.start()
+                kidx = self.kg_order.next_indices()
+            kidx = self._index(kidx)
+            head = self._gather(self.kg_head, kidx)
+            batch = {"head_id": head, "relation_id": self._gather(self.kg_rel, kidx),
+                     "tail_id": self._gather(self.kg_tail, kidx),
+                     "neg_tail_id": self.kg_sampler.sample_by_entity_ids(head, 1)}   # knowledge_dataloader.py:51
+            ridx = self.rec_order.next_indices()
+            if ridx is None:
+                return
+            ridx = self._index(ridx)
+            user, item = self._gather(self.inter_user, ridx), self._gather(self.inter_item, ridx)
+            batch["user_id"], batch["item_id"] = user, item
+            batch["neg_item_id"] = self.rec_sampler.sample_by_user_ids(user, item, self.neg_sample_num)
+            yield batch
