@@ -383,6 +383,44 @@ def main():
                     torch.cuda.empty_cache()
                 except Exception as exc:  # report, never hide
                     extras[name] = {"error": repr(exc)}
+        # the whole reference step at its default batch, loader included: batch order from the CPU torch
+        # generators, gathers + both MT19937 samplers + fused step on the device (hopwise_b200.loader.DeviceKGLoader)
+        if args.workload == "cfg2_transe_ml1m" and world == 1:
+            try:
+                from hopwise_b200.loader import DeviceKGLoader
+                from hopwise_b200.sampler import KGSampler, MTStream, RecSampler
+
+                wx = WORKLOADS["cfg2_transe_ml1m_b2048"]
+                rng = np.random.default_rng(2024)
+                iu, ii = rng.integers(1, wx["U"], wx["inters"]), rng.integers(1, wx["I"], wx["inters"])
+                kh, kr, kt = (rng.integers(1, wx["E"], wx["triples"]), rng.integers(1, wx["R"] - 1, wx["triples"]),
+                              rng.integers(1, wx["E"], wx["triples"]))
+                mt = MTStream(seed=2024, device=device)
+                loader = DeviceKGLoader(iu, ii, kh, kr, kt, RecSampler(iu, ii, wx["U"], wx["I"], stream=mt, device=device),
+                                        KGSampler(heads=kh, tails=kt, entity_num=wx["E"], stream=mt, device=device),
+                                        batch_size=wx["n_rec"], seed=2024, device=device)
+                mx = make_model(wx, device)
+                n_steps = max(args.steps, 20) * 5
+                it = iter(loader)
+                for _ in range(10):
+                    b = next(it)
+                    mx.calculate_loss(b).backward()
+                torch.cuda.synchronize()
+                t0 = time.perf_counter()
+                for _ in range(n_steps):
+                    b = next(it)
+                    loss = mx.calculate_loss(b)
+                    loss.item()
+                    loss.backward()
+                torch.cuda.synchronize()
+                dt = (time.perf_counter() - t0) / n_steps
+                extras["cfg2_b2048_device_loader"] = {
+                    "what": "loader (order + gathers + KG and rec negative sampling) + fused step + loss.item(), wall clock",
+                    "ms_per_step": dt * 1e3, "triples_per_s": (wx["n_rec"] + wx["n_kg"]) / dt}
+                del mx, loader
+                torch.cuda.empty_cache()
+            except Exception as exc:
+                extras["cfg2_b2048_device_loader"] = {"error": repr(exc)}
         # second headline metric: users/s of full-sort top-k (user blocks sharded across ranks)
         for name, fs in FULLSORT.items():
             try:

@@ -52,7 +52,7 @@ def test_device_kg_loader_feeds_the_fused_step():
                    stream=stream)
     loader = DeviceKGLoader(g["inter_user"], g["inter_item"], g["kg_head"], g["kg_rel"], g["kg_tail"], rec, kg,
                             batch_size=2048, seed=2024)
-    m = make_product_model("TransE", n_users, n_items, n_ent, n_rel + 1, 64, lr=1e-2)
+    m = make_product_model("TransE", n_users, n_items, n_ent, n_rel, 64, lr=1e-2)   # relation_num counts [UI-Relation]
     epoch_loss = []
     for _ in range(3):
         tot = 0.0
