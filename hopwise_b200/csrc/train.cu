@@ -27,6 +27,8 @@
 #include <stdarg.h>
 #include <stdio.h>
 
+#include <type_traits>
+
 #include "common.cuh"
 
 namespace {
@@ -134,7 +136,6 @@ __global__ void __launch_bounds__(256, FwdBounds<MODEL, VEC, NCH>::MIN_CTAS) tra
   const int gl = (threadIdx.x & 31) % G;
   const int groups_per_cta = blockDim.x / G;
   const int64_t n_groups = (int64_t)gridDim.x * groups_per_cta;
-  const int64_t n_rec = a.b.n_rec, n_total = a.b.n_rec + a.b.n_kg;
   const int step = a.adam.step;
   const float margin = a.m.margin;
   const kge_table_t& ET = a.m.entity;
@@ -151,10 +152,12 @@ __global__ void __launch_bounds__(256, FwdBounds<MODEL, VEC, NCH>::MIN_CTAS) tra
     for (int e = 0; e < E; ++e) racc[p][e] = 0.f;
   bool rec_seen = false;
 
-  for (int64_t inst = (int64_t)blockIdx.x * groups_per_cta + threadIdx.x / G; inst < n_total; inst += n_groups) {
-    const bool is_rec = inst < n_rec;
-    const int64_t i = is_rec ? inst : inst - n_rec;
-    const int64_t n_seg = is_rec ? a.b.n_rec : a.b.n_kg;
+  // The recommendation half and the KG half run as two loops over one body: with the half known at compile
+  // time the table / id-array selections fold away (they cost ~100 instructions per triple as run-time selects).
+  auto run_half = [&](auto rec_tag) {
+  constexpr bool is_rec = decltype(rec_tag)::value;
+  const int64_t n_seg = is_rec ? a.b.n_rec : a.b.n_kg;
+  for (int64_t i = (int64_t)blockIdx.x * groups_per_cta + threadIdx.x / G; i < n_seg; i += n_groups) {
     const int K = is_rec ? a.b.k_rec : a.b.k_kg;
     const kge_table_t& HT = is_rec ? a.m.user : a.m.entity;
     const int64_t* negs = is_rec ? a.b.neg_item : a.b.neg_tail;
@@ -215,14 +218,15 @@ __global__ void __launch_bounds__(256, FwdBounds<MODEL, VEC, NCH>::MIN_CTAS) tra
         c0[e] = h[0][e] + r[0][e];
         const float dp = frag_valid<VEC, G, NCH>(d, gl, e) ? (c0[e] - tp[0][e] + 1e-6f) : 0.f;
         c1[e] = dp;
-        sp += dp * dp;
+        sp = __fmaf_rn(dp, dp, sp);
       }
       s_pos = sqrtf(group_sum<G>(sp));
       const float inv_p = s_pos > 0.f ? 1.f / s_pos : 0.f;
       // positive and negative terms are formed by the same operations so that a pair whose
-      // negative equals its positive cancels exactly, as it does under autograd
+      // negative equals its positive cancels exactly, as it does under autograd (explicit _rn
+      // intrinsics: the compiler must not contract one side's product into the subtraction)
 #pragma unroll
-      for (int e = 0; e < E; ++e) c1[e] = w * (c1[e] * inv_p);
+      for (int e = 0; e < E; ++e) c1[e] = __fmul_rn(w, __fmul_rn(c1[e], inv_p));
     } else if (MODEL == KGE_DISTMULT) {
       float sp = 0.f;
 #pragma unroll
@@ -283,7 +287,7 @@ __global__ void __launch_bounds__(256, FwdBounds<MODEL, VEC, NCH>::MIN_CTAS) tra
         for (int e = 0; e < E; ++e) {
           const float dn = frag_valid<VEC, G, NCH>(d, gl, e) ? (c0[e] - t[0][e] + 1e-6f) : 0.f;
           t[0][e] = dn;
-          sn += dn * dn;
+          sn = __fmaf_rn(dn, dn, sn);
         }
         const float nn_ = sqrtf(group_sum<G>(sn));
         const float z = margin + s_pos - nn_;
@@ -294,8 +298,8 @@ __global__ void __launch_bounds__(256, FwdBounds<MODEL, VEC, NCH>::MIN_CTAS) tra
             nact += 1.f;
 #pragma unroll
             for (int e = 0; e < E; ++e) {
-              t[0][e] = w * (t[0][e] * inv_n);  // gradient of the negative tail
-              gh[0][e] += c1[e] - t[0][e];
+              t[0][e] = __fmul_rn(w, __fmul_rn(t[0][e], inv_n));  // gradient of the negative tail
+              gh[0][e] += __fsub_rn(c1[e], t[0][e]);
               gtp[0][e] -= c1[e];
             }
             frag_atomic_add<VEC, G, NCH>(ET.g[0], t_id, d, gl, t[0]);
@@ -452,6 +456,10 @@ __global__ void __launch_bounds__(256, FwdBounds<MODEL, VEC, NCH>::MIN_CTAS) tra
       }
     }
   }
+
+  };
+  run_half(std::true_type{});
+  run_half(std::false_type{});
 
   // ---- CTA epilogue: user->item relation gradient and the loss --------------------------------
   if (rec_seen) {
