@@ -37,6 +37,7 @@
 // 8x16-byte core matrices, SBO = 128 B, LBO = rows * 16 B.
 #include <cuda_bf16.h>
 #include <math.h>
+#include <stdio.h>
 #include <stdlib.h>
 
 #include "common.cuh"
@@ -51,9 +52,11 @@ constexpr int GRP = 4;     // targets per candidate group (what the rescore kern
 #endif
 constexpr int CAND = KGE_MMA_CAND;  // candidate chunks kept per (row, split)
 constexpr int MAX_SPLITS = 4;
-constexpr int SWEEP_THREADS = 320;  // warps 0..7 epilogue, warp 8 producer, warp 9 MMA issuer: the issue
-                                    // arbiter favours high warp ids, and the MMA issuer must never starve
-constexpr int PRODUCER_WARP = 8, MMA_WARP = 9;
+// Warp roles of the sweep: 8 * NCOL epilogue warps (warp % 4 = TMEM lane quadrant, (warp / 4) % 2 = row half,
+// warp / 8 = column slice of the tile), then the producer warp, then one MMA issuer warp per row half (the issue
+// arbiter favours high warp ids, and an MMA issuer must never starve; one warp cannot issue fast enough for both
+// halves: a free-running issuer needs ~125 cycles per tcgen05.mma).
+__host__ __device__ constexpr int sweep_threads(int ncol, int nmma) { return (8 * ncol + 1 + nmma) * 32; }
 constexpr int IMG_HEADER = 128;  // bytes before the first tile image: {float tmax}
 constexpr uint32_t SPIN_LIMIT = 1u << 26;
 
@@ -65,6 +68,15 @@ __device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
 }
 __device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity) {
   uint32_t ok;
+#if defined(KGE_MBAR_TEST)
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "mbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(ok)
+      : "r"(bar), "r"(parity)
+      : "memory");
+#elif defined(KGE_MBAR_HINT)
   asm volatile(
       "{\n\t.reg .pred p;\n\t"
       "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\t"
@@ -72,6 +84,15 @@ __device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity) {
       : "=r"(ok)
       : "r"(bar), "r"(parity), "r"(0x989680u)   // suspend-time hint: sleep in hardware instead of polling
       : "memory");
+#else
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(ok)
+      : "r"(bar), "r"(parity)
+      : "memory");
+#endif
   return ok != 0;
 }
 // A wait that cannot hang the GPU: a protocol bug traps instead of spinning forever.
@@ -131,7 +152,11 @@ __device__ __forceinline__ void umma_commit(uint32_t bar) {
       : "r"(ADDR)                                                                                                  \
       : "memory")
 // 32 consecutive accumulator columns of this thread's TMEM lane, issued without waiting ...
-__device__ __forceinline__ void tmem_ld32_issue(uint32_t taddr, uint32_t (&r)[32]) { KGE_TMEM_LD32_ASM(r, taddr); }
+__device__ __forceinline__ void tmem_ld32_issue(uint32_t taddr, uint32_t (&r)[32]) {
+#ifndef KGE_EXP_NOLD
+  KGE_TMEM_LD32_ASM(r, taddr);
+#endif
+}
 // ... and the wait; naming the registers keeps every use of them behind it.
 __device__ __forceinline__ void tmem_ld_wait(uint32_t (&r)[32]) {
   asm volatile("tcgen05.wait::ld.sync.aligned;"
@@ -270,6 +295,7 @@ struct MmaArgs {
   float* eps_out;     // [rows_pad]
   const uint32_t* unsafe_bits;  // [rows_pad][unsafe_wpr]: bit c = chunk c holds a masked / out-of-range target
   int64_t unsafe_wpr;
+  const float* thr_init;  // experiment (KGE_EXP_THRINIT): thresholds the lists start from
   float* dbg_out;     // optional dense approximate scores [n, dbg_stride]
   int64_t dbg_stride;
 };
@@ -381,10 +407,11 @@ __device__ __noinline__ int compact_row(uint2* buf, int cnt, int k, float eps, c
 }
 
 // Bitmap of the chunks a row must not trust for its threshold: chunks with a history item, the
-// [PAD] chunk and the partial last chunk.  One warp per row; the buffer is zeroed by the caller.
+// [PAD] chunk, the partial last chunk and the padding chunks behind it (their entries are dropped by the
+// rescore kernel, which never scores a target id >= n_targets).  One warp per row; the buffer is zeroed by the caller.
 __global__ void __launch_bounds__(256) unsafe_bitmap_kernel(uint32_t* bits, int64_t wpr, int64_t n, int64_t n_targets,
-                                                            const int64_t* hist_off, const int64_t* hist_items,
-                                                            int mask_first) {
+                                                            int64_t n_chunks, const int64_t* hist_off,
+                                                            const int64_t* hist_items, int mask_first) {
   const int lane = threadIdx.x & 31;
   const int64_t warp = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const int64_t n_warps = ((int64_t)gridDim.x * blockDim.x) >> 5;
@@ -397,13 +424,9 @@ __global__ void __launch_bounds__(256) unsafe_bitmap_kernel(uint32_t* bits, int6
         if (c >= 0 && (c >> 5) < wpr) atomicOr(b + (c >> 5), 1u << (c & 31));
       }
     }
-    if (lane == 0) {
-      if (mask_first) atomicOr(b, 1u);
-      if (n_targets % CH) {
-        const int64_t c = n_targets / CH;
-        atomicOr(b + (c >> 5), 1u << (c & 31));
-      }
-    }
+    if (lane == 0 && mask_first) atomicOr(b, 1u);
+    // the partial last chunk and the chunks of zero rows that pad the last tile of the image
+    for (int64_t c = n_targets / CH + lane; c < n_chunks; c += 32) atomicOr(b + (c >> 5), 1u << (c & 31));
   }
 }
 
@@ -415,29 +438,37 @@ struct EpiState {
 };
 
 // One chunk (32 columns = 8 groups of 4) of one row: group maxima, chunk maximum, and (rarely) one list entry.
-template <bool TAIL>
-__device__ __forceinline__ void epi_chunk(const uint32_t (&r)[32], EpiState& st, uint32_t cid, int g_valid) {
+__device__ __forceinline__ void epi_chunk(const uint32_t (&r)[32], EpiState& st, uint32_t cid, uint32_t uword) {
   float gm[8];
 #pragma unroll
-  for (int g = 0; g < 8; ++g) {
+  for (int g = 0; g < 8; ++g)
     gm[g] = fmaxf(max3f(__uint_as_float(r[4 * g]), __uint_as_float(r[4 * g + 1]), __uint_as_float(r[4 * g + 2])),
                   __uint_as_float(r[4 * g + 3]));
-    if (TAIL && g >= g_valid) gm[g] = -INFINITY;
-  }
   const float tm = fmaxf(max3f(gm[0], gm[1], gm[2]), max3f(max3f(gm[3], gm[4], gm[5]), gm[6], gm[7]));
-  if (tm >= st.thr && (!TAIL || g_valid > 0)) {  // rare after the first tiles
+  if (tm >= st.thr) {  // rare per row after the first tiles (but most warps have one such row per chunk)
     uint32_t mask = 0u;
 #pragma unroll
     for (int g = 0; g < 8; ++g) mask |= (gm[g] >= st.thr) ? (1u << g) : 0u;
-    if (TAIL) mask &= (1u << g_valid) - 1u;
-    st.buf[st.cnt] = make_uint2(__float_as_uint(tm), (cid << CID_SHIFT) | mask);
+    const uint32_t flags = F_KNOWN | (((uword >> (cid & 31u)) & 1u) << 31);   // bit 31 = F_UNSAFE
+    st.buf[st.cnt] = make_uint2(__float_as_uint(tm), (cid << CID_SHIFT) | mask | flags);
     ++st.cnt;
   }
 }
 
-template <int TN, bool DBG>
-__global__ void __launch_bounds__(SWEEP_THREADS, 2) fullsort_mma_kernel(const MmaArgs a) {
+// TN targets per tile (one MMA instruction covers 128 rows x TN targets x 16 of K), NBUF accumulator buffers per
+// half.  TMEM columns = 2 * TN * NBUF: (128, 1) and (64, 2) take 256 (two CTAs per SM), (128, 2) all 512.
+// NCOL column slices per tile: the 128 rows of a half are covered by NCOL warps per quadrant, each filtering
+// TN / NCOL columns into its own list (a row then owns splits * NCOL lists, merged by the rescore kernel).
+// NMMA issuer warps: 2 = one per row half (needed when the CTA has the SM to itself), 1 = one warp for both.
+template <int TN, int NBUF, int NCOL, int NMMA, bool DBG>
+__global__ void __launch_bounds__(sweep_threads(NCOL, NMMA), NBUF == 1 ? 2 : 1)
+    fullsort_mma_kernel(const MmaArgs a) {
   constexpr int ROOM = 16;              // list room demanded after a compaction
+  constexpr int NCH = TN / CH / NCOL;   // chunks of 32 columns per tile and epilogue thread
+  constexpr int EPI_WARPS = 8 * NCOL, PRODUCER_WARP = EPI_WARPS, MMA_WARP0 = EPI_WARPS + 1;
+  constexpr int N_WARPS = EPI_WARPS + 1 + NMMA;
+  constexpr uint32_t TMEM_COLS = 2 * TN * NBUF;
+  static_assert(NCH % 2 == 0 && (NBUF == 1 || NBUF == 2), "the chunk pipeline alternates two register sets");
   constexpr uint32_t IDESC = make_idesc(TN);
   extern __shared__ __align__(128) unsigned char smem[];
   const int kp = a.kp;
@@ -464,7 +495,7 @@ __global__ void __launch_bounds__(SWEEP_THREADS, 2) fullsort_mma_kernel(const Mm
   for (uint32_t i = threadIdx.x; i < a_bytes / 16; i += blockDim.x) reinterpret_cast<uint4*>(As)[i] = make_uint4(0, 0, 0, 0);
   __syncthreads();
   const float tmax = a.header[0];
-  for (int u = warp; u < MM; u += SWEEP_THREADS / 32) {
+  for (int u = warp; u < MM; u += N_WARPS) {
     float nq = 0.f;
     if (u < nrows) {
       for (int c = lane; c < d; c += 32) {
@@ -488,22 +519,22 @@ __global__ void __launch_bounds__(SWEEP_THREADS, 2) fullsort_mma_kernel(const Mm
       float eps = 1.02f * 0.00390625f * sqrtf(nq) * tmax;                // 2^-8 ||q|| max||t||
       if (a.dist) eps += 9.5367431640625e-7f * 0.5f * tmax * tmax;        // 2^-20 * ||t||^2 / 2 (split remainder)
       eps_row[u] = eps;
-      if (split == 0) a.eps_out[row0 + u] = eps;
+      if (split == 0) a.eps_out[row0 + u] = eps;   // (every split writes the same value)
     }
   }
   if (threadIdx.x == 0) {
     for (int s = 0; s < a.stages; ++s) {
       mbar_init(smem_u32(&bars[s]), 1);              // full: producer's expect_tx arrive
-      mbar_init(smem_u32(&bars[a.stages + s]), 1);   // empty: one tcgen05.commit
+      mbar_init(smem_u32(&bars[a.stages + s]), NMMA);   // empty: one tcgen05.commit per MMA warp
     }
     for (int x = 0; x < 4; ++x) {
       mbar_init(smem_u32(&bars[2 * a.stages + x]), 1);      // tfull[buf][half]: one commit
-      mbar_init(smem_u32(&bars[2 * a.stages + 4 + x]), 4);  // tempty[buf][half]: the 4 warps of the half
+      mbar_init(smem_u32(&bars[2 * a.stages + 4 + x]), 4 * NCOL);  // tempty[buf][half]: the epilogue warps of the half
     }
     fence_mbar_init();
   }
-  if (warp == MMA_WARP) {
-    tmem_alloc(smem_u32(tmem_slot), 4 * TN);
+  if (warp == MMA_WARP0) {
+    tmem_alloc(smem_u32(tmem_slot), TMEM_COLS);
     tmem_relinquish();
   }
   fence_proxy_async();  // the generic-proxy writes of A must be visible to the tensor core (async proxy)
@@ -533,9 +564,10 @@ __global__ void __launch_bounds__(SWEEP_THREADS, 2) fullsort_mma_kernel(const Mm
         ph ^= 1u;
       }
     }
-  } else if (warp == MMA_WARP) {
-    // ===== MMA issuer: the warp runs the loop with uniform control flow (descriptors live in uniform
-    // registers), one elected lane issues.  Only the 14-bit start-address field of a descriptor changes.
+  } else if (warp >= MMA_WARP0) {
+    // ===== MMA issuers, one warp per row half: the warp runs the loop with uniform control flow (descriptors
+    // live in uniform registers), one elected lane issues.  Only the 14-bit start-address field of a descriptor
+    // changes.
     const bool leader = elect_one();
     const uint32_t a_lbo = MM * 16, b_lbo = TN * 16;
     const uint32_t desc_hi = (128u >> 4) | (1u << 14);   // SBO = 128 B, descriptor version 1
@@ -544,15 +576,15 @@ __global__ void __launch_bounds__(SWEEP_THREADS, 2) fullsort_mma_kernel(const Mm
     const uint32_t a_kstep = (2 * a_lbo) >> 4, b_kstep = (2 * b_lbo) >> 4, a_hstep = (128 * 16) >> 4;
     const uint32_t b_sstep = b_bytes >> 4;
     const int ksteps = kp / 16;
+    const int h_lo = NMMA == 2 ? warp - MMA_WARP0 : 0, h_hi = NMMA == 2 ? h_lo + 1 : 2;
     int s = 0;
     uint32_t ph = 0;
     for (int64_t i = 0; i < nt; ++i) {
-      const uint32_t buf = (uint32_t)(i & 1);
-      const uint32_t tph = (uint32_t)((i >> 1) & 1);
-      mbar_wait(full0 + 8 * s, ph);            // tile landed
+      const uint32_t buf = NBUF == 1 ? 0u : (uint32_t)(i & 1);
+      const uint32_t tph = (uint32_t)((i / NBUF) & 1);
+      mbar_wait(full0 + 8 * s, ph);                       // tile landed
       const uint32_t b_lo = b_lo0 + (uint32_t)s * b_sstep;
-#pragma unroll
-      for (int h = 0; h < 2; ++h) {
+      for (int h = h_lo; h < h_hi; ++h) {
         mbar_wait(tempty0 + 8 * (buf * 2 + h), tph ^ 1u);  // the half's epilogue warps have drained this accumulator
         tc_fence_after();
         if (leader) {
@@ -561,10 +593,12 @@ __global__ void __launch_bounds__(SWEEP_THREADS, 2) fullsort_mma_kernel(const Mm
           for (int ks = 0; ks < ksteps; ++ks) {
             const uint64_t adesc = ((uint64_t)desc_hi << 32) | (a_lo + (uint32_t)ks * a_kstep);
             const uint64_t bdesc = ((uint64_t)desc_hi << 32) | (b_lo + (uint32_t)ks * b_kstep);
+#ifndef KGE_EXP_NOMMA   // timing experiments only (scripts/gpu_exp_sweep.sh); results are wrong with a knob set
             umma_f16(dcol, adesc, bdesc, IDESC, ks > 0 ? 1u : 0u);
+#endif
           }
-          umma_commit(tfull0 + 8 * (buf * 2 + h));   // this half's accumulator is ready
-          if (h == 1) umma_commit(empty0 + 8 * s);   // smem stage reusable once all its MMAs have read it
+          umma_commit(tfull0 + 8 * (buf * 2 + h));               // this half's accumulator is ready
+          if (h == h_hi - 1) umma_commit(empty0 + 8 * s);        // smem stage reusable once its MMAs have read it
         }
       }
       __syncwarp();
@@ -575,26 +609,40 @@ __global__ void __launch_bounds__(SWEEP_THREADS, 2) fullsort_mma_kernel(const Mm
     }
   } else {
     // ===== epilogue: one thread per query row =====
-    const int h = warp >> 2, quad = warp & 3;   // quad == warp % 4: the TMEM lane quadrant this warp may read
+    const int h = (warp >> 2) & 1, quad = warp & 3;   // quad == warp % 4: the TMEM lane quadrant this warp may read
+    const int cs = warp >> 3;                         // column slice of the tile
+    const int64_t lsplit = (int64_t)split * NCOL + cs;   // list index of this (target split, column slice)
     const int u = h * 128 + quad * 32 + lane;
     const bool active = u < nrows;
     const int64_t qrow = row0 + u;
-    const int64_t lrow = (int64_t)split * a.rows_pad + qrow;   // list index of (row, split)
+    const int64_t lrow = lsplit * a.rows_pad + qrow;   // list of (row, split, slice)
     EpiState st;
     st.thr = active ? -INFINITY : INFINITY;
     st.thr_pub = -INFINITY;
+#ifdef KGE_EXP_THRINIT
+    if (active && a.thr_init) st.thr = st.thr_pub = a.thr_init[lrow];
+#endif
     st.cnt = 0;
     st.overflow = false;
     st.buf = a.cand + lrow * CAND;
     const float eps = eps_row[u];
-    uint32_t tlane = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(h * TN);
+    uint32_t tlane = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(h * TN + cs * NCH * CH);
     asm volatile("" : "+r"(tlane));   // keep the address in a register (ptxas would rebuild it from tid every tile)
     const int64_t wrow0 = row0 + h * 128 + quad * 32;   // first row of this warp
-    const uint32_t my_tfull = tfull0 + 8 * h, my_tempty = tempty0 + 8 * h;   // + 16 * buf
+    uint32_t my_tfull = tfull0 + 8 * h, my_tempty = tempty0 + 8 * h;   // + 16 * buf
+    asm volatile("" : "+r"(my_tfull), "+r"(my_tempty));
 
+    // The row's "unsafe chunk" bitmap, one 32-chunk word at a time (the next word is fetched a window ahead), so
+    // that a list entry is born with its safety flag and a compaction never has to look it up.
+    const uint32_t* urow = a.unsafe_bits + qrow * a.unsafe_wpr;
+    auto uload = [&](int64_t w) -> uint32_t { return (active && w < a.unsafe_wpr) ? __ldg(urow + w) : 0u; };
+    uint32_t uw_cur = 0u, uw_nxt = uload((int64_t)((t0 * (TN / CH)) >> 5));
+    uint32_t uw_idx = 0xFFFFFFFFu;
     // One chunk of 32 columns: optional debug dump, then the filter.
-    const int tail_i = (t1 == a.n_tiles) ? (int)nt - 1 : -1;   // groups beyond the table exist only in the last tile
-    auto process = [&](const uint32_t (&r)[32], int i, uint32_t cid) {
+    auto process = [&](const uint32_t (&r)[32], int, uint32_t cid) {
+#ifdef KGE_EXP_NOFILTER
+      return;
+#endif
       if (DBG) {
         if (active) {
           float* o = a.dbg_out + qrow * a.dbg_stride + (int64_t)cid * CH;
@@ -602,48 +650,78 @@ __global__ void __launch_bounds__(SWEEP_THREADS, 2) fullsort_mma_kernel(const Mm
           for (int j = 0; j < CH; ++j) o[j] = __uint_as_float(r[j]);
         }
       }
-      if (i != tail_i) {
-        epi_chunk<false>(r, st, cid, 8);
-      } else {  // (the image pads the last tile with zero rows)
-        const int64_t left = a.n_targets - (int64_t)cid * CH;
-        epi_chunk<true>(r, st, cid, left <= 0 ? 0 : (left >= CH ? 8 : (int)((left + GRP - 1) / GRP)));
-      }
+      epi_chunk(r, st, cid, uw_cur);   // (targets beyond the table: zero rows of the image, chunks marked unsafe)
     };
 
     // Software pipeline over chunks: the load of the next chunk is in flight while the current one is
     // filtered, and an accumulator goes back to the tensor core as soon as its last chunk sits in registers.
-    static_assert(TN == 2 * CH, "the pipeline below alternates two register sets over two chunks per tile");
+    // With one buffer per half (NBUF == 1) the next tile of this half is only being computed while the last
+    // chunk is filtered, so that chunk is filtered before the warp waits for it.
+#ifdef KGE_EXP_CLK
+    long long clk_wait = 0, clk_comp = 0, clk_t0 = clock64();
+    int n_comp = 0;
+#define CLK_BEGIN() const long long clk_b = clock64()
+#define CLK_END(acc) acc += clock64() - clk_b
+#else
+#define CLK_BEGIN()
+#define CLK_END(acc)
+#endif
     uint32_t va[32], vb[32];
     mbar_wait(my_tfull, 0u);
     tc_fence_after();
     tmem_ld32_issue(tlane, va);
     tmem_ld_wait(va);
     const int nti = (int)nt;
-    uint32_t cid = (uint32_t)(t0 * (TN / CH));
-    for (int i = 0; i < nti; ++i, cid += 2) {
-      const uint32_t buf = (uint32_t)(i & 1);
-      tmem_ld32_issue(tlane + buf * 2 * TN + CH, vb);
-      process(va, i, cid);
-      tmem_ld_wait(vb);
-      tc_fence_before();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(my_tempty + 16 * buf);   // both chunks are in registers: release the accumulator
-      if (i + 1 < nti) {
-        const uint32_t nbuf = buf ^ 1u;
-        mbar_wait(my_tfull + 16 * nbuf, (uint32_t)(((i + 1) >> 1) & 1));
-        tc_fence_after();
-        tmem_ld32_issue(tlane + nbuf * 2 * TN, va);
+    uint32_t cid = (uint32_t)(t0 * (TN / CH) + cs * NCH);
+    for (int i = 0; i < nti; ++i, cid += TN / CH) {
+      const uint32_t buf = NBUF == 1 ? 0u : (uint32_t)(i & 1);
+      const uint32_t tbase = tlane + buf * 2 * TN;
+      if ((cid >> 5) != uw_idx) {   // a tile never straddles a bitmap word (TN / CH divides 32)
+        uw_idx = cid >> 5;
+        uw_cur = uw_nxt;
+        uw_nxt = uload((int64_t)uw_idx + 1);
       }
-      process(vb, i, cid + 1);
-      if (i + 1 < nti) tmem_ld_wait(va);
-      unsigned full = __ballot_sync(0xffffffffu, st.cnt > CAND - 3);
+#pragma unroll
+      for (int c = 0; c < NCH; ++c) {
+        uint32_t(&cur)[32] = (c & 1) ? vb : va;
+        uint32_t(&nxt)[32] = (c & 1) ? va : vb;
+        if (c + 1 < NCH) {
+          tmem_ld32_issue(tbase + (uint32_t)((c + 1) * CH), nxt);
+          process(cur, i, cid + c);
+          tmem_ld_wait(nxt);
+          if (c + 1 == NCH - 1) {   // every chunk of the tile is in registers: release the accumulator
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(my_tempty + 16 * buf);
+          }
+        } else {
+          if (NBUF == 1) process(cur, i, cid + c);
+          if (i + 1 < nti) {
+            const uint32_t nbuf = NBUF == 1 ? 0u : (buf ^ 1u);
+            {
+              CLK_BEGIN();
+              mbar_wait(my_tfull + 16 * nbuf, (uint32_t)(((i + 1) / NBUF) & 1));
+              CLK_END(clk_wait);
+            }
+            tc_fence_after();
+            tmem_ld32_issue(tlane + nbuf * 2 * TN, nxt);
+          }
+          if (NBUF != 1) process(cur, i, cid + c);
+          if (i + 1 < nti) tmem_ld_wait(nxt);
+        }
+      }
+      unsigned full = __ballot_sync(0xffffffffu, st.cnt > CAND - (NCH + 1));
+#ifdef KGE_EXP_CLK
+      const long long clk_c0 = clock64();
+      n_comp += __popc(full);
+#endif
       while (full) {
         const int r = __ffs(full) - 1;
         full &= full - 1;
         const int cnt_r = __shfl_sync(0xffffffffu, st.cnt, r);
         const float eps_r = __shfl_sync(0xffffffffu, eps, r);
         const int64_t qrow_r = wrow0 + r;
-        uint2* buf_r = a.cand + ((int64_t)split * a.rows_pad + qrow_r) * CAND;
+        uint2* buf_r = a.cand + (lsplit * a.rows_pad + qrow_r) * CAND;
         __syncwarp();
         float thr_new;
         const int n_new = compact_row(buf_r, cnt_r, a.k, eps_r, a.unsafe_bits + qrow_r * a.unsafe_wpr, ROOM, &thr_new);
@@ -659,7 +737,15 @@ __global__ void __launch_bounds__(SWEEP_THREADS, 2) fullsort_mma_kernel(const Mm
           }
         }
       }
+#ifdef KGE_EXP_CLK
+      clk_comp += clock64() - clk_c0;
+#endif
     }
+#ifdef KGE_EXP_CLK
+    if (blockIdx.x == 7 && blockIdx.y == 0 && lane == 0)
+      printf("warp %2d: total %lld  wait_tfull %lld  compaction-loop %lld  compactions %d  tiles %d\n", warp,
+             clock64() - clk_t0, clk_wait, clk_comp, n_comp, nti);
+#endif
     if (active) {
       a.cand_cnt[lrow] = st.overflow ? -1 : st.cnt;
       a.cand_thr[lrow] = st.thr_pub;
@@ -669,7 +755,7 @@ __global__ void __launch_bounds__(SWEEP_THREADS, 2) fullsort_mma_kernel(const Mm
   // ---- teardown ------------------------------------------------------------------------------------
   tc_fence_before();
   __syncthreads();
-  if (warp == MMA_WARP) tmem_dealloc(tmem_base, 4 * TN);
+  if (warp == MMA_WARP0) tmem_dealloc(tmem_base, TMEM_COLS);
 }
 
 // ---- exact re-score + top-k ------------------------------------------------------------------------------
@@ -978,10 +1064,8 @@ __global__ void __launch_bounds__(RS_WARPS * 32) rescore_topk_kernel(const Resco
   }
 }
 
-constexpr int SWEEP_TN = 64;   // targets per tile: 256 TMEM columns and <= 113 KB shared memory per CTA -> two CTAs per SM
-
 struct MmaPlan {
-  int parts, dist, kp, stages, tn, splits, tiles_per_split;
+  int parts, dist, kp, stages, tn, nbuf, ncol, ctas_per_sm, splits, tiles_per_split;
   size_t smem;
   int64_t n_tiles, rows_pad, unsafe_wpr;
 };
@@ -995,23 +1079,42 @@ int plan_mma(const kge_model_t* m, int64_t n, int64_t n_targets, int k, MmaPlan&
   KGE_REQUIRE(pl.kp <= 256, KGE_E_UNSUPPORTED, "K = %d too large for the tensor-core path", pl.kp);
   KGE_REQUIRE(k >= 1 && k <= 32, KGE_E_UNSUPPORTED, "k = %d too large for the tensor-core path (max 32)", k);
   KGE_REQUIRE(n_targets >= 1 && n_targets < (int64_t)CID_MASK * CH, KGE_E_UNSUPPORTED, "bad n_targets");
-  pl.tn = SWEEP_TN;
-  const size_t a_bytes = (size_t)MM * pl.kp * 2, b_bytes = (size_t)pl.tn * pl.kp * 2;
+  // Tile shape (TN targets per tile, NBUF accumulators per row half, NCOL column slices per tile).  SS-mode
+  // tcgen05.mma with N = 64 runs at well under half rate (operand fetch + per-instruction cost), so TN = 128:
+  //   (a) TN 128, NBUF 1, NCOL 1: 256 TMEM columns, two CTAs per SM = four accumulator streams per SM; a stream
+  //       that stalls (list compaction) leaves the tensor pipe to the other three          -- K <= 80
+  //   (f) TN 128, NBUF 2, NCOL 2: all 512 columns, one CTA of 16 epilogue warps and two MMA issuer warps per SM
+  //                                                                                          -- larger K
+  //   (c) TN 64,  NBUF 2, NCOL 1: one CTA per SM -- K so large that (f) has no room for a ring of tiles
+  // KGE_MMA_CFG = a | f | c forces a shape (experiments); the target image depends on TN only.
+  const size_t a_bytes = (size_t)MM * pl.kp * 2;
   const size_t fixed = a_bytes + 32 * 8 + MM * 4 + 64;
-  // two CTAs per SM when the operands allow it (227 KB per SM, 1 KB reserved per CTA)
-  size_t budget = 112 * 1024;
-  if (fixed + 4 * b_bytes > budget) budget = 200 * 1024;
+  const size_t two_per_sm = 112 * 1024, one_per_sm = 200 * 1024;   // 227 KB per SM, 1 KB reserved per CTA
+  const char* force = getenv("KGE_MMA_CFG");
+  char cfg = 0;
+  if (force && (force[0] == 'a' || force[0] == 'f' || force[0] == 'c')) cfg = force[0];
+  if (cfg == 'a' && fixed + 2 * (size_t)128 * pl.kp * 2 > two_per_sm) cfg = 0;
+  if (!cfg) {
+    if (fixed + 3 * (size_t)128 * pl.kp * 2 <= two_per_sm) cfg = 'a';
+    else cfg = (fixed + 2 * (size_t)128 * pl.kp * 2 <= one_per_sm) ? 'f' : 'c';
+  }
+  pl.tn = cfg == 'c' ? 64 : 128;
+  pl.nbuf = cfg == 'a' ? 1 : 2;
+  pl.ncol = cfg == 'f' ? 2 : 1;
+  const size_t b_bytes = (size_t)pl.tn * pl.kp * 2;
+  size_t budget = cfg == 'a' ? two_per_sm : one_per_sm;
   KGE_REQUIRE(fixed + 2 * b_bytes <= budget, KGE_E_UNSUPPORTED, "K = %d leaves no room for a pipeline", pl.kp);
+  pl.ctas_per_sm = cfg == 'a' ? 2 : 1;
   int stages = (int)((budget - fixed) / b_bytes);
   if (stages > 8) stages = 8;
   pl.stages = stages;
   pl.smem = a_bytes + (size_t)stages * b_bytes + (size_t)(2 * stages + 8) * 8 + MM * 4 + 64;
   pl.n_tiles = (n_targets + pl.tn - 1) / pl.tn;
   pl.rows_pad = (n + MM - 1) / MM * MM;
-  pl.unsafe_wpr = ((n_targets + CH - 1) / CH + 31) / 32;
+  pl.unsafe_wpr = (pl.n_tiles * (pl.tn / CH) + 31) / 32;
   // target splits: fill the resident CTA slots (2 per SM) when there are few row blocks
   const int64_t row_blocks = pl.rows_pad / MM > 0 ? pl.rows_pad / MM : 1;
-  const int64_t slots = (int64_t)kge_num_sms() * (budget == 112 * 1024 ? 2 : 1);
+  const int64_t slots = (int64_t)kge_num_sms() * pl.ctas_per_sm;
   int64_t s = slots / row_blocks;
   if (s > MAX_SPLITS) s = MAX_SPLITS;
   if (s > pl.n_tiles / 16) s = pl.n_tiles / 16;
@@ -1061,7 +1164,7 @@ extern "C" int64_t kge_full_sort_topk_mma_workspace_bytes(const kge_model_t* mod
                                                           int32_t k) {
   MmaPlan pl;
   if (!model || n < 0 || plan_mma(model, n, n_targets, k, pl)) return -1;
-  return (int64_t)pl.splits * pl.rows_pad * (CAND * 8 + 4 + 4) + pl.rows_pad * 4 + pl.rows_pad * pl.unsafe_wpr * 4;
+  return (int64_t)pl.splits * pl.ncol * pl.rows_pad * (CAND * 8 + 4 + 4) + pl.rows_pad * 4 + pl.rows_pad * pl.unsafe_wpr * 4;
 }
 
 extern "C" int kge_full_sort_topk_mma(const kge_model_t* model, const int64_t* heads, const int64_t* rels, int64_t n,
@@ -1078,7 +1181,7 @@ extern "C" int kge_full_sort_topk_mma(const kge_model_t* model, const int64_t* h
   const int64_t need = kge_full_sort_topk_mma_workspace_bytes(model, n, n_targets, k);
   KGE_REQUIRE(workspace_bytes >= need, KGE_E_ARG, "workspace too small: need %lld bytes", (long long)need);
   cudaStream_t st = (cudaStream_t)stream;
-  const int64_t lists = (int64_t)pl.splits * pl.rows_pad;
+  const int64_t lists = (int64_t)pl.splits * pl.ncol * pl.rows_pad;
 
   MmaArgs a = {};
   a.s.m = *model;
@@ -1113,29 +1216,50 @@ extern "C" int kge_full_sort_topk_mma(const kge_model_t* model, const int64_t* h
   a.dbg_out = debug_scores;
   a.dbg_stride = (n_targets + 127) / 128 * 128;
 
+#ifdef KGE_EXP_THRINIT   // timing experiment: start from the thresholds the previous call ended with
+  static float* saved_thr = nullptr;
+  static int64_t saved_lists = 0;
+  a.thr_init = (saved_thr && saved_lists == lists) ? saved_thr : nullptr;
+#endif
   KGE_CUDA(cudaMemsetAsync(unsafe_bits, 0, (size_t)pl.rows_pad * pl.unsafe_wpr * 4, st));
   {
     int64_t g = (n + 7) / 8;
     const int64_t cap = (int64_t)kge_num_sms() * 8;
-    unsafe_bitmap_kernel<<<(unsigned)(g < cap ? g : cap), 256, 0, st>>>(unsafe_bits, pl.unsafe_wpr, n, n_targets, hist_off,
-                                                                       hist_items, mask_first);
+    unsafe_bitmap_kernel<<<(unsigned)(g < cap ? g : cap), 256, 0, st>>>(unsafe_bits, pl.unsafe_wpr, n, n_targets,
+                                                                       pl.n_tiles * (pl.tn / CH), hist_off, hist_items,
+                                                                       mask_first);
     KGE_LAUNCH_CHECK();
   }
   const dim3 grid((unsigned)(pl.rows_pad / MM), (unsigned)pl.splits);
-  if (debug_scores) {
-    KGE_CUDA(cudaFuncSetAttribute(fullsort_mma_kernel<SWEEP_TN, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pl.smem));
-    fullsort_mma_kernel<SWEEP_TN, true><<<grid, SWEEP_THREADS, pl.smem, st>>>(a);
+#define KGE_SWEEP(TN_, NB_, NC_, NM_, DBG_)                                                                        \
+  do {                                                                                                            \
+    KGE_CUDA(cudaFuncSetAttribute(fullsort_mma_kernel<TN_, NB_, NC_, NM_, DBG_>,                                  \
+                                  cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pl.smem));                    \
+    fullsort_mma_kernel<TN_, NB_, NC_, NM_, DBG_><<<grid, sweep_threads(NC_, NM_), pl.smem, st>>>(a);             \
+  } while (0)
+  if (pl.tn == 128 && pl.nbuf == 1) {
+    if (debug_scores) KGE_SWEEP(128, 1, 1, 1, true); else KGE_SWEEP(128, 1, 1, 1, false);
+  } else if (pl.tn == 128) {
+    if (debug_scores) KGE_SWEEP(128, 2, 2, 2, true); else KGE_SWEEP(128, 2, 2, 2, false);
   } else {
-    KGE_CUDA(cudaFuncSetAttribute(fullsort_mma_kernel<SWEEP_TN, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pl.smem));
-    fullsort_mma_kernel<SWEEP_TN, false><<<grid, SWEEP_THREADS, pl.smem, st>>>(a);
+    if (debug_scores) KGE_SWEEP(64, 2, 1, 2, true); else KGE_SWEEP(64, 2, 1, 2, false);
   }
+#undef KGE_SWEEP
+#ifdef KGE_EXP_THRINIT
+  if (saved_lists != lists) {
+    if (saved_thr) cudaFree(saved_thr);
+    KGE_CUDA(cudaMalloc(&saved_thr, lists * 4));
+    saved_lists = lists;
+    KGE_CUDA(cudaMemcpyAsync(saved_thr, a.cand_thr, lists * 4, cudaMemcpyDeviceToDevice, st));
+  }
+#endif
   KGE_LAUNCH_CHECK();
 
   RescoreArgs r = {};
   r.s = a.s;
   r.n_targets = n_targets;
   r.rows_pad = pl.rows_pad;
-  r.splits = pl.splits;
+  r.splits = pl.splits * pl.ncol;
   r.parts = pl.parts;
   r.hist_off = hist_off;
   r.hist_items = hist_items;
@@ -1148,7 +1272,7 @@ extern "C" int kge_full_sort_topk_mma(const kge_model_t* model, const int64_t* h
   r.ids_out = ids_out;
   r.scores_out = scores_out;
   r.row_flags = row_flags;
-  r.nent = pl.splits * CAND > RS_GIDS ? pl.splits * CAND : RS_GIDS;
+  r.nent = r.splits * CAND > RS_GIDS ? r.splits * CAND : RS_GIDS;
   const size_t rs_smem = rescore_smem_per_warp(pl.parts * model->d, r.nent) * RS_WARPS;
   int64_t g = (n + RS_WARPS - 1) / RS_WARPS;
   const int64_t cap = (int64_t)kge_num_sms() * 8;
