@@ -340,11 +340,22 @@ __device__ __forceinline__ bool chunk_unsafe(const MaskInfo& mi, uint32_t cid) {
 template <int NQ>
 __device__ __forceinline__ uint32_t warp_kth_largest(const uint32_t (&key)[NQ], int k) {
   int n_t = 0;
+  uint32_t k_or = 0u, k_and = 0xFFFFFFFFu;
 #pragma unroll
-  for (int q = 0; q < NQ; ++q) n_t += __popc(__ballot_sync(0xffffffffu, key[q] != 0u));
+  for (int q = 0; q < NQ; ++q) {
+    n_t += __popc(__ballot_sync(0xffffffffu, key[q] != 0u));
+    k_or |= key[q];
+    if (key[q] != 0u) k_and &= key[q];
+  }
   if (n_t < k) return 0u;
-  uint32_t P = 0u;  // invariant: #(key >= max(P, 1)) = n_t >= k
-  for (int bit = 31; bit >= 0 && n_t > k; --bit) {
+  // the keys of a list sit in a narrow band: the descent starts at the highest bit in which they differ
+  k_or = __reduce_or_sync(0xffffffffu, k_or);
+  k_and = __reduce_and_sync(0xffffffffu, k_and);
+  const uint32_t diff = k_or ^ k_and;
+  if (diff == 0u) return k_or;   // all present keys are equal
+  const int top = 31 - __clz(diff);
+  uint32_t P = top == 31 ? 0u : (k_and & ~((2u << top) - 1u));  // invariant: #(key >= max(P, 1)) = n_t >= k
+  for (int bit = top; bit >= 0 && n_t > k; --bit) {
     const uint32_t c = P | (1u << bit);
     int n = 0;
 #pragma unroll
@@ -430,15 +441,27 @@ __global__ void __launch_bounds__(256) unsafe_bitmap_kernel(uint32_t* bits, int6
   }
 }
 
+// Filter state of one (row, split, slice) list.  widx = index of the next free entry in the global `cand` array
+// (list base + count: lists are CAND entries long and CAND-aligned, and a count never reaches CAND).
 struct EpiState {
   float thr, thr_pub;
-  int cnt;
+  uint32_t widx;
   bool overflow;
-  uint2* buf;
 };
+#ifndef KGE_MMA_TRIG
+#define KGE_MMA_TRIG (CAND - 5)
+#endif
+constexpr int TRIG = KGE_MMA_TRIG;   // a list is compacted when it holds more than TRIG entries at the end of a tile
+
+// y |= bit when a >= b, as a compare and a predicated OR (the C form costs a compare, a select and an add)
+template <uint32_t BIT>
+__device__ __forceinline__ void or_if_ge(uint32_t& y, float a, float b) {
+  asm("{\n\t.reg .pred p;\n\tsetp.ge.f32 p, %1, %2;\n\t@p or.b32 %0, %0, %3;\n\t}" : "+r"(y) : "f"(a), "f"(b), "n"(BIT));
+}
 
 // One chunk (32 columns = 8 groups of 4) of one row: group maxima, chunk maximum, and (rarely) one list entry.
-__device__ __forceinline__ void epi_chunk(const uint32_t (&r)[32], EpiState& st, uint32_t cid, uint32_t uword) {
+__device__ __forceinline__ void epi_chunk(const uint32_t (&r)[32], EpiState& st, uint32_t cid, uint32_t uword,
+                                          uint2* __restrict__ cand) {
   float gm[8];
 #pragma unroll
   for (int g = 0; g < 8; ++g)
@@ -446,12 +469,18 @@ __device__ __forceinline__ void epi_chunk(const uint32_t (&r)[32], EpiState& st,
                   __uint_as_float(r[4 * g + 3]));
   const float tm = fmaxf(max3f(gm[0], gm[1], gm[2]), max3f(max3f(gm[3], gm[4], gm[5]), gm[6], gm[7]));
   if (tm >= st.thr) {  // rare per row after the first tiles (but most warps have one such row per chunk)
-    uint32_t mask = 0u;
-#pragma unroll
-    for (int g = 0; g < 8; ++g) mask |= (gm[g] >= st.thr) ? (1u << g) : 0u;
-    const uint32_t flags = F_KNOWN | (((uword >> (cid & 31u)) & 1u) << 31);   // bit 31 = F_UNSAFE
-    st.buf[st.cnt] = make_uint2(__float_as_uint(tm), (cid << CID_SHIFT) | mask | flags);
-    ++st.cnt;
+    uint32_t y = (cid << CID_SHIFT) | F_KNOWN;
+    y |= ((uword >> (cid & 31u)) & 1u) << 31;   // bit 31 = F_UNSAFE
+    or_if_ge<1u>(y, gm[0], st.thr);
+    or_if_ge<2u>(y, gm[1], st.thr);
+    or_if_ge<4u>(y, gm[2], st.thr);
+    or_if_ge<8u>(y, gm[3], st.thr);
+    or_if_ge<16u>(y, gm[4], st.thr);
+    or_if_ge<32u>(y, gm[5], st.thr);
+    or_if_ge<64u>(y, gm[6], st.thr);
+    or_if_ge<128u>(y, gm[7], st.thr);
+    cand[st.widx] = make_uint2(__float_as_uint(tm), y);
+    ++st.widx;
   }
 }
 
@@ -622,9 +651,9 @@ __global__ void __launch_bounds__(sweep_threads(NCOL, NMMA), NBUF == 1 ? 2 : 1)
 #ifdef KGE_EXP_THRINIT
     if (active && a.thr_init) st.thr = st.thr_pub = a.thr_init[lrow];
 #endif
-    st.cnt = 0;
+    const uint32_t wbase = (uint32_t)(lrow * CAND);
+    st.widx = wbase;
     st.overflow = false;
-    st.buf = a.cand + lrow * CAND;
     const float eps = eps_row[u];
     uint32_t tlane = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(h * TN + cs * NCH * CH);
     asm volatile("" : "+r"(tlane));   // keep the address in a register (ptxas would rebuild it from tid every tile)
@@ -650,7 +679,7 @@ __global__ void __launch_bounds__(sweep_threads(NCOL, NMMA), NBUF == 1 ? 2 : 1)
           for (int j = 0; j < CH; ++j) o[j] = __uint_as_float(r[j]);
         }
       }
-      epi_chunk(r, st, cid, uw_cur);   // (targets beyond the table: zero rows of the image, chunks marked unsafe)
+      epi_chunk(r, st, cid, uw_cur, a.cand);   // (targets beyond the table: zero rows of the image, chunks marked unsafe)
     };
 
     // Software pipeline over chunks: the load of the next chunk is in flight while the current one is
@@ -710,7 +739,7 @@ __global__ void __launch_bounds__(sweep_threads(NCOL, NMMA), NBUF == 1 ? 2 : 1)
           if (i + 1 < nti) tmem_ld_wait(nxt);
         }
       }
-      unsigned full = __ballot_sync(0xffffffffu, st.cnt > CAND - (NCH + 1));
+      unsigned full = __ballot_sync(0xffffffffu, (int)(st.widx & (CAND - 1)) > (TRIG < CAND - (NCH + 1) ? TRIG : CAND - (NCH + 1)));
 #ifdef KGE_EXP_CLK
       const long long clk_c0 = clock64();
       n_comp += __popc(full);
@@ -718,7 +747,7 @@ __global__ void __launch_bounds__(sweep_threads(NCOL, NMMA), NBUF == 1 ? 2 : 1)
       while (full) {
         const int r = __ffs(full) - 1;
         full &= full - 1;
-        const int cnt_r = __shfl_sync(0xffffffffu, st.cnt, r);
+        const int cnt_r = __shfl_sync(0xffffffffu, (int)(st.widx & (CAND - 1)), r);
         const float eps_r = __shfl_sync(0xffffffffu, eps, r);
         const int64_t qrow_r = wrow0 + r;
         uint2* buf_r = a.cand + (lsplit * a.rows_pad + qrow_r) * CAND;
@@ -729,9 +758,9 @@ __global__ void __launch_bounds__(sweep_threads(NCOL, NMMA), NBUF == 1 ? 2 : 1)
           if (n_new < 0) {
             st.overflow = true;
             st.thr = INFINITY;  // stop collecting: the row goes to the exact path
-            st.cnt = 0;
+            st.widx = wbase;
           } else {
-            st.cnt = n_new;
+            st.widx = wbase + (uint32_t)n_new;
             st.thr = thr_new;
             st.thr_pub = thr_new;
           }
@@ -747,7 +776,7 @@ __global__ void __launch_bounds__(sweep_threads(NCOL, NMMA), NBUF == 1 ? 2 : 1)
              clock64() - clk_t0, clk_wait, clk_comp, n_comp, nti);
 #endif
     if (active) {
-      a.cand_cnt[lrow] = st.overflow ? -1 : st.cnt;
+      a.cand_cnt[lrow] = st.overflow ? -1 : (int)(st.widx - wbase);
       a.cand_thr[lrow] = st.thr_pub;
     }
   }
