@@ -66,6 +66,17 @@ def measured_peaks():
     return dict(hbm_gbs=6650.0, bf16_tflops=1590.0, source="fallback")
 
 
+def profiled_traffic(workload):
+    """DRAM bytes (read + write) of the two launches of one step, from the committed `ncu --set full` capture of
+    this workload (profiles/r1_traffic.json, written by scripts/traffic_from_profiles.py); None when not captured."""
+    path = os.path.join(ROOT, "profiles", "r1_traffic.json")
+    if os.path.exists(path):
+        t = json.load(open(path)).get(workload)
+        if t:
+            return t["per_step_bytes"], t["source"]
+    return None, None
+
+
 def synth_batches(w, n_batches, seed):
     """Positive triples drawn from a fixed synthetic KG + uniform negatives (ids only)."""
     rng = np.random.default_rng(seed)
@@ -228,21 +239,22 @@ def time_fullsort(fs, device, n_users_step, steps, warmup, world, rank, path="au
         hist = np.sort(rng.integers(1, fs["I"], (n_users_step, fs["hist"])), axis=1)
         off = torch.arange(0, fs["hist"] * n_users_step + 1, fs["hist"], dtype=torch.long, device=device)
         blocks.append((users, off, torch.from_numpy(hist.reshape(-1)).to(device)))
-    for i in range(warmup):
+    for i in range(max(warmup, len(blocks))):   # every block once before the timed region (first-touch effects)
         u, o, h = blocks[i % len(blocks)]
         m.full_sort_topk(u, fs["k"], o, h, return_scores=False, path=path)
     barrier(world)
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e0.record()
+    ev = [torch.cuda.Event(enable_timing=True) for _ in range(steps + 1)]
+    ev[0].record()
     for i in range(steps):
-        u, o, h = blocks[(warmup + i) % len(blocks)]
+        u, o, h = blocks[i % len(blocks)]
         ids, _ = m.full_sort_topk(u, fs["k"], o, h, return_scores=False, path=path)
-    e1.record()
+        ev[i + 1].record()
     barrier(world)
-    ms = e0.elapsed_time(e1)
+    ms = ev[0].elapsed_time(ev[-1])
+    per_rep = sorted(ev[i].elapsed_time(ev[i + 1]) for i in range(steps))
     fallback = m._mma_last_fallback_rows
     del m
-    return ms, fallback
+    return ms, fallback, per_rep[len(per_rep) // 2]
 
 
 def cpu_reference_steps(w, steps, warmup, budget_s=None, threads=None):
@@ -347,8 +359,10 @@ def main():
     peaks = measured_peaks()
     bpt = bytes_per_triple(w["model"], w["d"], w["k"])
     achieved = triples_step * bpt / (step_ms * 1e-3) / 1e9
+    traffic, traffic_src = profiled_traffic(args.workload)
     roof = {"bound": "hbm", "achieved": achieved, "peak": peaks["hbm_gbs"], "unit": "GB/s",
-            "frac": achieved / peaks["hbm_gbs"], "traffic": None, "peak_source": peaks["source"],
+            "frac": achieved / peaks["hbm_gbs"], "traffic": traffic, "traffic_source": traffic_src,
+            "algorithmic_bytes": triples_step * bpt, "peak_source": peaks["source"],
             "kernels": "train_fwd_kernel + adam_apply_kernel (the two launches of one step)",
             "fwd_ms": fwd_ms_avg, "adam_ms": upd_ms_avg, "bytes_per_triple": bpt}
 
@@ -425,16 +439,18 @@ def main():
         for name, fs in FULLSORT.items():
             try:
                 n_users_step = 148 * 512   # two CTAs of 256 users per SM: one full wave of the tcgen05 sweep
-                reps = max(3, args.steps // 4)
+                reps = max(6, args.steps // 2)
                 flops = 2.0 * fs["I"] * fs["d"] * PARTS[fs["model"]]
                 entry = {"metric": "users/sec (full-sort top-20)", "users_per_block_per_gpu": n_users_step}
                 for path in ("mma", "cuda"):
-                    ms, fb = time_fullsort(fs, device, n_users_step, reps, 3, world, rank, path=path)
+                    if path == "cuda":
+                        reps = 3   # ~0.1 s per block
+                    ms, fb, med = time_fullsort(fs, device, n_users_step, reps, 3, world, rank, path=path)
                     ms = max_over_ranks(ms / reps, device, world)
                     ups = world * n_users_step / (ms * 1e-3)
                     entry[path] = {"users_per_s": ups, "ms_per_block": ms, "algorithmic_tflops": ups * flops / 1e12,
                                    "tensor_frac_of_bf16_peak": ups / world * flops / 1e12 / peaks["bf16_tflops"],
-                                   "rows_recomputed_exactly": fb}
+                                   "median_ms_per_block": med, "rows_recomputed_exactly": fb}
                     torch.cuda.empty_cache()
                 entry["paths"] = {"mma": "tcgen05 bf16 filter + exact fp32 re-score (same ids/scores)",
                                   "cuda": "fp32 CUDA-core tile kernel"}

@@ -834,8 +834,11 @@ __device__ __forceinline__ uint64_t warp_sort_desc(uint64_t key, int lane) {
   return key;
 }
 
+#ifndef KGE_RS_MINB
+#define KGE_RS_MINB 2
+#endif
 template <bool DIST>
-__global__ void __launch_bounds__(RS_WARPS * 32) rescore_topk_kernel(const RescoreArgs a) {
+__global__ void __launch_bounds__(RS_WARPS * 32, KGE_RS_MINB) rescore_topk_kernel(const RescoreArgs a) {
   extern __shared__ __align__(128) unsigned char smem[];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int d = a.s.m.d;
