@@ -300,6 +300,33 @@ def test_mma_topk_equals_cuda_core_topk(name, d, I, k):
     np.testing.assert_array_equal(sc_m.cpu().numpy(), sc_c.cpu().numpy())
 
 
+@pytest.mark.parametrize("cfg,name,d,I,k", [("a", "DistMult", 64, 20000, 20), ("f", "DistMult", 64, 20000, 20),
+                                            ("c", "DistMult", 64, 20000, 20), ("f", "RotatE", 20, 9000, 10),
+                                            ("", "RotatE", 120, 8300, 10), ("", "ComplEx", 128, 8300, 20)])
+def test_mma_tile_shapes(monkeypatch, cfg, name, d, I, k):
+    """Every sweep shape (csrc/mma_topk.cu plan_mma: a = two CTAs per SM, f = column-sliced single CTA, c = 64-wide
+    tiles for K > 195) gives the CUDA-core kernel's ids and scores bit for bit; "" = the shape the plan picks
+    (K = 256 lands on c)."""
+    if cfg:
+        monkeypatch.setenv("KGE_MMA_CFG", cfg)
+    else:
+        monkeypatch.delenv("KGE_MMA_CFG", raising=False)
+    U, E, R = 700, I + 50, 5
+    m = make_product_model(name, U, I, E, R, d)   # fresh model: the cached target image depends on the tile width
+    rng = np.random.default_rng(11)
+    n = 600
+    users = torch.from_numpy(rng.integers(1, U, n)).cuda()
+    lens = rng.integers(0, 60, n)
+    hist = [np.sort(rng.choice(np.arange(1, I), size=int(l), replace=False)) for l in lens]
+    off = torch.from_numpy(np.concatenate([[0], np.cumsum(lens)])).cuda()
+    items = torch.from_numpy(np.concatenate(hist)).cuda()
+    ids_c, sc_c = m.full_sort_topk(users, k, off, items, path="cuda")
+    ids_m, sc_m = m.full_sort_topk(users, k, off, items, path="mma")
+    assert m._mma_last_fallback_rows < 0.1 * n
+    np.testing.assert_array_equal(ids_m.cpu().numpy(), ids_c.cpu().numpy())
+    np.testing.assert_array_equal(sc_m.cpu().numpy(), sc_c.cpu().numpy())
+
+
 def test_mma_topk_trained_like_weights_and_cache_invalidation():
     """Heavy-tailed item norms (a few items dominate) and a weight update between calls."""
     name, U, I, E, R, d, k = "DistMult", 600, 30000, 30000, 4, 64, 20
