@@ -154,6 +154,11 @@ def ptr(t):
 
 
 def stream_ptr():
+    """cudaStream_t of torch's current stream on the current device (the raw getter: torch.cuda.current_stream()
+    builds a Stream object, ~10 us of host time per call on the step's critical path)."""
     import torch
 
+    raw = getattr(torch._C, "_cuda_getCurrentRawStream", None)
+    if raw is not None:
+        return raw(torch.cuda.current_device())
     return torch.cuda.current_stream().cuda_stream

@@ -93,14 +93,20 @@ __device__ __forceinline__ int2 row_state(const kge_table_t& T, int64_t row) {
 }
 
 // Bring a fragment that was loaded from w up to step-1 when the row lags behind (rare path).
+// With `mark` (a training pass) the lagging row is also marked as touched, even if it will receive no gradient:
+// the Adam kernel then brings it up to date with a zero-gradient step (exactly what dense Adam does to it), so
+// the lag of a row that keeps being referenced by inactive triples stays bounded -- without this every forward
+// pass would replay the same (growing, up to the cap) run of skipped steps for it again.
 template <int VEC, int G, int NCH>
-__device__ __forceinline__ void catch_up(const kge_table_t& T, int part, int64_t row, int last, int d, int gl,
-                                         const AdamDev& A, float (&x)[VEC * NCH]) {
+__device__ __forceinline__ void catch_up(const kge_table_t& T, int part, int64_t row, int2 st, int d, int gl,
+                                         const AdamDev& A, float (&x)[VEC * NCH], int mark) {
+  const int last = st.x;
   if (last >= 0 && last < A.step - 1) {
     float m[VEC * NCH], v[VEC * NCH];
     frag_load<VEC, G, NCH>(T.m[part], row, d, gl, m);
     frag_load<VEC, G, NCH>(T.v[part], row, d, gl, v);
     adam_replay<VEC * NCH>(x, m, v, last, A.step - 1, A);
+    if (mark && part == 0 && gl == 0 && st.y != A.step) T.row_state[2 * row + 1] = A.step;
   }
 }
 
@@ -181,11 +187,11 @@ __global__ void __launch_bounds__(256, FwdBounds<MODEL, VEC, NCH>::MIN_CTAS) tra
 #pragma unroll
     for (int p = 0; p < PH; ++p) frag_load<VEC, G, NCH>(ET.w[p], tn_id, d, gl, tnx[p]);
 #pragma unroll
-    for (int p = 0; p < PH; ++p) catch_up<VEC, G, NCH>(HT, p, h_id, sh.x, d, gl, a.adam, h[p]);
+    for (int p = 0; p < PH; ++p) catch_up<VEC, G, NCH>(HT, p, h_id, sh, d, gl, a.adam, h[p], a.with_grad);
 #pragma unroll
-    for (int p = 0; p < PR; ++p) catch_up<VEC, G, NCH>(RT, p, r_id, sr.x, d, gl, a.adam, r[p]);
+    for (int p = 0; p < PR; ++p) catch_up<VEC, G, NCH>(RT, p, r_id, sr, d, gl, a.adam, r[p], a.with_grad);
 #pragma unroll
-    for (int p = 0; p < PH; ++p) catch_up<VEC, G, NCH>(ET, p, tp_id, stp.x, d, gl, a.adam, tp[p]);
+    for (int p = 0; p < PH; ++p) catch_up<VEC, G, NCH>(ET, p, tp_id, stp, d, gl, a.adam, tp[p], a.with_grad);
 
     // gradient fragments of the anchor, relation and positive tail
     float gh[PH][E], gr[PR][E], gtp[PH][E];
@@ -278,7 +284,7 @@ __global__ void __launch_bounds__(256, FwdBounds<MODEL, VEC, NCH>::MIN_CTAS) tra
           for (int p = 0; p < PH; ++p) frag_load<VEC, G, NCH>(ET.w[p], tn_id, d, gl, tnx[p]);
         }
 #pragma unroll
-        for (int p = 0; p < PH; ++p) catch_up<VEC, G, NCH>(ET, p, t_id, st.x, d, gl, a.adam, t[p]);
+        for (int p = 0; p < PH; ++p) catch_up<VEC, G, NCH>(ET, p, t_id, st, d, gl, a.adam, t[p], a.with_grad);
       }
 
       if (MODEL == KGE_TRANSE) {

@@ -105,6 +105,10 @@ class KnowledgeRecommender(nn.Module):
         return super().__str__() + f"\nTrainable parameters: {params}"
 
 
+# per-step bookkeeping attributes are plain Python values: nn.Module.__setattr__ costs ~5 us per store
+_plain_set = object.__setattr__
+
+
 class _FusedStep(torch.autograd.Function):
     """loss = forward kernel; backward = Adam on the touched rows, scaled by grad_output."""
 
@@ -291,11 +295,15 @@ class FusedKGEModel(KnowledgeRecommender):
         return m
 
     def _adam_struct(self, step: int) -> _abi.kge_adam_t:
-        a = _abi.kge_adam_t()
-        a.lr, a.beta1, a.beta2, a.eps = self.learning_rate, self.betas[0], self.betas[1], self.adam_eps
-        a.step = step
-        a.replay_cap = self.replay_cap
-        return a
+        hp = (self.learning_rate, self.betas[0], self.betas[1], self.adam_eps, self.replay_cap)
+        a = self.__dict__.get("_adam_cache")
+        if a is None or a[0] != hp:   # one struct per hyper-parameter set; only the step changes between calls
+            s = _abi.kge_adam_t()
+            s.lr, s.beta1, s.beta2, s.eps, s.replay_cap = hp
+            a = (hp, s)
+            self.__dict__["_adam_cache"] = a
+        a[1].step = step
+        return a[1]
 
     # ------------------------------------------------------------------ training
     @staticmethod
@@ -352,7 +360,7 @@ class FusedKGEModel(KnowledgeRecommender):
         if self._pending:  # a loss whose backward never ran: drop its gradient
             m = self._model_struct(True)
             _abi.check(lib.kge_grad_discard(C.byref(m), self._step + 1, stream), "kge_grad_discard")
-            self._pending = False
+            _plain_set(self, "_pending", False)
         m = self._model_struct(lazy)
         b, keep = self._batch_struct(interaction, device)
         a = self._adam_struct(self._step + 1)
@@ -361,15 +369,15 @@ class FusedKGEModel(KnowledgeRecommender):
             lib.kge_train_forward(C.byref(m), C.byref(b), C.byref(a), 1 if with_grad else 0, loss.data_ptr(), stream),
             "kge_train_forward",
         )
-        self._keepalive = keep
+        _plain_set(self, "_keepalive", keep)
         # upper bounds on the distinct rows this batch can touch (sizes the row-sparse exchange)
-        self._touch_bounds = (
+        _plain_set(self, "_touch_bounds", (
             int(b.n_rec),
             int(b.n_rec) * (1 + int(b.k_rec)) + int(b.n_kg) * (2 + int(b.k_kg)),
             int(b.n_kg) + 1,
-        )
+        ))
         if with_grad:
-            self._pending = True
+            _plain_set(self, "_pending", True)
         return loss.reshape(())
 
     def _launch_apply(self, grad_out):
@@ -379,16 +387,18 @@ class FusedKGEModel(KnowledgeRecommender):
         if self._grad_sync is not None:
             self._grad_sync(self)
         # the incoming grad stays on the device: no host sync inside backward
-        g = grad_out.detach().to(torch.float32).reshape(1).contiguous()
+        g = grad_out
+        if g.dtype != torch.float32 or g.numel() != 1 or g.requires_grad:
+            g = g.detach().to(torch.float32).reshape(1).contiguous()
         m = self._model_struct(True)
         a = self._adam_struct(self._step + 1)
         _abi.check(
             lib.kge_adam_apply(C.byref(m), C.byref(a), float(self._grad_scale), g.data_ptr(), _abi.stream_ptr()),
             "kge_adam_apply",
         )
-        self._step += 1
-        self._pending = False
-        self._dirty = True
+        _plain_set(self, "_step", self._step + 1)
+        _plain_set(self, "_pending", False)
+        _plain_set(self, "_dirty", True)
 
     def calculate_loss(self, interaction):
         """transe.py:75-98 / distmult.py:68-95 / rotate.py:98-131 / complex.py:95-128."""

@@ -227,6 +227,34 @@ def test_long_idle_rows_follow_dense_adam():
         assert_weights_close(vp.cpu().numpy(), vo.numpy(), rtol=RTOL, atol=1e-6, err_msg=k)
 
 
+def test_rows_of_inactive_triples_stay_current():
+    """Rows that keep being referenced by margin-inactive triples (no gradient) must not fall behind the
+    optimiser: a lagging referenced row is marked and caught up by the Adam kernel, so its lag is bounded by the
+    gap between two references (otherwise every forward pass replays a growing run of skipped steps).  The
+    trajectory is dense Adam's either way."""
+    name, U, I, E, R, d = "DistMult", 50, 40, 200, 6, 16   # (margin_ranking_loss accepts the negative margin below)
+    rng = np.random.default_rng(21)
+    b = random_batch(rng, U, I, E, R, 64, 64)
+    m = make_product_model(name, U, I, E, R, d, margin=1.0)
+    ora = make_oracle_model(name, U, I, E, R, d, margin=1.0)
+    opt_o = make_optimizer(ora)
+    opt = torch.optim.Adam(m.parameters(), lr=1e-3)
+    steps = 30
+    for step in range(steps):
+        if step == 3:   # from here on no triple is active: margin - s(pos) + s(neg) < 0 for every pair
+            m.margin = -1e3
+            m._struct_cache = {}
+            ora.shapes.margin = -1e3
+        train_step(ora, opt_o, to_cpu_batch(b))
+        _trainer_step(m, opt, to_device_batch(b))
+    rs = m._state["entity"]["row_state"].cpu().numpy()
+    ref = np.unique(np.concatenate([b["item_id"], b["neg_item_id"], b["head_id"], b["tail_id"], b["neg_tail_id"]]))
+    last = rs[ref, 0]
+    assert (last[last >= 0] >= steps - 1).all(), "a referenced row lags behind the optimiser"
+    for (k, vo), (_, vp) in zip(ora.state_dict().items(), m.state_dict().items()):
+        assert_weights_close(vp.cpu().numpy(), vo.numpy(), rtol=RTOL, atol=1e-6, err_msg=k)
+
+
 def test_checkpoint_round_trip_continues_the_trajectory():
     name, U, I, E, R, d = "ComplEx", 60, 40, 150, 6, 16
     rng = np.random.default_rng(13)
