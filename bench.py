@@ -371,7 +371,9 @@ def main():
             "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": config,
             "e2e": {"value": e2e_value, "unit": "triples/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4,
                     "ms_per_step": e2e_ms},
-            "gpu_launches": 2 * args.steps * (1 if world == 1 else 1) + (0 if world == 1 else 6 * args.steps),
+            # this library's kernels in the timed region: forward + Adam per step, plus the pack / add kernels of
+            # the row-sparse exchange when a table takes that route (NCCL's own kernels are not counted)
+            "gpu_launches": args.steps * (2 + (exchange.kernels_per_step if exchange is not None else 0)),
             "roofline": roof, "clocks": clk, "final_loss": last_loss}
     if exchange is not None:
         line["exchange_bytes_per_rank_per_step"] = exchange.bytes_per_step

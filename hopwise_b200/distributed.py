@@ -16,9 +16,10 @@ Bytes per rank per step: sum over tables of min(rows, touched) * (8 + parts*d*4)
 4 bytes * every parameter.
 
 A table whose batch can touch at least half of its rows (small tables, or the roofline batches of
-bench.py) takes the dense route instead: its gradient accumulator is all-reduced (sum) and its
-row states are all-reduced (max = union of the touch marks); both live in flat buffers so that
-one collective covers every dense table.  NCCL delivers the same sums to every rank, so the
+bench.py) takes the dense route instead: its gradient accumulator is all-reduced (sum) and every one
+of its rows is marked as touched (a row nobody touched then takes the zero-gradient Adam step dense
+Adam gives it); the accumulators live in one flat buffer so that one collective covers every dense
+table.  NCCL delivers the same sums to every rank, so the
 replicas stay bit-identical on this route too.
 """
 
@@ -105,6 +106,7 @@ class RowSparseExchange:
         self.send = self.recv = None
         self.dense = [False, False, False]
         self.bytes_per_step = 0
+        self.kernels_per_step = 0   # launches of this library's pack / add kernels in the last step
 
     def _plan(self, model, batch_rows):
         """Tighten the per-table capacity to what this batch shape can touch; pick the route per table."""
@@ -119,8 +121,7 @@ class RowSparseExchange:
             self.send = torch.zeros(self.layout.nbytes, dtype=torch.uint8, device=device)
             self.recv = torch.zeros(self.world * self.layout.nbytes, dtype=torch.uint8, device=device)
         st = model._state
-        dense_bytes = sum((st[f]["g_span"][1] - st[f]["g_span"][0]) * 4 + (st[f]["rs_span"][1] - st[f]["rs_span"][0]) * 8
-                          for f, dn in zip(FAMILIES, self.dense) if dn)
+        dense_bytes = sum((st[f]["g_span"][1] - st[f]["g_span"][0]) * 4 for f, dn in zip(FAMILIES, self.dense) if dn)
         self.bytes_per_step = (0 if all(self.dense) else self.layout.nbytes) + dense_bytes
 
     def _dense_spans(self, model):
@@ -140,13 +141,17 @@ class RowSparseExchange:
         step = model._step + 1
         self._plan(model, model._touch_bounds)
         sparse = [w for w in range(3) if not self.dense[w]]
+        self.kernels_per_step = len(sparse) * (1 + self.world)
         for which in sparse:
             count, ids, rows = self.layout.views(self.send, which)
             self.pack_fn(model, which, step, count, ids, rows)
         st = model._state
         for g0, g1, r0, r1 in self._dense_spans(model):
             dist.all_reduce(st["g_flat"][g0:g1], op=dist.ReduceOp.SUM, group=self.group)
-            dist.all_reduce(st["row_state_flat"][r0:r1], op=dist.ReduceOp.MAX, group=self.group)
+            # Every row of a dense table is marked as touched instead of all-reducing the touch marks: a row
+            # nobody touched holds a zero gradient, and a zero-gradient Adam step is exactly what dense Adam (and
+            # the lazy replay) does to it -- same weights, one collective less per step.
+            st["row_state_flat"][r0:r1, 1].fill_(step)
         if not sparse:
             return
         dist.all_gather_into_tensor(self.recv, self.send, group=self.group)
