@@ -37,7 +37,6 @@
 // 8x16-byte core matrices, SBO = 128 B, LBO = rows * 16 B.
 #include <cuda_bf16.h>
 #include <math.h>
-#include <stdio.h>
 #include <stdlib.h>
 
 #include "common.cuh"
@@ -67,24 +66,7 @@ __device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
   asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
 }
 __device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity) {
-  uint32_t ok;
-#if defined(KGE_MBAR_TEST)
-  asm volatile(
-      "{\n\t.reg .pred p;\n\t"
-      "mbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
-      "selp.u32 %0, 1, 0, p;\n\t}"
-      : "=r"(ok)
-      : "r"(bar), "r"(parity)
-      : "memory");
-#elif defined(KGE_MBAR_HINT)
-  asm volatile(
-      "{\n\t.reg .pred p;\n\t"
-      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\t"
-      "selp.u32 %0, 1, 0, p;\n\t}"
-      : "=r"(ok)
-      : "r"(bar), "r"(parity), "r"(0x989680u)   // suspend-time hint: sleep in hardware instead of polling
-      : "memory");
-#else
+  uint32_t ok;   // (a suspend-time hint or a pure test_wait spin made no difference: measured, scripts/gpu_exp_sweep.sh)
   asm volatile(
       "{\n\t.reg .pred p;\n\t"
       "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
@@ -92,7 +74,6 @@ __device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity) {
       : "=r"(ok)
       : "r"(bar), "r"(parity)
       : "memory");
-#endif
   return ok != 0;
 }
 // A wait that cannot hang the GPU: a protocol bug traps instead of spinning forever.
@@ -295,7 +276,6 @@ struct MmaArgs {
   float* eps_out;     // [rows_pad]
   const uint32_t* unsafe_bits;  // [rows_pad][unsafe_wpr]: bit c = chunk c holds a masked / out-of-range target
   int64_t unsafe_wpr;
-  const float* thr_init;  // experiment (KGE_EXP_THRINIT): thresholds the lists start from
   float* dbg_out;     // optional dense approximate scores [n, dbg_stride]
   int64_t dbg_stride;
 };
@@ -648,9 +628,6 @@ __global__ void __launch_bounds__(sweep_threads(NCOL, NMMA), NBUF == 1 ? 2 : 1)
     EpiState st;
     st.thr = active ? -INFINITY : INFINITY;
     st.thr_pub = -INFINITY;
-#ifdef KGE_EXP_THRINIT
-    if (active && a.thr_init) st.thr = st.thr_pub = a.thr_init[lrow];
-#endif
     const uint32_t wbase = (uint32_t)(lrow * CAND);
     st.widx = wbase;
     st.overflow = false;
@@ -686,15 +663,6 @@ __global__ void __launch_bounds__(sweep_threads(NCOL, NMMA), NBUF == 1 ? 2 : 1)
     // filtered, and an accumulator goes back to the tensor core as soon as its last chunk sits in registers.
     // With one buffer per half (NBUF == 1) the next tile of this half is only being computed while the last
     // chunk is filtered, so that chunk is filtered before the warp waits for it.
-#ifdef KGE_EXP_CLK
-    long long clk_wait = 0, clk_comp = 0, clk_t0 = clock64();
-    int n_comp = 0;
-#define CLK_BEGIN() const long long clk_b = clock64()
-#define CLK_END(acc) acc += clock64() - clk_b
-#else
-#define CLK_BEGIN()
-#define CLK_END(acc)
-#endif
     uint32_t va[32], vb[32];
     mbar_wait(my_tfull, 0u);
     tc_fence_after();
@@ -727,11 +695,7 @@ __global__ void __launch_bounds__(sweep_threads(NCOL, NMMA), NBUF == 1 ? 2 : 1)
           if (NBUF == 1) process(cur, i, cid + c);
           if (i + 1 < nti) {
             const uint32_t nbuf = NBUF == 1 ? 0u : (buf ^ 1u);
-            {
-              CLK_BEGIN();
-              mbar_wait(my_tfull + 16 * nbuf, (uint32_t)(((i + 1) / NBUF) & 1));
-              CLK_END(clk_wait);
-            }
+            mbar_wait(my_tfull + 16 * nbuf, (uint32_t)(((i + 1) / NBUF) & 1));
             tc_fence_after();
             tmem_ld32_issue(tlane + nbuf * 2 * TN, nxt);
           }
@@ -740,10 +704,6 @@ __global__ void __launch_bounds__(sweep_threads(NCOL, NMMA), NBUF == 1 ? 2 : 1)
         }
       }
       unsigned full = __ballot_sync(0xffffffffu, (int)(st.widx & (CAND - 1)) > (TRIG < CAND - (NCH + 1) ? TRIG : CAND - (NCH + 1)));
-#ifdef KGE_EXP_CLK
-      const long long clk_c0 = clock64();
-      n_comp += __popc(full);
-#endif
       while (full) {
         const int r = __ffs(full) - 1;
         full &= full - 1;
@@ -766,15 +726,7 @@ __global__ void __launch_bounds__(sweep_threads(NCOL, NMMA), NBUF == 1 ? 2 : 1)
           }
         }
       }
-#ifdef KGE_EXP_CLK
-      clk_comp += clock64() - clk_c0;
-#endif
     }
-#ifdef KGE_EXP_CLK
-    if (blockIdx.x == 7 && blockIdx.y == 0 && lane == 0)
-      printf("warp %2d: total %lld  wait_tfull %lld  compaction-loop %lld  compactions %d  tiles %d\n", warp,
-             clock64() - clk_t0, clk_wait, clk_comp, n_comp, nti);
-#endif
     if (active) {
       a.cand_cnt[lrow] = st.overflow ? -1 : (int)(st.widx - wbase);
       a.cand_thr[lrow] = st.thr_pub;
@@ -1248,11 +1200,6 @@ extern "C" int kge_full_sort_topk_mma(const kge_model_t* model, const int64_t* h
   a.dbg_out = debug_scores;
   a.dbg_stride = (n_targets + 127) / 128 * 128;
 
-#ifdef KGE_EXP_THRINIT   // timing experiment: start from the thresholds the previous call ended with
-  static float* saved_thr = nullptr;
-  static int64_t saved_lists = 0;
-  a.thr_init = (saved_thr && saved_lists == lists) ? saved_thr : nullptr;
-#endif
   KGE_CUDA(cudaMemsetAsync(unsafe_bits, 0, (size_t)pl.rows_pad * pl.unsafe_wpr * 4, st));
   {
     int64_t g = (n + 7) / 8;
@@ -1277,14 +1224,6 @@ extern "C" int kge_full_sort_topk_mma(const kge_model_t* model, const int64_t* h
     if (debug_scores) KGE_SWEEP(64, 2, 1, 2, true); else KGE_SWEEP(64, 2, 1, 2, false);
   }
 #undef KGE_SWEEP
-#ifdef KGE_EXP_THRINIT
-  if (saved_lists != lists) {
-    if (saved_thr) cudaFree(saved_thr);
-    KGE_CUDA(cudaMalloc(&saved_thr, lists * 4));
-    saved_lists = lists;
-    KGE_CUDA(cudaMemcpyAsync(saved_thr, a.cand_thr, lists * 4, cudaMemcpyDeviceToDevice, st));
-  }
-#endif
   KGE_LAUNCH_CHECK();
 
   RescoreArgs r = {};
