@@ -57,6 +57,48 @@ def test_host_only_entry_points():
     assert b"NULL" in lib.kge_last_error()
 
 
+def _model_struct(kind, d, rows=1000):
+    from hopwise_b200 import _abi
+
+    m = _abi.kge_model_t()
+    m.model = _abi.MODEL_KINDS[kind]
+    m.d = d
+    parts = 2 if kind in ("RotatE", "ComplEx") else 1
+    for fam in ("user", "entity", "relation"):
+        t = getattr(m, fam)
+        t.rows, t.parts = rows, parts
+    m.relation.parts = 2 if kind == "ComplEx" else 1
+    return m
+
+
+@pytest.mark.parametrize("kind,d,tn", [("DistMult", 64, 128), ("ComplEx", 64, 128), ("TransE", 100, 128),
+                                       ("RotatE", 120, 64), ("ComplEx", 128, 64)])
+def test_sweep_plan_sizes(monkeypatch, kind, d, tn):
+    """plan_mma (csrc/mma_topk.cu) without a GPU: the operand image is tiles of TN rows of the padded K, the
+    workspace holds one 128-entry list per (row, split, slice) plus the per-row bitmap; K > 256 is refused."""
+    from hopwise_b200 import _abi
+
+    monkeypatch.delenv("KGE_MMA_CFG", raising=False)
+    lib = _abi.lib()
+    m = _model_struct(kind, d)
+    n_targets = 200_001
+    parts = 2 if kind in ("RotatE", "ComplEx") else 1
+    kd = parts * d + (3 if kind in ("TransE", "RotatE") else 0)
+    kp = (kd + 15) // 16 * 16
+    tiles = (n_targets + tn - 1) // tn
+    img = lib.kge_mma_image_bytes(C.byref(m), n_targets)
+    assert img == 128 + tiles * tn * kp * 2 + (n_targets * 4 + 127) // 128 * 128
+    n = 75_776
+    ws = lib.kge_full_sort_topk_mma_workspace_bytes(C.byref(m), n, n_targets, 20)
+    rows_pad = (n + 255) // 256 * 256
+    wpr = (tiles * (tn // 32) + 31) // 32
+    ncol = 2 if (tn == 128 and kp > 80) else 1           # shape (f): two column slices per tile
+    assert ws == ncol * rows_pad * (128 * 8 + 8) + rows_pad * 4 + rows_pad * wpr * 4   # one split at this size
+    assert lib.kge_full_sort_topk_mma_workspace_bytes(C.byref(m), n, n_targets, 64) == -1    # k > 32
+    big = _model_struct("ComplEx", 160)
+    assert lib.kge_mma_image_bytes(C.byref(big), n_targets) == -1                          # K = 320 > 256
+
+
 def test_product_has_no_cpu_fallback_and_no_oracle_import():
     import torch
 
