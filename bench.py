@@ -338,7 +338,11 @@ def main():
         from hopwise_b200.distributed import broadcast_weights, enable_row_sparse_data_parallel
 
         broadcast_weights(model)
-        exchange = enable_row_sparse_data_parallel(model)
+        # dense route: this library's in-switch (NVLS multimem) all-reduce from 4 GPUs on -- measured at 8 B200:
+        # 0.527 ms/step vs 0.564 with NCCL; at 2 GPUs NCCL's single exchange is faster (0.462 vs 0.483 ms).
+        # KGE_MULTIMEM=0 / 1 forces the choice.
+        mm = os.environ.get("KGE_MULTIMEM")
+        exchange = enable_row_sparse_data_parallel(model, multimem=(world >= 4) if mm is None else mm != "0")
 
     n_batches = 4
     host = synth_batches(w, n_batches, seed=2024 + rank)
@@ -380,6 +384,7 @@ def main():
             "roofline": roof, "clocks": clk, "final_loss": last_loss}
     if exchange is not None:
         line["exchange_bytes_per_rank_per_step"] = exchange.bytes_per_step
+        line["exchange"] = "nvls multimem all-reduce (csrc/collective.cu)" if exchange.multimem else "nccl all-reduce"
 
     if not args.no_extras:
         extras = {}

@@ -15,6 +15,11 @@ order on every rank, so the replicas stay bit-identical without ever moving a de
 Bytes per rank per step: sum over tables of min(rows, touched) * (8 + parts*d*4), instead of
 4 bytes * every parameter.
 
+With ``multimem=True`` the dense route reduces in the NVSwitch instead of through NCCL: the gradient
+accumulators are allocated as a symmetric buffer with an NVLS multicast mapping (torch's symmetric-memory
+rendezvous is the plumbing: allocation, handle exchange, cross-rank barrier) and
+``kge_multimem_all_reduce_f32`` sums the N copies in place (csrc/collective.cu).
+
 A table whose batch can touch at least half of its rows (small tables, or the roofline batches of
 bench.py) takes the dense route instead: its gradient accumulator is all-reduced (sum) and every one
 of its rows is marked as touched (a row nobody touched then takes the zero-gradient Adam step dense
@@ -92,8 +97,12 @@ class RowSparseExchange:
     """Callable installed as ``model._grad_sync``; runs between the forward/gradient kernel and
     the Adam kernel of every step."""
 
-    def __init__(self, model, group=None, pack_fn=_cuda_pack, add_fn=_cuda_add, device=None):
+    def __init__(self, model, group=None, pack_fn=_cuda_pack, add_fn=_cuda_add, device=None, multimem=False):
         self.group = group
+        self.symm = None           # symmetric-memory handle of the gradient buffer (multimem route)
+        self.multimem = False
+        if multimem:
+            self._install_multimem(model)
         self.world = dist.get_world_size(group)
         self.rank = dist.get_rank(group)
         self.pack_fn, self.add_fn = pack_fn, add_fn
@@ -107,6 +116,53 @@ class RowSparseExchange:
         self.dense = [False, False, False]
         self.bytes_per_step = 0
         self.kernels_per_step = 0   # launches of this library's pack / add kernels in the last step
+
+    def _install_multimem(self, model):
+        """Have the model allocate its flat gradient buffer in symmetric memory with a multicast mapping.
+        Must run before the first training step (the optimiser state is created lazily there); every rank
+        reaches that allocation together, which makes the rendezvous inside it a proper collective."""
+        import torch.distributed._symmetric_memory as symm_mem
+
+        if model._state is not None:
+            raise RuntimeError("multimem exchange must be enabled before the first training step")
+        group = self.group if self.group is not None else dist.group.WORLD
+        ex = self
+
+        def alloc(numel, device):
+            padded = (numel + 3) // 4 * 4
+            try:
+                buf = symm_mem.empty(padded, dtype=torch.float32, device=device)
+                buf.zero_()
+                hdl = symm_mem.rendezvous(buf, group)
+                if not hdl.has_multicast_support or not hdl.multicast_ptr:
+                    raise RuntimeError("no NVLS multicast mapping for the gradient buffer")
+            except Exception as exc:   # same hardware on every rank: all ranks take this branch together
+                import warnings
+
+                warnings.warn(f"multimem exchange unavailable ({exc}); the dense route uses NCCL's all-reduce")
+                ex.multimem = False
+                return torch.zeros(numel, device=device)
+            ex.symm = hdl
+            ex._mc_base = int(hdl.multicast_ptr) + (buf.data_ptr() - int(hdl.buffer_ptrs[hdl.rank]))
+            ex._symm_keep = buf
+            return buf[:numel]
+
+        object.__setattr__(model, "_g_alloc", alloc)
+        self.multimem = True
+
+    def _all_reduce_dense(self, g_flat, g0, g1):
+        """Sum the [g0, g1) float range of the flat gradient buffer over the ranks, in place."""
+        if self.multimem and self.symm is not None and g0 % 4 == 0 and (g1 - g0) % 4 == 0:
+            self.symm.barrier(channel=0)      # every rank's forward kernel has written its gradients
+            _abi.check(
+                _abi.lib().kge_multimem_all_reduce_f32(self._mc_base + 4 * g0, g1 - g0, self.rank, self.world,
+                                                       _abi.stream_ptr()),
+                "kge_multimem_all_reduce_f32",
+            )
+            self.symm.barrier(channel=1)      # every slice has been reduced and broadcast
+            self.kernels_per_step += 1
+        else:
+            dist.all_reduce(g_flat[g0:g1], op=dist.ReduceOp.SUM, group=self.group)
 
     def _plan(self, model, batch_rows):
         """Tighten the per-table capacity to what this batch shape can touch; pick the route per table."""
@@ -147,7 +203,7 @@ class RowSparseExchange:
             self.pack_fn(model, which, step, count, ids, rows)
         st = model._state
         for g0, g1, r0, r1 in self._dense_spans(model):
-            dist.all_reduce(st["g_flat"][g0:g1], op=dist.ReduceOp.SUM, group=self.group)
+            self._all_reduce_dense(st["g_flat"], g0, g1)
             # Every row of a dense table is marked as touched instead of all-reducing the touch marks: a row
             # nobody touched holds a zero gradient, and a zero-gradient Adam step is exactly what dense Adam (and
             # the lazy replay) does to it -- same weights, one collective less per step.
@@ -163,11 +219,13 @@ class RowSparseExchange:
                 self.add_fn(model, which, step, count, ids, rows)
 
 
-def enable_row_sparse_data_parallel(model, group=None):
+def enable_row_sparse_data_parallel(model, group=None, multimem=False):
     """Turn a FusedKGEModel replica into a data-parallel one (call once, after model.to(device),
     on every rank, with identical initial weights: the reference gets that from DDP's rank-0
-    broadcast, here `broadcast_weights` does it)."""
-    ex = RowSparseExchange(model, group=group)
+    broadcast, here `broadcast_weights` does it).  ``multimem=True``: dense tables are reduced in the
+    NVSwitch (NVLS multicast) by this library's own kernel instead of NCCL; needs a multicast-capable
+    fabric and must be enabled before the first training step."""
+    ex = RowSparseExchange(model, group=group, multimem=multimem)
     model._grad_sync = ex
     model._grad_scale = 1.0 / ex.world
     return ex

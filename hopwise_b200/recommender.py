@@ -225,7 +225,10 @@ class FusedKGEModel(KnowledgeRecommender):
         d = self.embedding_size
         # gradient accumulators and row states of all tables live in two flat buffers, so that the dense
         # data-parallel path reduces them with one collective each (hopwise_b200/distributed.py)
-        st["g_flat"] = torch.zeros(sum(rows * len(names) for _, names, rows in fams) * d, device=device)
+        # (a data-parallel exchange may place them in symmetric / multicast memory: distributed.py sets _g_alloc)
+        g_numel = sum(rows * len(names) for _, names, rows in fams) * d
+        alloc = self.__dict__.get("_g_alloc")
+        st["g_flat"] = alloc(g_numel, device) if alloc is not None else torch.zeros(g_numel, device=device)
         st["row_state_flat"] = torch.full((sum(rows for _, _, rows in fams), 2), -1, dtype=torch.int32, device=device)
         g_off = rs_off = 0
         for fam, names, rows in fams:

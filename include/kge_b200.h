@@ -137,6 +137,14 @@ int kge_grad_pack(const kge_model_t* model, int32_t which, int32_t step, int64_t
 int kge_grad_add(const kge_model_t* model, int32_t which, int32_t step, const int64_t* ids, const float* rows,
                  const int32_t* count_dev, int64_t max_count, kge_stream_t stream);
 
+/* Dense route of the same exchange, in the NVSwitch: sum the N ranks' copies of a symmetric buffer in place.
+ * multicast_ptr = the NVLS multicast address of the buffer (16-byte aligned; n_floats % 4 == 0), i.e. one
+ * address that names every rank's copy.  Rank `rank` reduces the rank-th slice with multimem.ld_reduce and
+ * broadcasts the sums with multimem.st, so every copy ends up holding identical sums.  The caller puts a
+ * cross-rank barrier before (all copies written) and after (all slices reduced) the call. */
+int kge_multimem_all_reduce_f32(void* multicast_ptr, int64_t n_floats, int32_t rank, int32_t world,
+                                kge_stream_t stream);
+
 /* ---- scoring --------------------------------------------------------------------------
  * kge_predict: <Model>.predict / predict_kg (transe.py:100-110,128-137 and twins).
  * heads index the user tables when head_is_user != 0, else the entity tables; rels == NULL

@@ -44,7 +44,7 @@ def _shard(b, rank, k):
     return out
 
 
-def _worker(rank, world, port, name, route, out_dir):
+def _worker(rank, world, port, name, route, out_dir, multimem=False):
     import torch.distributed as dist
 
     from hopwise_b200.distributed import broadcast_weights, enable_row_sparse_data_parallel
@@ -57,7 +57,7 @@ def _worker(rank, world, port, name, route, out_dir):
         SHAPE = SHAPES[route]
         m = make_product_model(name, device=dev, seed=2024 + rank, **SHAPE)   # different init: broadcast must fix it
         broadcast_weights(m)
-        ex = enable_row_sparse_data_parallel(m)
+        ex = enable_row_sparse_data_parallel(m, multimem=multimem)
         batches, k = _batches(name, SHAPE)
         losses = []
         for b in batches:
@@ -65,6 +65,8 @@ def _worker(rank, world, port, name, route, out_dir):
             loss.backward()
             losses.append(float(loss.item()))
         assert ex.bytes_per_step > 0
+        if multimem:   # the in-switch reduction really ran (one launch of this library's kernel per step)
+            assert ex.symm is not None and ex.kernels_per_step >= 1
         assert ex.dense == ([True, True, True] if route == "dense" else [False, False, True])
         sd = {key: v.cpu().numpy() for key, v in m.state_dict().items()}
         np.savez(os.path.join(out_dir, f"rank{rank}.npz"), losses=np.array(losses), **sd)
@@ -72,14 +74,17 @@ def _worker(rank, world, port, name, route, out_dir):
         dist.destroy_process_group()
 
 
-@pytest.mark.parametrize("name,route", [("TransE", "dense"), ("ComplEx", "dense"), ("TransE", "sparse"), ("RotatE", "sparse")])
-def test_two_rank_row_sparse_step_matches_single_gpu(name, route, tmp_path):
+@pytest.mark.parametrize("name,route,multimem", [("TransE", "dense", False), ("ComplEx", "dense", False),
+                                                 ("TransE", "sparse", False), ("RotatE", "sparse", False),
+                                                 ("TransE", "dense", True), ("ComplEx", "dense", True)])
+def test_two_rank_row_sparse_step_matches_single_gpu(name, route, multimem, tmp_path):
+    """multimem = the dense route reduced in the NVSwitch by kge_multimem_all_reduce_f32 instead of NCCL."""
     if torch.cuda.device_count() < 2:
         pytest.skip("needs 2 GPUs")
     import torch.multiprocessing as mp
 
     SHAPE = SHAPES[route]
-    mp.spawn(_worker, args=(2, _free_port(), name, route, str(tmp_path)), nprocs=2, join=True)
+    mp.spawn(_worker, args=(2, _free_port(), name, route, str(tmp_path), multimem), nprocs=2, join=True)
     r0, r1 = np.load(tmp_path / "rank0.npz"), np.load(tmp_path / "rank1.npz")
     keys = [k_ for k_ in r0.files if k_ != "losses"]
     for key in keys:   # same values added in the same order on every rank
