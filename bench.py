@@ -338,11 +338,11 @@ def main():
         from hopwise_b200.distributed import broadcast_weights, enable_row_sparse_data_parallel
 
         broadcast_weights(model)
-        # dense route: this library's in-switch (NVLS multimem) all-reduce from 4 GPUs on -- measured at 8 B200:
-        # 0.527 ms/step vs 0.564 with NCCL; at 2 GPUs NCCL's single exchange is faster (0.462 vs 0.483 ms).
-        # KGE_MULTIMEM=0 / 1 forces the choice.
+        # dense route: this library's in-switch (NVLS multimem) all-reduce on more than 4 GPUs -- measured, ms/step
+        # in-switch vs NCCL: 8 B200 0.527 vs 0.564, 4 B200 0.487 vs 0.479, 2 B200 0.483 vs 0.462 (the two barriers
+        # around the kernel cost more than NCCL's exchange until the ring gets long).  KGE_MULTIMEM=0 / 1 forces it.
         mm = os.environ.get("KGE_MULTIMEM")
-        exchange = enable_row_sparse_data_parallel(model, multimem=(world >= 4) if mm is None else mm != "0")
+        exchange = enable_row_sparse_data_parallel(model, multimem=(world > 4) if mm is None else mm != "0")
 
     n_batches = 4
     host = synth_batches(w, n_batches, seed=2024 + rank)
