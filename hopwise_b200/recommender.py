@@ -115,7 +115,7 @@ class _FusedStep(torch.autograd.Function):
     @staticmethod
     def forward(ctx, anchor, model, batch):
         ctx.model = model
-        return model._launch_forward(batch, with_grad=True)
+        return model._launch_forward(batch, with_grad=True, device=anchor.device)
 
     @staticmethod
     def backward(ctx, grad_out):
@@ -315,6 +315,8 @@ class FusedKGEModel(KnowledgeRecommender):
             x = torch.as_tensor(x)
         if x.device != device:
             raise RuntimeError(f"batch ids are on {x.device}, the model is on {device} (call interaction.to(device))")
+        if x.dtype is torch.int64 and x.is_contiguous():   # what hopwise's Interaction holds: nothing to convert
+            return x
         return x.to(torch.int64).contiguous()
 
     def _batch_struct(self, interaction, device):
@@ -352,8 +354,9 @@ class FusedKGEModel(KnowledgeRecommender):
             keep += [head, rel, tail, neg_tail]
         return b, keep
 
-    def _launch_forward(self, interaction, with_grad: bool):
-        device = self._check_ready()
+    def _launch_forward(self, interaction, with_grad: bool, device=None):
+        if device is None:
+            device = self._check_ready()
         lib = _abi.lib()
         stream = _abi.stream_ptr()
         lazy = self._state is not None
@@ -407,7 +410,7 @@ class FusedKGEModel(KnowledgeRecommender):
         """transe.py:75-98 / distmult.py:68-95 / rotate.py:98-131 / complex.py:95-128."""
         device = self._check_ready()
         if not torch.is_grad_enabled():
-            return self._launch_forward(interaction, with_grad=False)
+            return self._launch_forward(interaction, with_grad=False, device=device)
         if self._anchor is None or self._anchor.device != device:
             self._anchor = torch.zeros(1, device=device, requires_grad=True)
         return _FusedStep.apply(self._anchor, self, interaction)
