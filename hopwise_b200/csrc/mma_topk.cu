@@ -165,16 +165,8 @@ __device__ __forceinline__ bool elect_one() {
   return pred != 0;
 }
 
-// No-swizzle K-major shared-memory matrix descriptor (bits: start>>4 [0,14), LBO>>4 [16,30),
-// SBO>>4 [32,46), version=1 [46,48), layout type 0 = SWIZZLE_NONE [61,64)).
-__device__ __forceinline__ uint64_t make_smem_desc(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
-  uint64_t d = 0;
-  d |= (uint64_t)((saddr >> 4) & 0x3FFFu);
-  d |= (uint64_t)((lbo_bytes >> 4) & 0x3FFFu) << 16;
-  d |= (uint64_t)((sbo_bytes >> 4) & 0x3FFFu) << 32;
-  d |= (uint64_t)1 << 46;
-  return d;
-}
+// Shared-memory matrix descriptors (no-swizzle, K-major) are assembled in the MMA issuer: bits start>>4 [0,14),
+// LBO>>4 [16,30), SBO>>4 [32,46), version = 1 [46,48), layout type 0 = SWIZZLE_NONE [61,64).
 // kind::f16 instruction descriptor: D fp32, A/B bf16, both K-major, N = tn, M = 128.
 __host__ __device__ constexpr uint32_t make_idesc(int tn) {
   return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(tn >> 3) << 17) | ((128u >> 4) << 24);
@@ -1111,14 +1103,14 @@ int plan_mma(const kge_model_t* m, int64_t n, int64_t n_targets, int k, MmaPlan&
 }  // namespace
 
 extern "C" int64_t kge_mma_image_bytes(const kge_model_t* model, int64_t n_targets) {
-  MmaPlan pl;
+  MmaPlan pl = {};
   if (!model || plan_mma(model, 1, n_targets, 1, pl)) return -1;
   return IMG_HEADER + pl.n_tiles * pl.tn * (int64_t)pl.kp * 2 + ((n_targets * 4 + 127) / 128) * 128;
 }
 
 extern "C" int kge_mma_prepare_targets(const kge_model_t* model, int64_t n_targets, void* image, int64_t image_bytes,
                                        kge_stream_t stream) {
-  MmaPlan pl;
+  MmaPlan pl = {};
   if (int e = plan_mma(model, 1, n_targets, 1, pl)) return e;
   KGE_REQUIRE(n_targets <= model->entity.rows, KGE_E_ARG, "n_targets beyond the entity table");
   const int64_t need = kge_mma_image_bytes(model, n_targets);
@@ -1146,7 +1138,7 @@ extern "C" int kge_mma_prepare_targets(const kge_model_t* model, int64_t n_targe
 
 extern "C" int64_t kge_full_sort_topk_mma_workspace_bytes(const kge_model_t* model, int64_t n, int64_t n_targets,
                                                           int32_t k) {
-  MmaPlan pl;
+  MmaPlan pl = {};
   if (!model || n < 0 || plan_mma(model, n, n_targets, k, pl)) return -1;
   return (int64_t)pl.splits * pl.ncol * pl.rows_pad * (CAND * 8 + 4 + 4) + pl.rows_pad * 4 + pl.rows_pad * pl.unsafe_wpr * 4;
 }
@@ -1156,7 +1148,7 @@ extern "C" int kge_full_sort_topk_mma(const kge_model_t* model, const int64_t* h
                                       const int64_t* hist_items, int mask_first, int32_t k, int64_t* ids_out,
                                       float* scores_out, int32_t* row_flags, void* workspace, int64_t workspace_bytes,
                                       float* debug_scores, kge_stream_t stream) {
-  MmaPlan pl;
+  MmaPlan pl = {};
   if (int e = plan_mma(model, n, n_targets, k, pl)) return e;
   KGE_REQUIRE(n >= 0 && n_targets <= model->entity.rows && k <= n_targets, KGE_E_ARG, "bad n / n_targets / k");
   if (n == 0) return 0;

@@ -492,7 +492,7 @@ extern "C" int kge_predict(const kge_model_t* model, const int64_t* heads, const
   KGE_REQUIRE(n >= 0, KGE_E_ARG, "negative n");
   if (n == 0) return 0;
   KGE_REQUIRE(heads && tails && out, KGE_E_ARG, "NULL heads / tails / out");
-  RowCfg c;
+  RowCfg c = {};
   KGE_REQUIRE(kge_pick_rowcfg(model->d, c), KGE_E_UNSUPPORTED, "embedding_size %d unsupported", model->d);
   ScoreArgs a;
   a.m = *model;
@@ -537,7 +537,7 @@ extern "C" int kge_full_sort_scores(const kge_model_t* model, const int64_t* hea
   KGE_REQUIRE(n >= 0 && n_targets >= 1 && n_targets <= model->entity.rows, KGE_E_ARG, "bad n / n_targets");
   if (n == 0) return 0;
   KGE_REQUIRE(heads && out, KGE_E_ARG, "NULL heads / out");
-  TilePlan pl;
+  TilePlan pl = {};
   if (int e = plan_tiles(model, n, n_targets, 0, false, pl)) return e;
   TileArgs a = {};
   a.s.m = *model;
@@ -559,7 +559,7 @@ extern "C" int kge_full_sort_scores(const kge_model_t* model, const int64_t* hea
 extern "C" int64_t kge_full_sort_topk_workspace_bytes(const kge_model_t* model, int64_t n, int64_t n_targets,
                                                       int32_t k) {
   if (!model || n < 0 || n_targets < 1 || k < 1 || k > KMAX) return -1;
-  TilePlan pl;
+  TilePlan pl = {};
   if (plan_tiles(model, n > 0 ? n : 1, n_targets, k, true, pl)) return -1;
   return (int64_t)n * pl.n_splits * k * 8;
 }
@@ -576,7 +576,7 @@ extern "C" int kge_full_sort_topk(const kge_model_t* model, const int64_t* heads
   if (n == 0) return 0;
   KGE_REQUIRE(heads && ids_out, KGE_E_ARG, "NULL heads / ids_out");
   KGE_REQUIRE((hist_off == nullptr) == (hist_items == nullptr) || hist_off, KGE_E_ARG, "hist_items without hist_off");
-  TilePlan pl;
+  TilePlan pl = {};
   if (int e = plan_tiles(model, n, n_targets, k, true, pl)) return e;
   const int64_t need = n * pl.n_splits * k * 8;
   KGE_REQUIRE(workspace && workspace_bytes >= need, KGE_E_ARG, "workspace too small: need %lld bytes", (long long)need);

@@ -729,7 +729,7 @@ int check_model(const kge_model_t* m, bool need_state) {
               "table parts do not match the model kind");
   for (int p = 0; p < ph; ++p) KGE_REQUIRE(m->user.w[p] && m->entity.w[p], KGE_E_ARG, "NULL weight table");
   for (int p = 0; p < pr; ++p) KGE_REQUIRE(m->relation.w[p], KGE_E_ARG, "NULL relation table");
-  RowCfg c;
+  RowCfg c = {};
   KGE_REQUIRE(kge_pick_rowcfg(m->d, c), KGE_E_UNSUPPORTED,
               "embedding_size %d unsupported (max 512, or 256 when not a multiple of 4)", m->d);
   if (need_state) {
@@ -790,7 +790,7 @@ extern "C" int kge_train_forward(const kge_model_t* model, const kge_batch_t* b,
     a.wpos_rec = pr > 0 ? (float)(0.5 / (double)b->n_rec) : 0.f;
     a.wpos_kg = pk > 0 ? (float)(0.5 / (double)b->n_kg) : 0.f;
   }
-  RowCfg c;
+  RowCfg c = {};
   kge_pick_rowcfg(model->d, c);
   const int threads = 256;
   const int grid = grid_for(n_total, threads / c.g, 8);
@@ -818,7 +818,7 @@ extern "C" int kge_adam_apply(const kge_model_t* model, const kge_adam_t* adam, 
   a.adam = make_adam_dev(model, adam);
   a.scale = grad_scale;
   a.scale_dev = grad_scale_dev;
-  RowCfg c;
+  RowCfg c = {};
   kge_pick_rowcfg(model->d, c);
   const int threads = 256;
   const int64_t max_rows = model->entity.rows > model->user.rows ? model->entity.rows : model->user.rows;
@@ -839,7 +839,7 @@ extern "C" int kge_adam_flush(const kge_model_t* model, const kge_adam_t* adam, 
   KGE_REQUIRE(adam && adam->step >= 0, KGE_E_ARG, "bad adam");
   if (adam->step == 0) return 0;
   AdamDev A = make_adam_dev(model, adam);
-  RowCfg c;
+  RowCfg c = {};
   kge_pick_rowcfg(model->d, c);
   const int threads = 256;
   cudaStream_t st = (cudaStream_t)stream;
@@ -859,7 +859,7 @@ static int grad_take(const kge_model_t* model, int which, int step, int64_t* ids
                      int32_t* count_out, cudaStream_t st) {
   const kge_table_t* tabs[3] = {&model->user, &model->entity, &model->relation};
   const kge_table_t& T = *tabs[which];
-  RowCfg c;
+  RowCfg c = {};
   kge_pick_rowcfg(model->d, c);
   const int threads = 256;
   const int grid = scan_grid(T.rows, 32, 4);
@@ -892,7 +892,7 @@ extern "C" int kge_grad_add(const kge_model_t* model, int32_t which, int32_t ste
   KGE_REQUIRE(which >= 0 && which < 3 && ids && rows && count_dev && max_count >= 0, KGE_E_ARG, "bad add arguments");
   if (max_count == 0) return 0;
   const kge_table_t* tabs[3] = {&model->user, &model->entity, &model->relation};
-  RowCfg c;
+  RowCfg c = {};
   kge_pick_rowcfg(model->d, c);
   const int threads = 256;
   const int grid = grid_for(max_count, threads / c.g, 4);
