@@ -219,12 +219,15 @@ def time_train_e2e(model, host_batches, steps, warmup, world, device):
     loader.batches = [host_batches[(warmup + i) % nb] for i in range(steps)]
     barrier(world)
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    stamps = [time.perf_counter()]
     e0.record(stream)
     for db in loader:
         one(db)
+        stamps.append(time.perf_counter())   # (each step ends with a host sync: loss.item())
     e1.record(stream)
     barrier(world)
-    return e0.elapsed_time(e1)
+    per_step = np.diff(np.array(stamps)) * 1e3
+    return e0.elapsed_time(e1), float(np.median(per_step)), float(per_step.max())
 
 
 def time_fullsort(fs, device, n_users_step, steps, warmup, world, rank, path="auto"):
@@ -359,7 +362,7 @@ def main():
     upd_ms_avg = max_over_ranks(upd_ms / args.steps, device, world)
     value = world * triples_step / (step_ms * 1e-3)
 
-    e2e_ms = time_train_e2e(model, host_t, args.steps, args.warmup, world, device)
+    e2e_ms, e2e_median_ms, e2e_max_ms = time_train_e2e(model, host_t, args.steps, args.warmup, world, device)
     e2e_ms = max_over_ranks(e2e_ms / args.steps, device, world)
     e2e_value = world * triples_step / (e2e_ms * 1e-3)
 
@@ -377,7 +380,7 @@ def main():
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": step_ms, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": config,
             "e2e": {"value": e2e_value, "unit": "triples/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4,
-                    "ms_per_step": e2e_ms},
+                    "ms_per_step": e2e_ms, "median_ms_per_step": e2e_median_ms, "max_ms_per_step": e2e_max_ms},
             # this library's kernels in the timed region: forward + Adam per step, plus the pack / add kernels of
             # the row-sparse exchange when a table takes that route (NCCL's own kernels are not counted)
             "gpu_launches": args.steps * (2 + (exchange.kernels_per_step if exchange is not None else 0)),

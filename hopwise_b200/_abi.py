@@ -102,6 +102,7 @@ PROTOTYPES = {
         C.c_int,
         [_MP, _P, _P, C.c_int64, C.c_int, C.c_int64, _P, _P, C.c_int, C.c_int32, _P, _P, _P, C.c_int64, _P],
     ),
+    "kge_copy_h2d_async": (C.c_int, [_P, _P, C.c_int64, _P]),
     "kge_multimem_all_reduce_f32": (C.c_int, [_P, C.c_int64, C.c_int32, C.c_int32, _P]),
     "kge_mma_image_bytes": (C.c_int64, [_MP, C.c_int64]),
     "kge_mma_prepare_targets": (C.c_int, [_MP, C.c_int64, _P, C.c_int64, _P]),

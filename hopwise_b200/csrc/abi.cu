@@ -29,3 +29,10 @@ int kge_num_sms() {
 
 extern "C" int kge_abi_version(void) { return KGE_ABI_VERSION; }
 extern "C" const char* kge_last_error(void) { return g_last_error; }
+
+extern "C" int kge_copy_h2d_async(void* dst_device, const void* src_host, int64_t nbytes, kge_stream_t stream) {
+  KGE_REQUIRE(nbytes >= 0 && (nbytes == 0 || (dst_device && src_host)), KGE_E_ARG, "bad copy arguments");
+  if (nbytes == 0) return 0;
+  KGE_CUDA(cudaMemcpyAsync(dst_device, src_host, (size_t)nbytes, cudaMemcpyHostToDevice, (cudaStream_t)stream));
+  return 0;
+}

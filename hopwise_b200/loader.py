@@ -97,22 +97,37 @@ class DevicePrefetcher:
         return len(self.batches)
 
     def _stage(self, slot: dict, batch):
+        """Issue the copies of one batch on the copy stream (which must be current for foreign batch types)."""
         host = _host_tensors(batch)
         if host is None:   # foreign batch type: its own .to(), allocator-managed lifetime
-            db = batch.to(self.device)
+            with torch.cuda.stream(self._stream):
+                db = batch.to(self.device)
             inner = getattr(db, "interaction", None)
             for t in (inner.values() if isinstance(inner, dict) else []):
                 if torch.is_tensor(t):
                     t.record_stream(torch.cuda.current_stream(self.device))
             return db
+        from . import _abi
+
+        lib, sptr = _abi.lib(), self._stream.cuda_stream
+        # the raw copies below are invisible to torch's pinned-memory allocator: the slot keeps the host tensors
+        # alive until it is staged again, which only happens after the consumer is done with this batch
+        slot["__host__"] = host
         out = {}
         for k, v in host.items():
-            buf = slot.get(k)
+            buf = slot.get("dev:" + k)
             if buf is None or buf.dtype != v.dtype or buf.numel() < v.numel():
-                buf = torch.empty(v.numel(), dtype=v.dtype, device=self.device)
-                slot[k] = buf
+                with torch.cuda.stream(self._stream):   # the slot's memory belongs to the copy stream's pool
+                    buf = torch.empty(v.numel(), dtype=v.dtype, device=self.device)
+                slot["dev:" + k] = buf
             dst = buf[: v.numel()].view(v.shape)
-            dst.copy_(v, non_blocking=True)
+            if v.is_contiguous() and not v.is_cuda:
+                # one cudaMemcpyAsync on the copy stream (no stream switch on the host: ~20 us less per step)
+                _abi.check(lib.kge_copy_h2d_async(dst.data_ptr(), v.data_ptr(), v.numel() * v.element_size(), sptr),
+                           "kge_copy_h2d_async")
+            else:
+                with torch.cuda.stream(self._stream):
+                    dst.copy_(v, non_blocking=True)
             out[k] = dst
         if isinstance(batch, PackedBatch):
             return batch.views(out["__base__"])
@@ -122,7 +137,12 @@ class DevicePrefetcher:
         it = iter(self.batches)
         queue = deque()
         n_slots = len(self._slots)
-        released = [None] * n_slots   # consumer-side event after which a slot may be overwritten
+        # per slot: the copy's completion event and the consumer-side event after which the slot may be
+        # overwritten (created once, re-recorded every use)
+        if not hasattr(self, "_copied"):
+            self._copied = [torch.cuda.Event() for _ in range(n_slots)]
+            self._released = [torch.cuda.Event() for _ in range(n_slots)]
+        used = [False] * n_slots
         nxt = 0
 
         def issue():
@@ -132,24 +152,22 @@ class DevicePrefetcher:
                 return
             idx = nxt % n_slots
             nxt += 1
-            with torch.cuda.stream(self._stream):
-                if released[idx] is not None:
-                    self._stream.wait_event(released[idx])
-                db = self._stage(self._slots[idx], b)
-                ev = torch.cuda.Event()
-                ev.record(self._stream)
-            queue.append((db, ev, idx))
+            if used[idx]:
+                self._stream.wait_event(self._released[idx])
+            db = self._stage(self._slots[idx], b)
+            self._copied[idx].record(self._stream)
+            queue.append((db, idx))
 
         for _ in range(self.depth):
             issue()
         prev = None
         while queue:
-            db, ev, idx = queue.popleft()
+            db, idx = queue.popleft()
             cur = torch.cuda.current_stream(self.device)
             if prev is not None:   # everything the consumer enqueued for the previous batch is behind this event
-                released[prev] = torch.cuda.Event()
-                released[prev].record(cur)
-            cur.wait_event(ev)
+                self._released[prev].record(cur)
+                used[prev] = True
+            cur.wait_event(self._copied[idx])
             issue()
             prev = idx
             yield db

@@ -137,6 +137,10 @@ int kge_grad_pack(const kge_model_t* model, int32_t which, int32_t step, int64_t
 int kge_grad_add(const kge_model_t* model, int32_t which, int32_t step, const int64_t* ids, const float* rows,
                  const int32_t* count_dev, int64_t max_count, kge_stream_t stream);
 
+/* Host -> device staging of a batch's id vectors (replaces the blocking interaction.to(device) of
+ * trainer/trainer.py:250-256): cudaMemcpyAsync from (pinned) host memory on the given copy stream. */
+int kge_copy_h2d_async(void* dst_device, const void* src_host, int64_t nbytes, kge_stream_t stream);
+
 /* Dense route of the same exchange, in the NVSwitch: sum the N ranks' copies of a symmetric buffer in place.
  * multicast_ptr = the NVLS multicast address of the buffer (16-byte aligned; n_floats % 4 == 0), i.e. one
  * address that names every rank's copy.  Rank `rank` reduces the rank-th slice with multimem.ld_reduce and
