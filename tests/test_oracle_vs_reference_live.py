@@ -103,3 +103,53 @@ def test_kg_sampler_stream_matches_the_reference(case):
     # and the generator the reference leaves behind continues like the oracle's (numpy refills its block
     # lazily, so the next draws are compared rather than the raw state words)
     np.testing.assert_array_equal(gen.randint(0, 1 << 30, 700), np.random.randint(0, 1 << 30, 700))
+
+
+@pytest.mark.parametrize("case", range(4))
+def test_collector_and_metrics_match_the_reference(case):
+    """Masking + top-k + hit matrix + Recall/MRR/NDCG/Hit/Precision of oracle/fullsort.py against the reference's
+    Collector / Evaluator / metric classes on random scores (continuous scores: no ties to disagree on)."""
+    import_reference()
+    from hopwise.evaluator import Collector, Evaluator
+    from hopwise.evaluator.register import metrics_dict
+
+    from oracle import fullsort as fs
+
+    rng = np.random.default_rng(900 + case)
+    n, I = int(rng.integers(3, 40)), int(rng.integers(30, 200))
+    k = int(rng.integers(2, 21))
+    scores = rng.standard_normal((n, I)).astype(np.float32)
+    hist_u, hist_i, pos_u, pos_i = [], [], [], []
+    for u in range(n):
+        perm = rng.permutation(np.arange(1, I))
+        nh, npos = int(rng.integers(0, I // 3)), int(rng.integers(1, 6))
+        hist_u += [u] * nh
+        hist_i += list(perm[:nh])
+        pos_u += [u] * npos
+        pos_i += list(perm[nh:nh + npos])
+    cfg = {"eval_args": {"mode": "full"}, "topk": [max(1, k // 2), k], "device": torch.device("cpu"),
+           "metrics": ["Recall", "MRR", "NDCG", "Hit", "Precision"], "metric_decimal_place": 4, "tsne": None}
+    coll = Collector(cfg)
+    s = torch.from_numpy(scores.copy())
+    s[:, 0] = -np.inf
+    if hist_u:
+        s[(torch.as_tensor(hist_u), torch.as_tensor(hist_i))] = -np.inf
+    coll.eval_batch_collect(s, None, torch.as_tensor(pos_u), torch.as_tensor(pos_i))
+    struct = coll.get_data_struct()
+    want_rec = struct.get("rec.topk").numpy()
+    want = Evaluator(cfg).evaluate(struct)
+
+    masked = fs.mask_scores(scores, np.array(hist_u, dtype=np.int64), np.array(hist_i, dtype=np.int64))
+    ids, _ = fs.topk_canonical(masked, k)
+    np.testing.assert_array_equal(ids, torch.topk(s, k, dim=-1)[1].numpy())
+    rec = fs.hits(ids, np.array(pos_u), np.array(pos_i), I)
+    np.testing.assert_array_equal(rec, want_rec)
+    got = fs.metric_values(rec, topk=tuple(cfg["topk"]), decimals=4)
+    for name, v in want.items():
+        assert got[name] == v, name
+    mats = fs.metric_matrices(rec[:, :k], rec[:, k])
+    for name in ("recall", "mrr", "ndcg", "hit", "precision"):
+        m = metrics_dict[name](cfg)
+        ref = m.metric_info(rec[:, :k].astype(bool), rec[:, k]) if name in ("recall", "ndcg") else m.metric_info(
+            rec[:, :k].astype(bool))
+        np.testing.assert_array_equal(mats[name], np.asarray(ref, dtype=np.float64), err_msg=name)
