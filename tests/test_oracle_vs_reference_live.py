@@ -153,3 +153,46 @@ def test_collector_and_metrics_match_the_reference(case):
         ref = m.metric_info(rec[:, :k].astype(bool), rec[:, k]) if name in ("recall", "ndcg") else m.metric_info(
             rec[:, :k].astype(bool))
         np.testing.assert_array_equal(mats[name], np.asarray(ref, dtype=np.float64), err_msg=name)
+
+
+class _RecDataset:
+    """What hopwise's rec-side Sampler reads from a dataset (sampler.py:199-252)."""
+
+    def __init__(self, users, items, n_users, n_items):
+        self.uid_field, self.iid_field = "user_id", "item_id"
+        self.user_num, self.item_num = n_users, n_items
+        self.inter_feat = {"user_id": torch.as_tensor(users), "item_id": torch.as_tensor(items)}
+
+
+@pytest.mark.parametrize("case", range(4))
+def test_rec_and_kg_samplers_share_one_stream_like_the_reference(case):
+    """One training step draws KG negatives first, then rec negatives, from numpy's one global generator
+    (knowledge_dataloader.py:137-145); the oracle reproduces both with one MT19937 stream."""
+    import_reference()
+    from hopwise.sampler import KGSampler, Sampler
+
+    rng = np.random.default_rng(700 + case)
+    U, I = int(rng.integers(5, 60)), int(rng.integers(6, 80))
+    E = I + int(rng.integers(1, 100))
+    heads, tails = rng.integers(1, E, 600), rng.integers(1, E, 600)
+    ru, ri = rng.integers(1, U, 400), rng.integers(1, I, 400)
+    # no user may own every item (the reference raises then)
+    keep = np.ones(len(ru), dtype=bool)
+    for u in range(1, U):
+        if len(set(ri[ru == u])) >= I - 2:
+            keep &= ru != u
+    ru, ri = ru[keep], ri[keep]
+    kg = KGSampler(FakeDataset(U, I, E, 6, heads=heads, tails=tails))
+    rec = Sampler("train", _RecDataset(ru, ri, U, I)).set_phase("train")
+    kg_off, kg_vals = omt.build_used_csr(heads, tails, E)
+    rec_off, rec_vals = omt.build_used_csr(ru, ri, U)
+    seed = 31 + case
+    np.random.seed(seed)
+    gen = omt.MT19937(seed)
+    for num in (1, 2, 1):
+        qh = heads[rng.integers(0, len(heads), int(rng.integers(1, 120)))]
+        qu = ru[rng.integers(0, len(ru), int(rng.integers(1, 120)))]
+        np.testing.assert_array_equal(omt.sample_by_key_ids(gen, qh, num, kg_off, kg_vals, 1, E),
+                                      kg.sample_by_entity_ids(qh, num).numpy())
+        np.testing.assert_array_equal(omt.sample_by_key_ids(gen, qu, num, rec_off, rec_vals, 1, I),
+                                      rec.sample_by_user_ids(qu, None, num).numpy())
