@@ -258,7 +258,7 @@ def time_fullsort(fs, device, n_users_step, steps, warmup, world, rank, path="au
     barrier(world)
     ms = ev[0].elapsed_time(ev[-1])
     per_rep = sorted(ev[i].elapsed_time(ev[i + 1]) for i in range(steps))
-    fallback = m._mma_last_fallback_rows
+    fallback = m._mma_total_fallback_rows   # over warm-up and timed blocks
     del m
     return ms, fallback, per_rep[len(per_rep) // 2]
 

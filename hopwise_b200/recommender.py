@@ -201,6 +201,7 @@ class FusedKGEModel(KnowledgeRecommender):
         self._touch_bounds = (0, 0, 0)
         self._mma_cache = None
         self._mma_last_fallback_rows = 0
+        self._mma_total_fallback_rows = 0   # over the model's lifetime (diagnostics)
         self._ready_key = None
         self._struct_cache = {}
 
@@ -655,6 +656,7 @@ class FusedKGEModel(KnowledgeRecommender):
         )
         bad = torch.nonzero(flags, as_tuple=False).flatten()  # rows the filter could not bound (host sync)
         self._mma_last_fallback_rows = int(bad.numel())
+        self._mma_total_fallback_rows += self._mma_last_fallback_rows
         if bad.numel():
             sub_off = sub_items = None
             if hist_off is not None:
