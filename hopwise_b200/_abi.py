@@ -13,7 +13,7 @@ import os
 
 from . import _build
 
-KGE_ABI_VERSION = 1
+KGE_ABI_VERSION = 2
 MODEL_KINDS = {"TransE": 0, "DistMult": 1, "RotatE": 2, "ComplEx": 3}
 
 
@@ -104,12 +104,13 @@ PROTOTYPES = {
     ),
     "kge_copy_h2d_async": (C.c_int, [_P, _P, C.c_int64, _P]),
     "kge_multimem_all_reduce_f32": (C.c_int, [_P, C.c_int64, C.c_int32, C.c_int32, _P]),
-    "kge_mma_image_bytes": (C.c_int64, [_MP, C.c_int64]),
-    "kge_mma_prepare_targets": (C.c_int, [_MP, C.c_int64, _P, C.c_int64, _P]),
-    "kge_full_sort_topk_mma_workspace_bytes": (C.c_int64, [_MP, C.c_int64, C.c_int64, C.c_int32]),
+    "kge_mma_image_bytes": (C.c_int64, [_MP, C.c_int64, C.c_int32]),
+    "kge_mma_prepare_targets": (C.c_int, [_MP, C.c_int64, _P, C.c_int64, C.c_int32, _P]),
+    "kge_full_sort_topk_mma_workspace_bytes": (C.c_int64, [_MP, C.c_int64, C.c_int64, C.c_int32, C.c_int32]),
     "kge_full_sort_topk_mma": (
         C.c_int,
-        [_MP, _P, _P, C.c_int64, C.c_int, C.c_int64, _P, _P, _P, C.c_int, C.c_int32, _P, _P, _P, _P, C.c_int64, _P, _P],
+        [_MP, _P, _P, C.c_int64, C.c_int, C.c_int64, _P, _P, _P, C.c_int, C.c_int32, _P, _P, _P, _P, _P, C.c_int64, _P,
+         C.c_int32, _P],
     ),
     "kge_topk_hits": (C.c_int, [_P, C.c_int64, C.c_int32, _P, _P, _P, _P]),
     "kge_topk_metric_sums": (C.c_int, [_P, C.c_int64, C.c_int32, _P, _P]),
@@ -129,9 +130,13 @@ def lib():
     global _lib
     if _lib is not None:
         return _lib
-    path = os.environ.get("KGE_B200_LIB") or _build.LIB_PATH   # KGE_B200_LIB: an experimental build (scripts/build_variant.sh)
-    if not os.path.exists(path):
-        path = _build.build()  # raises when nvcc is missing: no fallback
+    path = os.environ.get("KGE_B200_LIB")   # an experimental build (scripts/build_variant.sh)
+    if not path:
+        path = _build.LIB_PATH
+        if not os.path.exists(path):
+            path = _build.build()  # raises when nvcc is missing: no fallback
+        elif _build.needs_build() and _build.have_nvcc():
+            path = _build.build()  # a source is newer than the library: never test or time stale kernels
     handle = C.CDLL(path)
     for name, (res, args) in PROTOTYPES.items():
         fn = getattr(handle, name)  # AttributeError = ABI mismatch, deliberately loud

@@ -38,6 +38,14 @@ def _nvcc() -> str:
     raise RuntimeError("nvcc not found: cannot build libkge_b200.so")
 
 
+def have_nvcc() -> bool:
+    try:
+        _nvcc()
+        return True
+    except RuntimeError:
+        return False
+
+
 def sources():
     return sorted(os.path.join(CSRC, f) for f in os.listdir(CSRC) if f.endswith(".cu"))
 

@@ -8,8 +8,14 @@
 // does not change the order; -||t||^2/2 rides in three extra K columns as a bf16 hi/mid/lo split).
 //
 // The tensor cores only FILTER; the answer is exact:
-//   1. bf16 GEMM  a^_ij ~ q_i . t_j  with fp32 accumulation in TMEM.  |a^ - a| <= eps_i =
-//      1.02 * 2^-8 * ||q_i|| * max_j ||t_j||   (two bf16 roundings per product, Cauchy-Schwarz).
+//   1. fp16 GEMM  a^_ij ~ S_i (q_i . t_j)  with fp32 accumulation in TMEM.  Operands are scaled by powers of two
+//      (exact): the target image by 2^e_t so that max |t_c| lands in [2^7, 2^8), every query row by its own 2^e_i
+//      the same way, S_i = 2^(e_i + e_t).  fp16 keeps 11 significant bits: fl(x) = x (1 + d), |d| <= 2^-11 (or an
+//      absolute error below 2^-14 in the subnormal range, flushed or not), so with Cauchy-Schwarz
+//        |a^ - S a| <= eps_i = (2^-10 + 2^-20) |q^| |t^|max + 2^-14 sqrt(K) (|q^| + |t^|max) + K 2^-22 (...)
+//      (two roundings per product, the subnormal floor, fp32 accumulation; see row_eps()).  Round 1 used bf16
+//      with 1.02 * 2^-8: too small by 2x (two roundings of 2^-8 each) -- fp16 is 8x tighter than the valid bf16
+//      bound at the same tensor-core rate.
 //   2. sweep epilogue, one thread per query row: maxima of groups of 8 adjacent targets are compared
 //      with a running threshold thr_i = tau_i - 2 eps_i, where tau_i is the k-th largest group
 //      maximum among groups without masked targets seen so far (a lower bound of the k-th largest
@@ -35,9 +41,8 @@
 // (row blocks) x (target splits) fills the GPU when few users are evaluated; every (row, split)
 // owns a list.  Operands use the no-swizzle K-major canonical layout [K/8][rows][8 bf16]:
 // 8x16-byte core matrices, SBO = 128 B, LBO = rows * 16 B.
-#include <cuda_bf16.h>
+#include <cuda_fp16.h>
 #include <math.h>
-#include <stdlib.h>
 
 #include "common.cuh"
 #include "score_common.cuh"
@@ -55,8 +60,16 @@ constexpr int MAX_SPLITS = 4;
 // warp / 8 = column slice of the tile), then the producer warp, then one MMA issuer warp per row half (the issue
 // arbiter favours high warp ids, and an MMA issuer must never starve; one warp cannot issue fast enough for both
 // halves: a free-running issuer needs ~125 cycles per tcgen05.mma).
-__host__ __device__ constexpr int sweep_threads(int ncol, int nmma) { return (8 * ncol + 1 + nmma) * 32; }
-constexpr int IMG_HEADER = 128;  // bytes before the first tile image: {float tmax}
+// The tile producer (one cp.async.bulk per tile) has a warp of its own; KGE_MMA_MERGED_PRODUCER lets the first MMA warp
+// do it instead (experiment: one spinning warp less per CTA; the register cap stays at 96 either way, because two
+// CTAs of nine or ten warps both put five warps on an SM sub-partition of 16384 registers).
+#ifdef KGE_MMA_MERGED_PRODUCER
+constexpr int PRODUCER_WARPS = 0;
+#else
+constexpr int PRODUCER_WARPS = 1;
+#endif
+__host__ __device__ constexpr int sweep_threads(int ncol, int nmma) { return (8 * ncol + PRODUCER_WARPS + nmma) * 32; }
+constexpr int IMG_HEADER = 128;  // bytes before the first tile image: {max |t|, max |t_c|, max |t|^2} (floats)
 constexpr uint32_t SPIN_LIMIT = 1u << 26;
 
 // ---- PTX wrappers -------------------------------------------------------------------------------
@@ -148,6 +161,17 @@ __device__ __forceinline__ void tmem_ld_wait(uint32_t (&r)[32]) {
                :
                : "memory");
 }
+// The same wait for two register sets in flight (tcgen05.wait::ld covers every load the thread has issued).
+__device__ __forceinline__ void tmem_ld_wait2(uint32_t (&r)[32], uint32_t (&q)[32]) {
+  tmem_ld_wait(r);
+  asm volatile(""
+               : "+r"(q[0]), "+r"(q[1]), "+r"(q[2]), "+r"(q[3]), "+r"(q[4]), "+r"(q[5]), "+r"(q[6]), "+r"(q[7]),
+                 "+r"(q[8]), "+r"(q[9]), "+r"(q[10]), "+r"(q[11]), "+r"(q[12]), "+r"(q[13]), "+r"(q[14]), "+r"(q[15]),
+                 "+r"(q[16]), "+r"(q[17]), "+r"(q[18]), "+r"(q[19]), "+r"(q[20]), "+r"(q[21]), "+r"(q[22]), "+r"(q[23]),
+                 "+r"(q[24]), "+r"(q[25]), "+r"(q[26]), "+r"(q[27]), "+r"(q[28]), "+r"(q[29]), "+r"(q[30]), "+r"(q[31])
+               :
+               : "memory");
+}
 __device__ __forceinline__ float max3f(float a, float b, float c) {
   float r;
   asm("max.f32 %0, %1, %2, %3;" : "=f"(r) : "f"(a), "f"(b), "f"(c));
@@ -167,13 +191,54 @@ __device__ __forceinline__ bool elect_one() {
 
 // Shared-memory matrix descriptors (no-swizzle, K-major) are assembled in the MMA issuer: bits start>>4 [0,14),
 // LBO>>4 [16,30), SBO>>4 [32,46), version = 1 [46,48), layout type 0 = SWIZZLE_NONE [61,64).
-// kind::f16 instruction descriptor: D fp32, A/B bf16, both K-major, N = tn, M = 128.
+// kind::f16 instruction descriptor: D fp32 (bit 4), A/B fp16 (format 0), both K-major, N = tn, M = 128.
 __host__ __device__ constexpr uint32_t make_idesc(int tn) {
-  return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(tn >> 3) << 17) | ((128u >> 4) << 24);
+  return (1u << 4) | ((uint32_t)(tn >> 3) << 17) | ((128u >> 4) << 24);
 }
 
-__device__ __forceinline__ uint16_t bf16_bits(float x) { return __bfloat16_as_ushort(__float2bfloat16_rn(x)); }
-__device__ __forceinline__ float bf16_back(uint16_t b) { return __uint_as_float((uint32_t)b << 16); }
+__device__ __forceinline__ uint16_t f16_bits(float x) { return __half_as_ushort(__float2half_rn(x)); }
+__device__ __forceinline__ float f16_back(uint16_t b) { return __half2float(__ushort_as_half(b)); }
+
+// ---- operand scaling ------------------------------------------------------------------------------
+// Powers of two, so exact.  The image header holds {tmax = max_j |t_j| (x 1.0001), max |t_jc|, max |t_j|^2}:
+//   e_t: targets are stored as fp16(t * 2^e_t), the largest element in [2^7, 2^8)
+//   e_w: the L2 models' extra K columns hold W_j = -|t_j|^2 / 2 * 2^e_w (|W| < 2^8) as an fp16 hi/mid/lo split; a
+//        query row carries the constant c_i = 2^(e_i + e_t - e_w) there, so c_i W_j = -S_i |t_j|^2 / 2.
+// Exponents are clamped to +-60 so that S_i and 1 / S_i stay finite fp32 numbers.
+constexpr int E_CLAMP = 60;
+struct ImgScale {
+  float tmax;
+  int e_t, e_w;
+};
+__device__ __forceinline__ int clamp_exp(int e) { return e > E_CLAMP ? E_CLAMP : (e < -E_CLAMP ? -E_CLAMP : e); }
+__device__ __forceinline__ ImgScale img_scale(const float* header) {
+  ImgScale s;
+  s.tmax = header[0];
+  const float ma = header[1], w = 0.5f * header[2];
+  s.e_t = ma > 0.f ? clamp_exp(7 - ilogbf(ma)) : 0;
+  s.e_w = w > 0.f ? clamp_exp(7 - ilogbf(w)) : 0;
+  return s;
+}
+
+// Error bound of one row, in the row's scaled units.  nqs = |q| 2^e_i, tms = tmax 2^e_t, K = padded depth,
+// c = the A-side constant of the L2 columns (0 for the bilinear models).  Terms:
+//   (2^-10 + 2^-20) nqs tms            two fp16 roundings per product: (1 + u)^2 - 1 with u = 2^-11, Cauchy-Schwarz
+//   2^-14 sqrt(K) (nqs + tms) 1.001    elements in the fp16 subnormal range: absolute error < 2^-14 each whether the
+//                                      tensor core flushes them or rounds them (sum |x_c| <= sqrt(K) |x|)
+//   K 2^-28                            products of two such elements
+//   K 2^-22 (nqs tms 1.001 + 2^8 c)    fp32 accumulation of K products (one truncated ulp each, partial sums bounded by
+//                                      the sum of magnitudes)
+//   3 * 2^-14 c                        the hi/mid/lo split of W (exact up to the subnormal floor of each piece)
+// and 1 % on top for the fp32 evaluation of the bound itself.
+__device__ __forceinline__ float row_eps(float nqs, float tms, int kp, float c) {
+  const float K = (float)kp;
+  float e = (9.765625e-4f + 9.5367431640625e-7f) * nqs * tms;
+  e += 6.103515625e-5f * sqrtf(K) * (nqs + tms) * 1.001f;
+  e += K * 3.725290298461914e-9f;
+  e += K * 2.384185791015625e-7f * (nqs * tms * 1.001f + 256.f * c);
+  e += 3.f * 6.103515625e-5f * c;
+  return e * 1.01f;
+}
 
 // ---- target image ---------------------------------------------------------------------------------
 struct PrepArgs {
@@ -181,8 +246,8 @@ struct PrepArgs {
   int64_t n_targets;
   int parts, kp, dist, tn;
   float* tn2;        // [n_targets] squared norms (scratch inside the image buffer's tail)
-  float* header;     // {tmax}
-  uint16_t* tiles;   // [n_tiles][kp/8][tn][8]
+  float* header;     // {tmax, max |t_c|, max |t|^2}
+  uint16_t* tiles;   // [n_tiles][kp/8][tn][8] fp16
 };
 
 __global__ void __launch_bounds__(256) target_norm_kernel(const PrepArgs a) {
@@ -190,19 +255,27 @@ __global__ void __launch_bounds__(256) target_norm_kernel(const PrepArgs a) {
   const int64_t warp = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const int64_t n_warps = ((int64_t)gridDim.x * blockDim.x) >> 5;
   const int d = a.m.d;
-  float wmax = 0.f;
+  float wmax = 0.f, amax = 0.f;
   for (int64_t j = warp; j < a.n_targets; j += n_warps) {
     float s = 0.f;
     for (int p = 0; p < a.parts; ++p)
       for (int c = lane; c < d; c += 32) {
         const float x = __ldg(a.m.entity.w[p] + j * d + c);
         s = fmaf(x, x, s);
+        amax = fmaxf(amax, fabsf(x));
       }
     s = warp_sum(s);
     if (lane == 0) a.tn2[j] = s;
     wmax = fmaxf(wmax, s);
   }
-  if (lane == 0 && wmax > 0.f) atomicMax(reinterpret_cast<int*>(a.header), __float_as_int(sqrtf(wmax) * 1.0001f));
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) amax = fmaxf(amax, __shfl_xor_sync(0xffffffffu, amax, o));
+  // non-negative floats order like their bit patterns (the header is zeroed by the caller)
+  if (lane == 0 && wmax > 0.f) {
+    atomicMax(reinterpret_cast<int*>(a.header), __float_as_int(sqrtf(wmax) * 1.0001f));
+    atomicMax(reinterpret_cast<int*>(a.header) + 1, __float_as_int(amax));
+    atomicMax(reinterpret_cast<int*>(a.header) + 2, __float_as_int(wmax));
+  }
 }
 
 __global__ void __launch_bounds__(256) target_image_kernel(const PrepArgs a) {
@@ -212,6 +285,7 @@ __global__ void __launch_bounds__(256) target_image_kernel(const PrepArgs a) {
   const int64_t n_tiles = (a.n_targets + tn - 1) / tn;
   const int64_t total = n_tiles * kchunks * tn;
   const int kd = a.parts * d;
+  const ImgScale sc = img_scale(a.header);
   for (int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total;
        idx += (int64_t)gridDim.x * blockDim.x) {
     const int r = (int)(idx % tn);
@@ -227,17 +301,17 @@ __global__ void __launch_bounds__(256) target_image_kernel(const PrepArgs a) {
         if (k < kd) {
           const int p = k / d, c = k - p * d;
           x = __ldg(a.m.entity.w[p] + j * d + c);
-          out[e] = bf16_bits(x);
+          out[e] = f16_bits(scalbnf(x, sc.e_t));
           continue;
         }
-        if (a.dist && k < kd + 3) {  // bf16 hi / mid / lo of -||t||^2 / 2
-          const float s = -0.5f * a.tn2[j];
-          const float hi = bf16_back(bf16_bits(s));
-          const float mid = bf16_back(bf16_bits(s - hi));
+        if (a.dist && k < kd + 3) {  // fp16 hi / mid / lo of W = -||t||^2 / 2 * 2^e_w
+          const float s = scalbnf(-0.5f * a.tn2[j], sc.e_w);
+          const float hi = f16_back(f16_bits(s));
+          const float mid = f16_back(f16_bits(s - hi));
           x = (k == kd) ? hi : (k == kd + 1 ? mid : (s - hi - mid));
         }
       }
-      out[e] = bf16_bits(x);
+      out[e] = f16_bits(x);
     }
     uint4 v;
     v.x = out[0] | ((uint32_t)out[1] << 16);
@@ -265,7 +339,8 @@ struct MmaArgs {
   uint2* cand;        // [splits][rows_pad][CAND]: {group maximum bits, group id | flags}
   int32_t* cand_cnt;  // [splits][rows_pad]: entries, or -1 when the list could not be compacted
   float* cand_thr;    // [splits][rows_pad]: threshold the list was last compacted with (-inf: never)
-  float* eps_out;     // [rows_pad]
+  float* eps_out;     // [rows_pad] error bound of the row, in the row's scaled units
+  float* inv_scale_out;  // [rows_pad] 1 / S_i (a power of two): scaled approximate score -> score
   const uint32_t* unsafe_bits;  // [rows_pad][unsafe_wpr]: bit c = chunk c holds a masked / out-of-range target
   int64_t unsafe_wpr;
   float* dbg_out;     // optional dense approximate scores [n, dbg_stride]
@@ -416,9 +491,8 @@ __global__ void __launch_bounds__(256) unsafe_bitmap_kernel(uint32_t* bits, int6
 // Filter state of one (row, split, slice) list.  widx = index of the next free entry in the global `cand` array
 // (list base + count: lists are CAND entries long and CAND-aligned, and a count never reaches CAND).
 struct EpiState {
-  float thr, thr_pub;
+  float thr;       // +inf: the row collects nothing (inactive, not representable, or its list overflowed)
   uint32_t widx;
-  bool overflow;
 };
 #ifndef KGE_MMA_TRIG
 #define KGE_MMA_TRIG (CAND - 5)
@@ -431,15 +505,18 @@ __device__ __forceinline__ void or_if_ge(uint32_t& y, float a, float b) {
   asm("{\n\t.reg .pred p;\n\tsetp.ge.f32 p, %1, %2;\n\t@p or.b32 %0, %0, %3;\n\t}" : "+r"(y) : "f"(a), "f"(b), "n"(BIT));
 }
 
-// One chunk (32 columns = 8 groups of 4) of one row: group maxima, chunk maximum, and (rarely) one list entry.
-__device__ __forceinline__ void epi_chunk(const uint32_t (&r)[32], EpiState& st, uint32_t cid, uint32_t uword,
-                                          uint2* __restrict__ cand) {
-  float gm[8];
+// One chunk (32 columns = 8 groups of 4) of one row, in two steps so that the registers of the chunk are free for
+// the next tcgen05.ld as early as possible: the group maxima and the chunk maximum ...
+__device__ __forceinline__ float chunk_reduce(const uint32_t (&r)[32], float (&gm)[8]) {
 #pragma unroll
   for (int g = 0; g < 8; ++g)
     gm[g] = fmaxf(max3f(__uint_as_float(r[4 * g]), __uint_as_float(r[4 * g + 1]), __uint_as_float(r[4 * g + 2])),
                   __uint_as_float(r[4 * g + 3]));
-  const float tm = fmaxf(max3f(gm[0], gm[1], gm[2]), max3f(max3f(gm[3], gm[4], gm[5]), gm[6], gm[7]));
+  return fmaxf(max3f(gm[0], gm[1], gm[2]), max3f(max3f(gm[3], gm[4], gm[5]), gm[6], gm[7]));
+}
+// ... and (rarely) one list entry.
+__device__ __forceinline__ void chunk_push(const float (&gm)[8], float tm, EpiState& st, uint32_t cid, uint32_t uword,
+                                           uint2* __restrict__ cand) {
   if (tm >= st.thr) {  // rare per row after the first tiles (but most warps have one such row per chunk)
     uint32_t y = (cid << CID_SHIFT) | F_KNOWN;
     y |= ((uword >> (cid & 31u)) & 1u) << 31;   // bit 31 = F_UNSAFE
@@ -466,8 +543,9 @@ __global__ void __launch_bounds__(sweep_threads(NCOL, NMMA), NBUF == 1 ? 2 : 1)
     fullsort_mma_kernel(const MmaArgs a) {
   constexpr int ROOM = 16;              // list room demanded after a compaction
   constexpr int NCH = TN / CH / NCOL;   // chunks of 32 columns per tile and epilogue thread
-  constexpr int EPI_WARPS = 8 * NCOL, PRODUCER_WARP = EPI_WARPS, MMA_WARP0 = EPI_WARPS + 1;
-  constexpr int N_WARPS = EPI_WARPS + 1 + NMMA;
+  constexpr int EPI_WARPS = 8 * NCOL, MMA_WARP0 = EPI_WARPS + PRODUCER_WARPS;
+  constexpr int PRODUCER_WARP = PRODUCER_WARPS ? EPI_WARPS : -1;
+  constexpr int N_WARPS = EPI_WARPS + PRODUCER_WARPS + NMMA;
   constexpr uint32_t TMEM_COLS = 2 * TN * NBUF;
   static_assert(NCH % 2 == 0 && (NBUF == 1 || NBUF == 2), "the chunk pipeline alternates two register sets");
   constexpr uint32_t IDESC = make_idesc(TN);
@@ -480,7 +558,8 @@ __global__ void __launch_bounds__(sweep_threads(NCOL, NMMA), NBUF == 1 ? 2 : 1)
   uint64_t* bars = reinterpret_cast<uint64_t*>(Bs + (size_t)a.stages * b_bytes);
   // bars: full[stages], empty[stages], tfull[buf][half] (4), tempty[buf][half] (4)
   float* eps_row = reinterpret_cast<float*>(bars + 2 * a.stages + 8);  // [MM]
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(eps_row + MM);
+  float* inv_row = eps_row + MM;                                        // [MM] 1 / S_i
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(inv_row + MM);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int64_t row0 = (int64_t)blockIdx.x * MM;
@@ -492,36 +571,61 @@ __global__ void __launch_bounds__(sweep_threads(NCOL, NMMA), NBUF == 1 ? 2 : 1)
   const int d = a.s.m.d;
   const int kd = a.parts * d;
 
-  // ---- setup: zero A, build bf16 queries, barriers, TMEM ---------------------------------------------
+  // ---- setup: zero A, build the scaled fp16 queries, barriers, TMEM ---------------------------------
   for (uint32_t i = threadIdx.x; i < a_bytes / 16; i += blockDim.x) reinterpret_cast<uint4*>(As)[i] = make_uint4(0, 0, 0, 0);
   __syncthreads();
-  const float tmax = a.header[0];
+  const ImgScale isc = img_scale(a.header);
+  // one fp32 query row per warp, staged in the (still idle) tile ring: the row's scale needs its largest element
+  float* scratch = reinterpret_cast<float*>(Bs) + warp * kp;
   for (int u = warp; u < MM; u += N_WARPS) {
-    float nq = 0.f;
+    float nq = 0.f, amax = 0.f;
     if (u < nrows) {
       for (int c = lane; c < d; c += 32) {
         float q0, q1;
         query_value(a.s, row0 + u, c, q0, q1);
         nq = fmaf(q0, q0, nq);
-        As[((size_t)(c >> 3) * MM + u) * 8 + (c & 7)] = bf16_bits(q0);
+        amax = fmaxf(amax, fabsf(q0));
+        scratch[c] = q0;
         if (a.parts == 2) {
           nq = fmaf(q1, q1, nq);
-          const int k1 = d + c;
-          As[((size_t)(k1 >> 3) * MM + u) * 8 + (k1 & 7)] = bf16_bits(q1);
+          amax = fmaxf(amax, fabsf(q1));
+          scratch[d + c] = q1;
         }
-      }
-      if (a.dist && lane < 3) {
-        const int k1 = kd + lane;
-        As[((size_t)(k1 >> 3) * MM + u) * 8 + (k1 & 7)] = bf16_bits(1.0f);
       }
     }
     nq = warp_sum(nq);
-    if (lane == 0) {
-      float eps = 1.02f * 0.00390625f * sqrtf(nq) * tmax;                // 2^-8 ||q|| max||t||
-      if (a.dist) eps += 9.5367431640625e-7f * 0.5f * tmax * tmax;        // 2^-20 * ||t||^2 / 2 (split remainder)
-      eps_row[u] = eps;
-      if (split == 0) a.eps_out[row0 + u] = eps;   // (every split writes the same value)
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) amax = fmaxf(amax, __shfl_xor_sync(0xffffffffu, amax, o));
+    int e_i = amax > 0.f ? clamp_exp(7 - ilogbf(amax)) : 0;   // largest |q_c| 2^e_i in [2^7, 2^8)
+    int e_c = 0;
+    bool bad = !(nq < INFINITY);                              // inf / nan in the query: exact path
+    if (a.dist) {
+      e_c = e_i + isc.e_t - isc.e_w;                          // c_i = 2^e_c must be a normal fp16 number
+      if (e_c > 15) {
+        e_i -= e_c - 15;                                      // lower the row's scale (never raise it: no overflow)
+        e_c = 15;
+      }
+      if (e_c < -14 || e_i < -E_CLAMP) bad = true;
     }
+    __syncwarp();
+    if (u < nrows && !bad) {
+      for (int k1 = lane; k1 < kd; k1 += 32)
+        As[((size_t)(k1 >> 3) * MM + u) * 8 + (k1 & 7)] = f16_bits(scalbnf(scratch[k1], e_i));
+      if (a.dist && lane < 3) {
+        const int k1 = kd + lane;
+        As[((size_t)(k1 >> 3) * MM + u) * 8 + (k1 & 7)] = f16_bits(scalbnf(1.0f, e_c));
+      }
+    }
+    if (lane == 0) {
+      const float nqs = scalbnf(sqrtf(nq) * 1.0001f, e_i), tms = scalbnf(isc.tmax, isc.e_t);
+      const float eps = bad ? INFINITY : row_eps(nqs, tms, kp, a.dist ? scalbnf(1.0f, e_c) : 0.f);
+      const float inv = scalbnf(1.0f, -(e_i + isc.e_t));
+      eps_row[u] = eps;
+      inv_row[u] = inv;
+      a.eps_out[row0 + u] = eps;        // (every split writes the same values)
+      a.inv_scale_out[row0 + u] = inv;
+    }
+    __syncwarp();   // the scratch row is reused by the warp's next query
   }
   if (threadIdx.x == 0) {
     for (int s = 0; s < a.stages; ++s) {
@@ -580,7 +684,33 @@ __global__ void __launch_bounds__(sweep_threads(NCOL, NMMA), NBUF == 1 ? 2 : 1)
     const int h_lo = NMMA == 2 ? warp - MMA_WARP0 : 0, h_hi = NMMA == 2 ? h_lo + 1 : 2;
     int s = 0;
     uint32_t ph = 0;
+    // producer duty of the first MMA warp: keep the ring topped up.  Tile i itself must be on its way before the
+    // warp blocks on it; tiles further ahead are only requested when their stage is already free (no blocking:
+    // the stage of tile p frees when the MMAs of tile p - stages complete, usually long ago).
+    const bool produce = PRODUCER_WARPS == 0 && warp == MMA_WARP0;
+    const unsigned char* src = reinterpret_cast<const unsigned char*>(a.tiles) + (size_t)t0 * b_bytes;
+    const uint32_t bs0 = smem_u32(Bs);
+    int64_t pi = 0;      // next tile to request
+    int ps = 0;          // its stage
+    uint32_t pph = 0;    // phase of that stage's empty barrier
     for (int64_t i = 0; i < nt; ++i) {
+      if (produce) {
+        while (pi < nt && pi < i + a.stages) {
+          if (pi >= a.stages) {   // the stage has been used before: its MMAs must have read it
+            if (pi <= i) mbar_wait(empty0 + 8 * ps, pph ^ 1u);
+            else if (!mbar_try_wait(empty0 + 8 * ps, pph ^ 1u)) break;
+          }
+          if (leader) {
+            mbar_arrive_expect_tx(full0 + 8 * ps, b_bytes);
+            bulk_g2s(bs0 + (uint32_t)ps * b_bytes, src + (size_t)pi * b_bytes, b_bytes, full0 + 8 * ps);
+          }
+          ++pi;
+          if (++ps == a.stages) {
+            ps = 0;
+            pph ^= 1u;
+          }
+        }
+      }
       const uint32_t buf = NBUF == 1 ? 0u : (uint32_t)(i & 1);
       const uint32_t tph = (uint32_t)((i / NBUF) & 1);
       mbar_wait(full0 + 8 * s, ph);                       // tile landed
@@ -618,15 +748,13 @@ __global__ void __launch_bounds__(sweep_threads(NCOL, NMMA), NBUF == 1 ? 2 : 1)
     const int64_t qrow = row0 + u;
     const int64_t lrow = lsplit * a.rows_pad + qrow;   // list of (row, split, slice)
     EpiState st;
-    st.thr = active ? -INFINITY : INFINITY;
-    st.thr_pub = -INFINITY;
+    const bool usable = active && eps_row[u] < INFINITY;   // a row the fp16 scaling cannot represent goes to the exact path
+    st.thr = usable ? -INFINITY : INFINITY;
     const uint32_t wbase = (uint32_t)(lrow * CAND);
     st.widx = wbase;
-    st.overflow = false;
-    const float eps = eps_row[u];
+    const float inv_scale = DBG ? inv_row[u] : 0.f;
     uint32_t tlane = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(h * TN + cs * NCH * CH);
     asm volatile("" : "+r"(tlane));   // keep the address in a register (ptxas would rebuild it from tid every tile)
-    const int64_t wrow0 = row0 + h * 128 + quad * 32;   // first row of this warp
     uint32_t my_tfull = tfull0 + 8 * h, my_tempty = tempty0 + 8 * h;   // + 16 * buf
     asm volatile("" : "+r"(my_tfull), "+r"(my_tempty));
 
@@ -636,92 +764,105 @@ __global__ void __launch_bounds__(sweep_threads(NCOL, NMMA), NBUF == 1 ? 2 : 1)
     auto uload = [&](int64_t w) -> uint32_t { return (active && w < a.unsafe_wpr) ? __ldg(urow + w) : 0u; };
     uint32_t uw_cur = 0u, uw_nxt = uload((int64_t)((t0 * (TN / CH)) >> 5));
     uint32_t uw_idx = 0xFFFFFFFFu;
-    // One chunk of 32 columns: optional debug dump, then the filter.
-    auto process = [&](const uint32_t (&r)[32], int, uint32_t cid) {
-#ifdef KGE_EXP_NOFILTER
-      return;
-#endif
-      if (DBG) {
-        if (active) {
-          float* o = a.dbg_out + qrow * a.dbg_stride + (int64_t)cid * CH;
+    // debug dump of one chunk (unscaled approximate scores)
+    auto dump = [&](const uint32_t (&r)[32], uint32_t cid) {
+      if (DBG && active) {
+        float* o = a.dbg_out + qrow * a.dbg_stride + (int64_t)cid * CH;
 #pragma unroll
-          for (int j = 0; j < CH; ++j) o[j] = __uint_as_float(r[j]);
-        }
+        for (int j = 0; j < CH; ++j) o[j] = __uint_as_float(r[j]) * inv_scale;
       }
-      epi_chunk(r, st, cid, uw_cur, a.cand);   // (targets beyond the table: zero rows of the image, chunks marked unsafe)
     };
 
-    // Software pipeline over chunks: the load of the next chunk is in flight while the current one is
-    // filtered, and an accumulator goes back to the tensor core as soon as its last chunk sits in registers.
-    // With one buffer per half (NBUF == 1) the next tile of this half is only being computed while the last
-    // chunk is filtered, so that chunk is filtered before the warp waits for it.
+    // Chunk pipeline.  A tile is NCH chunks of 32 columns per thread, taken two at a time (register sets va / vb):
+    //   wait for the pair | reduce va -> 8 group maxima, re-issue va | reduce vb, re-issue vb | the two (rare) list
+    //   appends
+    // so the TMEM loads of the next pair are in flight under the append paths, and a set is overwritten as soon as
+    // its 20-instruction max tree has consumed it.  The accumulator goes back to the tensor core when the tile's
+    // LAST pair sits in registers, i.e. before half of the tile is filtered: with one buffer per half (NBUF == 1) the
+    // MMAs of the next tile then run under the second half of the filter instead of after it.  (Round 1 waited
+    // after every chunk, and ptxas had scheduled the first consumers right behind each LDTM: one exposed TMEM
+    // latency per chunk -- the sweep ran at 44 % issue / 44 % tensor activity, bound by neither.)
+    constexpr int NPAIR = NCH / 2;
     uint32_t va[32], vb[32];
+    float gm[8];
     mbar_wait(my_tfull, 0u);
     tc_fence_after();
     tmem_ld32_issue(tlane, va);
-    tmem_ld_wait(va);
+    tmem_ld32_issue(tlane + CH, vb);
     const int nti = (int)nt;
     uint32_t cid = (uint32_t)(t0 * (TN / CH) + cs * NCH);
     for (int i = 0; i < nti; ++i, cid += TN / CH) {
       const uint32_t buf = NBUF == 1 ? 0u : (uint32_t)(i & 1);
-      const uint32_t tbase = tlane + buf * 2 * TN;
+      const uint32_t nbuf = NBUF == 1 ? 0u : (buf ^ 1u);
+      const uint32_t tbase = tlane + buf * 2 * TN, nbase = tlane + nbuf * 2 * TN;
+      const bool more = i + 1 < nti;
       if ((cid >> 5) != uw_idx) {   // a tile never straddles a bitmap word (TN / CH divides 32)
         uw_idx = cid >> 5;
         uw_cur = uw_nxt;
         uw_nxt = uload((int64_t)uw_idx + 1);
       }
 #pragma unroll
-      for (int c = 0; c < NCH; ++c) {
-        uint32_t(&cur)[32] = (c & 1) ? vb : va;
-        uint32_t(&nxt)[32] = (c & 1) ? va : vb;
-        if (c + 1 < NCH) {
-          tmem_ld32_issue(tbase + (uint32_t)((c + 1) * CH), nxt);
-          process(cur, i, cid + c);
-          tmem_ld_wait(nxt);
-          if (c + 1 == NCH - 1) {   // every chunk of the tile is in registers: release the accumulator
-            tc_fence_before();
-            __syncwarp();
-            if (lane == 0) mbar_arrive(my_tempty + 16 * buf);
-          }
-        } else {
-          if (NBUF == 1) process(cur, i, cid + c);
-          if (i + 1 < nti) {
-            const uint32_t nbuf = NBUF == 1 ? 0u : (buf ^ 1u);
+      for (int p = 0; p < NPAIR; ++p) {
+        const bool last = p == NPAIR - 1;
+        tmem_ld_wait2(va, vb);
+        bool refill = !last;
+        if (last) {   // every chunk of the tile is in registers: release the accumulator
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(my_tempty + 16 * buf);
+          if (NBUF == 2 && more) {   // the other buffer was computed while this tile was filtered
             mbar_wait(my_tfull + 16 * nbuf, (uint32_t)(((i + 1) / NBUF) & 1));
             tc_fence_after();
-            tmem_ld32_issue(tlane + nbuf * 2 * TN, nxt);
+            refill = true;
           }
-          if (NBUF != 1) process(cur, i, cid + c);
-          if (i + 1 < nti) tmem_ld_wait(nxt);
         }
+        // (targets beyond the table: zero rows of the image, chunks marked unsafe)
+#ifndef KGE_EXP_NOFILTER
+        dump(va, cid + 2 * p);
+        const float tma = chunk_reduce(va, gm);
+#endif
+        if (refill) tmem_ld32_issue(last ? nbase : tbase + (uint32_t)((2 * p + 2) * CH), va);
+#ifndef KGE_EXP_NOFILTER
+        chunk_push(gm, tma, st, cid + 2 * p, uw_cur, a.cand);
+        dump(vb, cid + 2 * p + 1);
+        const float tmb = chunk_reduce(vb, gm);
+#endif
+        if (refill) tmem_ld32_issue(last ? nbase + CH : tbase + (uint32_t)((2 * p + 3) * CH), vb);
+#ifndef KGE_EXP_NOFILTER
+        chunk_push(gm, tmb, st, cid + 2 * p + 1, uw_cur, a.cand);
+#endif
       }
       unsigned full = __ballot_sync(0xffffffffu, (int)(st.widx & (CAND - 1)) > (TRIG < CAND - (NCH + 1) ? TRIG : CAND - (NCH + 1)));
       while (full) {
         const int r = __ffs(full) - 1;
         full &= full - 1;
         const int cnt_r = __shfl_sync(0xffffffffu, (int)(st.widx & (CAND - 1)), r);
-        const float eps_r = __shfl_sync(0xffffffffu, eps, r);
-        const int64_t qrow_r = wrow0 + r;
+        const float eps_r = eps_row[h * 128 + quad * 32 + r];
+        const int64_t qrow_r = row0 + h * 128 + quad * 32 + r;
         uint2* buf_r = a.cand + (lsplit * a.rows_pad + qrow_r) * CAND;
         __syncwarp();
         float thr_new;
         const int n_new = compact_row(buf_r, cnt_r, a.k, eps_r, a.unsafe_bits + qrow_r * a.unsafe_wpr, ROOM, &thr_new);
         if (lane == r) {
           if (n_new < 0) {
-            st.overflow = true;
             st.thr = INFINITY;  // stop collecting: the row goes to the exact path
             st.widx = wbase;
           } else {
             st.widx = wbase + (uint32_t)n_new;
             st.thr = thr_new;
-            st.thr_pub = thr_new;
           }
         }
       }
+      if (NBUF == 1 && more) {   // the tile computed while the second half of this one was filtered
+        mbar_wait(my_tfull, (uint32_t)((i + 1) & 1));
+        tc_fence_after();
+        tmem_ld32_issue(tlane, va);
+        tmem_ld32_issue(tlane + CH, vb);
+      }
     }
-    if (active) {
-      a.cand_cnt[lrow] = st.overflow ? -1 : (int)(st.widx - wbase);
-      a.cand_thr[lrow] = st.thr_pub;
+    if (active) {   // (a list's threshold starts at -inf and only ever rises to finite values)
+      a.cand_cnt[lrow] = st.thr == INFINITY ? -1 : (int)(st.widx - wbase);
+      a.cand_thr[lrow] = st.thr;
     }
   }
 
@@ -745,10 +886,13 @@ struct RescoreArgs {
   const uint2* cand;
   const int32_t* cand_cnt;
   const float* cand_thr;
-  const float* eps;
+  const float* eps;         // scaled units of the row
+  const float* inv_scale;   // 1 / S_i
   int64_t* ids_out;
   float* scores_out;
   int32_t* row_flags;
+  int32_t* row_map;      // rows handed to the exact kernel, in arrival order ...
+  int32_t* exact_rows;   // ... and their count (zeroed by the caller)
 };
 
 constexpr int RS_WARPS = 8;
@@ -815,7 +959,10 @@ __global__ void __launch_bounds__(RS_WARPS * 32, KGE_RS_MINB) rescore_topk_kerne
       E += c;
     }
     if (bad) {
-      if (lane == 0) a.row_flags[row] = 1;
+      if (lane == 0) {
+        a.row_flags[row] = 1;
+        a.row_map[atomicAdd(a.exact_rows, 1)] = (int32_t)row;
+      }
       continue;
     }
     float nq2 = 0.f;
@@ -898,9 +1045,10 @@ __global__ void __launch_bounds__(RS_WARPS * 32, KGE_RS_MINB) rescore_topk_kerne
     }
     const float tau = T ? from_orderable(T) : -INFINITY;
     const float thr = fmaxf(thr0, tau - 2.f * eps);
-    // The k targets behind tau have exact a >= tau - eps (a = q.t, or q.t - |t|^2/2 for the L2 models, where
-    // the squared distance is |q|^2 - 2a): nothing that scores below them can enter the top-k.
-    const float lo_a = tau - 1.25f * eps;
+    // The k targets behind tau have exact S a >= tau - eps (a = q.t, or q.t - |t|^2/2 for the L2 models, where
+    // the squared distance is |q|^2 - 2a): nothing that scores below them can enter the top-k.  The list lives in
+    // the row's scaled units, the exact chain does not: 1 / S is a power of two, the conversion is exact.
+    const float lo_a = (tau - 1.25f * eps) * a.inv_scale[row];
     const float hi_acc = (nq2 - 2.f * lo_a) * 1.00001f + 4e-6f * nq2;   // only used when tau is finite
     const bool have_tau = T != 0u;
     __syncwarp();
@@ -1021,7 +1169,10 @@ __global__ void __launch_bounds__(RS_WARPS * 32, KGE_RS_MINB) rescore_topk_kerne
     }
     // ---- order the keys: (score desc, id asc) ------------------------------------------------------------------
     if (n_pass < k) {
-      if (lane == 0) a.row_flags[row] = 1;
+      if (lane == 0) {
+        a.row_flags[row] = 1;
+        a.row_map[atomicAdd(a.exact_rows, 1)] = (int32_t)row;
+      }
     } else {
       uint64_t out;
       if (len == 0 && nk <= 32) {
@@ -1046,7 +1197,7 @@ struct MmaPlan {
   int64_t n_tiles, rows_pad, unsafe_wpr;
 };
 
-int plan_mma(const kge_model_t* m, int64_t n, int64_t n_targets, int k, MmaPlan& pl) {
+int plan_mma(const kge_model_t* m, int64_t n, int64_t n_targets, int k, int shape, MmaPlan& pl) {
   KGE_REQUIRE(m && m->model >= KGE_TRANSE && m->model <= KGE_COMPLEX, KGE_E_ARG, "bad model");
   pl.parts = (m->model == KGE_ROTATE || m->model == KGE_COMPLEX) ? 2 : 1;
   pl.dist = (m->model == KGE_TRANSE || m->model == KGE_ROTATE) ? 1 : 0;
@@ -1062,13 +1213,12 @@ int plan_mma(const kge_model_t* m, int64_t n, int64_t n_targets, int k, MmaPlan&
   //   (f) TN 128, NBUF 2, NCOL 2: all 512 columns, one CTA of 16 epilogue warps and two MMA issuer warps per SM
   //                                                                                          -- larger K
   //   (c) TN 64,  NBUF 2, NCOL 1: one CTA per SM -- K so large that (f) has no room for a ring of tiles
-  // KGE_MMA_CFG = a | f | c forces a shape (experiments); the target image depends on TN only.
+  // `shape` = 'a' | 'f' | 'c' forces one (tests, experiments; 0 = pick); the target image depends on TN only.
   const size_t a_bytes = (size_t)MM * pl.kp * 2;
-  const size_t fixed = a_bytes + 32 * 8 + MM * 4 + 64;
+  const size_t fixed = a_bytes + 32 * 8 + 2 * MM * 4 + 64;
   const size_t two_per_sm = 112 * 1024, one_per_sm = 200 * 1024;   // 227 KB per SM, 1 KB reserved per CTA
-  const char* force = getenv("KGE_MMA_CFG");
-  char cfg = 0;
-  if (force && (force[0] == 'a' || force[0] == 'f' || force[0] == 'c')) cfg = force[0];
+  KGE_REQUIRE(shape == 0 || shape == 'a' || shape == 'f' || shape == 'c', KGE_E_ARG, "unknown sweep shape %d", shape);
+  char cfg = (char)shape;
   if (cfg == 'a' && fixed + 2 * (size_t)128 * pl.kp * 2 > two_per_sm) cfg = 0;
   if (!cfg) {
     if (fixed + 3 * (size_t)128 * pl.kp * 2 <= two_per_sm) cfg = 'a';
@@ -1084,7 +1234,9 @@ int plan_mma(const kge_model_t* m, int64_t n, int64_t n_targets, int k, MmaPlan&
   int stages = (int)((budget - fixed) / b_bytes);
   if (stages > 8) stages = 8;
   pl.stages = stages;
-  pl.smem = a_bytes + (size_t)stages * b_bytes + (size_t)(2 * stages + 8) * 8 + MM * 4 + 64;
+  pl.smem = a_bytes + (size_t)stages * b_bytes + (size_t)(2 * stages + 8) * 8 + 2 * MM * 4 + 64;
+  // the setup stages one fp32 query row per warp in the ring
+  KGE_REQUIRE((size_t)stages * b_bytes >= (size_t)(8 * pl.ncol + 3) * pl.kp * 4, KGE_E_UNSUPPORTED, "ring too small");
   pl.n_tiles = (n_targets + pl.tn - 1) / pl.tn;
   pl.rows_pad = (n + MM - 1) / MM * MM;
   pl.unsafe_wpr = (pl.n_tiles * (pl.tn / CH) + 31) / 32;
@@ -1102,18 +1254,18 @@ int plan_mma(const kge_model_t* m, int64_t n, int64_t n_targets, int k, MmaPlan&
 
 }  // namespace
 
-extern "C" int64_t kge_mma_image_bytes(const kge_model_t* model, int64_t n_targets) {
+extern "C" int64_t kge_mma_image_bytes(const kge_model_t* model, int64_t n_targets, int32_t shape) {
   MmaPlan pl = {};
-  if (!model || plan_mma(model, 1, n_targets, 1, pl)) return -1;
+  if (!model || plan_mma(model, 1, n_targets, 1, shape, pl)) return -1;
   return IMG_HEADER + pl.n_tiles * pl.tn * (int64_t)pl.kp * 2 + ((n_targets * 4 + 127) / 128) * 128;
 }
 
 extern "C" int kge_mma_prepare_targets(const kge_model_t* model, int64_t n_targets, void* image, int64_t image_bytes,
-                                       kge_stream_t stream) {
+                                       int32_t shape, kge_stream_t stream) {
   MmaPlan pl = {};
-  if (int e = plan_mma(model, 1, n_targets, 1, pl)) return e;
+  if (int e = plan_mma(model, 1, n_targets, 1, shape, pl)) return e;
   KGE_REQUIRE(n_targets <= model->entity.rows, KGE_E_ARG, "n_targets beyond the entity table");
-  const int64_t need = kge_mma_image_bytes(model, n_targets);
+  const int64_t need = kge_mma_image_bytes(model, n_targets, shape);
   KGE_REQUIRE(image && image_bytes >= need, KGE_E_ARG, "image buffer too small: need %lld bytes", (long long)need);
   KGE_REQUIRE((reinterpret_cast<uintptr_t>(image) & 127) == 0, KGE_E_ARG, "image buffer must be 128-byte aligned");
   cudaStream_t st = (cudaStream_t)stream;
@@ -1136,28 +1288,58 @@ extern "C" int kge_mma_prepare_targets(const kge_model_t* model, int64_t n_targe
   return 0;
 }
 
+namespace {
+// Workspace layout (all offsets 16-byte aligned): candidate lists | counts | thresholds | eps | 1/S | unsafe bitmap |
+// row map of the rows handed to the exact kernel | that kernel's partial lists.
+struct WsLayout {
+  int64_t cand, cnt, thr, eps, inv, bits, rowmap, exact, total;
+};
+int64_t align16(int64_t x) { return (x + 15) / 16 * 16; }
+int ws_layout(const kge_model_t* model, const MmaPlan& pl, int64_t n, int64_t n_targets, int k, WsLayout& w) {
+  const int64_t lists = (int64_t)pl.splits * pl.ncol * pl.rows_pad;
+  const int64_t exact = kge_topk_rows_indirect_workspace_bytes(model, n, n_targets, k);
+  KGE_REQUIRE(exact >= 0, KGE_E_UNSUPPORTED, "the exact fallback kernel does not support this shape");
+  int64_t o = 0;
+  w.cand = o; o = align16(o + lists * CAND * 8);
+  w.cnt = o; o = align16(o + lists * 4);
+  w.thr = o; o = align16(o + lists * 4);
+  w.eps = o; o = align16(o + pl.rows_pad * 4);
+  w.inv = o; o = align16(o + pl.rows_pad * 4);
+  w.bits = o; o = align16(o + pl.rows_pad * pl.unsafe_wpr * 4);
+  w.rowmap = o; o = align16(o + pl.rows_pad * 4);
+  w.exact = o; o = align16(o + exact);
+  w.total = o;
+  return 0;
+}
+}  // namespace
+
 extern "C" int64_t kge_full_sort_topk_mma_workspace_bytes(const kge_model_t* model, int64_t n, int64_t n_targets,
-                                                          int32_t k) {
+                                                          int32_t k, int32_t shape) {
   MmaPlan pl = {};
-  if (!model || n < 0 || plan_mma(model, n, n_targets, k, pl)) return -1;
-  return (int64_t)pl.splits * pl.ncol * pl.rows_pad * (CAND * 8 + 4 + 4) + pl.rows_pad * 4 + pl.rows_pad * pl.unsafe_wpr * 4;
+  WsLayout w = {};
+  if (!model || n < 0 || plan_mma(model, n, n_targets, k, shape, pl) || ws_layout(model, pl, n, n_targets, k, w)) return -1;
+  return w.total;
 }
 
 extern "C" int kge_full_sort_topk_mma(const kge_model_t* model, const int64_t* heads, const int64_t* rels, int64_t n,
                                       int head_is_user, int64_t n_targets, const void* image, const int64_t* hist_off,
                                       const int64_t* hist_items, int mask_first, int32_t k, int64_t* ids_out,
-                                      float* scores_out, int32_t* row_flags, void* workspace, int64_t workspace_bytes,
-                                      float* debug_scores, kge_stream_t stream) {
+                                      float* scores_out, int32_t* row_flags, int32_t* exact_rows, void* workspace,
+                                      int64_t workspace_bytes, float* debug_scores, int32_t shape,
+                                      kge_stream_t stream) {
   MmaPlan pl = {};
-  if (int e = plan_mma(model, n, n_targets, k, pl)) return e;
+  if (int e = plan_mma(model, n, n_targets, k, shape, pl)) return e;
   KGE_REQUIRE(n >= 0 && n_targets <= model->entity.rows && k <= n_targets, KGE_E_ARG, "bad n / n_targets / k");
+  KGE_REQUIRE(exact_rows, KGE_E_ARG, "NULL exact_rows");
+  cudaStream_t st = (cudaStream_t)stream;
+  KGE_CUDA(cudaMemsetAsync(exact_rows, 0, 4, st));
   if (n == 0) return 0;
   KGE_REQUIRE(heads && image && ids_out && row_flags && workspace, KGE_E_ARG, "NULL argument");
   KGE_REQUIRE((hist_off == nullptr) == (hist_items == nullptr), KGE_E_ARG, "hist_off / hist_items must come together");
-  const int64_t need = kge_full_sort_topk_mma_workspace_bytes(model, n, n_targets, k);
-  KGE_REQUIRE(workspace_bytes >= need, KGE_E_ARG, "workspace too small: need %lld bytes", (long long)need);
-  cudaStream_t st = (cudaStream_t)stream;
-  const int64_t lists = (int64_t)pl.splits * pl.ncol * pl.rows_pad;
+  KGE_REQUIRE((reinterpret_cast<uintptr_t>(workspace) & 15) == 0, KGE_E_ARG, "workspace must be 16-byte aligned");
+  WsLayout w = {};
+  if (int e = ws_layout(model, pl, n, n_targets, k, w)) return e;
+  KGE_REQUIRE(workspace_bytes >= w.total, KGE_E_ARG, "workspace too small: need %lld bytes", (long long)w.total);
 
   MmaArgs a = {};
   a.s.m = *model;
@@ -1182,11 +1364,12 @@ extern "C" int kge_full_sort_topk_mma(const kge_model_t* model, const int64_t* h
   a.mask_first = mask_first;
   a.k = k;
   unsigned char* ws = reinterpret_cast<unsigned char*>(workspace);
-  a.cand = reinterpret_cast<uint2*>(ws);
-  a.cand_cnt = reinterpret_cast<int32_t*>(ws + lists * CAND * 8);
-  a.cand_thr = reinterpret_cast<float*>(ws + lists * (CAND * 8 + 4));
-  a.eps_out = reinterpret_cast<float*>(ws + lists * (CAND * 8 + 8));
-  uint32_t* unsafe_bits = reinterpret_cast<uint32_t*>(ws + lists * (CAND * 8 + 8) + pl.rows_pad * 4);
+  a.cand = reinterpret_cast<uint2*>(ws + w.cand);
+  a.cand_cnt = reinterpret_cast<int32_t*>(ws + w.cnt);
+  a.cand_thr = reinterpret_cast<float*>(ws + w.thr);
+  a.eps_out = reinterpret_cast<float*>(ws + w.eps);
+  a.inv_scale_out = reinterpret_cast<float*>(ws + w.inv);
+  uint32_t* unsafe_bits = reinterpret_cast<uint32_t*>(ws + w.bits);
   a.unsafe_bits = unsafe_bits;
   a.unsafe_wpr = pl.unsafe_wpr;
   a.dbg_out = debug_scores;
@@ -1232,9 +1415,12 @@ extern "C" int kge_full_sort_topk_mma(const kge_model_t* model, const int64_t* h
   r.cand_cnt = a.cand_cnt;
   r.cand_thr = a.cand_thr;
   r.eps = a.eps_out;
+  r.inv_scale = a.inv_scale_out;
   r.ids_out = ids_out;
   r.scores_out = scores_out;
   r.row_flags = row_flags;
+  r.row_map = reinterpret_cast<int32_t*>(ws + w.rowmap);
+  r.exact_rows = exact_rows;
   r.nent = r.splits * CAND > RS_GIDS ? r.splits * CAND : RS_GIDS;
   const size_t rs_smem = rescore_smem_per_warp(pl.parts * model->d, r.nent) * RS_WARPS;
   int64_t g = (n + RS_WARPS - 1) / RS_WARPS;
@@ -1248,5 +1434,8 @@ extern "C" int kge_full_sort_topk_mma(const kge_model_t* model, const int64_t* h
     rescore_topk_kernel<false><<<rs_grid, RS_WARPS * 32, rs_smem, st>>>(r);
   }
   KGE_LAUNCH_CHECK();
-  return 0;
+  // the rows the filter could not bound (row_map[0 .. *exact_rows)), through the exact fp32 kernel: sized and gated
+  // on the device, no host round trip
+  return kge_topk_rows_indirect(model, heads, rels, n, head_is_user, n_targets, hist_off, hist_items, mask_first, k,
+                                r.row_map, exact_rows, ids_out, scores_out, ws + w.exact, st);
 }

@@ -105,16 +105,23 @@ struct TileArgs {
   int k;
   uint64_t* part_keys;  // [n, n_splits, k]
   int n_splits;
+  // Indirect rows (the tensor-core path's device-side fallback): the CTA works on entries [row_begin, min(*row_count,
+  // row_end)) of row_map instead of rows [0, n); the row count is only known on the device, so the grid is sized for
+  // a capacity, CTAs beyond the count leave at once and the others stride over the row blocks.  part_keys is
+  // indexed by (entry - row_begin).
+  const int32_t* row_map;
+  const int32_t* row_count;
+  int64_t row_begin, row_end;
 };
 
-__device__ __forceinline__ void build_queries(const ScoreArgs& a, int64_t row0, int nrows, int kpad, float* Qs) {
+__device__ __forceinline__ void build_queries(const ScoreArgs& a, const int64_t* rowid, int nrows, int kpad, float* Qs) {
   const int d = a.m.d;
   const int parts = (a.m.model == KGE_ROTATE || a.m.model == KGE_COMPLEX) ? 2 : 1;
   const int qstride = parts * kpad;
   for (int idx = threadIdx.x; idx < BU * kpad; idx += blockDim.x) {
     const int u = idx / kpad, c = idx - u * kpad;
     float q0 = 0.f, q1 = 0.f;
-    if (u < nrows && c < d) query_value(a, row0 + u, c, q0, q1);
+    if (u < nrows && c < d) query_value(a, rowid[u], c, q0, q1);
     Qs[u * qstride + c] = q0;
     if (parts == 2) Qs[u * qstride + kpad + c] = q1;
   }
@@ -163,17 +170,23 @@ __global__ void __launch_bounds__(TILE_THREADS) fullsort_tile_kernel(const TileA
   int* cnt = reinterpret_cast<int*>(maskbits + (TOPK ? BU * (BT / 32) : 0));  // [BU]
   int* llen = cnt + (TOPK ? BU : 0);                                        // [BU]
   int64_t* cursor = reinterpret_cast<int64_t*>(llen + (TOPK ? BU : 0));     // [BU] (8-byte aligned by layout)
+  int64_t* rowid = cursor + (TOPK ? BU : 0);                                // [BU] query row of each slot
 
-  const int64_t row0 = (int64_t)blockIdx.x * BU;
-  const int nrows = (int)min((int64_t)BU, a.s.n - row0);
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int tu = warp;  // users 4*tu .. 4*tu+3
 
   const int64_t n_tiles = (a.n_targets + BT - 1) / BT;
   const int64_t tile_lo = (int64_t)blockIdx.y * a.tiles_per_split;
   const int64_t tile_hi = min(n_tiles, tile_lo + a.tiles_per_split);
+  const int64_t row_stop = a.row_map ? min((int64_t)__ldg(a.row_count), a.row_end) : a.s.n;
 
-  build_queries(a.s, row0, nrows, kpad, Qs);
+  for (int64_t row0 = a.row_begin + (int64_t)blockIdx.x * BU; row0 < row_stop; row0 += (int64_t)gridDim.x * BU) {
+  const int nrows = (int)min((int64_t)BU, row_stop - row0);
+  __syncthreads();   // (indirect rows: the previous row block of this CTA is done with shared memory)
+  for (int u = threadIdx.x; u < BU; u += blockDim.x)
+    rowid[u] = u < nrows ? (a.row_map ? (int64_t)__ldg(a.row_map + row0 + u) : row0 + u) : 0;
+  __syncthreads();
+  build_queries(a.s, rowid, nrows, kpad, Qs);
   if (TOPK) {
     for (int u = threadIdx.x; u < BU; u += blockDim.x) {
       thr[u] = 0ull;
@@ -182,7 +195,7 @@ __global__ void __launch_bounds__(TILE_THREADS) fullsort_tile_kernel(const TileA
       int64_t cur = 0;
       if (u < nrows && a.hist_off) {
         // first history entry >= tile_lo * BT (history sorted ascending per row)
-        int64_t lo = a.hist_off[row0 + u], hi = a.hist_off[row0 + u + 1];
+        int64_t lo = a.hist_off[rowid[u]], hi = a.hist_off[rowid[u] + 1];
         const int64_t first = tile_lo * BT;
         while (lo < hi) {
           const int64_t mid = (lo + hi) >> 1;
@@ -209,7 +222,7 @@ __global__ void __launch_bounds__(TILE_THREADS) fullsort_tile_kernel(const TileA
       __syncthreads();
       if (a.hist_off) {
         for (int u = warp; u < nrows; u += TILE_THREADS / 32) {
-          const int64_t end = a.hist_off[row0 + u + 1];
+          const int64_t end = a.hist_off[rowid[u] + 1];
           int64_t cur = cursor[u];
           const int64_t limit = t0 + BT;
           while (true) {
@@ -279,7 +292,7 @@ __global__ void __launch_bounds__(TILE_THREADS) fullsort_tile_kernel(const TileA
         if (j >= a.n_targets) continue;
         float sc = DIST ? (margin - sqrtf(acc[x][y])) : acc[x][y];
         if (!TOPK) {
-          a.out[(row0 + u) * a.n_targets + j] = sc;
+          a.out[rowid[u] * a.n_targets + j] = sc;
         } else {
           const bool masked = (a.mask_first && j == 0) || ((maskbits[u * (BT / 32) + (jo >> 5)] >> (jo & 31)) & 1u);
           if (masked) sc = -INFINITY;
@@ -314,23 +327,32 @@ __global__ void __launch_bounds__(TILE_THREADS) fullsort_tile_kernel(const TileA
     for (int idx = threadIdx.x; idx < nrows * k; idx += blockDim.x) {
       const int u = idx / k, i = idx - u * k;
       const uint64_t key = (i < llen[u]) ? lists[u * k + i] : 0ull;
-      a.part_keys[((row0 + u) * a.n_splits + blockIdx.y) * k + i] = key;
+      a.part_keys[((row0 - a.row_begin + u) * a.n_splits + blockIdx.y) * k + i] = key;
     }
+  }
+  if (!a.row_map) break;   // direct rows: the grid covers every row block
   }
 }
 
 // Merge the per-split lists of one row (one warp per row) and decode.
+// With row_map: entry e in [row_begin, min(*row_count, row_end)) of the map, lists at (e - row_begin), output row
+// row_map[e]; warps stride over the entries (the count is only known on the device).
 __global__ void __launch_bounds__(256) topk_merge_kernel(const uint64_t* __restrict__ part_keys, int64_t n,
                                                          int n_splits, int k, int64_t* __restrict__ ids_out,
-                                                         float* __restrict__ scores_out) {
+                                                         float* __restrict__ scores_out,
+                                                         const int32_t* __restrict__ row_map,
+                                                         const int32_t* __restrict__ row_count, int64_t row_begin,
+                                                         int64_t row_end) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   uint64_t* lists = reinterpret_cast<uint64_t*>(smem_raw);  // [warps][k]
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  const int64_t row = (int64_t)blockIdx.x * (blockDim.x >> 5) + warp;
-  if (row >= n) return;
+  const int64_t stop = row_map ? min((int64_t)__ldg(row_count), row_end) : n;
+  const int64_t stride = row_map ? (int64_t)gridDim.x * (blockDim.x >> 5) : stop;   // direct rows: one pass
+  for (int64_t ent = row_begin + (int64_t)blockIdx.x * (blockDim.x >> 5) + warp; ent < stop; ent += stride) {
+  const int64_t row = row_map ? (int64_t)__ldg(row_map + ent) : ent;
   uint64_t* list = lists + warp * k;
   int len = 0;
-  const uint64_t* src = part_keys + row * (int64_t)n_splits * k;
+  const uint64_t* src = part_keys + (ent - row_begin) * (int64_t)n_splits * k;
   if (n_splits == 1) {
     for (int i = lane; i < k; i += 32) list[i] = src[i];
     len = k;
@@ -347,6 +369,8 @@ __global__ void __launch_bounds__(256) topk_merge_kernel(const uint64_t* __restr
     const uint64_t key = list[i];
     ids_out[row * k + i] = key ? key_id(key) : -1;
     if (scores_out) scores_out[row * k + i] = key ? key_score(key) : -INFINITY;
+  }
+  __syncwarp();
   }
 }
 
@@ -461,6 +485,7 @@ int plan_tiles(const kge_model_t* m, int64_t n, int64_t n_targets, int k, bool t
   pl.kpad = (m->d + KC - 1) / KC * KC;
   size_t smem = (size_t)BU * parts * pl.kpad * 4 + (size_t)BT * TS * 4;
   if (topk) smem += (size_t)BU * k * 8 + (size_t)BU * BT * 8 + BU * 8 + BU * (BT / 32) * 4 + BU * 4 * 2 + BU * 8;
+  smem += BU * 8;   // rowid
   pl.smem = smem;
   KGE_REQUIRE(smem <= 220 * 1024, KGE_E_UNSUPPORTED, "embedding_size %d needs %zu bytes of shared memory", m->d, smem);
   pl.n_blocks = (n + BU - 1) / BU;
@@ -602,8 +627,100 @@ extern "C" int kge_full_sort_topk(const kge_model_t* model, const int64_t* heads
   const int warps = 8;
   const int64_t mg = (n + warps - 1) / warps;
   topk_merge_kernel<<<(unsigned)mg, warps * 32, (size_t)warps * k * 8, st>>>(a.part_keys, n, pl.n_splits, k, ids_out,
-                                                                            scores_out);
+                                                                            scores_out, nullptr, nullptr, 0, 0);
   KGE_LAUNCH_CHECK();
+  return 0;
+}
+
+// ---- device-gated exact top-k for a row list that only exists on the device ------------------------------
+// Used by the tensor-core path (mma_topk.cu) for the rows its filter hands back: `row_map[0 .. *row_count)` are
+// their indices.  No host round trip: two fixed-size launches cover every possible count --
+//   entries [0, FB_SPLIT_ROWS)      row blocks x target splits, so that a handful of rows still fills the GPU
+//   entries [FB_SPLIT_ROWS, n)      one CTA per row block (plenty of rows: no splits needed), CTAs stride
+// -- and CTAs beyond the count leave at once (~10 us per call when nothing was flagged).
+namespace {
+constexpr int64_t FB_SPLIT_ROWS = 1024;
+constexpr int FB_SPLITS = 48;
+struct FallbackPlan {
+  TilePlan tp;
+  int splits, tiles_per_split;
+  int64_t keys_a, keys_b;   // part_keys elements of the two regions
+};
+int plan_fallback(const kge_model_t* m, int64_t n, int64_t n_targets, int k, FallbackPlan& fp) {
+  if (int e = plan_tiles(m, n > 0 ? n : 1, n_targets, k, true, fp.tp)) return e;
+  const int64_t n_tiles = (n_targets + BT - 1) / BT;
+  int64_t s = FB_SPLITS;
+  if (s > (n_tiles + 7) / 8) s = (n_tiles + 7) / 8;
+  if (s < 1) s = 1;
+  fp.tiles_per_split = (int)((n_tiles + s - 1) / s);
+  fp.splits = (int)((n_tiles + fp.tiles_per_split - 1) / fp.tiles_per_split);
+  const int64_t ra = n < FB_SPLIT_ROWS ? n : FB_SPLIT_ROWS;
+  fp.keys_a = ra * fp.splits * k;
+  fp.keys_b = (n - ra) * k;
+  return 0;
+}
+}  // namespace
+
+int64_t kge_topk_rows_indirect_workspace_bytes(const kge_model_t* model, int64_t n, int64_t n_targets, int32_t k) {
+  FallbackPlan fp = {};
+  if (!model || k < 1 || k > KMAX || plan_fallback(model, n, n_targets, k, fp)) return -1;
+  return (fp.keys_a + fp.keys_b) * 8;
+}
+
+int kge_topk_rows_indirect(const kge_model_t* model, const int64_t* heads, const int64_t* rels, int64_t n,
+                           int head_is_user, int64_t n_targets, const int64_t* hist_off, const int64_t* hist_items,
+                           int mask_first, int32_t k, const int32_t* row_map, const int32_t* row_count,
+                           int64_t* ids_out, float* scores_out, void* workspace, cudaStream_t st) {
+  if (int e = check_score_model(model)) return e;
+  FallbackPlan fp = {};
+  if (int e = plan_fallback(model, n, n_targets, k, fp)) return e;
+  TileArgs a = {};
+  a.s.m = *model;
+  a.s.heads = heads;
+  a.s.rels = rels;
+  a.s.n = n;
+  a.s.head_is_user = head_is_user;
+  a.s.rel_row = model->ui_relation_fullsort;
+  a.n_targets = n_targets;
+  a.kpad = fp.tp.kpad;
+  a.hist_off = hist_off;
+  a.hist_items = hist_items;
+  a.mask_first = mask_first;
+  a.k = k;
+  a.row_map = row_map;
+  a.row_count = row_count;
+  const bool dist = is_dist(model->model);
+  auto kern = dist ? fullsort_tile_kernel<true, true> : fullsort_tile_kernel<false, true>;
+  KGE_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fp.tp.smem));
+  const int warps = 8;
+  const int64_t ra = n < FB_SPLIT_ROWS ? n : FB_SPLIT_ROWS;
+  uint64_t* keys = reinterpret_cast<uint64_t*>(workspace);
+  // region A: few rows, many splits
+  a.part_keys = keys;
+  a.n_splits = fp.splits;
+  a.tiles_per_split = fp.tiles_per_split;
+  a.row_begin = 0;
+  a.row_end = ra;
+  kern<<<dim3((unsigned)((ra + BU - 1) / BU), (unsigned)fp.splits), TILE_THREADS, fp.tp.smem, st>>>(a);
+  KGE_LAUNCH_CHECK();
+  topk_merge_kernel<<<(unsigned)((ra + warps - 1) / warps), warps * 32, (size_t)warps * k * 8, st>>>(
+      a.part_keys, n, a.n_splits, k, ids_out, scores_out, row_map, row_count, 0, ra);
+  KGE_LAUNCH_CHECK();
+  if (n > ra) {   // region B: one CTA per row block, striding
+    a.part_keys = keys + fp.keys_a;
+    a.n_splits = 1;
+    a.tiles_per_split = (int)((n_targets + BT - 1) / BT);
+    a.row_begin = ra;
+    a.row_end = n;
+    int64_t g = (n - ra + BU - 1) / BU;
+    const int64_t cap = (int64_t)kge_num_sms() * 2;
+    if (g > cap) g = cap;
+    kern<<<dim3((unsigned)g, 1), TILE_THREADS, fp.tp.smem, st>>>(a);
+    KGE_LAUNCH_CHECK();
+    topk_merge_kernel<<<(unsigned)g, warps * 32, (size_t)warps * k * 8, st>>>(a.part_keys, n, 1, k, ids_out, scores_out,
+                                                                             row_map, row_count, ra, n);
+    KGE_LAUNCH_CHECK();
+  }
   return 0;
 }
 

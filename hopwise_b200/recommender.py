@@ -30,6 +30,7 @@ from __future__ import annotations
 import ctypes as C
 import enum
 import math
+import os
 
 import torch
 from torch import nn
@@ -200,8 +201,9 @@ class FusedKGEModel(KnowledgeRecommender):
         self._keepalive = None
         self._touch_bounds = (0, 0, 0)
         self._mma_cache = None
-        self._mma_last_fallback_rows = 0
-        self._mma_total_fallback_rows = 0   # over the model's lifetime (diagnostics)
+        self._mma_ws = {}             # (n, n_targets, k, shape) -> (workspace, row flags, exact-row counter)
+        self._mma_counters = []       # device counters of the calls since the last read of the diagnostics
+        self._mma_total = 0
         self._ready_key = None
         self._struct_cache = {}
 
@@ -235,6 +237,10 @@ class FusedKGEModel(KnowledgeRecommender):
     def _ensure_state(self, device):
         if self._state is not None and self._state["device"] == device:
             return self._state
+        old = self._state   # the model moved: the moments move with it (re-zeroing them would keep _step and
+        #                     silently restart Adam's bias correction from a wrong state)
+        if old is not None and self.__dict__.get("_g_alloc") is not None:
+            raise RuntimeError("a data-parallel replica (symmetric gradient buffer) cannot change device")
         st = {"device": device}
         fams = (
             ("user", self.USER_TABLES, self.n_users),
@@ -272,7 +278,14 @@ class FusedKGEModel(KnowledgeRecommender):
         st["adam_table"] = torch.tensor(list(host), dtype=torch.float32).to(device)
         st["adam_table_len"] = n
         st["loss"] = torch.zeros(1, device=device)
+        if old is not None:
+            st["row_state_flat"].copy_(old["row_state_flat"])
+            for fam, _, _ in fams:
+                for key in ("m", "v"):
+                    for dst, src in zip(st[fam][key], old[fam][key]):
+                        dst.copy_(src)
         self._state = st
+        self._struct_cache = {}
         return st
 
     def _model_struct(self, with_state: bool) -> _abi.kge_model_t:
@@ -465,12 +478,15 @@ class FusedKGEModel(KnowledgeRecommender):
 
     def load_state_dict(self, state_dict, *args, **kwargs):
         self.flush()  # every row current before the weights are overwritten
+        self.invalidate_target_image()
         return super().load_state_dict(state_dict, *args, **kwargs)
 
     def _apply(self, fn, *args, **kwargs):
         # .to(device): optimiser state is rebuilt lazily on the new device (after a flush)
         if self._state is not None:
             self.flush()
+        self.invalidate_target_image()
+        self._mma_ws = {}
         return super()._apply(fn, *args, **kwargs)
 
     @property
@@ -571,27 +587,57 @@ class FusedKGEModel(KnowledgeRecommender):
             "kge_full_sort_topk",
         )
 
+    @staticmethod
+    def _mma_shape() -> int:
+        """Sweep shape forced through KGE_MMA_CFG = a | f | c (tests, experiments); 0 = the library picks."""
+        cfg = os.environ.get("KGE_MMA_CFG", "")
+        return ord(cfg[0]) if cfg[:1] in ("a", "f", "c") else 0
+
     def _mma_supported(self, k: int, n_targets=None) -> bool:
         m = self._model_struct(False)
         n_targets = self.n_items if n_targets is None else n_targets
-        return _abi.lib().kge_full_sort_topk_mma_workspace_bytes(C.byref(m), 1, n_targets, k) >= 0
+        return _abi.lib().kge_full_sort_topk_mma_workspace_bytes(C.byref(m), 1, n_targets, k, self._mma_shape()) >= 0
 
-    def _mma_image(self, m, device, n_targets=None):
-        """bf16 operand image of the target rows, cached until the entity table changes."""
+    def invalidate_target_image(self):
+        """Drop the cached fp16 operand image of the entity table.  Called by everything in this package that
+        writes the weights; call it yourself after writing through ``weight.data`` (such writes do not bump the
+        tensor version the cache is keyed on)."""
+        self._mma_cache = None
+
+    def _mma_image(self, m, device, n_targets=None, shape: int = 0):
+        """fp16 operand image of the target rows, cached until the entity table changes."""
         n_targets = self.n_items if n_targets is None else n_targets
         tabs = self._tables(self.ENTITY_TABLES)
-        key = (self._step, n_targets, tuple(t.data_ptr() for t in tabs), tuple(t._version for t in tabs))
+        key = (self._step, n_targets, shape, tuple(t.data_ptr() for t in tabs), tuple(t._version for t in tabs))
         if self._mma_cache is not None and self._mma_cache[0] == key:
             return self._mma_cache[1]
         lib = _abi.lib()
-        nbytes = lib.kge_mma_image_bytes(C.byref(m), n_targets)
+        nbytes = lib.kge_mma_image_bytes(C.byref(m), n_targets, shape)
         image = torch.empty(nbytes, dtype=torch.uint8, device=device)
         _abi.check(
-            lib.kge_mma_prepare_targets(C.byref(m), n_targets, image.data_ptr(), nbytes, _abi.stream_ptr()),
+            lib.kge_mma_prepare_targets(C.byref(m), n_targets, image.data_ptr(), nbytes, shape, _abi.stream_ptr()),
             "kge_mma_prepare_targets",
         )
         self._mma_cache = (key, image)
         return image
+
+    @property
+    def _mma_last_fallback_rows(self) -> int:
+        """Rows of the most recent tensor-core call that went through the exact kernel (reads a device counter:
+        synchronises; diagnostics and tests only)."""
+        return int(self._mma_counters[-1].item()) if self._mma_counters else 0
+
+    def _fold_mma_counters(self):
+        old = self._mma_counters[:-1]   # the last one stays readable as _mma_last_fallback_rows
+        if old:
+            self._mma_total += int(torch.stack(old).sum().item())
+            self._mma_counters = self._mma_counters[-1:]
+
+    @property
+    def _mma_total_fallback_rows(self) -> int:
+        """The same over the model's lifetime."""
+        self._fold_mma_counters()
+        return self._mma_total + self._mma_last_fallback_rows
 
     def full_sort_topk_kg(self, head_ids, relation_ids, k: int, hist_off=None, hist_items=None, mask_pad: bool = True,
                           return_scores: bool = True, path: str = "auto"):
@@ -637,12 +683,24 @@ class FusedKGEModel(KnowledgeRecommender):
             self._topk_exact(m, users, k, hist_off, hist_items, mask_pad, ids, scores, rels, n_targets)
             return ids, scores
         lib = _abi.lib()
-        need = lib.kge_full_sort_topk_mma_workspace_bytes(C.byref(m), n, n_targets, k)
-        if need < 0:
-            raise _abi.KgeError(f"tensor-core top-k: {lib.kge_last_error().decode()}")
-        image = self._mma_image(m, device, n_targets)
-        ws = torch.empty(need, dtype=torch.uint8, device=device)
-        flags = torch.empty(n, dtype=torch.int32, device=device)
+        shape = self._mma_shape()
+        # workspace, row flags and the counter are cached per call shape: a fresh ~80 MB allocation per call costs
+        # more than the kernels' launch, and nothing in the call needs the host (rows the filter hands back are
+        # recomputed by the exact kernel inside the same call, gated by a device counter)
+        wkey = (n, n_targets, k, shape, device)
+        slot = self._mma_ws.get(wkey)
+        if slot is None:
+            need = lib.kge_full_sort_topk_mma_workspace_bytes(C.byref(m), n, n_targets, k, shape)
+            if need < 0:
+                raise _abi.KgeError(f"tensor-core top-k: {lib.kge_last_error().decode()}")
+            if len(self._mma_ws) >= 4:
+                self._mma_ws.clear()
+            slot = (torch.empty(need, dtype=torch.uint8, device=device),
+                    torch.empty(n, dtype=torch.int32, device=device))
+            self._mma_ws[wkey] = slot
+        ws, flags = slot
+        counter = torch.empty(1, dtype=torch.int32, device=device)
+        image = self._mma_image(m, device, n_targets, shape)
         dbg = None
         if _debug_scores:
             dbg = torch.zeros(n, (n_targets + 127) // 128 * 128, dtype=torch.float32, device=device)
@@ -650,30 +708,13 @@ class FusedKGEModel(KnowledgeRecommender):
             lib.kge_full_sort_topk_mma(
                 C.byref(m), users.data_ptr(), _abi.ptr(rels), n, head_is_user, n_targets, image.data_ptr(), _abi.ptr(hist_off),
                 _abi.ptr(hist_items), 1 if mask_pad else 0, k, ids.data_ptr(), _abi.ptr(scores), flags.data_ptr(),
-                ws.data_ptr(), ws.numel(), _abi.ptr(dbg), _abi.stream_ptr(),
+                counter.data_ptr(), ws.data_ptr(), ws.numel(), _abi.ptr(dbg), shape, _abi.stream_ptr(),
             ),
             "kge_full_sort_topk_mma",
         )
-        bad = torch.nonzero(flags, as_tuple=False).flatten()  # rows the filter could not bound (host sync)
-        self._mma_last_fallback_rows = int(bad.numel())
-        self._mma_total_fallback_rows += self._mma_last_fallback_rows
-        if bad.numel():
-            sub_off = sub_items = None
-            if hist_off is not None:
-                lens = (hist_off[1:] - hist_off[:-1])[bad]
-                sub_off = torch.zeros(bad.numel() + 1, dtype=torch.int64, device=device)
-                torch.cumsum(lens, 0, out=sub_off[1:])
-                total = int(sub_off[-1].item())
-                seg = torch.repeat_interleave(torch.arange(bad.numel(), device=device), lens)
-                pos = torch.arange(total, device=device) - sub_off[seg] + hist_off[bad][seg]
-                sub_items = hist_items[pos].contiguous()
-            sub_ids = torch.empty(bad.numel(), k, dtype=torch.int64, device=device)
-            sub_scores = torch.empty(bad.numel(), k, dtype=torch.float32, device=device) if return_scores else None
-            self._topk_exact(m, users[bad].contiguous(), k, sub_off, sub_items, mask_pad, sub_ids, sub_scores,
-                             None if rels is None else rels[bad].contiguous(), n_targets)
-            ids[bad] = sub_ids
-            if return_scores:
-                scores[bad] = sub_scores
+        self._mma_counters.append(counter)
+        if len(self._mma_counters) > 256:   # keeps the list bounded; one sync per 256 calls
+            self._fold_mma_counters()
         if _debug_scores:
             return ids, scores, dbg
         return ids, scores

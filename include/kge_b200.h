@@ -25,7 +25,7 @@
 extern "C" {
 #endif
 
-#define KGE_ABI_VERSION 1
+#define KGE_ABI_VERSION 2
 
 typedef void* kge_stream_t; /* cudaStream_t */
 
@@ -177,23 +177,29 @@ int kge_full_sort_topk(const kge_model_t* model, const int64_t* heads, const int
 
 /* ---- tensor-core full-sort top-k (tcgen05) -------------------------------------------------------
  * Same contract and same results as kge_full_sort_topk (ids and scores are bit-identical: the
- * bf16 tensor-core pass only filters, every reported score comes from the fp32 chain), for
- * k <= 32 and parts*d (+3 for the L2 models) <= 256.
- * kge_mma_prepare_targets converts entity rows [0, n_targets) into the tiled bf16 operand image
- * (128-byte aligned buffer of kge_mma_image_bytes bytes); rebuild it whenever the entity table
- * changes.  row_flags[n] (int32, device): 0 = row done, 1 = the row must be recomputed with
- * kge_full_sort_topk (its candidate list could not be bounded, or it has fewer than k unmasked
- * targets); ids/scores of flagged rows are not written.  debug_scores: NULL, or [n, ceil(n_targets
- * /128)*128] fp32 receiving the raw tensor-core scores (tests only). */
-int64_t kge_mma_image_bytes(const kge_model_t* model, int64_t n_targets);
+ * fp16 tensor-core pass only filters, under a proven error bound; every reported score comes from
+ * the fp32 chain), for k <= 32 and parts*d (+3 for the L2 models) <= 256.
+ * kge_mma_prepare_targets converts entity rows [0, n_targets) into the tiled, power-of-two-scaled
+ * fp16 operand image (128-byte aligned buffer of kge_mma_image_bytes bytes); rebuild it whenever
+ * the entity table changes.
+ * Rows the filter cannot bound (a candidate list that does not compact, fewer than k unmasked
+ * targets, a query the fp16 scaling cannot hold) are recomputed INSIDE the call by the exact
+ * kernel of kge_full_sort_topk, gated and sized on the device (no host synchronisation):
+ * row_flags[n] (int32, device) = 1 for those rows, *exact_rows (int32, device) = how many.
+ * debug_scores: NULL, or [n, ceil(n_targets/128)*128] fp32 receiving the raw tensor-core scores
+ * (tests only).  shape: 0 = let the library pick the sweep shape, or 'a' / 'f' / 'c' (tests and
+ * experiments; the image depends on it, so pass the same value to all four calls).
+ * workspace: 16-byte aligned, kge_full_sort_topk_mma_workspace_bytes bytes. */
+int64_t kge_mma_image_bytes(const kge_model_t* model, int64_t n_targets, int32_t shape);
 int kge_mma_prepare_targets(const kge_model_t* model, int64_t n_targets, void* image, int64_t image_bytes,
-                            kge_stream_t stream);
-int64_t kge_full_sort_topk_mma_workspace_bytes(const kge_model_t* model, int64_t n, int64_t n_targets, int32_t k);
+                            int32_t shape, kge_stream_t stream);
+int64_t kge_full_sort_topk_mma_workspace_bytes(const kge_model_t* model, int64_t n, int64_t n_targets, int32_t k,
+                                               int32_t shape);
 int kge_full_sort_topk_mma(const kge_model_t* model, const int64_t* heads, const int64_t* rels, int64_t n,
                            int head_is_user, int64_t n_targets, const void* image, const int64_t* hist_off,
                            const int64_t* hist_items, int mask_first, int32_t k, int64_t* ids_out, float* scores_out,
-                           int32_t* row_flags, void* workspace, int64_t workspace_bytes, float* debug_scores,
-                           kge_stream_t stream);
+                           int32_t* row_flags, int32_t* exact_rows, void* workspace, int64_t workspace_bytes,
+                           float* debug_scores, int32_t shape, kge_stream_t stream);
 
 /* kge_topk_hits: collector.py:178-183 without the [n, I] pos_matrix: out[n, k+1] int32 =
  * hit flags of ids[n,k] against the positives CSR (pos_off[n+1], pos_items sorted) then pos_len. */

@@ -73,12 +73,12 @@ def _model_struct(kind, d, rows=1000):
 
 @pytest.mark.parametrize("kind,d,tn", [("DistMult", 64, 128), ("ComplEx", 64, 128), ("TransE", 100, 128),
                                        ("RotatE", 120, 64), ("ComplEx", 128, 64)])
-def test_sweep_plan_sizes(monkeypatch, kind, d, tn):
-    """plan_mma (csrc/mma_topk.cu) without a GPU: the operand image is tiles of TN rows of the padded K, the
-    workspace holds one 128-entry list per (row, split, slice) plus the per-row bitmap; K > 256 is refused."""
+def test_sweep_plan_sizes(kind, d, tn):
+    """plan_mma (csrc/mma_topk.cu) without a GPU: the operand image is tiles of TN rows of the padded K (fp16), the
+    workspace holds one 128-entry list per (row, split, slice), the per-row scalars and bitmap, the row map and
+    the partial lists of the device-gated exact fallback; K > 256 and k > 32 are refused."""
     from hopwise_b200 import _abi
 
-    monkeypatch.delenv("KGE_MMA_CFG", raising=False)
     lib = _abi.lib()
     m = _model_struct(kind, d)
     n_targets = 200_001
@@ -86,17 +86,27 @@ def test_sweep_plan_sizes(monkeypatch, kind, d, tn):
     kd = parts * d + (3 if kind in ("TransE", "RotatE") else 0)
     kp = (kd + 15) // 16 * 16
     tiles = (n_targets + tn - 1) // tn
-    img = lib.kge_mma_image_bytes(C.byref(m), n_targets)
+    img = lib.kge_mma_image_bytes(C.byref(m), n_targets, 0)
     assert img == 128 + tiles * tn * kp * 2 + (n_targets * 4 + 127) // 128 * 128
-    n = 75_776
-    ws = lib.kge_full_sort_topk_mma_workspace_bytes(C.byref(m), n, n_targets, 20)
+    n, k = 75_776, 20
+    ws = lib.kge_full_sort_topk_mma_workspace_bytes(C.byref(m), n, n_targets, k, 0)
     rows_pad = (n + 255) // 256 * 256
     wpr = (tiles * (tn // 32) + 31) // 32
     ncol = 2 if (tn == 128 and kp > 80) else 1           # shape (f): two column slices per tile
-    assert ws == ncol * rows_pad * (128 * 8 + 8) + rows_pad * 4 + rows_pad * wpr * 4   # one split at this size
-    assert lib.kge_full_sort_topk_mma_workspace_bytes(C.byref(m), n, n_targets, 64) == -1    # k > 32
+    a16 = lambda x: (x + 15) // 16 * 16                  # noqa: E731
+    lists = ncol * rows_pad                              # one split at this size
+    exact_tiles = (n_targets + 127) // 128               # the fallback: 1024 rows x 48 target splits, the rest 1 list
+    tps = (exact_tiles + 47) // 48
+    exact = (1024 * ((exact_tiles + tps - 1) // tps) * k + (n - 1024) * k) * 8
+    want = (a16(lists * 128 * 8) + 2 * a16(lists * 4) + 2 * a16(rows_pad * 4) + a16(rows_pad * wpr * 4)
+            + a16(rows_pad * 4) + a16(exact))
+    assert ws == want
+    assert lib.kge_full_sort_topk_mma_workspace_bytes(C.byref(m), n, n_targets, 64, 0) == -1    # k > 32
     big = _model_struct("ComplEx", 160)
-    assert lib.kge_mma_image_bytes(C.byref(big), n_targets) == -1                          # K = 320 > 256
+    assert lib.kge_mma_image_bytes(C.byref(big), n_targets, 0) == -1                          # K = 320 > 256
+    # a forced shape is accepted ('c' always fits), an unknown one is refused
+    assert lib.kge_mma_image_bytes(C.byref(m), n_targets, ord("c")) > 0
+    assert lib.kge_mma_image_bytes(C.byref(m), n_targets, ord("x")) == -1
 
 
 def test_product_has_no_cpu_fallback_and_no_oracle_import():

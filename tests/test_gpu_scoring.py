@@ -236,14 +236,18 @@ def test_full_size_topk_properties():
 
 
 # ---- tensor-core (tcgen05) path: identical results to the fp32 CUDA-core path -----------------------
-def _bf16_round(x):
-    return torch.from_numpy(np.ascontiguousarray(x)).to(torch.bfloat16).to(torch.float32).numpy()
+def _f16_round(x):
+    """fp16 rounding after the power-of-two scaling of csrc/mma_topk.cu (largest element into [2^7, 2^8))."""
+    x = np.ascontiguousarray(x, dtype=np.float32)
+    e = 7 - int(np.floor(np.log2(np.abs(x).max())))
+    return np.ldexp(np.ldexp(x, e).astype(np.float16).astype(np.float32), -e)
 
 
 @pytest.mark.parametrize("name,d", [("DistMult", 64), ("ComplEx", 32), ("TransE", 100), ("RotatE", 24)])
-def test_mma_raw_scores_match_bf16_emulation(name, d):
-    """The raw tensor-core scores equal q^ . t^ (bf16-rounded operands, fp32 accumulation): checks the
-    operand layouts, descriptors and the TMEM read-back independently of the top-k logic."""
+def test_mma_raw_scores_match_fp16_emulation(name, d):
+    """The raw tensor-core scores (unscaled by the kernel's debug dump) equal q^ . t^ (scaled fp16 operands, fp32
+    accumulation): checks the operand layouts, descriptors, scaling and the TMEM read-back independently of the
+    top-k logic."""
     U, I, E, R, k = 400, 1000, 1300, 7, 10
     ora = make_oracle_model(name, U, I, E, R, d)
     m = make_product_model(name, U, I, E, R, d)
@@ -266,12 +270,12 @@ def test_mma_raw_scores_match_bf16_emulation(name, d):
         q = [u[0] * r[0], u[1] * r[0] + u[0] * r[1] - u[1] * r[1]]
     qc = np.concatenate(q, axis=1)
     tc = np.concatenate([t[:I].astype(np.float32) for t in en], axis=1)
-    want = _bf16_round(qc).astype(np.float64) @ _bf16_round(tc).astype(np.float64).T
+    want = np.stack([_f16_round(row) for row in qc]).astype(np.float64) @ _f16_round(tc).astype(np.float64).T
     if name in ("TransE", "RotatE"):
         want = want - 0.5 * (tc.astype(np.float64) ** 2).sum(1)[None, :]
     scale = np.abs(want).max()
-    np.testing.assert_allclose(raw, want, rtol=0, atol=2e-3 * scale)   # q of RotatE differs by sincos ulps
-    assert np.abs(raw - want).mean() < 2e-4 * scale
+    np.testing.assert_allclose(raw, want, rtol=0, atol=3e-4 * scale)   # q of RotatE differs by sincos ulps
+    assert np.abs(raw - want).mean() < 3e-5 * scale
 
 
 @pytest.mark.parametrize("name,d,I,k", [("DistMult", 64, 20000, 20), ("ComplEx", 64, 9000, 20), ("TransE", 100, 12000, 10),
