@@ -69,6 +69,9 @@ constexpr int PRODUCER_WARPS = 0;
 constexpr int PRODUCER_WARPS = 1;
 #endif
 __host__ __device__ constexpr int sweep_threads(int ncol, int nmma) { return (8 * ncol + PRODUCER_WARPS + nmma) * 32; }
+#ifndef KGE_MMA_A_NMMA
+#define KGE_MMA_A_NMMA 1   // MMA issuer warps of shape (a): 1 = one warp for both halves, 2 = one per half (experiment)
+#endif
 constexpr int IMG_HEADER = 128;  // bytes before the first tile image: {max |t|, max |t_c|, max |t|^2} (floats)
 constexpr uint32_t SPIN_LIMIT = 1u << 26;
 
@@ -89,12 +92,24 @@ __device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity) {
       : "memory");
   return ok != 0;
 }
-// A wait that cannot hang the GPU: a protocol bug traps instead of spinning forever.
+// A wait that cannot hang the GPU: a protocol bug traps instead of spinning forever.  The loop is written in PTX:
+// the C form let the compiler re-derive the barrier address (S2R + shifts) inside the spin, eight instructions
+// per poll that compete with the working warps for issue slots.
 __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
-  uint32_t spins = 0;
-  while (!mbar_try_wait(bar, parity)) {
-    if (++spins > SPIN_LIMIT) __trap();
-  }
+  asm volatile(
+      "{\n\t.reg .pred p, q;\n\t.reg .u32 n;\n\t"
+      "mov.u32 n, 0;\n"
+      "KGE_WAIT:\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+      "@p bra KGE_DONE;\n\t"
+      "add.u32 n, n, 1;\n\t"
+      "setp.lt.u32 q, n, %2;\n\t"
+      "@q bra KGE_WAIT;\n\t"
+      "trap;\n"
+      "KGE_DONE:\n\t}"
+      :
+      : "r"(bar), "r"(parity), "n"(SPIN_LIMIT)
+      : "memory");
 }
 __device__ __forceinline__ void mbar_arrive(uint32_t bar) {
   asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
@@ -538,12 +553,15 @@ __device__ __forceinline__ void chunk_push(const float (&gm)[8], float tm, EpiSt
 // NCOL column slices per tile: the 128 rows of a half are covered by NCOL warps per quadrant, each filtering
 // TN / NCOL columns into its own list (a row then owns splits * NCOL lists, merged by the rescore kernel).
 // NMMA issuer warps: 2 = one per row half (needed when the CTA has the SM to itself), 1 = one warp for both.
-template <int TN, int NBUF, int NCOL, int NMMA, bool DBG>
-__global__ void __launch_bounds__(sweep_threads(NCOL, NMMA), NBUF == 1 ? 2 : 1)
+// SPAN (single-buffered shape): an epilogue warp owns a column slice of BOTH row halves and alternates between the
+// two accumulators, so the MMAs that refill one run while the warp filters the other (see the epilogue).
+template <int TN, int NBUF, int NCOL, int NMMA, bool SPAN, bool DBG>
+__global__ void __launch_bounds__(sweep_threads(SPAN ? 1 : NCOL, NMMA), NBUF == 1 ? 2 : 1)
     fullsort_mma_kernel(const MmaArgs a) {
   constexpr int ROOM = 16;              // list room demanded after a compaction
-  constexpr int NCH = TN / CH / NCOL;   // chunks of 32 columns per tile and epilogue thread
-  constexpr int EPI_WARPS = 8 * NCOL, MMA_WARP0 = EPI_WARPS + PRODUCER_WARPS;
+  constexpr int NCH = TN / CH / NCOL;   // chunks of 32 columns per (half) tile and epilogue thread
+  constexpr int EPI_WARPS = SPAN ? 8 : 8 * NCOL, MMA_WARP0 = EPI_WARPS + PRODUCER_WARPS;
+  static_assert(!SPAN || (NBUF == 1 && NCOL == 2 && NCH == 2), "SPAN: two slices of two chunks, one accumulator per half");
   constexpr int PRODUCER_WARP = PRODUCER_WARPS ? EPI_WARPS : -1;
   constexpr int N_WARPS = EPI_WARPS + PRODUCER_WARPS + NMMA;
   constexpr uint32_t TMEM_COLS = 2 * TN * NBUF;
@@ -561,7 +579,9 @@ __global__ void __launch_bounds__(sweep_threads(NCOL, NMMA), NBUF == 1 ? 2 : 1)
   float* inv_row = eps_row + MM;                                        // [MM] 1 / S_i
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(inv_row + MM);
 
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  // (the shuffle tells the compiler that the warp index is warp-uniform: TMEM addresses, barrier addresses and the
+  // role tests then live in uniform registers instead of the 96 vector registers the epilogue is short of)
+  const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0), lane = threadIdx.x & 31;
   const int64_t row0 = (int64_t)blockIdx.x * MM;
   const int nrows = (int)min((int64_t)MM, a.s.n - row0);
   const int split = blockIdx.y;
@@ -634,7 +654,7 @@ __global__ void __launch_bounds__(sweep_threads(NCOL, NMMA), NBUF == 1 ? 2 : 1)
     }
     for (int x = 0; x < 4; ++x) {
       mbar_init(smem_u32(&bars[2 * a.stages + x]), 1);      // tfull[buf][half]: one commit
-      mbar_init(smem_u32(&bars[2 * a.stages + 4 + x]), 4 * NCOL);  // tempty[buf][half]: the epilogue warps of the half
+      mbar_init(smem_u32(&bars[2 * a.stages + 4 + x]), SPAN ? 8 : 4 * NCOL);  // tempty[buf][half]: the warps that read it
     }
     fence_mbar_init();
   }
@@ -739,106 +759,19 @@ __global__ void __launch_bounds__(sweep_threads(NCOL, NMMA), NBUF == 1 ? 2 : 1)
       }
     }
   } else {
-    // ===== epilogue: one thread per query row =====
-    const int h = (warp >> 2) & 1, quad = warp & 3;   // quad == warp % 4: the TMEM lane quadrant this warp may read
-    const int cs = warp >> 3;                         // column slice of the tile
-    const int64_t lsplit = (int64_t)split * NCOL + cs;   // list index of this (target split, column slice)
-    const int u = h * 128 + quad * 32 + lane;
-    const bool active = u < nrows;
-    const int64_t qrow = row0 + u;
-    const int64_t lrow = lsplit * a.rows_pad + qrow;   // list of (row, split, slice)
-    EpiState st;
-    const bool usable = active && eps_row[u] < INFINITY;   // a row the fp16 scaling cannot represent goes to the exact path
-    st.thr = usable ? -INFINITY : INFINITY;
-    const uint32_t wbase = (uint32_t)(lrow * CAND);
-    st.widx = wbase;
-    const float inv_scale = DBG ? inv_row[u] : 0.f;
-    uint32_t tlane = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(h * TN + cs * NCH * CH);
-    asm volatile("" : "+r"(tlane));   // keep the address in a register (ptxas would rebuild it from tid every tile)
-    uint32_t my_tfull = tfull0 + 8 * h, my_tempty = tempty0 + 8 * h;   // + 16 * buf
-    asm volatile("" : "+r"(my_tfull), "+r"(my_tempty));
-
-    // The row's "unsafe chunk" bitmap, one 32-chunk word at a time (the next word is fetched a window ahead), so
-    // that a list entry is born with its safety flag and a compaction never has to look it up.
-    const uint32_t* urow = a.unsafe_bits + qrow * a.unsafe_wpr;
-    auto uload = [&](int64_t w) -> uint32_t { return (active && w < a.unsafe_wpr) ? __ldg(urow + w) : 0u; };
-    uint32_t uw_cur = 0u, uw_nxt = uload((int64_t)((t0 * (TN / CH)) >> 5));
-    uint32_t uw_idx = 0xFFFFFFFFu;
-    // debug dump of one chunk (unscaled approximate scores)
-    auto dump = [&](const uint32_t (&r)[32], uint32_t cid) {
-      if (DBG && active) {
-        float* o = a.dbg_out + qrow * a.dbg_stride + (int64_t)cid * CH;
-#pragma unroll
-        for (int j = 0; j < CH; ++j) o[j] = __uint_as_float(r[j]) * inv_scale;
-      }
-    };
-
-    // Chunk pipeline.  A tile is NCH chunks of 32 columns per thread, taken two at a time (register sets va / vb):
-    //   wait for the pair | reduce va -> 8 group maxima, re-issue va | reduce vb, re-issue vb | the two (rare) list
-    //   appends
-    // so the TMEM loads of the next pair are in flight under the append paths, and a set is overwritten as soon as
-    // its 20-instruction max tree has consumed it.  The accumulator goes back to the tensor core when the tile's
-    // LAST pair sits in registers, i.e. before half of the tile is filtered: with one buffer per half (NBUF == 1) the
-    // MMAs of the next tile then run under the second half of the filter instead of after it.  (Round 1 waited
-    // after every chunk, and ptxas had scheduled the first consumers right behind each LDTM: one exposed TMEM
-    // latency per chunk -- the sweep ran at 44 % issue / 44 % tensor activity, bound by neither.)
-    constexpr int NPAIR = NCH / 2;
-    uint32_t va[32], vb[32];
-    float gm[8];
-    mbar_wait(my_tfull, 0u);
-    tc_fence_after();
-    tmem_ld32_issue(tlane, va);
-    tmem_ld32_issue(tlane + CH, vb);
-    const int nti = (int)nt;
-    uint32_t cid = (uint32_t)(t0 * (TN / CH) + cs * NCH);
-    for (int i = 0; i < nti; ++i, cid += TN / CH) {
-      const uint32_t buf = NBUF == 1 ? 0u : (uint32_t)(i & 1);
-      const uint32_t nbuf = NBUF == 1 ? 0u : (buf ^ 1u);
-      const uint32_t tbase = tlane + buf * 2 * TN, nbase = tlane + nbuf * 2 * TN;
-      const bool more = i + 1 < nti;
-      if ((cid >> 5) != uw_idx) {   // a tile never straddles a bitmap word (TN / CH divides 32)
-        uw_idx = cid >> 5;
-        uw_cur = uw_nxt;
-        uw_nxt = uload((int64_t)uw_idx + 1);
-      }
-#pragma unroll
-      for (int p = 0; p < NPAIR; ++p) {
-        const bool last = p == NPAIR - 1;
-        tmem_ld_wait2(va, vb);
-        bool refill = !last;
-        if (last) {   // every chunk of the tile is in registers: release the accumulator
-          tc_fence_before();
-          __syncwarp();
-          if (lane == 0) mbar_arrive(my_tempty + 16 * buf);
-          if (NBUF == 2 && more) {   // the other buffer was computed while this tile was filtered
-            mbar_wait(my_tfull + 16 * nbuf, (uint32_t)(((i + 1) / NBUF) & 1));
-            tc_fence_after();
-            refill = true;
-          }
-        }
-        // (targets beyond the table: zero rows of the image, chunks marked unsafe)
-#ifndef KGE_EXP_NOFILTER
-        dump(va, cid + 2 * p);
-        const float tma = chunk_reduce(va, gm);
-#endif
-        if (refill) tmem_ld32_issue(last ? nbase : tbase + (uint32_t)((2 * p + 2) * CH), va);
-#ifndef KGE_EXP_NOFILTER
-        chunk_push(gm, tma, st, cid + 2 * p, uw_cur, a.cand);
-        dump(vb, cid + 2 * p + 1);
-        const float tmb = chunk_reduce(vb, gm);
-#endif
-        if (refill) tmem_ld32_issue(last ? nbase + CH : tbase + (uint32_t)((2 * p + 3) * CH), vb);
-#ifndef KGE_EXP_NOFILTER
-        chunk_push(gm, tmb, st, cid + 2 * p + 1, uw_cur, a.cand);
-#endif
-      }
-      unsigned full = __ballot_sync(0xffffffffu, (int)(st.widx & (CAND - 1)) > (TRIG < CAND - (NCH + 1) ? TRIG : CAND - (NCH + 1)));
+    // ===== epilogue =====
+    const int quad = warp & 3;   // == warp % 4: the TMEM lane quadrant this warp may read
+    // Compaction of the lists of this warp's rows that are (nearly) full; `st` is the lane's list of row `u`.
+    auto compact_full = [&](EpiState& st, int u, int64_t lsplit, int trig) {
+      const uint32_t wbase = (uint32_t)((lsplit * a.rows_pad + row0 + u) * CAND);
+      unsigned full = __ballot_sync(0xffffffffu, (int)(st.widx & (CAND - 1)) > trig);
       while (full) {
         const int r = __ffs(full) - 1;
         full &= full - 1;
         const int cnt_r = __shfl_sync(0xffffffffu, (int)(st.widx & (CAND - 1)), r);
-        const float eps_r = eps_row[h * 128 + quad * 32 + r];
-        const int64_t qrow_r = row0 + h * 128 + quad * 32 + r;
+        const int u_r = u - lane + r;
+        const float eps_r = eps_row[u_r];
+        const int64_t qrow_r = row0 + u_r;
         uint2* buf_r = a.cand + (lsplit * a.rows_pad + qrow_r) * CAND;
         __syncwarp();
         float thr_new;
@@ -853,16 +786,186 @@ __global__ void __launch_bounds__(sweep_threads(NCOL, NMMA), NBUF == 1 ? 2 : 1)
           }
         }
       }
-      if (NBUF == 1 && more) {   // the tile computed while the second half of this one was filtered
-        mbar_wait(my_tfull, (uint32_t)((i + 1) & 1));
-        tc_fence_after();
-        tmem_ld32_issue(tlane, va);
-        tmem_ld32_issue(tlane + CH, vb);
+    };
+    auto init_state = [&](EpiState& st, int u, int64_t lsplit) {
+      const bool usable = u < nrows && eps_row[u] < INFINITY;   // rows the fp16 scaling cannot hold: exact path
+      st.thr = usable ? -INFINITY : INFINITY;
+      st.widx = (uint32_t)((lsplit * a.rows_pad + row0 + u) * CAND);
+    };
+    auto store_state = [&](const EpiState& st, int u, int64_t lsplit) {
+      if (u < nrows) {   // (a list's threshold starts at -inf and only ever rises to finite values)
+        const int64_t lrow = lsplit * a.rows_pad + row0 + u;
+        a.cand_cnt[lrow] = st.thr == INFINITY ? -1 : (int)(st.widx - (uint32_t)(lrow * CAND));
+        a.cand_thr[lrow] = st.thr;
       }
-    }
-    if (active) {   // (a list's threshold starts at -inf and only ever rises to finite values)
-      a.cand_cnt[lrow] = st.thr == INFINITY ? -1 : (int)(st.widx - wbase);
-      a.cand_thr[lrow] = st.thr;
+    };
+    auto dump = [&](const uint32_t (&r)[32], int u, uint32_t cid) {   // debug: unscaled approximate scores
+      if (DBG && u < nrows) {
+        const float inv = inv_row[u];
+        float* o = a.dbg_out + (row0 + u) * a.dbg_stride + (int64_t)cid * CH;
+#pragma unroll
+        for (int j = 0; j < CH; ++j) o[j] = __uint_as_float(r[j]) * inv;
+      }
+    };
+    const int nti = (int)nt;
+    uint32_t va[32], vb[32];
+    float gm[8];
+
+    if constexpr (SPAN) {
+      // ---- one warp = (lane quadrant, 64-column slice) of BOTH halves --------------------------------------
+      // Per tile the warp takes its two chunks of half 0, then its two chunks of half 1.  A half's chunks are loaded
+      // as one batch (two tcgen05.ld in flight, one wait) and the accumulator is released the moment the batch has
+      // landed, so an accumulator is held for one TMEM latency only; its MMAs for the next tile then run while the
+      // warp filters this batch and the other half's batch (about half a tile period), and the loads of the other
+      // half -- already computed -- are in flight under the filter of this one.  With a warp bound to one half and
+      // one accumulator per half (round 1, and the first pair-wise version of this round) tensor phase and filter
+      // phase of a half strictly alternate: MMA-only 1.28 ms + filter-only 1.33 ms gave 2.48 ms, their sum.
+      const int cs = warp >> 2;
+      const int64_t lsplit = (int64_t)split * NCOL + cs;
+      const int ua = quad * 32 + lane, ub = ua + 128;
+      EpiState sa, sb;
+      init_state(sa, ua, lsplit);
+      init_state(sb, ub, lsplit);
+      const uint32_t tlane = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(cs * NCH * CH);   // half 1: + TN
+      const uint32_t my_tfull = tfull0, my_tempty = tempty0;   // half 1: + 8
+      // "unsafe chunk" bitmap words of the two rows (one word = 32 chunks = 8 tiles; reloaded when the tile enters
+      // a new word: one exposed L2 latency per 8 tiles instead of two more live registers for a prefetch)
+      uint32_t uwa = 0u, uwb = 0u, uw_idx = 0xFFFFFFFFu;
+      auto release = [&](int half) {   // this warp's share of the half's accumulator sits in registers
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(my_tempty + 8 * half);
+      };
+      mbar_wait(my_tfull, 0u);
+      tc_fence_after();
+      tmem_ld32_issue(tlane, va);
+      tmem_ld32_issue(tlane + CH, vb);
+      uint32_t cid = (uint32_t)(t0 * (TN / CH) + cs * NCH);
+      for (int i = 0; i < nti; ++i, cid += TN / CH) {
+        const bool more = i + 1 < nti;
+        const uint32_t ph = (uint32_t)(i & 1);
+        if ((cid >> 5) != uw_idx) {   // a tile never straddles a bitmap word (TN / CH divides 32)
+          uw_idx = cid >> 5;
+          const uint32_t* ura = a.unsafe_bits + (row0 + ua) * a.unsafe_wpr + uw_idx;   // (addresses rebuilt here: rare)
+          uwa = (ua < nrows && uw_idx < a.unsafe_wpr) ? __ldg(ura) : 0u;
+          uwb = (ub < nrows && uw_idx < a.unsafe_wpr) ? __ldg(ura + 128 * a.unsafe_wpr) : 0u;
+        }
+        // half 0
+        tmem_ld_wait2(va, vb);
+        release(0);
+        mbar_wait(my_tfull + 8, ph);   // half 1 of this tile: its MMAs were issued a filter phase ago
+        tc_fence_after();
+#ifndef KGE_EXP_NOFILTER
+        dump(va, ua, cid);
+        float tm = chunk_reduce(va, gm);
+#endif
+        tmem_ld32_issue(tlane + TN, va);
+#ifndef KGE_EXP_NOFILTER
+        chunk_push(gm, tm, sa, cid, uwa, a.cand);
+        dump(vb, ua, cid + 1);
+        tm = chunk_reduce(vb, gm);
+#endif
+        tmem_ld32_issue(tlane + TN + CH, vb);
+#ifndef KGE_EXP_NOFILTER
+        chunk_push(gm, tm, sa, cid + 1, uwa, a.cand);
+#endif
+        // half 1
+        tmem_ld_wait2(va, vb);
+        release(1);
+        if (more) {
+          mbar_wait(my_tfull, ph ^ 1u);   // half 0 of the next tile
+          tc_fence_after();
+        }
+#ifndef KGE_EXP_NOFILTER
+        dump(va, ub, cid);
+        tm = chunk_reduce(va, gm);
+#endif
+        if (more) tmem_ld32_issue(tlane, va);
+#ifndef KGE_EXP_NOFILTER
+        chunk_push(gm, tm, sb, cid, uwb, a.cand);
+        dump(vb, ub, cid + 1);
+        tm = chunk_reduce(vb, gm);
+#endif
+        if (more) tmem_ld32_issue(tlane + CH, vb);
+#ifndef KGE_EXP_NOFILTER
+        chunk_push(gm, tm, sb, cid + 1, uwb, a.cand);
+#endif
+        constexpr int trig = TRIG < CAND - (NCH + 1) ? TRIG : CAND - (NCH + 1);
+        compact_full(sa, ua, lsplit, trig);
+        compact_full(sb, ub, lsplit, trig);
+      }
+      store_state(sa, ua, lsplit);
+      store_state(sb, ub, lsplit);
+    } else {
+      // ---- one warp = (row half, lane quadrant, column slice); two accumulators per half -------------------
+      // Software pipeline over chunks: the load of the next chunk is in flight while the current one is filtered,
+      // and an accumulator goes back to the tensor core as soon as its last chunk sits in registers (the MMAs of
+      // the next tile already run in the other buffer).
+      const int h = (warp >> 2) & 1;
+      const int cs = warp >> 3;                         // column slice of the tile
+      const int64_t lsplit = (int64_t)split * NCOL + cs;   // list index of this (target split, column slice)
+      const int u = h * 128 + quad * 32 + lane;
+      const bool active = u < nrows;
+      EpiState st;
+      init_state(st, u, lsplit);
+      uint32_t tlane = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(h * TN + cs * NCH * CH);
+      asm volatile("" : "+r"(tlane));   // keep the address in a register (ptxas would rebuild it from tid every tile)
+      uint32_t my_tfull = tfull0 + 8 * h, my_tempty = tempty0 + 8 * h;   // + 16 * buf
+      asm volatile("" : "+r"(my_tfull), "+r"(my_tempty));
+      // The row's "unsafe chunk" bitmap, one 32-chunk word at a time (the next word is fetched a window ahead), so
+      // that a list entry is born with its safety flag and a compaction never has to look it up.
+      const uint32_t* urow = a.unsafe_bits + (row0 + u) * a.unsafe_wpr;
+      auto uload = [&](int64_t w) -> uint32_t { return (active && w < a.unsafe_wpr) ? __ldg(urow + w) : 0u; };
+      uint32_t uw_cur = 0u, uw_nxt = uload((int64_t)((t0 * (TN / CH)) >> 5));
+      uint32_t uw_idx = 0xFFFFFFFFu;
+      auto process = [&](const uint32_t (&r)[32], uint32_t cid) {
+#ifndef KGE_EXP_NOFILTER
+        dump(r, u, cid);
+        const float tm = chunk_reduce(r, gm);
+        chunk_push(gm, tm, st, cid, uw_cur, a.cand);   // (targets beyond the table: zero rows, chunks marked unsafe)
+#endif
+      };
+      mbar_wait(my_tfull, 0u);
+      tc_fence_after();
+      tmem_ld32_issue(tlane, va);
+      tmem_ld_wait(va);
+      uint32_t cid = (uint32_t)(t0 * (TN / CH) + cs * NCH);
+      for (int i = 0; i < nti; ++i, cid += TN / CH) {
+        const uint32_t buf = NBUF == 1 ? 0u : (uint32_t)(i & 1);
+        const uint32_t tbase = tlane + buf * 2 * TN;
+        if ((cid >> 5) != uw_idx) {   // a tile never straddles a bitmap word (TN / CH divides 32)
+          uw_idx = cid >> 5;
+          uw_cur = uw_nxt;
+          uw_nxt = uload((int64_t)uw_idx + 1);
+        }
+#pragma unroll
+        for (int c = 0; c < NCH; ++c) {
+          uint32_t(&cur)[32] = (c & 1) ? vb : va;
+          uint32_t(&nxt)[32] = (c & 1) ? va : vb;
+          if (c + 1 < NCH) {
+            tmem_ld32_issue(tbase + (uint32_t)((c + 1) * CH), nxt);
+            process(cur, cid + c);
+            tmem_ld_wait(nxt);
+            if (c + 1 == NCH - 1) {   // every chunk of the tile is in registers: release the accumulator
+              tc_fence_before();
+              __syncwarp();
+              if (lane == 0) mbar_arrive(my_tempty + 16 * buf);
+            }
+          } else {
+            if (NBUF == 1) process(cur, cid + c);
+            if (i + 1 < nti) {
+              const uint32_t nbuf = NBUF == 1 ? 0u : (buf ^ 1u);
+              mbar_wait(my_tfull + 16 * nbuf, (uint32_t)(((i + 1) / NBUF) & 1));
+              tc_fence_after();
+              tmem_ld32_issue(tlane + nbuf * 2 * TN, nxt);
+            }
+            if (NBUF != 1) process(cur, cid + c);
+            if (i + 1 < nti) tmem_ld_wait(nxt);
+          }
+        }
+        compact_full(st, u, lsplit, TRIG < CAND - (NCH + 1) ? TRIG : CAND - (NCH + 1));
+      }
+      store_state(st, u, lsplit);
     }
   }
 
@@ -1226,7 +1329,7 @@ int plan_mma(const kge_model_t* m, int64_t n, int64_t n_targets, int k, int shap
   }
   pl.tn = cfg == 'c' ? 64 : 128;
   pl.nbuf = cfg == 'a' ? 1 : 2;
-  pl.ncol = cfg == 'f' ? 2 : 1;
+  pl.ncol = cfg == 'c' ? 1 : 2;   // (a): two 64-column slices per tile, each filtered by warps that span both halves
   const size_t b_bytes = (size_t)pl.tn * pl.kp * 2;
   size_t budget = cfg == 'a' ? two_per_sm : one_per_sm;
   KGE_REQUIRE(fixed + 2 * b_bytes <= budget, KGE_E_UNSUPPORTED, "K = %d leaves no room for a pipeline", pl.kp);
@@ -1385,18 +1488,19 @@ extern "C" int kge_full_sort_topk_mma(const kge_model_t* model, const int64_t* h
     KGE_LAUNCH_CHECK();
   }
   const dim3 grid((unsigned)(pl.rows_pad / MM), (unsigned)pl.splits);
-#define KGE_SWEEP(TN_, NB_, NC_, NM_, DBG_)                                                                        \
+#define KGE_SWEEP(TN_, NB_, NC_, NM_, SP_, DBG_)                                                                   \
   do {                                                                                                            \
-    KGE_CUDA(cudaFuncSetAttribute(fullsort_mma_kernel<TN_, NB_, NC_, NM_, DBG_>,                                  \
+    KGE_CUDA(cudaFuncSetAttribute(fullsort_mma_kernel<TN_, NB_, NC_, NM_, SP_, DBG_>,                             \
                                   cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pl.smem));                    \
-    fullsort_mma_kernel<TN_, NB_, NC_, NM_, DBG_><<<grid, sweep_threads(NC_, NM_), pl.smem, st>>>(a);             \
+    fullsort_mma_kernel<TN_, NB_, NC_, NM_, SP_, DBG_>                                                            \
+        <<<grid, sweep_threads(SP_ ? 1 : NC_, NM_), pl.smem, st>>>(a);                                            \
   } while (0)
   if (pl.tn == 128 && pl.nbuf == 1) {
-    if (debug_scores) KGE_SWEEP(128, 1, 1, 1, true); else KGE_SWEEP(128, 1, 1, 1, false);
+    if (debug_scores) KGE_SWEEP(128, 1, 2, KGE_MMA_A_NMMA, true, true); else KGE_SWEEP(128, 1, 2, KGE_MMA_A_NMMA, true, false);
   } else if (pl.tn == 128) {
-    if (debug_scores) KGE_SWEEP(128, 2, 2, 2, true); else KGE_SWEEP(128, 2, 2, 2, false);
+    if (debug_scores) KGE_SWEEP(128, 2, 2, 2, false, true); else KGE_SWEEP(128, 2, 2, 2, false, false);
   } else {
-    if (debug_scores) KGE_SWEEP(64, 2, 1, 2, true); else KGE_SWEEP(64, 2, 1, 2, false);
+    if (debug_scores) KGE_SWEEP(64, 2, 1, 2, false, true); else KGE_SWEEP(64, 2, 1, 2, false, false);
   }
 #undef KGE_SWEEP
   KGE_LAUNCH_CHECK();

@@ -1,41 +1,29 @@
-"""Import the real hopwise from /root/reference (build container only).
+"""Import the real hopwise (oracle/_ref, built from /root/reference by oracle/build_ref.py).
 
-Used by make_golden.py and by the few CPU tests that compare the oracle with the live
-reference when it happens to be present.  Nothing that runs on the GPU box imports this.
+Used by make_golden.py and by the tests that compare the oracle or the product with the live
+reference.  Test infrastructure only.
 """
 
 import os
 import sys
-import types
 
-REFERENCE_ROOT = "/root/reference"
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
 
 
 def reference_available() -> bool:
-    return os.path.isdir(os.path.join(REFERENCE_ROOT, "hopwise"))
+    from oracle import ref
+
+    return ref.ref_available()
 
 
 def import_reference():
-    """Stub the three logging-only dependencies the container lacks, then import hopwise."""
-    if not reference_available():
-        raise RuntimeError("reference tree not present")
-    if "colorama" not in sys.modules:
-        m = types.ModuleType("colorama")
-        m.init = lambda *a, **k: None
-        sys.modules["colorama"] = m
-    if "colorlog" not in sys.modules:
-        m = types.ModuleType("colorlog")
-        m.ColoredFormatter = type("ColoredFormatter", (), {"__init__": lambda self, *a, **k: None})
-        sys.modules["colorlog"] = m
-    if "texttable" not in sys.modules:
-        m = types.ModuleType("texttable")
-        m.Texttable = type("Texttable", (), {"__init__": lambda self, *a, **k: None})
-        sys.modules["texttable"] = m
-    if REFERENCE_ROOT not in sys.path:
-        sys.path.insert(0, REFERENCE_ROOT)
-    import hopwise  # noqa: F401
+    """hopwise from oracle/_ref: the unmodified copy of /root/reference/hopwise that oracle/build_ref.py makes (plus
+    stubs for the three logging-only dependencies the image lacks).  One copy per process, whoever asks first."""
+    from oracle import ref
 
-    return hopwise
+    return ref.import_ref()
 
 
 class FakeDataset:
