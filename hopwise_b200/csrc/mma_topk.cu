@@ -1329,7 +1329,11 @@ int plan_mma(const kge_model_t* m, int64_t n, int64_t n_targets, int k, int shap
   }
   pl.tn = cfg == 'c' ? 64 : 128;
   pl.nbuf = cfg == 'a' ? 1 : 2;
-  pl.ncol = cfg == 'c' ? 1 : 2;   // (a): two 64-column slices per tile, each filtered by warps that span both halves
+#ifdef KGE_MMA_SPAN   // experiment: shape (a) with warps that span both row halves (measured slower: 3.06 vs 2.1 ms)
+  pl.ncol = cfg == 'c' ? 1 : 2;
+#else
+  pl.ncol = cfg == 'f' ? 2 : 1;
+#endif
   const size_t b_bytes = (size_t)pl.tn * pl.kp * 2;
   size_t budget = cfg == 'a' ? two_per_sm : one_per_sm;
   KGE_REQUIRE(fixed + 2 * b_bytes <= budget, KGE_E_UNSUPPORTED, "K = %d leaves no room for a pipeline", pl.kp);
@@ -1496,7 +1500,11 @@ extern "C" int kge_full_sort_topk_mma(const kge_model_t* model, const int64_t* h
         <<<grid, sweep_threads(SP_ ? 1 : NC_, NM_), pl.smem, st>>>(a);                                            \
   } while (0)
   if (pl.tn == 128 && pl.nbuf == 1) {
+#ifdef KGE_MMA_SPAN
     if (debug_scores) KGE_SWEEP(128, 1, 2, KGE_MMA_A_NMMA, true, true); else KGE_SWEEP(128, 1, 2, KGE_MMA_A_NMMA, true, false);
+#else
+    if (debug_scores) KGE_SWEEP(128, 1, 1, KGE_MMA_A_NMMA, false, true); else KGE_SWEEP(128, 1, 1, KGE_MMA_A_NMMA, false, false);
+#endif
   } else if (pl.tn == 128) {
     if (debug_scores) KGE_SWEEP(128, 2, 2, 2, false, true); else KGE_SWEEP(128, 2, 2, 2, false, false);
   } else {

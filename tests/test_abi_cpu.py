@@ -92,7 +92,7 @@ def test_sweep_plan_sizes(kind, d, tn):
     ws = lib.kge_full_sort_topk_mma_workspace_bytes(C.byref(m), n, n_targets, k, 0)
     rows_pad = (n + 255) // 256 * 256
     wpr = (tiles * (tn // 32) + 31) // 32
-    ncol = 2 if tn == 128 else 1                         # shapes (a) and (f): two column slices per tile
+    ncol = 2 if (tn == 128 and kp > 80) else 1           # shape (f): two column slices per tile
     a16 = lambda x: (x + 15) // 16 * 16                  # noqa: E731
     lists = ncol * rows_pad                              # one split at this size
     exact_tiles = (n_targets + 127) // 128               # the fallback: 1024 rows x 48 target splits, the rest 1 list
