@@ -514,12 +514,6 @@ struct EpiState {
 #endif
 constexpr int TRIG = KGE_MMA_TRIG;   // a list is compacted when it holds more than TRIG entries at the end of a tile
 
-// y |= bit when a >= b, as a compare and a predicated OR (the C form costs a compare, a select and an add)
-template <uint32_t BIT>
-__device__ __forceinline__ void or_if_ge(uint32_t& y, float a, float b) {
-  asm("{\n\t.reg .pred p;\n\tsetp.ge.f32 p, %1, %2;\n\t@p or.b32 %0, %0, %3;\n\t}" : "+r"(y) : "f"(a), "f"(b), "n"(BIT));
-}
-
 // One chunk (32 columns = 8 groups of 4) of one row, in two steps so that the registers of the chunk are free for
 // the next tcgen05.ld as early as possible: the group maxima and the chunk maximum ...
 __device__ __forceinline__ float chunk_reduce(const uint32_t (&r)[32], float (&gm)[8]) {
@@ -530,19 +524,23 @@ __device__ __forceinline__ float chunk_reduce(const uint32_t (&r)[32], float (&g
   return fmaxf(max3f(gm[0], gm[1], gm[2]), max3f(max3f(gm[3], gm[4], gm[5]), gm[6], gm[7]));
 }
 // ... and (rarely) one list entry.
-__device__ __forceinline__ void chunk_push(const float (&gm)[8], float tm, EpiState& st, uint32_t cid, uint32_t uword,
+// The entry is born without its safety flag (F_KNOWN clear): whoever needs it -- the next compaction of the list, or
+// the rescore kernel -- reads one word of the row's "unsafe chunk" bitmap.  Carrying the bitmap through the sweep
+// (round 1) cost three live registers and ~13 ALU-pipe instructions per tile in a loop that is bound by exactly
+// that pipe (FMNMX / FSETP / IADD / LOP3 issue every other cycle per scheduler: B300_MICROARCH "pipe rates").
+__device__ __forceinline__ void chunk_push(const float (&gm)[8], float tm, EpiState& st, uint32_t cid8,
                                            uint2* __restrict__ cand) {
   if (tm >= st.thr) {  // rare per row after the first tiles (but most warps have one such row per chunk)
-    uint32_t y = (cid << CID_SHIFT) | F_KNOWN;
-    y |= ((uword >> (cid & 31u)) & 1u) << 31;   // bit 31 = F_UNSAFE
-    or_if_ge<1u>(y, gm[0], st.thr);
-    or_if_ge<2u>(y, gm[1], st.thr);
-    or_if_ge<4u>(y, gm[2], st.thr);
-    or_if_ge<8u>(y, gm[3], st.thr);
-    or_if_ge<16u>(y, gm[4], st.thr);
-    or_if_ge<32u>(y, gm[5], st.thr);
-    or_if_ge<64u>(y, gm[6], st.thr);
-    or_if_ge<128u>(y, gm[7], st.thr);
+    // Group mask from sign bits: gm - thr on the FMA pipe, one funnel shift per group on the ALU pipe (a compare
+    // plus a predicated add per group costs twice the ALU slots).  acc collects "below the threshold" bits, first
+    // group in the highest position: mask bit (7 - g) <=> group g cleared the threshold.
+    uint32_t acc = 0u;
+#pragma unroll
+    for (int g = 0; g < 8; ++g) {
+      const uint32_t d = __float_as_uint(__fsub_rn(gm[g], st.thr));   // sign bit set <=> gm < thr (gm == thr: +0)
+      asm("shf.l.wrap.b32 %0, %1, %0, 1;" : "+r"(acc) : "r"(d));
+    }
+    const uint32_t y = cid8 | (~acc & 0xFFu);
     cand[st.widx] = make_uint2(__float_as_uint(tm), y);
     ++st.widx;
   }
@@ -553,15 +551,12 @@ __device__ __forceinline__ void chunk_push(const float (&gm)[8], float tm, EpiSt
 // NCOL column slices per tile: the 128 rows of a half are covered by NCOL warps per quadrant, each filtering
 // TN / NCOL columns into its own list (a row then owns splits * NCOL lists, merged by the rescore kernel).
 // NMMA issuer warps: 2 = one per row half (needed when the CTA has the SM to itself), 1 = one warp for both.
-// SPAN (single-buffered shape): an epilogue warp owns a column slice of BOTH row halves and alternates between the
-// two accumulators, so the MMAs that refill one run while the warp filters the other (see the epilogue).
-template <int TN, int NBUF, int NCOL, int NMMA, bool SPAN, bool DBG>
-__global__ void __launch_bounds__(sweep_threads(SPAN ? 1 : NCOL, NMMA), NBUF == 1 ? 2 : 1)
+template <int TN, int NBUF, int NCOL, int NMMA, bool DBG>
+__global__ void __launch_bounds__(sweep_threads(NCOL, NMMA), NBUF == 1 ? 2 : 1)
     fullsort_mma_kernel(const MmaArgs a) {
   constexpr int ROOM = 16;              // list room demanded after a compaction
-  constexpr int NCH = TN / CH / NCOL;   // chunks of 32 columns per (half) tile and epilogue thread
-  constexpr int EPI_WARPS = SPAN ? 8 : 8 * NCOL, MMA_WARP0 = EPI_WARPS + PRODUCER_WARPS;
-  static_assert(!SPAN || (NBUF == 1 && NCOL == 2 && NCH == 2), "SPAN: two slices of two chunks, one accumulator per half");
+  constexpr int NCH = TN / CH / NCOL;   // chunks of 32 columns per tile and epilogue thread
+  constexpr int EPI_WARPS = 8 * NCOL, MMA_WARP0 = EPI_WARPS + PRODUCER_WARPS;
   constexpr int PRODUCER_WARP = PRODUCER_WARPS ? EPI_WARPS : -1;
   constexpr int N_WARPS = EPI_WARPS + PRODUCER_WARPS + NMMA;
   constexpr uint32_t TMEM_COLS = 2 * TN * NBUF;
@@ -654,7 +649,7 @@ __global__ void __launch_bounds__(sweep_threads(SPAN ? 1 : NCOL, NMMA), NBUF == 
     }
     for (int x = 0; x < 4; ++x) {
       mbar_init(smem_u32(&bars[2 * a.stages + x]), 1);      // tfull[buf][half]: one commit
-      mbar_init(smem_u32(&bars[2 * a.stages + 4 + x]), SPAN ? 8 : 4 * NCOL);  // tempty[buf][half]: the warps that read it
+      mbar_init(smem_u32(&bars[2 * a.stages + 4 + x]), 4 * NCOL);  // tempty[buf][half]: the epilogue warps of the half
     }
     fence_mbar_init();
   }
@@ -811,92 +806,7 @@ __global__ void __launch_bounds__(sweep_threads(SPAN ? 1 : NCOL, NMMA), NBUF == 
     uint32_t va[32], vb[32];
     float gm[8];
 
-    if constexpr (SPAN) {
-      // ---- one warp = (lane quadrant, 64-column slice) of BOTH halves --------------------------------------
-      // Per tile the warp takes its two chunks of half 0, then its two chunks of half 1.  A half's chunks are loaded
-      // as one batch (two tcgen05.ld in flight, one wait) and the accumulator is released the moment the batch has
-      // landed, so an accumulator is held for one TMEM latency only; its MMAs for the next tile then run while the
-      // warp filters this batch and the other half's batch (about half a tile period), and the loads of the other
-      // half -- already computed -- are in flight under the filter of this one.  With a warp bound to one half and
-      // one accumulator per half (round 1, and the first pair-wise version of this round) tensor phase and filter
-      // phase of a half strictly alternate: MMA-only 1.28 ms + filter-only 1.33 ms gave 2.48 ms, their sum.
-      const int cs = warp >> 2;
-      const int64_t lsplit = (int64_t)split * NCOL + cs;
-      const int ua = quad * 32 + lane, ub = ua + 128;
-      EpiState sa, sb;
-      init_state(sa, ua, lsplit);
-      init_state(sb, ub, lsplit);
-      const uint32_t tlane = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(cs * NCH * CH);   // half 1: + TN
-      const uint32_t my_tfull = tfull0, my_tempty = tempty0;   // half 1: + 8
-      // "unsafe chunk" bitmap words of the two rows (one word = 32 chunks = 8 tiles; reloaded when the tile enters
-      // a new word: one exposed L2 latency per 8 tiles instead of two more live registers for a prefetch)
-      uint32_t uwa = 0u, uwb = 0u, uw_idx = 0xFFFFFFFFu;
-      auto release = [&](int half) {   // this warp's share of the half's accumulator sits in registers
-        tc_fence_before();
-        __syncwarp();
-        if (lane == 0) mbar_arrive(my_tempty + 8 * half);
-      };
-      mbar_wait(my_tfull, 0u);
-      tc_fence_after();
-      tmem_ld32_issue(tlane, va);
-      tmem_ld32_issue(tlane + CH, vb);
-      uint32_t cid = (uint32_t)(t0 * (TN / CH) + cs * NCH);
-      for (int i = 0; i < nti; ++i, cid += TN / CH) {
-        const bool more = i + 1 < nti;
-        const uint32_t ph = (uint32_t)(i & 1);
-        if ((cid >> 5) != uw_idx) {   // a tile never straddles a bitmap word (TN / CH divides 32)
-          uw_idx = cid >> 5;
-          const uint32_t* ura = a.unsafe_bits + (row0 + ua) * a.unsafe_wpr + uw_idx;   // (addresses rebuilt here: rare)
-          uwa = (ua < nrows && uw_idx < a.unsafe_wpr) ? __ldg(ura) : 0u;
-          uwb = (ub < nrows && uw_idx < a.unsafe_wpr) ? __ldg(ura + 128 * a.unsafe_wpr) : 0u;
-        }
-        // half 0
-        tmem_ld_wait2(va, vb);
-        release(0);
-        mbar_wait(my_tfull + 8, ph);   // half 1 of this tile: its MMAs were issued a filter phase ago
-        tc_fence_after();
-#ifndef KGE_EXP_NOFILTER
-        dump(va, ua, cid);
-        float tm = chunk_reduce(va, gm);
-#endif
-        tmem_ld32_issue(tlane + TN, va);
-#ifndef KGE_EXP_NOFILTER
-        chunk_push(gm, tm, sa, cid, uwa, a.cand);
-        dump(vb, ua, cid + 1);
-        tm = chunk_reduce(vb, gm);
-#endif
-        tmem_ld32_issue(tlane + TN + CH, vb);
-#ifndef KGE_EXP_NOFILTER
-        chunk_push(gm, tm, sa, cid + 1, uwa, a.cand);
-#endif
-        // half 1
-        tmem_ld_wait2(va, vb);
-        release(1);
-        if (more) {
-          mbar_wait(my_tfull, ph ^ 1u);   // half 0 of the next tile
-          tc_fence_after();
-        }
-#ifndef KGE_EXP_NOFILTER
-        dump(va, ub, cid);
-        tm = chunk_reduce(va, gm);
-#endif
-        if (more) tmem_ld32_issue(tlane, va);
-#ifndef KGE_EXP_NOFILTER
-        chunk_push(gm, tm, sb, cid, uwb, a.cand);
-        dump(vb, ub, cid + 1);
-        tm = chunk_reduce(vb, gm);
-#endif
-        if (more) tmem_ld32_issue(tlane + CH, vb);
-#ifndef KGE_EXP_NOFILTER
-        chunk_push(gm, tm, sb, cid + 1, uwb, a.cand);
-#endif
-        constexpr int trig = TRIG < CAND - (NCH + 1) ? TRIG : CAND - (NCH + 1);
-        compact_full(sa, ua, lsplit, trig);
-        compact_full(sb, ub, lsplit, trig);
-      }
-      store_state(sa, ua, lsplit);
-      store_state(sb, ub, lsplit);
-    } else {
+    {
       // ---- one warp = (row half, lane quadrant, column slice); two accumulators per half -------------------
       // Software pipeline over chunks: the load of the next chunk is in flight while the current one is filtered,
       // and an accumulator goes back to the tensor core as soon as its last chunk sits in registers (the MMAs of
@@ -905,24 +815,16 @@ __global__ void __launch_bounds__(sweep_threads(SPAN ? 1 : NCOL, NMMA), NBUF == 
       const int cs = warp >> 3;                         // column slice of the tile
       const int64_t lsplit = (int64_t)split * NCOL + cs;   // list index of this (target split, column slice)
       const int u = h * 128 + quad * 32 + lane;
-      const bool active = u < nrows;
       EpiState st;
       init_state(st, u, lsplit);
-      uint32_t tlane = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(h * TN + cs * NCH * CH);
-      asm volatile("" : "+r"(tlane));   // keep the address in a register (ptxas would rebuild it from tid every tile)
-      uint32_t my_tfull = tfull0 + 8 * h, my_tempty = tempty0 + 8 * h;   // + 16 * buf
-      asm volatile("" : "+r"(my_tfull), "+r"(my_tempty));
-      // The row's "unsafe chunk" bitmap, one 32-chunk word at a time (the next word is fetched a window ahead), so
-      // that a list entry is born with its safety flag and a compaction never has to look it up.
-      const uint32_t* urow = a.unsafe_bits + (row0 + u) * a.unsafe_wpr;
-      auto uload = [&](int64_t w) -> uint32_t { return (active && w < a.unsafe_wpr) ? __ldg(urow + w) : 0u; };
-      uint32_t uw_cur = 0u, uw_nxt = uload((int64_t)((t0 * (TN / CH)) >> 5));
-      uint32_t uw_idx = 0xFFFFFFFFu;
+      // (warp-uniform: these live in uniform registers)
+      const uint32_t tlane = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(h * TN + cs * NCH * CH);
+      const uint32_t my_tfull = tfull0 + 8 * h, my_tempty = tempty0 + 8 * h;   // + 16 * buf
       auto process = [&](const uint32_t (&r)[32], uint32_t cid) {
 #ifndef KGE_EXP_NOFILTER
         dump(r, u, cid);
         const float tm = chunk_reduce(r, gm);
-        chunk_push(gm, tm, st, cid, uw_cur, a.cand);   // (targets beyond the table: zero rows, chunks marked unsafe)
+        chunk_push(gm, tm, st, cid << CID_SHIFT, a.cand);   // (targets beyond the table: zero rows, chunks marked unsafe)
 #endif
       };
       mbar_wait(my_tfull, 0u);
@@ -933,11 +835,6 @@ __global__ void __launch_bounds__(sweep_threads(SPAN ? 1 : NCOL, NMMA), NBUF == 
       for (int i = 0; i < nti; ++i, cid += TN / CH) {
         const uint32_t buf = NBUF == 1 ? 0u : (uint32_t)(i & 1);
         const uint32_t tbase = tlane + buf * 2 * TN;
-        if ((cid >> 5) != uw_idx) {   // a tile never straddles a bitmap word (TN / CH divides 32)
-          uw_idx = cid >> 5;
-          uw_cur = uw_nxt;
-          uw_nxt = uload((int64_t)uw_idx + 1);
-        }
 #pragma unroll
         for (int c = 0; c < NCH; ++c) {
           uint32_t(&cur)[32] = (c & 1) ? vb : va;
@@ -994,6 +891,8 @@ struct RescoreArgs {
   int64_t* ids_out;
   float* scores_out;
   int32_t* row_flags;
+  const uint32_t* unsafe_bits;   // [rows_pad][unsafe_wpr] the sweep's bitmap (entries may come without their flag)
+  int64_t unsafe_wpr;
   int32_t* row_map;      // rows handed to the exact kernel, in arrival order ...
   int32_t* exact_rows;   // ... and their count (zeroed by the caller)
 };
@@ -1101,21 +1000,9 @@ __global__ void __launch_bounds__(RS_WARPS * 32, KGE_RS_MINB) rescore_topk_kerne
       uint32_t key = 0u;
       if (__uint_as_float(e.x) >= thr0) {
         bool unsafe = (e.y & F_UNSAFE) != 0;
-        if (!(e.y & F_KNOWN)) {
+        if (!(e.y & F_KNOWN)) {   // appended since the list's last compaction: one word of the row's bitmap
           const uint32_t cid = (e.y >> CID_SHIFT) & CID_MASK;
-          const int64_t j0 = (int64_t)cid * CH;
-          if (j0 + CH > mi.n_targets || (mi.mask_first && cid == 0)) {
-            unsafe = true;
-          } else if (hist_sm) {
-            int lo = 0, hi = hlen;
-            while (lo < hi) {
-              const int mid = (lo + hi) >> 1;
-              if ((int64_t)hist[mid] < j0) lo = mid + 1; else hi = mid;
-            }
-            unsafe = lo < hlen && (int64_t)hist[lo] < j0 + CH;
-          } else {
-            unsafe = chunk_unsafe(mi, cid);
-          }
+          unsafe = (__ldg(a.unsafe_bits + row * a.unsafe_wpr + (cid >> 5)) >> (cid & 31u)) & 1u;
         }
         if (!unsafe) key = orderable(__uint_as_float(e.x));
       }
@@ -1175,9 +1062,9 @@ __global__ void __launch_bounds__(RS_WARPS * 32, KGE_RS_MINB) rescore_topk_kerne
       pos = incl - pos;
       __syncwarp();
       while (gmask) {
-        const int g = __ffs(gmask) - 1;
+        const int b = __ffs(gmask) - 1;   // mask bit b = group 7 - b of the chunk (see chunk_push)
         gmask &= gmask - 1;
-        kbuf[pos++] = cid * 8u + (uint32_t)g;
+        kbuf[pos++] = cid * 8u + (uint32_t)(7 - b);
       }
       __syncwarp();
       // exact scores of the members
@@ -1329,11 +1216,7 @@ int plan_mma(const kge_model_t* m, int64_t n, int64_t n_targets, int k, int shap
   }
   pl.tn = cfg == 'c' ? 64 : 128;
   pl.nbuf = cfg == 'a' ? 1 : 2;
-#ifdef KGE_MMA_SPAN   // experiment: shape (a) with warps that span both row halves (measured slower: 3.06 vs 2.1 ms)
-  pl.ncol = cfg == 'c' ? 1 : 2;
-#else
   pl.ncol = cfg == 'f' ? 2 : 1;
-#endif
   const size_t b_bytes = (size_t)pl.tn * pl.kp * 2;
   size_t budget = cfg == 'a' ? two_per_sm : one_per_sm;
   KGE_REQUIRE(fixed + 2 * b_bytes <= budget, KGE_E_UNSUPPORTED, "K = %d leaves no room for a pipeline", pl.kp);
@@ -1492,23 +1375,18 @@ extern "C" int kge_full_sort_topk_mma(const kge_model_t* model, const int64_t* h
     KGE_LAUNCH_CHECK();
   }
   const dim3 grid((unsigned)(pl.rows_pad / MM), (unsigned)pl.splits);
-#define KGE_SWEEP(TN_, NB_, NC_, NM_, SP_, DBG_)                                                                   \
+#define KGE_SWEEP(TN_, NB_, NC_, NM_, DBG_)                                                                        \
   do {                                                                                                            \
-    KGE_CUDA(cudaFuncSetAttribute(fullsort_mma_kernel<TN_, NB_, NC_, NM_, SP_, DBG_>,                             \
+    KGE_CUDA(cudaFuncSetAttribute(fullsort_mma_kernel<TN_, NB_, NC_, NM_, DBG_>,                                  \
                                   cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pl.smem));                    \
-    fullsort_mma_kernel<TN_, NB_, NC_, NM_, SP_, DBG_>                                                            \
-        <<<grid, sweep_threads(SP_ ? 1 : NC_, NM_), pl.smem, st>>>(a);                                            \
+    fullsort_mma_kernel<TN_, NB_, NC_, NM_, DBG_><<<grid, sweep_threads(NC_, NM_), pl.smem, st>>>(a);             \
   } while (0)
   if (pl.tn == 128 && pl.nbuf == 1) {
-#ifdef KGE_MMA_SPAN
-    if (debug_scores) KGE_SWEEP(128, 1, 2, KGE_MMA_A_NMMA, true, true); else KGE_SWEEP(128, 1, 2, KGE_MMA_A_NMMA, true, false);
-#else
-    if (debug_scores) KGE_SWEEP(128, 1, 1, KGE_MMA_A_NMMA, false, true); else KGE_SWEEP(128, 1, 1, KGE_MMA_A_NMMA, false, false);
-#endif
+    if (debug_scores) KGE_SWEEP(128, 1, 1, KGE_MMA_A_NMMA, true); else KGE_SWEEP(128, 1, 1, KGE_MMA_A_NMMA, false);
   } else if (pl.tn == 128) {
-    if (debug_scores) KGE_SWEEP(128, 2, 2, 2, false, true); else KGE_SWEEP(128, 2, 2, 2, false, false);
+    if (debug_scores) KGE_SWEEP(128, 2, 2, 2, true); else KGE_SWEEP(128, 2, 2, 2, false);
   } else {
-    if (debug_scores) KGE_SWEEP(64, 2, 1, 2, false, true); else KGE_SWEEP(64, 2, 1, 2, false, false);
+    if (debug_scores) KGE_SWEEP(64, 2, 1, 2, true); else KGE_SWEEP(64, 2, 1, 2, false);
   }
 #undef KGE_SWEEP
   KGE_LAUNCH_CHECK();
@@ -1531,6 +1409,8 @@ extern "C" int kge_full_sort_topk_mma(const kge_model_t* model, const int64_t* h
   r.ids_out = ids_out;
   r.scores_out = scores_out;
   r.row_flags = row_flags;
+  r.unsafe_bits = a.unsafe_bits;
+  r.unsafe_wpr = a.unsafe_wpr;
   r.row_map = reinterpret_cast<int32_t*>(ws + w.rowmap);
   r.exact_rows = exact_rows;
   r.nent = r.splits * CAND > RS_GIDS ? r.splits * CAND : RS_GIDS;
