@@ -336,6 +336,78 @@ def cpu_reference_steps(w, steps, warmup, budget_s=None, threads=None):
     return done * (w["n_rec"] + w["n_kg"]) / dt, done, torch.get_num_threads(), dt, kind, per
 
 
+def config1_pipeline(arm):
+    """BASELINE config 1 -- TransE on the bundled ml-100k, d = 64, batch 2048, 1 negative -- through hopwise's OWN
+    pipeline (Config -> create_dataset -> data_preparation -> get_model / get_trainer -> trainer), run from
+    oracle/_ref.  arm "reference": hopwise's TransE + KGTrainer on the host cores.  arm "ours": the same
+    factories after hopwise_b200.trainer.install(), i.e. hopwise_b200.TransE + FusedKGTrainer on the GPU; config,
+    dataset, loaders and the (CPU, numpy) samplers are the reference's in both arms.  Timed: one training epoch
+    (39 steps, 158,708 positive triples incl. the loader) and one full-sort evaluation of the test split."""
+    try:
+        from oracle import ref as oref
+
+        if not oref.ref_available():
+            return {"unavailable": "oracle/_ref is not built (oracle/build_ref.py needs /root/reference)"}
+        oref.import_ref()
+        import tempfile
+
+        from hopwise.config import Config
+        from hopwise.data import create_dataset, data_preparation
+        from hopwise.utils import get_model, get_trainer, init_seed
+
+        ours = arm == "ours"
+        if ours:
+            import hopwise_b200.trainer as fused
+
+            fused.install()
+        cwd = os.getcwd()
+        os.chdir(tempfile.mkdtemp(prefix="hopwise_bench_"))   # hopwise writes log/ and log_tensorboard/ into the cwd
+        try:
+            torch.set_num_threads(host_threads())
+            config = Config(model="TransE", dataset="ml-100k",
+                            config_dict={"embedding_size": 64, "train_batch_size": 2048, "epochs": 1, "use_gpu": ours,
+                                         "show_progress": False, "eval_step": 1, "seed": 2024})
+            init_seed(config["seed"], config["reproducibility"])
+            dataset = create_dataset(config)
+            train_data, valid_data, test_data = data_preparation(config, dataset)
+            init_seed(config["seed"], config["reproducibility"])
+            model = get_model(config["model"])(config, train_data.dataset).to(config["device"])
+            trainer = get_trainer(config["MODEL_TYPE"], config["model"])(config, model)
+            sync = torch.cuda.synchronize if ours else (lambda: None)
+            triples = 0
+            if ours:   # warm-up epoch: CUDA context, optimiser state, pinned staging (the reference needs none)
+                trainer._train_epoch(train_data, 0)
+            n_rec = len(train_data._dataset.inter_feat) if hasattr(train_data, "_dataset") else 78836
+            steps = len(train_data)
+            triples = n_rec + steps * 2048
+            sync()
+            t0 = time.perf_counter()
+            loss = trainer._train_epoch(train_data, 1 if ours else 0)
+            sync()
+            t_train = time.perf_counter() - t0
+            if ours:
+                trainer.evaluate(test_data, load_best_model=False)   # builds the device plan of the loader
+            sync()
+            t0 = time.perf_counter()
+            result = trainer.evaluate(test_data, load_best_model=False)
+            sync()
+            t_eval = time.perf_counter() - t0
+            n_eval = len(test_data.uid_list)
+            return {"arm": arm, "model": type(model).__module__ + "." + type(model).__name__,
+                    "trainer": type(trainer).__name__, "device": str(config["device"]),
+                    "train_epoch_s": t_train, "steps": steps, "triples_per_s": triples / t_train,
+                    "epoch_loss": float(loss), "eval_s": t_eval, "eval_users": n_eval,
+                    "eval_users_per_s": n_eval / t_eval, "metrics": {k: float(v) for k, v in result.items()},
+                    "cores": torch.get_num_threads(),
+                    "what": "one epoch (hopwise's loader + CPU samplers included) and one test-split evaluation"}
+        finally:
+            os.chdir(cwd)
+            if ours:
+                fused.uninstall()
+    except Exception as exc:   # report, never hide
+        return {"error": repr(exc)}
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)

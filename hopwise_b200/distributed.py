@@ -110,12 +110,15 @@ class RowSparseExchange:
         parts = (len(model.USER_TABLES), len(model.ENTITY_TABLES), len(model.RELATION_TABLES))
         # a step cannot touch more distinct rows than the table has
         self.layout = FlatLayout(rows, parts, model.embedding_size)
-        self._caps_for = None
+        self._agreed = None        # per-table bounds on touched rows that every rank plans with
         self.device = device
         self.send = self.recv = None
         self.dense = [False, False, False]
         self.bytes_per_step = 0
         self.kernels_per_step = 0   # launches of this library's pack / add kernels in the last step
+        self.timing = False        # record CUDA events around pack / collective / add (bench.py)
+        self.timings = []          # [(pack_ms, collective_ms, add_ms)] of the timed steps, read by take_timings()
+        self._events = []
 
     def _install_multimem(self, model):
         """Have the model allocate its flat gradient buffer in symmetric memory with a multicast mapping.
@@ -164,10 +167,33 @@ class RowSparseExchange:
         else:
             dist.all_reduce(g_flat[g0:g1], op=dist.ReduceOp.SUM, group=self.group)
 
+    def _agree(self, batch_rows):
+        """Bounds on the rows a step can touch, identical on every rank.
+
+        The message layout, the all-gather size and the dense / sparse route per table all derive from these
+        bounds, so ranks that planned with their LOCAL batch shapes would disagree as soon as the shapes differ (a
+        short last batch on one rank, an empty KG half): mismatched all-gather sizes, or an all-reduce on some
+        ranks against an all-gather on others -- an NCCL hang.  The first step agrees on the element-wise maximum
+        (every rank takes its first step together, so the collective is safe there); later steps only check that
+        the local shape still fits.  A job whose batches can grow passes `max_batch_rows` to
+        enable_row_sparse_data_parallel instead."""
+        if self._agreed is None:
+            t = torch.tensor(list(batch_rows), dtype=torch.int64, device=self.device or "cpu")
+            dist.all_reduce(t, op=dist.ReduceOp.MAX, group=self.group)
+            self._agreed = tuple(int(x) for x in t.tolist())
+        if any(b > a for b, a in zip(batch_rows, self._agreed)):
+            raise RuntimeError(
+                f"a batch can touch {tuple(batch_rows)} rows (user, entity, relation) but the ranks agreed on "
+                f"{self._agreed} at the first step; pass max_batch_rows= to enable_row_sparse_data_parallel")
+        return self._agreed
+
     def _plan(self, model, batch_rows):
-        """Tighten the per-table capacity to what this batch shape can touch; pick the route per table."""
+        """Tighten the per-table capacity to what a batch can touch (agreed across ranks); pick the route per table."""
         rows = (model.n_users, model.n_entities, model.n_relations)
         parts = self.layout.parts
+        if self.device is None:
+            self.device = next(model.parameters()).device
+        batch_rows = self._agree(batch_rows)
         caps = [max(1, min(r, b)) for r, b in zip(rows, batch_rows)]
         self.dense = [2 * c >= r for c, r in zip(caps, rows)]
         caps = [1 if dn else c for c, dn in zip(caps, self.dense)]   # dense tables send nothing through the lists
@@ -193,14 +219,30 @@ class RowSparseExchange:
                 runs.append((g0, g1, r0, r1))
         return runs
 
+    def _mark(self):
+        if self.timing:
+            e = torch.cuda.Event(enable_timing=True)
+            e.record()
+            self._events.append(e)
+
+    def take_timings(self):
+        """[(pack_ms, collective_ms, add_ms)] of the steps since the last call (needs .timing = True; synchronises)."""
+        torch.cuda.synchronize()
+        out = [(ev[0].elapsed_time(ev[1]), ev[1].elapsed_time(ev[2]), ev[2].elapsed_time(ev[3]))
+               for ev in (self._events[i : i + 4] for i in range(0, len(self._events) - 3, 4))]
+        self._events = []
+        return out
+
     def __call__(self, model):
         step = model._step + 1
         self._plan(model, model._touch_bounds)
         sparse = [w for w in range(3) if not self.dense[w]]
         self.kernels_per_step = len(sparse) * (1 + self.world)
+        self._mark()
         for which in sparse:
             count, ids, rows = self.layout.views(self.send, which)
             self.pack_fn(model, which, step, count, ids, rows)
+        self._mark()
         st = model._state
         for g0, g1, r0, r1 in self._dense_spans(model):
             self._all_reduce_dense(st["g_flat"], g0, g1)
@@ -209,23 +251,33 @@ class RowSparseExchange:
             # the lazy replay) does to it -- same weights, one collective less per step.
             st["row_state_flat"][r0:r1, 1].fill_(step)
         if not sparse:
+            self._mark()
+            self._mark()
             return
         dist.all_gather_into_tensor(self.recv, self.send, group=self.group)
+        self._mark()
         n = self.layout.nbytes
         for r in range(self.world):  # fixed order on every rank => identical fp32 sums
             chunk = self.recv[r * n : (r + 1) * n]
             for which in sparse:
                 count, ids, rows = self.layout.views(chunk, which)
                 self.add_fn(model, which, step, count, ids, rows)
+        self._mark()
 
 
-def enable_row_sparse_data_parallel(model, group=None, multimem=False):
+def enable_row_sparse_data_parallel(model, group=None, multimem=False, max_batch_rows=None):
     """Turn a FusedKGEModel replica into a data-parallel one (call once, after model.to(device),
     on every rank, with identical initial weights: the reference gets that from DDP's rank-0
     broadcast, here `broadcast_weights` does it).  ``multimem=True``: dense tables are reduced in the
     NVSwitch (NVLS multicast) by this library's own kernel instead of NCCL; needs a multicast-capable
-    fabric and must be enabled before the first training step."""
+    fabric and must be enabled before the first training step.
+
+    Every rank must plan with the same bounds on the rows a step can touch (message layout, collective sizes and the
+    dense / sparse choice derive from them): they are agreed with one MAX all-reduce at the first step, or given as
+    ``max_batch_rows`` when later batches can be larger than the first."""
     ex = RowSparseExchange(model, group=group, multimem=multimem)
+    if max_batch_rows is not None:   # (user rows, entity rows, relation rows) a step can touch, same on all ranks
+        ex._agreed = tuple(int(x) for x in max_batch_rows)
     model._grad_sync = ex
     model._grad_scale = 1.0 / ex.world
     return ex
@@ -234,6 +286,8 @@ def enable_row_sparse_data_parallel(model, group=None, multimem=False):
 def broadcast_weights(model, src: int = 0, group=None):
     for p in model.parameters():
         dist.broadcast(p.data, src=src, group=group)
+    if hasattr(model, "invalidate_target_image"):
+        model.invalidate_target_image()   # writes through .data do not bump the version the image cache is keyed on
 
 
 def reduce_metric_sums(sums: torch.Tensor, n_users: int, group=None):
