@@ -42,6 +42,9 @@ WORKLOADS = {
     # BASELINE.json configs[4] shape on one GPU: tables far larger than L2 (no-duplicate regime)
     "cfg5_transe_alibaba": dict(model="TransE", U=115001, I=30001, E=1000001, R=54, d=128, k=1,
                                 n_rec=262144, n_kg=262144, triples=50_000_000, inters=5_000_000),
+    # the same shape at the reference's batch: the row-sparse exchange regime (4k rows of a 1M-row table per step)
+    "cfg5_transe_alibaba_b2048": dict(model="TransE", U=115001, I=30001, E=1000001, R=54, d=128, k=1,
+                                      n_rec=2048, n_kg=2048, triples=50_000_000, inters=5_000_000),
     # BASELINE.json configs[2]: RotatE d=256, 64 negatives per triple
     "cfg3_rotate_yelp": dict(model="RotatE", U=45920, I=45539, E=90001, R=44, d=256, k=64,
                              n_rec=2048, n_kg=2048, triples=1_800_000, inters=1_200_000),
@@ -193,9 +196,9 @@ def time_train_device(model, dev_batches, steps, warmup, flush_buf, world):
         loss.backward()
         ev[i][2].record()
     barrier(world)
-    fwd = sum(e[0].elapsed_time(e[1]) for e in ev)
-    upd = sum(e[1].elapsed_time(e[2]) for e in ev)
-    return fwd, upd, float(loss.item())
+    fwd = np.array([e[0].elapsed_time(e[1]) for e in ev])
+    upd = np.array([e[1].elapsed_time(e[2]) for e in ev])
+    return fwd, upd, float(loss.item())   # per-step milliseconds (forward / backward = exchange + Adam)
 
 
 def time_train_e2e(model, host_batches, steps, warmup, world, device):
@@ -258,9 +261,62 @@ def time_fullsort(fs, device, n_users_step, steps, warmup, world, rank, path="au
     barrier(world)
     ms = ev[0].elapsed_time(ev[-1])
     per_rep = sorted(ev[i].elapsed_time(ev[i + 1]) for i in range(steps))
-    fallback = m._mma_total_fallback_rows   # over warm-up and timed blocks
+    fallback = m._mma_total_fallback_rows if path != "cuda" else 0   # over warm-up and timed blocks
     del m
+    torch.cuda.empty_cache()   # (outside the timed region)
     return ms, fallback, per_rep[len(per_rep) // 2]
+
+
+def full_eval_leg(fs, device, world, rank):
+    """cfg4 end to end: every one of the 1,000,000 users once.  Users are sharded in contiguous blocks over the ranks
+    (hopwise_b200.distributed.shard_bounds); each rank runs fused full-sort top-20 + hit flags + metric sums over its
+    shard (hopwise_b200.evaluator.evaluate_full_sort in blocks of one sweep wave) and the per-rank sums are reduced
+    (reduce_metric_sums) -- all inside the timed region; the result dictionary is the Evaluator's."""
+    from hopwise_b200.distributed import reduce_metric_sums, shard_bounds
+    from hopwise_b200.evaluator import metrics_from_sums, topk_hits, topk_metric_sums
+    from kge_helpers import make_product_model
+
+    m = make_product_model(fs["model"], fs["U"], fs["I"], fs["E"], fs["R"], fs["d"], device=device)
+    n_total = fs["U"] - 1
+    lo, hi = shard_bounds(n_total, rank, world)
+    n = hi - lo
+    rng = np.random.default_rng(77 + rank)
+    users = torch.arange(1 + lo, 1 + hi, dtype=torch.long, device=device)
+    hist = torch.from_numpy(np.sort(rng.integers(1, fs["I"], (n, fs["hist"])), axis=1).reshape(-1)).to(device)
+    hoff = torch.arange(0, fs["hist"] * n + 1, fs["hist"], dtype=torch.long, device=device)
+    npos = 3
+    pos = torch.from_numpy(np.sort(rng.integers(1, fs["I"], (n, npos)), axis=1).reshape(-1)).to(device)
+    poff = torch.arange(0, npos * n + 1, npos, dtype=torch.long, device=device)
+    block = 148 * 512
+
+    def run():
+        sums = torch.zeros(5, fs["k"], dtype=torch.float64, device=device)
+        for s0 in range(0, n, block):
+            e0 = min(n, s0 + block)
+            ids, _ = m.full_sort_topk(users[s0:e0], fs["k"], hoff[s0 : e0 + 1] - s0 * fs["hist"],
+                                      hist[s0 * fs["hist"] : e0 * fs["hist"]], return_scores=False)
+            rec = topk_hits(ids, poff[s0 : e0 + 1] - s0 * npos, pos[s0 * npos : e0 * npos])
+            sums += topk_metric_sums(rec)
+        if world > 1:
+            sums, total = reduce_metric_sums(sums, n)
+        else:
+            total = n
+        return metrics_from_sums(sums, total, [fs["k"]], decimals=None)
+
+    run()   # warm-up: operand image, workspaces, first touches
+    barrier(world)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    result = run()   # ends with the D2H read of the metric sums
+    e1.record()
+    barrier(world)
+    ms = max_over_ranks(e0.elapsed_time(e1), device, world)
+    fb = m._mma_total_fallback_rows
+    del m
+    torch.cuda.empty_cache()
+    return {"users": n_total, "users_per_rank": n, "ms": ms, "users_per_s": n_total / (ms * 1e-3),
+            "metrics": {k: float(v) for k, v in result.items()}, "rows_recomputed_exactly": fb,
+            "what": "1M users x 200,001 items, top-20 + hits + Recall/MRR/NDCG/Hit/Precision, shards reduced over ranks"}
 
 
 def host_threads():
@@ -481,31 +537,43 @@ def main():
     dev_t = [{k: v.to(device) for k, v in b.items()} for b in host_t]
     flush_buf = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device=device)
     h2d = sum(v.numel() * 8 for v in host_t[0].values())
+    peaks = measured_peaks()
 
     with ClockSampler(local) as clocks:
-        fwd_ms, upd_ms, last_loss = time_train_device(model, dev_t, args.steps, args.warmup, flush_buf, world)
+        fwd, upd, last_loss = time_train_device(model, dev_t, args.steps, args.warmup, flush_buf, world)
     clk = clocks.summary()
-    step_ms = max_over_ranks((fwd_ms + upd_ms) / args.steps, device, world)
-    fwd_ms_avg = max_over_ranks(fwd_ms / args.steps, device, world)
-    upd_ms_avg = max_over_ranks(upd_ms / args.steps, device, world)
+    per_step = fwd + upd
+    step_ms = max_over_ranks(float(per_step.mean()), device, world)          # EXACTLY K timed steps, max over ranks
+    step_med_ms = max_over_ranks(float(np.median(per_step)), device, world)
+    fwd_ms_avg = max_over_ranks(float(fwd.mean()), device, world)
+    upd_ms_avg = max_over_ranks(float(upd.mean()), device, world)
     value = world * triples_step / (step_ms * 1e-3)
 
     e2e_ms, e2e_median_ms, e2e_max_ms = time_train_e2e(model, host_t, args.steps, args.warmup, world, device)
     e2e_ms = max_over_ranks(e2e_ms / args.steps, device, world)
     e2e_value = world * triples_step / (e2e_ms * 1e-3)
 
-    peaks = measured_peaks()
     bpt = bytes_per_triple(w["model"], w["d"], w["k"])
     achieved = triples_step * bpt / (step_ms * 1e-3) / 1e9
     traffic, traffic_src = profiled_traffic(args.workload)
-    roof = {"bound": "hbm", "achieved": achieved, "peak": peaks["hbm_gbs"], "unit": "GB/s",
-            "frac": achieved / peaks["hbm_gbs"], "traffic": traffic, "traffic_source": traffic_src,
+    dram_frac = None if traffic is None else traffic / (step_ms * 1e-3) / 1e9 / peaks["hbm_gbs"]
+    # What bounds the step depends on whether the tables fit the 126 MB L2.  cfg2 (36k rows, every row referenced
+    # ~40x per step) is L2-resident: DRAM moves a few % of the algorithmic bytes and the kernel is bound by
+    # instruction issue and L2 atomics, so the algorithmic fraction (> 1 there) is NOT a statement about HBM; the
+    # line says so (`bound`), carries the measured DRAM fraction beside it, and reports the HBM-regime workload
+    # (cfg5: 1M-row tables, no reuse) as `roofline_hbm`.
+    l2_resident = (w["U"] + w["E"]) * w["d"] * PARTS[w["model"]] * 16 < 100e6   # w, m, v, g of user + entity tables
+    roof = {"bound": "issue/L2 (tables L2-resident; see dram_frac)" if l2_resident else "hbm",
+            "achieved": achieved, "peak": peaks["hbm_gbs"], "unit": "GB/s",
+            "frac": achieved / peaks["hbm_gbs"], "algorithmic_frac": achieved / peaks["hbm_gbs"],
+            "dram_frac": dram_frac, "traffic": traffic, "traffic_source": traffic_src,
             "algorithmic_bytes": triples_step * bpt, "peak_source": peaks["source"],
             "kernels": "train_fwd_kernel + adam_apply_kernel (the two launches of one step)",
             "fwd_ms": fwd_ms_avg, "adam_ms": upd_ms_avg, "bytes_per_triple": bpt}
 
     line = {"metric": "KG triples/sec (train step)", "value": value, "unit": "triples/s", "n_gpus": world,
-            "steps": args.steps, "warmup": args.warmup, "ms_per_step": step_ms, "higher_is_better": True,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": step_ms, "median_ms_per_step": step_med_ms,
+            "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": config,
             "e2e": {"value": e2e_value, "unit": "triples/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4,
                     "ms_per_step": e2e_ms, "median_ms_per_step": e2e_median_ms, "max_ms_per_step": e2e_max_ms},
@@ -516,28 +584,65 @@ def main():
     if exchange is not None:
         line["exchange_bytes_per_rank_per_step"] = exchange.bytes_per_step
         line["exchange"] = "nvls multimem all-reduce (csrc/collective.cu)" if exchange.multimem else "nccl all-reduce"
+        line["exchange_routes_dense"] = list(exchange.dense)
+
+    def train_leg(name, steps, world_, data_parallel=False):
+        """One more training workload on this rank's GPU (and, with data_parallel, its exchange across ranks)."""
+        wx = WORKLOADS[name]
+        mx = make_model(wx, device)
+        ex = None
+        if data_parallel:
+            from hopwise_b200.distributed import broadcast_weights, enable_row_sparse_data_parallel
+
+            broadcast_weights(mx)
+            ex = enable_row_sparse_data_parallel(mx, multimem=False)
+            ex.timing = True
+        hb = synth_batches(wx, 4, seed=7 + rank)
+        db = [{k: torch.from_numpy(v).to(device) for k, v in b.items()} for b in hb]
+        f, u, _ = time_train_device(mx, db, steps, args.warmup, flush_buf, world_)
+        if ex is not None:
+            ex.take_timings()   # (drop the warm-up's events: time_train_device warms up first ... they are mixed in)
+        per = f + u
+        ms = max_over_ranks(float(per.mean()), device, world_)
+        med = max_over_ranks(float(np.median(per)), device, world_)
+        t = wx["n_rec"] + wx["n_kg"]
+        bx = bytes_per_triple(wx["model"], wx["d"], wx["k"])
+        out = {"triples_per_s": world_ * t / (ms * 1e-3), "ms_per_step": ms, "median_ms_per_step": med,
+               "fwd_ms": float(f.mean()), "adam_ms": float(u.mean()), "bytes_per_triple": bx,
+               "hbm_frac": t * bx / (ms * 1e-3) / 1e9 / peaks["hbm_gbs"],
+               "hbm_frac_from_median": t * bx / (med * 1e-3) / 1e9 / peaks["hbm_gbs"]}
+        if ex is not None:
+            # split of the exchange (inside `adam_ms`, which covers backward = exchange + Adam): a few more steps
+            for i in range(8):
+                mx.calculate_loss(db[i % 4]).backward()
+            tm = np.array(ex.take_timings())
+            out.update({"exchange": "row-sparse: pack -> one NCCL all-gather -> add" if not all(ex.dense) else
+                                    "dense all-reduce", "routes_dense": list(ex.dense),
+                        "exchange_bytes_per_rank_per_step": ex.bytes_per_step,
+                        "pack_ms": float(np.median(tm[:, 0])), "collective_ms": float(np.median(tm[:, 1])),
+                        "add_ms": float(np.median(tm[:, 2])), "kernels_per_step": 2 + ex.kernels_per_step})
+        del mx, db
+        torch.cuda.empty_cache()
+        return out
 
     if not args.no_extras:
         extras = {}
-        # the reference's default batch on the same KG (launch/latency-bound)
-        if args.workload == "cfg2_transe_ml1m" and world == 1:
-            for name in ("cfg2_transe_ml1m_b2048", "cfg5_transe_alibaba", "cfg3_rotate_yelp"):
-                wx = WORKLOADS[name]
+        # more training workloads: the reference's default batch on the same KG (launch / latency bound), the HBM
+        # regime (cfg5: 1M entities), 64 negatives (cfg3); on several GPUs the same with the exchange running
+        legs = ("cfg2_transe_ml1m_b2048", "cfg5_transe_alibaba", "cfg5_transe_alibaba_b2048", "cfg3_rotate_yelp")
+        if args.workload == "cfg2_transe_ml1m":
+            for name in legs:
                 try:
-                    mx = make_model(wx, device)
-                    hb = synth_batches(wx, 4, seed=7)
-                    db = [{k: torch.from_numpy(v).to(device) for k, v in b.items()} for b in hb]
-                    f, u, _ = time_train_device(mx, db, args.steps, args.warmup, flush_buf, 1)
-                    ms = (f + u) / args.steps
-                    t = wx["n_rec"] + wx["n_kg"]
-                    bx = bytes_per_triple(wx["model"], wx["d"], wx["k"])
-                    extras[name] = {"triples_per_s": t / (ms * 1e-3), "ms_per_step": ms, "fwd_ms": f / args.steps,
-                                    "adam_ms": u / args.steps, "bytes_per_triple": bx,
-                                    "hbm_frac": t * bx / (ms * 1e-3) / 1e9 / peaks["hbm_gbs"]}
-                    del mx, db
-                    torch.cuda.empty_cache()
+                    extras[name] = train_leg(name, args.steps, world, data_parallel=world > 1)
                 except Exception as exc:  # report, never hide
                     extras[name] = {"error": repr(exc)}
+            c5 = extras.get("cfg5_transe_alibaba", {})
+            if "hbm_frac" in c5:   # first-class: the HBM-regime roofline statement of the same kernels
+                line["roofline_hbm"] = {
+                    "workload": "cfg5_transe_alibaba (TransE d=128, E=1,000,001: tables 8x the L2, no row reuse)",
+                    "bound": "hbm", "achieved": c5["hbm_frac"] * peaks["hbm_gbs"], "peak": peaks["hbm_gbs"],
+                    "unit": "GB/s", "frac": c5["hbm_frac"], "frac_from_median": c5["hbm_frac_from_median"],
+                    "ms_per_step": c5["ms_per_step"], "bytes_per_triple": c5["bytes_per_triple"]}
         # the whole reference step at its default batch, loader included: batch order from the CPU torch
         # generators, gathers + both MT19937 samplers + fused step on the device (hopwise_b200.loader.DeviceKGLoader)
         if args.workload == "cfg2_transe_ml1m" and world == 1:
@@ -561,21 +666,26 @@ def main():
                     b = next(it)
                     mx.calculate_loss(b).backward()
                 torch.cuda.synchronize()
-                t0 = time.perf_counter()
+                stamps = [time.perf_counter()]
                 for _ in range(n_steps):
                     b = next(it)
                     loss = mx.calculate_loss(b)
                     loss.item()
                     loss.backward()
+                    stamps.append(time.perf_counter())
                 torch.cuda.synchronize()
-                dt = (time.perf_counter() - t0) / n_steps
+                per = np.diff(np.array(stamps))
                 extras["cfg2_b2048_device_loader"] = {
                     "what": "loader (order + gathers + KG and rec negative sampling) + fused step + loss.item(), wall clock",
-                    "ms_per_step": dt * 1e3, "triples_per_s": (wx["n_rec"] + wx["n_kg"]) / dt}
+                    "ms_per_step": float(per.mean()) * 1e3, "median_ms_per_step": float(np.median(per)) * 1e3,
+                    "triples_per_s": (wx["n_rec"] + wx["n_kg"]) / float(per.mean())}
                 del mx, loader
                 torch.cuda.empty_cache()
             except Exception as exc:
                 extras["cfg2_b2048_device_loader"] = {"error": repr(exc)}
+        # BASELINE config 1 through hopwise's own pipeline (oracle/_ref) with the fused models + FusedKGTrainer
+        if args.workload == "cfg2_transe_ml1m" and world == 1:
+            extras["cfg1_ml100k_pipeline"] = config1_pipeline("ours")
         # second headline metric: users/s of full-sort top-k (user blocks sharded across ranks)
         for name, fs in FULLSORT.items():
             try:
@@ -589,20 +699,25 @@ def main():
                     ms, fb, med = time_fullsort(fs, device, n_users_step, reps, 3, world, rank, path=path)
                     ms = max_over_ranks(ms / reps, device, world)
                     med = max_over_ranks(med, device, world)
-                    # throughput from the median block: every call ends with a host sync, so a host thread that the
-                    # (shared) box deschedules for tens of ms shows up as one slow block; the mean is reported too
-                    ups = world * n_users_step / (med * 1e-3)
-                    entry[path] = {"users_per_s": ups, "ms_per_block": med, "mean_ms_per_block": ms,
-                                   "users_per_s_from_mean": world * n_users_step / (ms * 1e-3),
+                    # headline = the MEAN block (nothing in the call waits for the host any more: the exact fallback
+                    # is gated on the device, the workspace is cached); the median is beside it
+                    ups = world * n_users_step / (ms * 1e-3)
+                    entry[path] = {"users_per_s": ups, "mean_ms_per_block": ms, "median_ms_per_block": med,
+                                   "users_per_s_from_median": world * n_users_step / (med * 1e-3),
                                    "algorithmic_tflops": ups * flops / 1e12,
                                    "tensor_frac_of_bf16_peak": ups / world * flops / 1e12 / peaks["bf16_tflops"],
                                    "rows_recomputed_exactly": fb}
-                    torch.cuda.empty_cache()
-                entry["paths"] = {"mma": "tcgen05 bf16 filter + exact fp32 re-score (same ids/scores)",
+                entry["paths"] = {"mma": "tcgen05 fp16 filter (proven bound) + exact fp32 re-score (same ids/scores)",
                                   "cuda": "fp32 CUDA-core tile kernel"}
                 extras[name] = entry
             except Exception as exc:
                 extras[name] = {"error": repr(exc)}
+        # the whole cfg4 evaluation: 1,000,000 users sharded in contiguous blocks over the ranks, top-20, hits,
+        # Recall / MRR / NDCG / Hit / Precision sums and their reduction over the ranks inside the timed region
+        try:
+            extras["cfg4_distmult_full_eval"] = full_eval_leg(FULLSORT["cfg4_distmult"], device, world, rank)
+        except Exception as exc:
+            extras["cfg4_distmult_full_eval"] = {"error": repr(exc)}
         line["extras"] = extras
 
     if rank == 0 and world == 1 and not args.no_cpu_baseline:

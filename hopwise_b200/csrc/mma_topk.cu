@@ -804,7 +804,7 @@ __global__ void __launch_bounds__(sweep_threads(NCOL, NMMA), NBUF == 1 ? 2 : 1)
     };
     const int nti = (int)nt;
     uint32_t va[32], vb[32];
-    float gm[8];
+    float gm[8], gm2[8];
 
     {
       // ---- one warp = (row half, lane quadrant, column slice); two accumulators per half -------------------
@@ -841,25 +841,27 @@ __global__ void __launch_bounds__(sweep_threads(NCOL, NMMA), NBUF == 1 ? 2 : 1)
         tmem_ld32_issue(tlane, va);
         tmem_ld32_issue(tlane + CH, vb);
         for (int i = 0; i < nti; ++i, cid += TN / CH) {
+          // While the accumulator is held only what frees the registers runs (the two max trees: 40 ALU-pipe
+          // instructions); the appends of the first batch wait until the accumulator is back with the tensor core.
           tmem_ld_wait2(va, vb);
 #ifndef KGE_EXP_NOFILTER
           dump(va, u, cid);
-          float tm = chunk_reduce(va, gm);
+          const float tma = chunk_reduce(va, gm);
 #endif
           tmem_ld32_issue(tlane + 2 * CH, va);
 #ifndef KGE_EXP_NOFILTER
-          chunk_push(gm, tm, st, cid << CID_SHIFT, a.cand);
           dump(vb, u, cid + 1);
-          tm = chunk_reduce(vb, gm);
+          const float tmb = chunk_reduce(vb, gm2);
 #endif
           tmem_ld32_issue(tlane + 3 * CH, vb);
-#ifndef KGE_EXP_NOFILTER
-          chunk_push(gm, tm, st, (cid + 1) << CID_SHIFT, a.cand);
-#endif
           tmem_ld_wait2(va, vb);
           tc_fence_before();   // every chunk of the tile is in registers: release the accumulator
           __syncwarp();
           if (lane == 0) mbar_arrive(my_tempty);
+#ifndef KGE_EXP_NOFILTER
+          chunk_push(gm, tma, st, cid << CID_SHIFT, a.cand);
+          chunk_push(gm2, tmb, st, (cid + 1) << CID_SHIFT, a.cand);
+#endif
           process(va, cid + 2);
           process(vb, cid + 3);
           compact_full(st, u, lsplit, TRIG < CAND - (NCH + 1) ? TRIG : CAND - (NCH + 1));
