@@ -118,6 +118,10 @@ __device__ __forceinline__ void mark_row(const kge_table_t& T, int64_t row, int 
 __device__ __forceinline__ float softplusf(float z) { return fmaxf(z, 0.f) + log1pf(expf(-fabsf(z))); }
 __device__ __forceinline__ float sigmoidf(float z) { return 1.f / (1.f + expf(-z)); }
 
+#ifndef KGE_FWD_TWO_PER_WARP
+#define KGE_FWD_TWO_PER_WARP 0   // experiment (scripts/build_variant.sh): see kge_train_forward
+#endif
+
 template <int MODEL, int VEC, int NCH>
 struct FwdBounds {
   static constexpr int E = VEC * NCH;
@@ -792,8 +796,13 @@ extern "C" int kge_train_forward(const kge_model_t* model, const kge_batch_t* b,
   }
   RowCfg c = {};
   kge_pick_rowcfg(model->d, c);
+  // Rows of 17..32 float4 (d = 68..128: cfg2's d = 100, cfg5's d = 128): two triples per warp -- half-warp groups,
+  // two fragments per lane -- instead of one.  The loop's scalar work (ids, row states, loss bookkeeping, branches)
+  // is then issued once per two triples; at d = 100 the layout also wastes 7 of 32 fragment slots either way.
+  const bool two_per_warp = c.vec == 4 && c.g == 32 && c.nch == 1 && KGE_FWD_TWO_PER_WARP &&
+                            (model->model == KGE_TRANSE || model->model == KGE_DISTMULT);
   const int threads = 256;
-  const int grid = grid_for(n_total, threads / c.g, 8);
+  const int grid = grid_for(n_total, threads / (two_per_warp ? 16 : c.g), 8);
   const size_t smem = (size_t)model->relation.parts * model->d * sizeof(float);
   cudaStream_t st = (cudaStream_t)stream;
 #define CALL(V, G, N)                                                                                   \
@@ -803,7 +812,12 @@ extern "C" int kge_train_forward(const kge_model_t* model, const kge_batch_t* b,
     case KGE_ROTATE: train_fwd_kernel<KGE_ROTATE, V, G, N><<<grid, threads, smem, st>>>(a); break;      \
     default: train_fwd_kernel<KGE_COMPLEX, V, G, N><<<grid, threads, smem, st>>>(a); break;             \
   }
-  KGE_DISPATCH_ROWCFG(c, CALL);
+  if (two_per_warp) {
+    if (model->model == KGE_TRANSE) train_fwd_kernel<KGE_TRANSE, 4, 16, 2><<<grid, threads, smem, st>>>(a);
+    else train_fwd_kernel<KGE_DISTMULT, 4, 16, 2><<<grid, threads, smem, st>>>(a);
+  } else {
+    KGE_DISPATCH_ROWCFG(c, CALL);
+  }
 #undef CALL
   KGE_LAUNCH_CHECK();
   return 0;

@@ -18,3 +18,4 @@ try:
 except Exception as e:
     print("bench parse failed", e)
 PY
+bash scripts/gpu_train_variants.sh TPW TPW2 MC3 2>&1 | tee gpurun_out/r2e_train_variants.log
