@@ -183,18 +183,53 @@ class EpochOrder:
     ``randperm(n)``; and an iterator that is advanced past its last batch draws one more, discarded,
     ``randperm(n)`` (RandomSampler's trailing ``[: num_samples % n]`` slice).  Unshuffled loaders still
     draw the base seed.  The generator lives on the CPU, exactly like the reference's.
+
+    With ``world > 1`` it is the multi-GPU loader of abstract_dataloader.py:59-64 instead: a
+    ``DistributedSampler(list(range(n)), shuffle=shuffle, drop_last=False)`` picks the indices -- the epoch's
+    permutation comes from ``Generator().manual_seed(0 + epoch)`` (the sampler's own seed 0, the epoch set through
+    ``set_epoch``, trainer.py:240-241 and knowledge_dataloader.py:170-172), is padded by wrapping around to a
+    multiple of ``world`` and strided ``rank::world`` -- and the batch is ``max(1, step // world)`` rows per rank.
+    The loader's generator still draws its base seed per ``__iter__`` but no longer decides the order.
     """
 
-    def __init__(self, n: int, step: int, seed: int, shuffle: bool = True):
-        self.n, self.step, self.shuffle = int(n), int(step), bool(shuffle)
+    def __init__(self, n: int, step: int, seed: int, shuffle: bool = True, rank: int = 0, world: int = 1):
+        self.n, self.shuffle = int(n), bool(shuffle)
+        self.rank, self.world = int(rank), int(world)
+        if not 0 <= self.rank < self.world:
+            raise ValueError("rank outside [0, world)")
+        self.step = int(step) if self.world == 1 else max(1, int(step) // self.world)
         self.generator = torch.Generator()
         self.generator.manual_seed(int(seed))
+        self.epoch = 0
         self._perm = None
         self._pos = 0
         self._live = False
 
+    @property
+    def n_local(self) -> int:
+        """Indices this rank visits per epoch (ceil(n / world): the tail is padded with repeats)."""
+        return self.n if self.world == 1 else (self.n + self.world - 1) // self.world
+
     def __len__(self):
-        return (self.n + self.step - 1) // self.step
+        return (self.n_local + self.step - 1) // self.step
+
+    def set_epoch(self, epoch: int):
+        """DistributedSampler.set_epoch (only matters when world > 1)."""
+        self.epoch = int(epoch)
+
+    def _distributed_indices(self):
+        if self.shuffle:
+            g = torch.Generator()
+            g.manual_seed(0 + self.epoch)            # torch.utils.data.DistributedSampler: self.seed + self.epoch
+            idx = torch.randperm(self.n, generator=g)
+        else:
+            idx = torch.arange(self.n)
+        total = self.n_local * self.world
+        pad = total - self.n
+        if pad > 0:                                   # drop_last=False: wrap around (repeat if n < pad)
+            reps = (pad + self.n - 1) // self.n
+            idx = torch.cat([idx, idx.repeat(reps)[:pad]])
+        return idx[self.rank : total : self.world]
 
     def start(self):
         """DataLoader.__iter__()."""
@@ -206,10 +241,13 @@ class EpochOrder:
         if not self._live:
             raise RuntimeError("EpochOrder.start() must be called first")
         if self._perm is None:
-            self._perm = torch.randperm(self.n, generator=self.generator) if self.shuffle else torch.arange(self.n)
-        if self._pos >= self.n:
-            if self.shuffle:
-                torch.randperm(self.n, generator=self.generator)   # the discarded trailing draw
+            if self.world > 1:
+                self._perm = self._distributed_indices()
+            else:
+                self._perm = torch.randperm(self.n, generator=self.generator) if self.shuffle else torch.arange(self.n)
+        if self._pos >= self._perm.numel():
+            if self.shuffle and self.world == 1:
+                torch.randperm(self.n, generator=self.generator)   # the discarded trailing draw (RandomSampler)
             self._live = False
             return None
         idx = self._perm[self._pos : self._pos + self.step]
@@ -235,19 +273,26 @@ class DeviceKGLoader:
     KEYS = ("user_id", "item_id", "neg_item_id", "head_id", "relation_id", "tail_id", "neg_tail_id")
 
     def __init__(self, inter_user, inter_item, kg_head, kg_rel, kg_tail, rec_sampler, kg_sampler, batch_size: int,
-                 seed: int, device="cuda", shuffle: bool = True, neg_sample_num: int = 1, gather=None):
+                 seed: int, device="cuda", shuffle: bool = True, neg_sample_num: int = 1, gather=None,
+                 rank: int = 0, world: int = 1):
         self.device = torch.device(device)
         as_dev = lambda x: torch.as_tensor(np.asarray(x), dtype=torch.int64).to(self.device)  # noqa: E731
         self.inter_user, self.inter_item = as_dev(inter_user), as_dev(inter_item)
         self.kg_head, self.kg_rel, self.kg_tail = as_dev(kg_head), as_dev(kg_rel), as_dev(kg_tail)
         self.rec_sampler, self.kg_sampler = rec_sampler, kg_sampler
-        self.rec_order = EpochOrder(self.inter_user.numel(), batch_size, seed, shuffle)
-        self.kg_order = EpochOrder(self.kg_head.numel(), batch_size, seed, True)   # "kg based dataloader must shuffle"
+        # (several GPUs: each rank walks its DistributedSampler shard with batch_size // world rows per step)
+        self.rec_order = EpochOrder(self.inter_user.numel(), batch_size, seed, shuffle, rank, world)
+        self.kg_order = EpochOrder(self.kg_head.numel(), batch_size, seed, True, rank, world)   # "must shuffle"
         self.neg_sample_num = int(neg_sample_num)
         self._gather = gather or (lambda table, idx: table.index_select(0, idx))
 
     def __len__(self):
         return len(self.rec_order)
+
+    def set_epoch(self, epoch: int):
+        """What the trainer does through ``train_data.sampler.set_epoch`` / ``knowledge_shuffle`` per epoch."""
+        self.rec_order.set_epoch(epoch)
+        self.kg_order.set_epoch(epoch)
 
     def _index(self, idx):
         if self.device.type == "cuda":

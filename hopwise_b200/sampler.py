@@ -91,6 +91,7 @@ class _FilteredUniformSampler:
     def __init__(self, keys, values, n_keys: int, value_num: int, stream: MTStream, what: str):
         self.stream = stream
         self.device = stream.device
+        self.to_host = False   # hand the ids back as a CPU tensor (inside hopwise's own CPU loaders)
         self.value_num = int(value_num)
         self.n_keys = int(n_keys)
         self.used_off, self.used_vals = build_used_csr(keys, values, n_keys, self.device)
@@ -121,14 +122,27 @@ class _FilteredUniformSampler:
                 ),
                 "kge_sample_negatives",
             )
-        return out
+        return out.cpu() if self.to_host else out
+
+
+def _sets_from_csr(off, vals, n_keys):
+    """np.ndarray (dtype=object) of Python sets, one per key -- the shape `used_ids` has in the reference
+    (sampler.py:229-252, 321-336), which FullSortEvalDataLoader subtracts positives from
+    (general_dataloader.py:204, 231-237).  Built on demand from the device CSR."""
+    off = off.cpu().numpy()
+    vals = vals.cpu().numpy()
+    out = np.empty(n_keys, dtype=object)
+    for k in range(n_keys):
+        out[k] = set(vals[off[k]:off[k + 1]].tolist())
+    return out
 
 
 class KGSampler(_FilteredUniformSampler):
     """Tail corruption filtered by the head's true tails (any relation), sampler.py:294-357.
 
     ``KGSampler(dataset)`` reads ``dataset.head_entities / tail_entities / entity_num`` like the
-    reference; arrays can be given directly instead.
+    reference; arrays can be given directly instead.  ``used_ids`` is the reference's attribute (an array of
+    sets indexed by head entity), materialised on first access.
     """
 
     def __init__(self, dataset=None, distribution="uniform", alpha=1.0, *, heads=None, tails=None, entity_num=None,
@@ -137,22 +151,123 @@ class KGSampler(_FilteredUniformSampler):
             raise NotImplementedError("only the uniform distribution is on the fused path")
         if dataset is not None:
             heads, tails, entity_num = dataset.head_entities, dataset.tail_entities, dataset.entity_num
+        self.distribution, self.alpha = distribution, alpha
         self.entity_num = int(entity_num)
         stream = stream if stream is not None else MTStream(device=device)
         super().__init__(heads, tails, self.entity_num, self.entity_num, stream, "head entities")
+        self._used_sets = None
+
+    @property
+    def used_ids(self):
+        if self._used_sets is None:
+            self._used_sets = _sets_from_csr(self.used_off, self.used_vals, self.n_keys)
+        return self._used_sets
 
     def sample_by_entity_ids(self, head_entity_ids, num: int = 1) -> torch.Tensor:
         """[len(heads) * num] int64 on the device, j-major: out[j*len + i] (sampler.py:338-357)."""
         return self.sample_by_key_ids(head_entity_ids, num)
 
 
-class RecSampler(_FilteredUniformSampler):
-    """Item negatives filtered by the user's interacted items (one phase of sampler.py:186-291)."""
+class RecSampler:
+    """Item negatives filtered by the user's interacted items: hopwise's ``Sampler`` (sampler.py:186-291).
 
-    def __init__(self, users, items, n_users: int, n_items: int, stream: MTStream | None = None, device="cuda"):
-        stream = stream if stream is not None else MTStream(device=device)
-        self.user_num, self.item_num = int(n_users), int(n_items)
-        super().__init__(users, items, self.user_num, self.item_num, stream, "users")
+    Two constructors:
+      * ``RecSampler(phases, datasets)`` -- the reference signature: ``datasets[i].inter_feat`` holds the
+        interactions of ``phases[i]``; the forbidden items of a phase are those of all phases up to it
+        (cumulative, sampler.py:229-252).  ``set_phase(phase)`` returns the shallow copy bound to one phase, with
+        ``.phase`` and ``.used_ids`` like the reference object the loaders hold (``train_data._sampler``,
+        and the one FullSortEvalDataLoader reads, general_dataloader.py:204).
+      * ``RecSampler(users, items, n_users, n_items)`` -- one phase given as id arrays (already bound).
+    Every copy shares one ``MTStream``: NumPy's global generator in the reference.
+    """
+
+    def __init__(self, phases_or_users, datasets_or_items, n_users=None, n_items=None, distribution="uniform",
+                 alpha=1.0, stream: MTStream | None = None, device="cuda"):
+        if distribution != "uniform":
+            raise NotImplementedError("only the uniform distribution is on the fused path")
+        self.distribution, self.alpha = distribution, alpha
+        self.stream = stream if stream is not None else MTStream(device=device)
+        self.device = self.stream.device
+        self._impl, self._sets, self.phase = {}, {}, None
+        by_phase = isinstance(phases_or_users, str) or (
+            isinstance(phases_or_users, (list, tuple)) and all(isinstance(p, str) for p in phases_or_users))
+        if by_phase:
+            phases = [phases_or_users] if isinstance(phases_or_users, str) else list(phases_or_users)
+            datasets = datasets_or_items if isinstance(datasets_or_items, (list, tuple)) else [datasets_or_items]
+            if len(phases) != len(datasets):
+                raise ValueError(f"Phases {phases} and datasets {datasets} should have the same length.")
+            self.phases, self.datasets = phases, list(datasets)
+            d0 = self.datasets[0]
+            self.uid_field, self.iid_field = d0.uid_field, d0.iid_field
+            self.user_num, self.item_num = int(d0.user_num), int(d0.item_num)
+            users, items = [], []
+            for phase, ds in zip(phases, self.datasets):   # cumulative: a phase forbids every earlier phase's items
+                users.append(np.asarray(ds.inter_feat[self.uid_field]))
+                items.append(np.asarray(ds.inter_feat[self.iid_field]))
+                self._impl[phase] = _FilteredUniformSampler(np.concatenate(users), np.concatenate(items),
+                                                            self.user_num, self.item_num, self.stream, "users")
+        else:
+            self.phases, self.datasets = ["train"], []
+            self.user_num, self.item_num = int(n_users), int(n_items)
+            self._impl["train"] = _FilteredUniformSampler(phases_or_users, datasets_or_items, self.user_num,
+                                                          self.item_num, self.stream, "users")
+            self.phase = "train"
+
+    def set_phase(self, phase):
+        """sampler.py:254-270: the copy of this sampler bound to `phase`."""
+        if phase not in self.phases:
+            raise ValueError(f"Phase [{phase}] not exist.")
+        import copy
+
+        bound = copy.copy(self)   # shallow: the CSRs, the set cache and the MT stream are shared
+        bound.phase = phase
+        return bound
+
+    @property
+    def used_ids(self):
+        """Bound to a phase: array of sets indexed by user (what the eval loader reads); unbound: {phase: array}."""
+        def sets(phase):
+            if phase not in self._sets:
+                impl = self._impl[phase]
+                self._sets[phase] = _sets_from_csr(impl.used_off, impl.used_vals, impl.n_keys)
+            return self._sets[phase]
+
+        return sets(self.phase) if self.phase is not None else {p: sets(p) for p in self.phases}
+
+    @property
+    def used_off(self):
+        return self._impl[self.phase or self.phases[0]].used_off
+
+    @property
+    def used_vals(self):
+        return self._impl[self.phase or self.phases[0]].used_vals
+
+    def sample_by_key_ids(self, key_ids, num: int = 1) -> torch.Tensor:
+        if self.phase is None:
+            raise RuntimeError("call set_phase() first (sampler.py:186-199)")
+        return self._impl[self.phase].sample_by_key_ids(key_ids, num)
 
     def sample_by_user_ids(self, user_ids, item_ids=None, num: int = 1) -> torch.Tensor:
+        """[len(users) * num] int64 on the device, j-major (sampler.py:272-291)."""
         return self.sample_by_key_ids(user_ids, num)
+
+
+def install_device_samplers(train_data, device="cuda", to_host=True):
+    """Swap the two CPU samplers of a hopwise ``KnowledgeBasedDataLoader`` for the device ones, in place:
+    ``train_data.general_dataloader._sampler`` (rec negatives) and ``train_data.kg_dataloader._sampler`` (KG
+    negatives, knowledge_dataloader.py:51,73).  Both continue NumPy's global MT19937 stream from where it stands
+    (``np.random.get_state()``), sharing it exactly like the reference's samplers share the global generator, so the
+    ids drawn are the ones the CPU samplers would have drawn.  hopwise's loaders assemble the batch on the host
+    (``dataset.join`` indexes CPU feature tables with the sampled ids, abstract_dataloader.py:192-198), so with
+    ``to_host`` (default) the ids come back as CPU tensors.  Returns the shared MTStream."""
+    stream = MTStream(state=np.random.get_state(), device=device)
+    gen, kg = train_data.general_dataloader, train_data.kg_dataloader
+    old = gen._sampler
+    rec = RecSampler(list(old.phases), list(old.datasets), stream=stream, device=device).set_phase(old.phase)
+    kgs = KGSampler(kg._dataset, stream=stream, device=device)
+    kgs.to_host = to_host
+    for impl in rec._impl.values():
+        impl.to_host = to_host
+    gen._sampler = rec
+    kg._sampler = kgs
+    return stream

@@ -10,6 +10,7 @@ element by element, and the sampler stream must end in the reference's final num
 import zlib
 
 import numpy as np
+import pytest
 import torch
 
 from conftest import load_golden
@@ -89,3 +90,35 @@ def test_epoch_order_matches_torch_dataloader():
                     break
                 assert got.tolist() == want
                 k += 1
+
+
+@pytest.mark.parametrize("n,step,world,shuffle", [(103, 16, 2, True), (103, 16, 4, False), (10, 64, 4, True),
+                                                  (3, 8, 8, True), (2049, 2048, 8, True)])
+def test_epoch_order_matches_torch_distributed_sampler(n, step, world, shuffle):
+    """abstract_dataloader.py:59-64: DistributedSampler(list(range(n)), shuffle, drop_last=False) + step // world.
+    No process group is needed to build the sampler when num_replicas and rank are given."""
+    from torch.utils.data import DataLoader
+    from torch.utils.data.distributed import DistributedSampler
+
+    from hopwise_b200.loader import EpochOrder
+
+    for rank in range(world):
+        sampler = DistributedSampler(list(range(n)), num_replicas=world, rank=rank, shuffle=shuffle, drop_last=False)
+        ref = DataLoader(list(range(n)), batch_size=max(1, step // world), sampler=sampler,
+                         collate_fn=lambda b: torch.tensor(b))
+        mine = EpochOrder(n, step, seed=2024, shuffle=shuffle, rank=rank, world=world)
+        assert len(mine) == len(ref)
+        for epoch in (0, 1, 5):
+            sampler.set_epoch(epoch)
+            mine.set_epoch(epoch)
+            mine.start()
+            want = list(ref)
+            got = []
+            while True:
+                idx = mine.next_indices()
+                if idx is None:
+                    break
+                got.append(idx)
+            assert len(got) == len(want)
+            for a, b in zip(got, want):
+                assert torch.equal(a, b)
