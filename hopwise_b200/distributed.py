@@ -187,6 +187,11 @@ class RowSparseExchange:
                 f"{self._agreed} at the first step; pass max_batch_rows= to enable_row_sparse_data_parallel")
         return self._agreed
 
+    def reset_bounds(self, max_batch_rows=None):
+        """Forget the agreed bounds (a new batch size, another model): the next step agrees again -- every rank must
+        call this at the same point -- or plans with `max_batch_rows` when given."""
+        self._agreed = None if max_batch_rows is None else tuple(int(x) for x in max_batch_rows)
+
     def _plan(self, model, batch_rows):
         """Tighten the per-table capacity to what a batch can touch (agreed across ranks); pick the route per table."""
         rows = (model.n_users, model.n_entities, model.n_relations)

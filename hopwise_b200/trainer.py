@@ -61,6 +61,14 @@ from . import recommender as _rec
 from .evaluator import topk_hits
 from .loader import DevicePrefetcher
 
+# hopwise's Config compares `model_class.type` / `.input_type` with ITS enums (configurator.py:219-224).  When
+# hopwise_b200.recommender was imported before hopwise was importable it carries look-alike enums of its own:
+# rebind the two class attributes to hopwise's members.
+from hopwise.utils import InputType as _InputType, ModelType as _ModelType  # noqa: E402
+
+_rec.KnowledgeRecommender.type = _ModelType.KNOWLEDGE
+_rec.FusedKGEModel.input_type = _InputType.PAIRWISE
+
 KMAX_FUSED = 128                 # largest k of kge_full_sort_topk
 DEFAULT_USER_BLOCK = 148 * 512   # users per fused call: one full wave of the tensor-core sweep
 

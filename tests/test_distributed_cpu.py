@@ -85,10 +85,24 @@ def _worker(rank, world, port, out_dir):
         np.save(os.path.join(out_dir, f"marks_{rank}.npy"), marks.numpy())
         np.save(os.path.join(out_dir, f"before_{rank}.npy"), np.concatenate([b.numpy().ravel() for b in before]))
         np.save(os.path.join(out_dir, f"after_{rank}.npy"), np.concatenate([g.numpy().ravel() for g in model.g]))
-        # a second step with another batch shape re-plans the buffers
+        # the bounds the ranks agreed on at the first step stay in force: a local batch that can touch more rows than
+        # agreed is refused (ranks planning with different shapes would issue mismatched collectives) ...
         model2 = _FakeModel(rank + 10, rows=(44, 68, 16))
+        model2._touch_bounds = (6, 9, 2)
+        try:
+            ex(model2)
+            raise AssertionError("a batch beyond the agreed bounds must be refused")
+        except RuntimeError as exc:
+            assert "max_batch_rows" in str(exc)
+        # ... a smaller one plans with the agreed bounds, and after reset_bounds() the ranks agree again: rank 1's
+        # batch can touch more user rows than rank 0's, both plan with the maximum
         model2._touch_bounds = (5, 9, 2)
         ex(model2)
+        assert ex.dense == [False, True, False] and ex.layout.caps == [5, 1, 3]
+        model3 = _FakeModel(rank + 20, rows=(44, 68, 16))
+        model3._touch_bounds = (4 + rank, 9, 2)
+        ex.reset_bounds()
+        ex(model3)
         assert ex.dense == [False, False, False] and ex.layout.caps == [5, 9, 2]
         # exact metric means from per-rank sums
         sums = torch.tensor([[1.0 + rank, 2.0], [3.0, 4.0 * (rank + 1)]], dtype=torch.float64)
