@@ -260,11 +260,12 @@ def time_fullsort(fs, device, n_users_step, steps, warmup, world, rank, path="au
         ev[i + 1].record()
     barrier(world)
     ms = ev[0].elapsed_time(ev[-1])
-    per_rep = sorted(ev[i].elapsed_time(ev[i + 1]) for i in range(steps))
+    in_order = [ev[i].elapsed_time(ev[i + 1]) for i in range(steps)]
+    per_rep = sorted(in_order)
     fallback = m._mma_total_fallback_rows if path != "cuda" else 0   # over warm-up and timed blocks
     del m
     torch.cuda.empty_cache()   # (outside the timed region)
-    return ms, fallback, per_rep[len(per_rep) // 2]
+    return ms, fallback, per_rep[len(per_rep) // 2], in_order
 
 
 def full_eval_leg(fs, device, world, rank):
@@ -696,7 +697,7 @@ def main():
                 for path in ("mma", "cuda"):
                     if path == "cuda":
                         reps = 3   # ~0.1 s per block
-                    ms, fb, med = time_fullsort(fs, device, n_users_step, reps, 3, world, rank, path=path)
+                    ms, fb, med, in_order = time_fullsort(fs, device, n_users_step, reps, 3, world, rank, path=path)
                     ms = max_over_ranks(ms / reps, device, world)
                     med = max_over_ranks(med, device, world)
                     # headline = the MEAN block (nothing in the call waits for the host any more: the exact fallback
@@ -706,7 +707,7 @@ def main():
                                    "users_per_s_from_median": world * n_users_step / (med * 1e-3),
                                    "algorithmic_tflops": ups * flops / 1e12,
                                    "tensor_frac_of_bf16_peak": ups / world * flops / 1e12 / peaks["bf16_tflops"],
-                                   "rows_recomputed_exactly": fb}
+                                   "rows_recomputed_exactly": fb, "per_block_ms": [round(x, 3) for x in in_order]}
                 entry["paths"] = {"mma": "tcgen05 fp16 filter (proven bound) + exact fp32 re-score (same ids/scores)",
                                   "cuda": "fp32 CUDA-core tile kernel"}
                 extras[name] = entry

@@ -1059,7 +1059,23 @@ __global__ void __launch_bounds__(RS_WARPS * 32, KGE_RS_MINB) rescore_topk_kerne
     }
     __syncwarp();
     uint32_t T = 0u;
-    {
+    if (E <= 256) {
+      // the usual case (one or two lists): the keys fit eight registers per lane, and the radix descent of the sweep's
+      // compaction (starts at the highest bit in which the keys differ, stops when exactly k remain) selects tau in
+      // ~20 ballots instead of 32 passes over shared memory
+      uint32_t key8[8];
+#pragma unroll
+      for (int q = 0; q < 8; ++q) {
+        const int i = q * 32 + lane;
+        key8[q] = i < E ? kbuf[i] : 0u;
+      }
+      if (E <= 128) {
+        const uint32_t key4[4] = {key8[0], key8[1], key8[2], key8[3]};
+        T = warp_kth_largest<4>(key4, k);
+      } else {
+        T = warp_kth_largest<8>(key8, k);
+      }
+    } else {
       int n_t = 0;
       for (int i = lane; i < E; i += 32) n_t += kbuf[i] != 0u;
       n_t = __reduce_add_sync(0xffffffffu, n_t);

@@ -119,10 +119,10 @@ __device__ __forceinline__ float softplusf(float z) { return fmaxf(z, 0.f) + log
 __device__ __forceinline__ float sigmoidf(float z) { return 1.f / (1.f + expf(-z)); }
 
 #ifndef KGE_FWD_TWO_PER_WARP
-#define KGE_FWD_TWO_PER_WARP 0   // experiment (scripts/build_variant.sh): see kge_train_forward
+#define KGE_FWD_TWO_PER_WARP 1   // see kge_train_forward (0: always one triple per warp for rows of 17..32 float4)
 #endif
 
-template <int MODEL, int VEC, int NCH>
+template <int MODEL, int VEC, int G, int NCH>
 struct FwdBounds {
   static constexpr int E = VEC * NCH;
   static constexpr int PH = (MODEL == KGE_ROTATE || MODEL == KGE_COMPLEX) ? 2 : 1;
@@ -130,12 +130,15 @@ struct FwdBounds {
 #ifdef KGE_FWD_MIN_CTAS
   static constexpr int MIN_CTAS = KGE_FWD_MIN_CTAS;   // experiment knob (scripts/build_variant.sh)
 #else
-  static constexpr int MIN_CTAS = (E * PH <= 4) ? 4 : (E * PH <= 8 ? 3 : (E * PH <= 16 ? 2 : 1));
+  // (the two-triples-per-warp shape, G = 16 with two fragments per lane, wants its 8-element fragments of h, r, both
+  // tails and three gradients in registers: measured 0.320 ms at two CTAs per SM vs 0.381 ms at three, cfg2)
+  static constexpr int MIN_CTAS = (VEC == 4 && G == 16 && NCH == 2) ? 2
+                                  : (E * PH <= 4) ? 4 : (E * PH <= 8 ? 3 : (E * PH <= 16 ? 2 : 1));
 #endif
 };
 
 template <int MODEL, int VEC, int G, int NCH>
-__global__ void __launch_bounds__(256, FwdBounds<MODEL, VEC, NCH>::MIN_CTAS) train_fwd_kernel(const TrainArgs a) {
+__global__ void __launch_bounds__(256, FwdBounds<MODEL, VEC, G, NCH>::MIN_CTAS) train_fwd_kernel(const TrainArgs a) {
   constexpr int E = VEC * NCH;
   constexpr int PH = (MODEL == KGE_ROTATE || MODEL == KGE_COMPLEX) ? 2 : 1;  // head / tail parts
   constexpr int PR = (MODEL == KGE_COMPLEX) ? 2 : 1;                          // relation parts
@@ -797,9 +800,13 @@ extern "C" int kge_train_forward(const kge_model_t* model, const kge_batch_t* b,
   RowCfg c = {};
   kge_pick_rowcfg(model->d, c);
   // Rows of 17..32 float4 (d = 68..128: cfg2's d = 100, cfg5's d = 128): two triples per warp -- half-warp groups,
-  // two fragments per lane -- instead of one.  The loop's scalar work (ids, row states, loss bookkeeping, branches)
-  // is then issued once per two triples; at d = 100 the layout also wastes 7 of 32 fragment slots either way.
-  const bool two_per_warp = c.vec == 4 && c.g == 32 && c.nch == 1 && KGE_FWD_TWO_PER_WARP &&
+  // two fragments per lane -- instead of one, when the tables (weights, moments, gradient accumulators: 16 B per
+  // element) fit the L2.  There the step is bound by instruction issue, and the loop's scalar work (ids, row states,
+  // loss bookkeeping, branches) is issued once per two triples: cfg2 0.395 -> 0.366 ms/step.  With tables beyond the
+  // L2 the step is bound by bytes in flight, which the fatter threads (two CTAs per SM instead of four) halve: cfg5
+  // 1.012 -> 1.055 ms/step, so that regime keeps one triple per warp.
+  const double table_bytes = ((double)model->user.rows + (double)model->entity.rows) * model->d * 16.0;
+  const bool two_per_warp = c.vec == 4 && c.g == 32 && c.nch == 1 && KGE_FWD_TWO_PER_WARP && table_bytes < 96e6 &&
                             (model->model == KGE_TRANSE || model->model == KGE_DISTMULT);
   const int threads = 256;
   const int grid = grid_for(n_total, threads / (two_per_warp ? 16 : c.g), 8);
