@@ -385,17 +385,6 @@ struct MaskInfo {
   int mask_first;
 };
 
-__device__ __forceinline__ bool chunk_unsafe(const MaskInfo& mi, uint32_t cid) {
-  const int64_t j0 = (int64_t)cid * CH;
-  if (j0 + CH > mi.n_targets || (mi.mask_first && cid == 0)) return true;
-  int64_t lo = mi.h_lo, hi = mi.h_hi;
-  while (lo < hi) {
-    const int64_t mid = (lo + hi) >> 1;
-    if (mi.hist_items[mid] < j0) lo = mid + 1; else hi = mid;
-  }
-  return lo < mi.h_hi && mi.hist_items[lo] < j0 + CH;
-}
-
 // k-th largest of the warp's keys (NQ per lane, 0 = absent; all present keys are > 0), or 0 when fewer
 // than k are present.  Radix descent on the order-preserving bit pattern that stops as soon as
 // exactly k keys remain above the prefix (their minimum is the answer).
@@ -995,19 +984,34 @@ __global__ void __launch_bounds__(RS_WARPS * 32, KGE_RS_MINB) rescore_topk_kerne
 
   for (int64_t row = (int64_t)blockIdx.x * RS_WARPS + warp; row < a.s.n; row += (int64_t)gridDim.x * RS_WARPS) {
     // ---- gather the row's lists ------------------------------------------------------------------------
+    // The kernel is a chain of dependent L2 round trips per row (one warp per row): everything that only depends
+    // on the row index is requested first, in one go -- lane s takes the count and threshold of list s.
+    int my_cnt = 0;
+    float my_thr = -INFINITY;
+    if (lane < a.splits) {
+      const int64_t lrow = (int64_t)lane * a.rows_pad + row;
+      my_cnt = __ldg(a.cand_cnt + lrow);
+      my_thr = __ldg(a.cand_thr + lrow);
+    }
+    int64_t h_lo = 0, h_hi = 0;
+    if (a.hist_off) {
+      h_lo = __ldg(a.hist_off + row);
+      h_hi = __ldg(a.hist_off + row + 1);
+    }
+    const float eps = __ldg(a.eps + row);
+    const float inv_scale = __ldg(a.inv_scale + row);
+    const bool bad = __any_sync(0xffffffffu, my_cnt < 0);
+    float thr0 = my_thr;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) thr0 = fmaxf(thr0, __shfl_xor_sync(0xffffffffu, thr0, o));
     int E = 0;
-    float thr0 = -INFINITY;
-    bool bad = false;
-    for (int s = 0; s < a.splits; ++s) {
-      const int64_t lrow = (int64_t)s * a.rows_pad + row;
-      const int c = a.cand_cnt[lrow];
-      if (c < 0) {
-        bad = true;
-        break;
+    if (!bad) {
+      for (int s = 0; s < a.splits; ++s) {
+        const int c = __shfl_sync(0xffffffffu, my_cnt, s);
+        const uint2* src = a.cand + ((int64_t)s * a.rows_pad + row) * CAND;
+        for (int i = lane; i < c; i += 32) ent[E + i] = src[i];
+        E += c;
       }
-      thr0 = fmaxf(thr0, a.cand_thr[lrow]);
-      for (int i = lane; i < c; i += 32) ent[E + i] = a.cand[lrow * CAND + i];
-      E += c;
     }
     if (bad) {
       if (lane == 0) {
@@ -1030,18 +1034,14 @@ __global__ void __launch_bounds__(RS_WARPS * 32, KGE_RS_MINB) rescore_topk_kerne
     nq2 = warp_sum(nq2);
     MaskInfo mi;
     mi.hist_items = a.hist_items;
-    mi.h_lo = mi.h_hi = 0;
-    if (a.hist_off) {
-      mi.h_lo = a.hist_off[row];
-      mi.h_hi = a.hist_off[row + 1];
-    }
+    mi.h_lo = h_lo;
+    mi.h_hi = h_hi;
     mi.n_targets = a.n_targets;
     mi.mask_first = a.mask_first;
     const int hlen = (int)(mi.h_hi - mi.h_lo);
     const bool hist_sm = hlen <= RS_HIST;
     if (hist_sm)
       for (int i = lane; i < hlen; i += 32) hist[i] = (uint32_t)a.hist_items[mi.h_lo + i];
-    const float eps = a.eps[row];
     __syncwarp();
     // ---- final tau: k-th largest maximum among the safe chunks that clear every split's threshold ------
     for (int i = lane; i < E; i += 32) {
@@ -1103,35 +1103,15 @@ __global__ void __launch_bounds__(RS_WARPS * 32, KGE_RS_MINB) rescore_topk_kerne
     // The k targets behind tau have exact S a >= tau - eps (a = q.t, or q.t - |t|^2/2 for the L2 models, where
     // the squared distance is |q|^2 - 2a): nothing that scores below them can enter the top-k.  The list lives in
     // the row's scaled units, the exact chain does not: 1 / S is a power of two, the conversion is exact.
-    const float lo_a = (tau - 1.25f * eps) * a.inv_scale[row];
+    const float lo_a = (tau - 1.25f * eps) * inv_scale;
     const float hi_acc = (nq2 - 2.f * lo_a) * 1.00001f + 4e-6f * nq2;   // only used when tau is finite
     const bool have_tau = T != 0u;
     __syncwarp();
-    // ---- survivors: the masked groups of the chunks >= thr, 32 chunks at a time ---------------------------
+    // ---- survivors: the masked groups of the chunks >= thr ----------------------------------------------------
+    // Group ids of all surviving entries are expanded first (kbuf, reused) and scored in full rounds of 32 targets;
+    // a row whose groups outgrow the buffer is scored in several fills.
     int n_pass = 0, nk = 0, len = 0;
-    for (int b0 = 0; b0 < E; b0 += 32) {
-      const int i = b0 + lane;
-      uint32_t gmask = 0u, cid = 0u;
-      if (i < E && __uint_as_float(ent[i].x) >= thr) {
-        gmask = ent[i].y & 0xFFu;
-        cid = (ent[i].y >> CID_SHIFT) & CID_MASK;
-      }
-      int pos = __popc(gmask);   // exclusive prefix over the lanes -> slot of this lane's first group
-      int incl = pos;
-#pragma unroll
-      for (int o = 1; o < 32; o <<= 1) {
-        const int y = __shfl_up_sync(0xffffffffu, incl, o);
-        if (lane >= o) incl += y;
-      }
-      const int ng = __shfl_sync(0xffffffffu, incl, 31);
-      pos = incl - pos;
-      __syncwarp();
-      while (gmask) {
-        const int b = __ffs(gmask) - 1;   // mask bit b = group 7 - b of the chunk (see chunk_push)
-        gmask &= gmask - 1;
-        kbuf[pos++] = cid * 8u + (uint32_t)(7 - b);
-      }
-      __syncwarp();
+    auto score_groups = [&](int ng) {
       // exact scores of the members
       const int total = ng * GRP;
       for (int m0 = 0; m0 < total; m0 += 32) {
@@ -1220,7 +1200,37 @@ __global__ void __launch_bounds__(RS_WARPS * 32, KGE_RS_MINB) rescore_topk_kerne
           __syncwarp();
         }
       }
+          };
+    for (int b0 = 0; b0 < E || b0 == 0;) {   // (one fill per pass; a single call site keeps the scoring code un-duplicated)
+      int ngt = 0;
+      for (; b0 < E; b0 += 32) {
+        const int i = b0 + lane;
+        uint32_t gmask = 0u, cid = 0u;
+        if (i < E && __uint_as_float(ent[i].x) >= thr) {
+          gmask = ent[i].y & 0xFFu;
+          cid = (ent[i].y >> CID_SHIFT) & CID_MASK;
+        }
+        int pos = __popc(gmask);   // exclusive prefix over the lanes -> slot of this lane's first group
+        int incl = pos;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+          const int y = __shfl_up_sync(0xffffffffu, incl, o);
+          if (lane >= o) incl += y;
+        }
+        const int ng = __shfl_sync(0xffffffffu, incl, 31);
+        if (ngt + ng > a.nent) break;   // (a batch holds at most 256 groups and the buffer at least 256 slots)
+        pos = ngt + incl - pos;
+        while (gmask) {
+          const int b = __ffs(gmask) - 1;   // mask bit b = group 7 - b of the chunk (see chunk_push)
+          gmask &= gmask - 1;
+          kbuf[pos++] = cid * 8u + (uint32_t)(7 - b);
+        }
+        ngt += ng;
+      }
       __syncwarp();
+      score_groups(ngt);
+      __syncwarp();   // kbuf is refilled by the next pass
+      if (b0 >= E) break;
     }
     // ---- order the keys: (score desc, id asc) ------------------------------------------------------------------
     if (n_pass < k) {

@@ -67,7 +67,8 @@ def test_device_samplers_reproduce_the_reference_loader(tmp_path):
     for u in (1, 7, 100, len(mine) - 1):
         assert mine[u] == set(int(x) for x in ref_used[u])
     # cumulative phases: the validation sampler forbids the train AND the validation items of a user
-    ref_valid = old_rec.set_phase("valid")
+    ref_valid = valid_dev._sampler      # the reference's sampler bound to the validation phase (data/utils.py)
+    assert ref_valid.phase == "valid"
     mine_valid = rec.set_phase("valid")
     assert mine_valid.phase == "valid" and mine_valid.stream is rec.stream
     for u in (1, 7, 100):
