@@ -72,7 +72,7 @@ def measured_peaks():
 def profiled_traffic(workload):
     """DRAM bytes (read + write) of the two launches of one step, from the committed `ncu --set full` capture of
     this workload (profiles/r1_traffic.json, written by scripts/traffic_from_profiles.py); None when not captured."""
-    path = os.path.join(ROOT, "profiles", "r1_traffic.json")
+    path = os.path.join(ROOT, "profiles", "r2_traffic.json")
     if os.path.exists(path):
         t = json.load(open(path)).get(workload)
         if t:

@@ -1,5 +1,5 @@
 #!/usr/bin/env python
-"""profiles/r1_train_<workload>.txt (ncu summaries) -> profiles/r1_traffic.json: DRAM bytes (read + write) per
+"""profiles/r2_train_<workload>.txt (ncu summaries) -> profiles/r2_traffic.json: DRAM bytes (read + write) per
 launch of the two kernels of one train step, per workload.  bench.py reports them as `roofline.traffic`."""
 import glob
 import json
@@ -9,8 +9,8 @@ import re
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 UNIT = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
 out = {}
-for path in sorted(glob.glob(os.path.join(ROOT, "profiles", "r1_train_*.txt"))):
-    name = os.path.basename(path)[len("r1_train_"):-4]
+for path in sorted(glob.glob(os.path.join(ROOT, "profiles", "r2_train_*.txt"))):
+    name = os.path.basename(path)[len("r2_train_"):-4]
     kernels, cur = {}, None
     for line in open(path):
         m = re.match(r"## void <unnamed>::(\w+)<", line)
@@ -25,5 +25,5 @@ for path in sorted(glob.glob(os.path.join(ROOT, "profiles", "r1_train_*.txt"))):
             kernels[cur] += float(m.group(2)) * UNIT[m.group(3)]
     if kernels:
         out[name] = {"per_launch_bytes": kernels, "per_step_bytes": sum(kernels.values()), "source": os.path.basename(path)}
-json.dump(out, open(os.path.join(ROOT, "profiles", "r1_traffic.json"), "w"), indent=1)
+json.dump(out, open(os.path.join(ROOT, "profiles", "r2_traffic.json"), "w"), indent=1)
 print(json.dumps(out, indent=1))
