@@ -418,11 +418,14 @@ def config1_pipeline(arm):
 
             fused.install()
         cwd = os.getcwd()
+        visible = os.environ.get("CUDA_VISIBLE_DEVICES")     # hopwise's Config exports gpu_id into it
         os.chdir(tempfile.mkdtemp(prefix="hopwise_bench_"))   # hopwise writes log/ and log_tensorboard/ into the cwd
         try:
             torch.set_num_threads(host_threads())
             config = Config(model="TransE", dataset="ml-100k",
                             config_dict={"embedding_size": 64, "train_batch_size": 2048, "epochs": 1, "use_gpu": ours,
+                                         # hopwise picks the device from gpu_id ("" = CPU, configurator.py:540-554)
+                                         "gpu_id": "0" if ours else "",
                                          "show_progress": False, "eval_step": 1, "seed": 2024})
             init_seed(config["seed"], config["reproducibility"])
             dataset = create_dataset(config)
@@ -459,6 +462,10 @@ def config1_pipeline(arm):
                     "what": "one epoch (hopwise's loader + CPU samplers included) and one test-split evaluation"}
         finally:
             os.chdir(cwd)
+            if visible is None:
+                os.environ.pop("CUDA_VISIBLE_DEVICES", None)
+            else:
+                os.environ["CUDA_VISIBLE_DEVICES"] = visible
             if ours:
                 fused.uninstall()
     except Exception as exc:   # report, never hide
@@ -531,6 +538,8 @@ def main():
         # around the kernel cost more than NCCL's exchange until the ring gets long).  KGE_MULTIMEM=0 / 1 forces it.
         mm = os.environ.get("KGE_MULTIMEM")
         exchange = enable_row_sparse_data_parallel(model, multimem=(world > 4) if mm is None else mm != "0")
+        if os.environ.get("KGE_MULTIMEM_FUSED") == "0":   # A/B: host-launched barriers around the plain kernel
+            exchange.fused_barriers = False
 
     n_batches = 4
     host = synth_batches(w, n_batches, seed=2024 + rank)
@@ -584,7 +593,9 @@ def main():
             "roofline": roof, "clocks": clk, "final_loss": last_loss}
     if exchange is not None:
         line["exchange_bytes_per_rank_per_step"] = exchange.bytes_per_step
-        line["exchange"] = "nvls multimem all-reduce (csrc/collective.cu)" if exchange.multimem else "nccl all-reduce"
+        line["exchange"] = ("nvls multimem all-reduce (csrc/collective.cu)"
+                            + (", barriers and touch marks inside the kernel" if exchange.fused_barriers else "")
+                            ) if exchange.multimem else "nccl all-reduce"
         line["exchange_routes_dense"] = list(exchange.dense)
 
     def train_leg(name, steps, world_, data_parallel=False):

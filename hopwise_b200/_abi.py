@@ -13,7 +13,7 @@ import os
 
 from . import _build
 
-KGE_ABI_VERSION = 2
+KGE_ABI_VERSION = 3
 MODEL_KINDS = {"TransE": 0, "DistMult": 1, "RotatE": 2, "ComplEx": 3}
 
 
@@ -104,6 +104,8 @@ PROTOTYPES = {
     ),
     "kge_copy_h2d_async": (C.c_int, [_P, _P, C.c_int64, _P]),
     "kge_multimem_all_reduce_f32": (C.c_int, [_P, C.c_int64, C.c_int32, C.c_int32, _P]),
+    "kge_multimem_all_reduce_fused_f32": (
+        C.c_int, [_P, C.c_int64, C.c_int32, C.c_int32, _P, C.c_int32, _P, C.c_uint32, _P, C.c_int64, C.c_int32, _P]),
     "kge_mma_image_bytes": (C.c_int64, [_MP, C.c_int64, C.c_int32]),
     "kge_mma_prepare_targets": (C.c_int, [_MP, C.c_int64, _P, C.c_int64, C.c_int32, _P]),
     "kge_full_sort_topk_mma_workspace_bytes": (C.c_int64, [_MP, C.c_int64, C.c_int64, C.c_int32, C.c_int32]),

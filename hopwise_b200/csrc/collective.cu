@@ -42,7 +42,113 @@ __global__ void __launch_bounds__(256) multimem_all_reduce_kernel(float* __restr
   __threadfence_system();
 }
 
+// ---- the same reduction with both cross-rank barriers inside the kernel ------------------------------------------
+// Around the plain kernel the caller needs two host-launched barriers (torch's symmetric-memory barrier: one more
+// kernel launch and signal round each) plus a fill of the touch marks: ~90 us of an 8-GPU step whose reduction moves
+// 14 MB in ~30 us.  Here block 0 performs barrier A (every rank's gradient kernel has finished: stream order on
+// each rank, made visible by release / acquire at system scope) and releases the other blocks through a flag in
+// local memory; every block reduces its part of this rank's slice; the touch marks of the dense tables are stored;
+// and the LAST block to finish performs barrier B (every slice has been reduced and broadcast), so that the kernel's
+// completion on this stream means the whole buffer is final on this GPU.  Barrier = the flag protocol of torch's own
+// symmetric-memory barrier: rank r raises slot [r] in every peer's signal pad (CAS 0 -> 1, release) and consumes
+// slot [p] in its own pad for every peer p (CAS 1 -> 0, acquire).  The grid must be co-resident (it is sized for
+// half of the SMs' block slots, and the stream runs nothing else); every spin is bounded and traps.
+constexpr uint32_t COLL_SPIN_LIMIT = 1u << 28;
+
+__device__ __forceinline__ uint32_t cas_release_sys(uint32_t* p, uint32_t cmp, uint32_t val) {
+  uint32_t old;
+  asm volatile("atom.global.release.sys.cas.b32 %0, [%1], %2, %3;" : "=r"(old) : "l"(p), "r"(cmp), "r"(val) : "memory");
+  return old;
+}
+__device__ __forceinline__ uint32_t cas_acquire_sys(uint32_t* p, uint32_t cmp, uint32_t val) {
+  uint32_t old;
+  asm volatile("atom.global.acquire.sys.cas.b32 %0, [%1], %2, %3;" : "=r"(old) : "l"(p), "r"(cmp), "r"(val) : "memory");
+  return old;
+}
+// threads [0, world) of one block; `slots` = first slot of this barrier inside every signal pad
+__device__ __forceinline__ void cross_rank_barrier(uint32_t* const* pads, int rank, int world, int slots) {
+  const int p = threadIdx.x;
+  if (p < world) {
+    uint32_t spins = 0;
+    while (cas_release_sys(pads[p] + slots + rank, 0u, 1u) != 0u)
+      if (++spins > COLL_SPIN_LIMIT) __trap();
+    spins = 0;
+    while (cas_acquire_sys(pads[rank] + slots + p, 1u, 0u) != 1u)
+      if (++spins > COLL_SPIN_LIMIT) __trap();
+  }
+}
+
+__global__ void __launch_bounds__(256) multimem_all_reduce_fused_kernel(float* __restrict__ mc, int64_t q_lo,
+                                                                        int64_t q_hi, uint32_t* const* pads, int rank,
+                                                                        int world, int slot_base, uint32_t* local,
+                                                                        uint32_t epoch, int32_t* row_state,
+                                                                        int64_t n_mark, int32_t step) {
+  __shared__ int s_last;
+  // ---- barrier A, then release the grid
+  if (blockIdx.x == 0) {
+    cross_rank_barrier(pads, rank, world, slot_base);
+    __syncthreads();
+    if (threadIdx.x == 0) asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(local), "r"(epoch) : "memory");
+  } else {
+    if (threadIdx.x == 0) {
+      uint32_t seen, spins = 0;
+      do {
+        asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(seen) : "l"(local) : "memory");
+        if (++spins > COLL_SPIN_LIMIT) __trap();
+      } while (seen != epoch);
+    }
+    __syncthreads();
+  }
+  // ---- this rank's slice: the switch fetches the N copies and returns their sum; one store writes all N copies
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  int64_t q = q_lo + (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  for (; q + 3 * stride < q_hi; q += 4 * stride) {
+    float4 v[4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) v[u] = multimem_ld_reduce_add(mc + 4 * (q + u * stride));
+#pragma unroll
+    for (int u = 0; u < 4; ++u) multimem_st(mc + 4 * (q + u * stride), v[u]);
+  }
+  for (; q < q_hi; q += stride) multimem_st(mc + 4 * q, multimem_ld_reduce_add(mc + 4 * q));
+  // every row of a dense table counts as touched in this step (a row nobody touched holds a zero gradient)
+  for (int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; r < n_mark; r += stride) row_state[2 * r + 1] = step;
+  __threadfence_system();
+  __syncthreads();
+  // ---- barrier B by the last block to get here
+  if (threadIdx.x == 0) {
+    const uint32_t done = atomicAdd(local + 1, 1u);
+    s_last = done == gridDim.x - 1;
+    if (s_last) local[1] = 0u;   // (re-armed for the next call; nobody else touches it any more)
+  }
+  __syncthreads();
+  if (s_last) cross_rank_barrier(pads, rank, world, slot_base + world);
+}
+
 }  // namespace
+
+extern "C" int kge_multimem_all_reduce_fused_f32(void* multicast_ptr, int64_t n_floats, int32_t rank, int32_t world,
+                                                 void* const* signal_pads_dev, int32_t slot_base, uint32_t* local_flags,
+                                                 uint32_t epoch, int32_t* row_state, int64_t n_mark_rows, int32_t step,
+                                                 kge_stream_t stream) {
+  KGE_REQUIRE(multicast_ptr && n_floats >= 0 && world >= 1 && world <= 32 && rank >= 0 && rank < world, KGE_E_ARG,
+              "bad multimem all-reduce arguments");
+  KGE_REQUIRE((reinterpret_cast<uintptr_t>(multicast_ptr) & 15) == 0 && (n_floats & 3) == 0, KGE_E_ARG,
+              "multimem all-reduce needs a 16-byte aligned buffer of a multiple of 4 floats");
+  KGE_REQUIRE(signal_pads_dev && local_flags && slot_base >= 0 && epoch != 0, KGE_E_ARG, "bad barrier arguments");
+  KGE_REQUIRE(n_mark_rows == 0 || row_state, KGE_E_ARG, "row_state missing");
+  const int64_t quads = n_floats / 4;
+  const int64_t per = (quads + world - 1) / world;
+  const int64_t lo = per * rank, hi = lo + per < quads ? lo + per : quads;   // (an empty slice still takes the barriers)
+  const int threads = 256;
+  int64_t grid = hi > lo ? (hi - lo + 4 * threads - 1) / (4 * threads) : 1;
+  const int64_t cap = (int64_t)kge_num_sms() * 4;   // co-resident: 8 blocks of 256 threads fit an SM
+  if (grid > cap) grid = cap;
+  multimem_all_reduce_fused_kernel<<<(unsigned)grid, threads, 0, (cudaStream_t)stream>>>(
+      reinterpret_cast<float*>(multicast_ptr), lo, hi > lo ? hi : lo, reinterpret_cast<uint32_t* const*>(signal_pads_dev),
+      rank, world, slot_base, local_flags, epoch, row_state, n_mark_rows, step);
+  KGE_LAUNCH_CHECK();
+  return 0;
+}
 
 extern "C" int kge_multimem_all_reduce_f32(void* multicast_ptr, int64_t n_floats, int32_t rank, int32_t world,
                                            kge_stream_t stream) {

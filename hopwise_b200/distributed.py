@@ -116,6 +116,8 @@ class RowSparseExchange:
         self.dense = [False, False, False]
         self.bytes_per_step = 0
         self.kernels_per_step = 0   # launches of this library's pack / add kernels in the last step
+        self.fused_barriers = True  # multimem route: barriers and touch marks inside the reduction kernel
+        self._local_flags, self._epoch = None, 0
         self.timing = False        # record CUDA events around pack / collective / add (bench.py)
         self.timings = []          # [(pack_ms, collective_ms, add_ms)] of the timed steps, read by take_timings()
         self._events = []
@@ -153,9 +155,29 @@ class RowSparseExchange:
         object.__setattr__(model, "_g_alloc", alloc)
         self.multimem = True
 
-    def _all_reduce_dense(self, g_flat, g0, g1):
-        """Sum the [g0, g1) float range of the flat gradient buffer over the ranks, in place."""
+    SIGNAL_SLOT_BASE = 1024   # uint32 slots of the symmetric signal pad this library uses (torch's barrier channels
+    #                           live at the front of the 9216-byte pad)
+
+    def _all_reduce_dense(self, g_flat, g0, g1, row_state=None, step=0):
+        """Sum the [g0, g1) float range of the flat gradient buffer over the ranks, in place.  Returns True when the
+        touch marks of `row_state` (the rows of the reduced tables) were set on the way."""
         if self.multimem and self.symm is not None and g0 % 4 == 0 and (g1 - g0) % 4 == 0:
+            if self.fused_barriers:
+                # one kernel: barrier (all gradients written) -> in-switch reduce + broadcast -> touch marks ->
+                # barrier (all slices final); csrc/collective.cu
+                if self._local_flags is None:
+                    self._local_flags = torch.zeros(2, dtype=torch.int32, device=g_flat.device)
+                self._epoch = self._epoch % 0x7FFFFFFF + 1
+                n_mark = 0 if row_state is None else row_state.shape[0]
+                _abi.check(
+                    _abi.lib().kge_multimem_all_reduce_fused_f32(
+                        self._mc_base + 4 * g0, g1 - g0, self.rank, self.world, int(self.symm.signal_pad_ptrs_dev),
+                        self.SIGNAL_SLOT_BASE, self._local_flags.data_ptr(), self._epoch,
+                        None if row_state is None else row_state.data_ptr(), n_mark, int(step), _abi.stream_ptr()),
+                    "kge_multimem_all_reduce_fused_f32",
+                )
+                self.kernels_per_step += 1
+                return row_state is not None
             self.symm.barrier(channel=0)      # every rank's forward kernel has written its gradients
             _abi.check(
                 _abi.lib().kge_multimem_all_reduce_f32(self._mc_base + 4 * g0, g1 - g0, self.rank, self.world,
@@ -166,6 +188,7 @@ class RowSparseExchange:
             self.kernels_per_step += 1
         else:
             dist.all_reduce(g_flat[g0:g1], op=dist.ReduceOp.SUM, group=self.group)
+        return False
 
     def _agree(self, batch_rows):
         """Bounds on the rows a step can touch, identical on every rank.
@@ -250,11 +273,11 @@ class RowSparseExchange:
         self._mark()
         st = model._state
         for g0, g1, r0, r1 in self._dense_spans(model):
-            self._all_reduce_dense(st["g_flat"], g0, g1)
             # Every row of a dense table is marked as touched instead of all-reducing the touch marks: a row
             # nobody touched holds a zero gradient, and a zero-gradient Adam step is exactly what dense Adam (and
             # the lazy replay) does to it -- same weights, one collective less per step.
-            st["row_state_flat"][r0:r1, 1].fill_(step)
+            if not self._all_reduce_dense(st["g_flat"], g0, g1, st["row_state_flat"][r0:r1], step):
+                st["row_state_flat"][r0:r1, 1].fill_(step)
         if not sparse:
             self._mark()
             self._mark()

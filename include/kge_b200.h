@@ -25,7 +25,7 @@
 extern "C" {
 #endif
 
-#define KGE_ABI_VERSION 2
+#define KGE_ABI_VERSION 3
 
 typedef void* kge_stream_t; /* cudaStream_t */
 
@@ -148,6 +148,16 @@ int kge_copy_h2d_async(void* dst_device, const void* src_host, int64_t nbytes, k
  * cross-rank barrier before (all copies written) and after (all slices reduced) the call. */
 int kge_multimem_all_reduce_f32(void* multicast_ptr, int64_t n_floats, int32_t rank, int32_t world,
                                 kge_stream_t stream);
+/* The same reduction with both cross-rank barriers and the touch marks inside one kernel (no host-launched barrier
+ * rounds): signal_pads_dev = device array of `world` pointers to the ranks' symmetric signal pads (uint32 slots,
+ * zero between calls; slots [slot_base, slot_base + 2*world) are used), local_flags = two zeroed uint32 in local
+ * device memory, epoch = a non-zero value that differs from the previous call's.  row_state / n_mark_rows / step:
+ * rows [0, n_mark_rows) of the {last_step, touch_step} array get touch_step = step (0 rows: nothing).  On return of
+ * the kernel on `stream` every copy of the buffer holds the sums. */
+int kge_multimem_all_reduce_fused_f32(void* multicast_ptr, int64_t n_floats, int32_t rank, int32_t world,
+                                      void* const* signal_pads_dev, int32_t slot_base, uint32_t* local_flags,
+                                      uint32_t epoch, int32_t* row_state, int64_t n_mark_rows, int32_t step,
+                                      kge_stream_t stream);
 
 /* ---- scoring --------------------------------------------------------------------------
  * kge_predict: <Model>.predict / predict_kg (transe.py:100-110,128-137 and twins).

@@ -100,3 +100,74 @@ def test_two_rank_row_sparse_step_matches_single_gpu(name, route, multimem, tmp_
     np.testing.assert_allclose(0.5 * (r0["losses"] + r1["losses"]), losses, rtol=1e-5)
     for key, v in m.state_dict().items():
         assert_weights_close(r0[key], v.cpu().numpy(), rtol=1e-5, atol=5e-7, err_msg=f"{name} {key}")
+
+
+def _eval_worker(rank, world, port, out_dir):
+    import torch.distributed as dist
+
+    from hopwise_b200.distributed import reduce_metric_sums, shard_bounds
+    from hopwise_b200.evaluator import topk_hits, topk_metric_sums
+
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    torch.cuda.set_device(rank)
+    dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", rank))
+    try:
+        dev = f"cuda:{rank}"
+        m = make_product_model("DistMult", device=dev, **EVAL_SHAPE)
+        users, hoff, hist, poff, pos = _eval_inputs()
+        lo, hi = shard_bounds(len(users), rank, world)          # contiguous user block of this rank
+        u = torch.from_numpy(users[lo:hi]).to(dev)
+        ho = torch.from_numpy(hoff[lo:hi + 1] - hoff[lo]).to(dev)
+        hi_items = torch.from_numpy(hist[hoff[lo]:hoff[hi]]).to(dev)
+        po = torch.from_numpy(poff[lo:hi + 1] - poff[lo]).to(dev)
+        pi = torch.from_numpy(pos[poff[lo]:poff[hi]]).to(dev)
+        ids, _ = m.full_sort_topk(u, EVAL_K, ho, hi_items, return_scores=False)
+        sums = topk_metric_sums(topk_hits(ids, po, pi))
+        total, n = reduce_metric_sums(sums, hi - lo)            # NCCL all-reduce of the float64 sums + user counts
+        np.savez(os.path.join(out_dir, f"eval{rank}.npz"), sums=total.cpu().numpy(), n=n, ids=ids.cpu().numpy())
+    finally:
+        dist.destroy_process_group()
+
+
+EVAL_SHAPE = dict(U=1501, I=9001, E=9101, R=4, d=32)
+EVAL_K = 20
+
+
+def _eval_inputs():
+    rng = np.random.default_rng(31)
+    n = 1237                                                     # not divisible by the world size
+    users = rng.integers(1, EVAL_SHAPE["U"], n)
+    hlen = rng.integers(0, 40, n)
+    hoff = np.concatenate([[0], np.cumsum(hlen)])
+    hist = np.concatenate([np.sort(rng.choice(np.arange(1, EVAL_SHAPE["I"]), size=int(l), replace=False)) for l in hlen])
+    plen = rng.integers(1, 6, n)
+    poff = np.concatenate([[0], np.cumsum(plen)])
+    pos = np.concatenate([np.sort(rng.choice(np.arange(1, EVAL_SHAPE["I"]), size=int(l), replace=False)) for l in plen])
+    return users, hoff, hist, poff, pos
+
+
+def test_two_rank_sharded_evaluation_matches_single_gpu(tmp_path):
+    """users in contiguous blocks per rank, per-rank metric sums reduced over NCCL = the single-GPU
+    evaluation of all users (exact global mean; the reference all-gathers rounded per-rank means)."""
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    import torch.multiprocessing as mp
+
+    from hopwise_b200.evaluator import metrics_from_sums, topk_hits, topk_metric_sums
+
+    mp.spawn(_eval_worker, args=(2, _free_port(), str(tmp_path)), nprocs=2, join=True)
+    r0, r1 = np.load(tmp_path / "eval0.npz"), np.load(tmp_path / "eval1.npz")
+    np.testing.assert_array_equal(r0["sums"], r1["sums"])        # every rank holds the global sums
+    users, hoff, hist, poff, pos = _eval_inputs()
+    assert int(r0["n"]) == len(users)
+    m = make_product_model("DistMult", device="cuda:0", **EVAL_SHAPE)
+    dev = "cuda:0"
+    ids, _ = m.full_sort_topk(torch.from_numpy(users).to(dev), EVAL_K, torch.from_numpy(hoff).to(dev),
+                              torch.from_numpy(hist).to(dev), return_scores=False)
+    np.testing.assert_array_equal(np.concatenate([r0["ids"], r1["ids"]]), ids.cpu().numpy())   # top-k ids: bit-exact
+    want = topk_metric_sums(topk_hits(ids, torch.from_numpy(poff).to(dev), torch.from_numpy(pos).to(dev)))
+    np.testing.assert_allclose(r0["sums"], want.cpu().numpy(), rtol=1e-12)
+    a = metrics_from_sums(torch.from_numpy(r0["sums"]), len(users), [10, 20], decimals=None)
+    b = metrics_from_sums(want, len(users), [10, 20], decimals=None)
+    for key in b:
+        assert abs(a[key] - b[key]) <= 1e-12

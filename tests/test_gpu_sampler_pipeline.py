@@ -24,7 +24,7 @@ def _pipeline():
     from hopwise.utils import init_seed
 
     config = Config(model="TransE", dataset="ml-100k",
-                    config_dict={"embedding_size": 16, "train_batch_size": 2048, "epochs": 1, "use_gpu": False,
+                    config_dict={"embedding_size": 16, "train_batch_size": 2048, "epochs": 1, "use_gpu": False, "gpu_id": "",
                                  "show_progress": False, "seed": 2024})
     init_seed(config["seed"], config["reproducibility"])
     dataset = create_dataset(config)
@@ -38,6 +38,8 @@ def test_device_samplers_reproduce_the_reference_loader(tmp_path):
     from hopwise.data.dataloader.knowledge_dataloader import KGDataLoaderState
     from hopwise_b200.sampler import KGSampler, RecSampler, install_device_samplers
 
+    torch.zeros(1, device="cuda")   # CUDA context before hopwise's Config exports CUDA_VISIBLE_DEVICES = gpu_id
+    visible = os.environ.get("CUDA_VISIBLE_DEVICES")
     cwd = os.getcwd()
     os.chdir(tmp_path)
     try:
@@ -53,6 +55,10 @@ def test_device_samplers_reproduce_the_reference_loader(tmp_path):
         got = [{k: v.clone() for k, v in b.interaction.items()} for b in train_dev]
     finally:
         os.chdir(cwd)
+        if visible is None:
+            os.environ.pop("CUDA_VISIBLE_DEVICES", None)
+        else:
+            os.environ["CUDA_VISIBLE_DEVICES"] = visible
     assert len(got) == len(want) == 39
     for i, (a, b) in enumerate(zip(got, want)):
         assert set(a) == set(b)

@@ -35,7 +35,11 @@ def _run(model_name, use_gpu, trainer_cls=None, steps_out=None):
     from hopwise.data import create_dataset, data_preparation
     from hopwise.utils import get_model, get_trainer, init_seed
 
-    config = Config(model=model_name, dataset="ml-100k", config_dict=dict(CFG, use_gpu=use_gpu))
+    # hopwise picks the device from `gpu_id` (configurator.py:540-554: an empty id means CPU); `use_gpu` only gates
+    # the trainer's progress-bar GPU read-out
+    config = Config(model=model_name, dataset="ml-100k",
+                    config_dict=dict(CFG, use_gpu=use_gpu, gpu_id="0" if use_gpu else ""))
+    assert config["device"].type == ("cuda" if use_gpu else "cpu")
     init_seed(config["seed"], config["reproducibility"])
     dataset = create_dataset(config)
     train_data, valid_data, test_data = data_preparation(config, dataset)
@@ -63,6 +67,10 @@ def runs(tmp_path_factory):
     import hopwise_b200.trainer as fused
     from hopwise.trainer import KGTrainer
 
+    # hopwise's Config exports CUDA_VISIBLE_DEVICES = gpu_id ("" for the CPU arm): make sure this process has its CUDA
+    # context before that, and put the variable back afterwards
+    torch.zeros(1, device="cuda")
+    visible = os.environ.get("CUDA_VISIBLE_DEVICES")
     cwd = os.getcwd()
     os.chdir(tmp_path_factory.mktemp("hopwise_run"))   # hopwise writes log/ and log_tensorboard/ into the cwd
     try:
@@ -79,6 +87,10 @@ def runs(tmp_path_factory):
             fused.uninstall()
     finally:
         os.chdir(cwd)
+        if visible is None:
+            os.environ.pop("CUDA_VISIBLE_DEVICES", None)
+        else:
+            os.environ["CUDA_VISIBLE_DEVICES"] = visible
     return out
 
 
