@@ -49,7 +49,7 @@
 
 namespace {
 
-constexpr int MM = 256;    // query rows per CTA
+constexpr int MH = 128;    // query rows per row half (one M = 128 accumulator); a CTA sweeps NH = 1 or 2 halves
 constexpr int GRP = 4;     // targets per candidate group (what the rescore kernel reads per mask bit)
 #ifndef KGE_MMA_CAND
 #define KGE_MMA_CAND 128
@@ -60,15 +60,11 @@ constexpr int MAX_SPLITS = 4;
 // warp / 8 = column slice of the tile), then the producer warp, then one MMA issuer warp per row half (the issue
 // arbiter favours high warp ids, and an MMA issuer must never starve; one warp cannot issue fast enough for both
 // halves: a free-running issuer needs ~125 cycles per tcgen05.mma).
-// The tile producer (one cp.async.bulk per tile) has a warp of its own; KGE_MMA_MERGED_PRODUCER lets the first MMA warp
-// do it instead (experiment: one spinning warp less per CTA; the register cap stays at 96 either way, because two
-// CTAs of nine or ten warps both put five warps on an SM sub-partition of 16384 registers).
-#ifdef KGE_MMA_MERGED_PRODUCER
-constexpr int PRODUCER_WARPS = 0;
-#else
+// Warps of a sweep CTA: 4 * NH * NCOL epilogue warps, one producer warp, NMMA issuer warps.
 constexpr int PRODUCER_WARPS = 1;
-#endif
-__host__ __device__ constexpr int sweep_threads(int ncol, int nmma) { return (8 * ncol + PRODUCER_WARPS + nmma) * 32; }
+__host__ __device__ constexpr int sweep_threads(int nh, int ncol, int nmma) {
+  return (4 * nh * ncol + PRODUCER_WARPS + nmma) * 32;
+}
 #ifndef KGE_MMA_A_NMMA
 #define KGE_MMA_A_NMMA 1   // MMA issuer warps of shape (a): 1 = one warp for both halves, 2 = one per half (experiment)
 #endif
@@ -345,6 +341,8 @@ struct MmaArgs {
   int64_t rows_pad;       // n rounded up to MM: stride of the per-split arrays
   int tiles_per_split;
   int parts, kp, dist, stages;
+  int kc, nkc;            // K columns per ring stage (a multiple of 16) and stages per tile: kc = kp, nkc = 1 unless K is
+                          // too large for whole tiles in shared memory
   const float* header;
   const uint16_t* tiles;
   const int64_t* hist_off;
@@ -536,28 +534,32 @@ __device__ __forceinline__ void chunk_push(const float (&gm)[8], float tm, EpiSt
 }
 
 // TN targets per tile (one MMA instruction covers 128 rows x TN targets x 16 of K), NBUF accumulator buffers per
-// half.  TMEM columns = 2 * TN * NBUF: (128, 1) and (64, 2) take 256 (two CTAs per SM), (128, 2) all 512.
+// half.  TMEM columns = NH * TN * NBUF: (2, 128, 1), (2, 64, 2) and (1, 128, 2) take 256, (2, 128, 2) all 512.
 // NCOL column slices per tile: the 128 rows of a half are covered by NCOL warps per quadrant, each filtering
 // TN / NCOL columns into its own list (a row then owns splits * NCOL lists, merged by the rescore kernel).
 // NMMA issuer warps: 2 = one per row half (needed when the CTA has the SM to itself), 1 = one warp for both.
-template <int TN, int NBUF, int NCOL, int NMMA, bool DBG>
-__global__ void __launch_bounds__(sweep_threads(NCOL, NMMA), NBUF == 1 ? 2 : 1)
+// NH row halves per CTA (MM = 128 * NH query rows).  NH = 1 is the large-K shape: the queries of 256 rows no longer fit
+// shared memory next to a tile ring, so a CTA keeps 128 rows and the tiles stream through the ring in K chunks.
+template <int NH, int TN, int NBUF, int NCOL, int NMMA, bool DBG>
+__global__ void __launch_bounds__(sweep_threads(NH, NCOL, NMMA), (NBUF == 1 && NH == 2) ? 2 : 1)
     fullsort_mma_kernel(const MmaArgs a) {
+  constexpr int MM = MH * NH;
   constexpr int ROOM = 16;              // list room demanded after a compaction
   constexpr int NCH = TN / CH / NCOL;   // chunks of 32 columns per tile and epilogue thread
-  constexpr int EPI_WARPS = 8 * NCOL, MMA_WARP0 = EPI_WARPS + PRODUCER_WARPS;
-  constexpr int PRODUCER_WARP = PRODUCER_WARPS ? EPI_WARPS : -1;
+  constexpr int EPI_WARPS = 4 * NH * NCOL, PRODUCER_WARP = EPI_WARPS, MMA_WARP0 = EPI_WARPS + PRODUCER_WARPS;
   constexpr int N_WARPS = EPI_WARPS + PRODUCER_WARPS + NMMA;
-  constexpr uint32_t TMEM_COLS = 2 * TN * NBUF;
+  constexpr uint32_t TMEM_COLS = NH * TN * NBUF;
+  static_assert(NMMA <= NH, "one issuer warp per row half at most");
   static_assert(NCH % 2 == 0 && (NBUF == 1 || NBUF == 2), "the chunk pipeline alternates two register sets");
   constexpr uint32_t IDESC = make_idesc(TN);
   extern __shared__ __align__(128) unsigned char smem[];
   const int kp = a.kp;
   const uint32_t a_bytes = (uint32_t)MM * kp * 2;
-  const uint32_t b_bytes = (uint32_t)TN * kp * 2;
+  const uint32_t b_bytes = (uint32_t)TN * kp * 2;          // one tile of the image
+  const uint32_t s_bytes = (uint32_t)TN * a.kc * 2;        // one ring stage: kc K columns of a tile
   uint16_t* As = reinterpret_cast<uint16_t*>(smem);
   unsigned char* Bs = smem + a_bytes;
-  uint64_t* bars = reinterpret_cast<uint64_t*>(Bs + (size_t)a.stages * b_bytes);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(Bs + (size_t)a.stages * s_bytes);
   // bars: full[stages], empty[stages], tfull[buf][half] (4), tempty[buf][half] (4)
   float* eps_row = reinterpret_cast<float*>(bars + 2 * a.stages + 8);  // [MM]
   float* inv_row = eps_row + MM;                                        // [MM] 1 / S_i
@@ -655,91 +657,73 @@ __global__ void __launch_bounds__(sweep_threads(NCOL, NMMA), NBUF == 1 ? 2 : 1)
   const uint32_t tfull0 = smem_u32(&bars[2 * a.stages]), tempty0 = smem_u32(&bars[2 * a.stages + 4]);
 
   if (warp == PRODUCER_WARP) {
-    // ===== producer: stream target tiles into the ring (uniform control flow, one elected lane issues) =====
+    // ===== producer: stream target tiles into the ring, one K chunk per stage (uniform control flow, one elected
+    // lane issues).  A chunk [kc K columns][TN rows] of a tile is contiguous in the image.
     const bool leader = elect_one();
     int s = 0;
     uint32_t ph = 0;
     const unsigned char* src = reinterpret_cast<const unsigned char*>(a.tiles) + (size_t)t0 * b_bytes;
     const uint32_t bs0 = smem_u32(Bs);
     for (int64_t i = 0; i < nt; ++i) {
-      mbar_wait(empty0 + 8 * s, ph ^ 1u);
-      if (leader) {
-        mbar_arrive_expect_tx(full0 + 8 * s, b_bytes);
-        bulk_g2s(bs0 + (uint32_t)s * b_bytes, src + (size_t)i * b_bytes, b_bytes, full0 + 8 * s);
-      }
-      __syncwarp();
-      if (++s == a.stages) {
-        s = 0;
-        ph ^= 1u;
+      for (int j = 0; j < a.nkc; ++j) {
+        const int kcols = min(a.kc, kp - j * a.kc);
+        const uint32_t bytes = (uint32_t)TN * kcols * 2;
+        mbar_wait(empty0 + 8 * s, ph ^ 1u);
+        if (leader) {
+          mbar_arrive_expect_tx(full0 + 8 * s, bytes);
+          bulk_g2s(bs0 + (uint32_t)s * s_bytes, src + (size_t)i * b_bytes + (size_t)j * s_bytes, bytes, full0 + 8 * s);
+        }
+        __syncwarp();
+        if (++s == a.stages) {
+          s = 0;
+          ph ^= 1u;
+        }
       }
     }
   } else if (warp >= MMA_WARP0) {
-    // ===== MMA issuers, one warp per row half: the warp runs the loop with uniform control flow (descriptors
-    // live in uniform registers), one elected lane issues.  Only the 14-bit start-address field of a descriptor
-    // changes.
+    // ===== MMA issuers, one warp per row half (or one for both): the warp runs the loop with uniform control flow
+    // (descriptors live in uniform registers), one elected lane issues.  Only the 14-bit start-address field of a
+    // descriptor changes.
     const bool leader = elect_one();
     const uint32_t a_lbo = MM * 16, b_lbo = TN * 16;
     const uint32_t desc_hi = (128u >> 4) | (1u << 14);   // SBO = 128 B, descriptor version 1
     const uint32_t a_lo0 = ((smem_u32(As) >> 4) & 0x3FFFu) | ((a_lbo >> 4) << 16);
     const uint32_t b_lo0 = ((smem_u32(Bs) >> 4) & 0x3FFFu) | ((b_lbo >> 4) << 16);
     const uint32_t a_kstep = (2 * a_lbo) >> 4, b_kstep = (2 * b_lbo) >> 4, a_hstep = (128 * 16) >> 4;
-    const uint32_t b_sstep = b_bytes >> 4;
-    const int ksteps = kp / 16;
-    const int h_lo = NMMA == 2 ? warp - MMA_WARP0 : 0, h_hi = NMMA == 2 ? h_lo + 1 : 2;
+    const uint32_t b_sstep = s_bytes >> 4;
+    const int h_lo = NMMA == NH ? warp - MMA_WARP0 : 0, h_hi = NMMA == NH ? h_lo + 1 : NH;
     int s = 0;
     uint32_t ph = 0;
-    // producer duty of the first MMA warp: keep the ring topped up.  Tile i itself must be on its way before the
-    // warp blocks on it; tiles further ahead are only requested when their stage is already free (no blocking:
-    // the stage of tile p frees when the MMAs of tile p - stages complete, usually long ago).
-    const bool produce = PRODUCER_WARPS == 0 && warp == MMA_WARP0;
-    const unsigned char* src = reinterpret_cast<const unsigned char*>(a.tiles) + (size_t)t0 * b_bytes;
-    const uint32_t bs0 = smem_u32(Bs);
-    int64_t pi = 0;      // next tile to request
-    int ps = 0;          // its stage
-    uint32_t pph = 0;    // phase of that stage's empty barrier
     for (int64_t i = 0; i < nt; ++i) {
-      if (produce) {
-        while (pi < nt && pi < i + a.stages) {
-          if (pi >= a.stages) {   // the stage has been used before: its MMAs must have read it
-            if (pi <= i) mbar_wait(empty0 + 8 * ps, pph ^ 1u);
-            else if (!mbar_try_wait(empty0 + 8 * ps, pph ^ 1u)) break;
-          }
-          if (leader) {
-            mbar_arrive_expect_tx(full0 + 8 * ps, b_bytes);
-            bulk_g2s(bs0 + (uint32_t)ps * b_bytes, src + (size_t)pi * b_bytes, b_bytes, full0 + 8 * ps);
-          }
-          ++pi;
-          if (++ps == a.stages) {
-            ps = 0;
-            pph ^= 1u;
-          }
-        }
-      }
       const uint32_t buf = NBUF == 1 ? 0u : (uint32_t)(i & 1);
       const uint32_t tph = (uint32_t)((i / NBUF) & 1);
-      mbar_wait(full0 + 8 * s, ph);                       // tile landed
-      const uint32_t b_lo = b_lo0 + (uint32_t)s * b_sstep;
-      for (int h = h_lo; h < h_hi; ++h) {
-        mbar_wait(tempty0 + 8 * (buf * 2 + h), tph ^ 1u);  // the half's epilogue warps have drained this accumulator
-        tc_fence_after();
-        if (leader) {
-          const uint32_t dcol = tmem_base + (buf * 2 + h) * TN;
-          const uint32_t a_lo = a_lo0 + (uint32_t)h * a_hstep;
-          for (int ks = 0; ks < ksteps; ++ks) {
-            const uint64_t adesc = ((uint64_t)desc_hi << 32) | (a_lo + (uint32_t)ks * a_kstep);
-            const uint64_t bdesc = ((uint64_t)desc_hi << 32) | (b_lo + (uint32_t)ks * b_kstep);
+      for (int j = 0; j < a.nkc; ++j) {
+        const int ksteps = min(a.kc, kp - j * a.kc) / 16;
+        const int ks0 = j * (a.kc / 16);                    // K step of the tile this chunk starts at
+        mbar_wait(full0 + 8 * s, ph);                       // chunk landed
+        const uint32_t b_lo = b_lo0 + (uint32_t)s * b_sstep;
+        for (int h = h_lo; h < h_hi; ++h) {
+          if (j == 0) mbar_wait(tempty0 + 8 * (buf * 2 + h), tph ^ 1u);  // the half's epilogue warps have drained this accumulator
+          tc_fence_after();
+          if (leader) {
+            const uint32_t dcol = tmem_base + (buf * NH + h) * TN;
+            const uint32_t a_lo = a_lo0 + (uint32_t)h * a_hstep + (uint32_t)ks0 * a_kstep;
+            for (int ks = 0; ks < ksteps; ++ks) {
+              const uint64_t adesc = ((uint64_t)desc_hi << 32) | (a_lo + (uint32_t)ks * a_kstep);
+              const uint64_t bdesc = ((uint64_t)desc_hi << 32) | (b_lo + (uint32_t)ks * b_kstep);
 #ifndef KGE_EXP_NOMMA   // timing experiments only (scripts/gpu_exp_sweep.sh); results are wrong with a knob set
-            umma_f16(dcol, adesc, bdesc, IDESC, ks > 0 ? 1u : 0u);
+              umma_f16(dcol, adesc, bdesc, IDESC, (ks0 + ks) > 0 ? 1u : 0u);
 #endif
+            }
+            if (j == a.nkc - 1) umma_commit(tfull0 + 8 * (buf * 2 + h));   // this half's accumulator is ready
+            if (h == h_hi - 1) umma_commit(empty0 + 8 * s);                // stage reusable once its MMAs have read it
           }
-          umma_commit(tfull0 + 8 * (buf * 2 + h));               // this half's accumulator is ready
-          if (h == h_hi - 1) umma_commit(empty0 + 8 * s);        // smem stage reusable once its MMAs have read it
         }
-      }
-      __syncwarp();
-      if (++s == a.stages) {
-        s = 0;
-        ph ^= 1u;
+        __syncwarp();
+        if (++s == a.stages) {
+          s = 0;
+          ph ^= 1u;
+        }
       }
     }
   } else {
@@ -800,8 +784,8 @@ __global__ void __launch_bounds__(sweep_threads(NCOL, NMMA), NBUF == 1 ? 2 : 1)
       // Software pipeline over chunks: the load of the next chunk is in flight while the current one is filtered,
       // and an accumulator goes back to the tensor core as soon as its last chunk sits in registers (the MMAs of
       // the next tile already run in the other buffer).
-      const int h = (warp >> 2) & 1;
-      const int cs = warp >> 3;                         // column slice of the tile
+      const int h = NH == 2 ? (warp >> 2) & 1 : 0;
+      const int cs = warp / (4 * NH);                   // column slice of the tile
       const int64_t lsplit = (int64_t)split * NCOL + cs;   // list index of this (target split, column slice)
       const int u = h * 128 + quad * 32 + lane;
       EpiState st;
@@ -871,7 +855,7 @@ __global__ void __launch_bounds__(sweep_threads(NCOL, NMMA), NBUF == 1 ? 2 : 1)
       tmem_ld_wait(va);
       for (int i = 0; i < nti; ++i, cid += TN / CH) {
         const uint32_t buf = NBUF == 1 ? 0u : (uint32_t)(i & 1);
-        const uint32_t tbase = tlane + buf * 2 * TN;
+        const uint32_t tbase = tlane + buf * NH * TN;
 #pragma unroll
         for (int c = 0; c < NCH; ++c) {
           uint32_t(&cur)[32] = (c & 1) ? vb : va;
@@ -891,7 +875,7 @@ __global__ void __launch_bounds__(sweep_threads(NCOL, NMMA), NBUF == 1 ? 2 : 1)
               const uint32_t nbuf = NBUF == 1 ? 0u : (buf ^ 1u);
               mbar_wait(my_tfull + 16 * nbuf, (uint32_t)(((i + 1) / NBUF) & 1));
               tc_fence_after();
-              tmem_ld32_issue(tlane + nbuf * 2 * TN, nxt);
+              tmem_ld32_issue(tlane + nbuf * NH * TN, nxt);
             }
             if (NBUF != 1) process(cur, cid + c);
             if (i + 1 < nti) tmem_ld_wait(nxt);
@@ -1257,10 +1241,12 @@ __global__ void __launch_bounds__(RS_WARPS * 32, KGE_RS_MINB) rescore_topk_kerne
 }
 
 struct MmaPlan {
-  int parts, dist, kp, stages, tn, nbuf, ncol, ctas_per_sm, splits, tiles_per_split;
+  int parts, dist, kp, stages, tn, nbuf, ncol, nh, kc, nkc, ctas_per_sm, splits, tiles_per_split;
+  char cfg;
   size_t smem;
   int64_t n_tiles, rows_pad, unsafe_wpr;
 };
+constexpr int KP_MAX = 640;   // largest padded K of the tensor-core path (shape k: 128 query rows x 640 x 2 B = 160 KB)
 
 int plan_mma(const kge_model_t* m, int64_t n, int64_t n_targets, int k, int shape, MmaPlan& pl) {
   KGE_REQUIRE(m && m->model >= KGE_TRANSE && m->model <= KGE_COMPLEX, KGE_E_ARG, "bad model");
@@ -1268,45 +1254,61 @@ int plan_mma(const kge_model_t* m, int64_t n, int64_t n_targets, int k, int shap
   pl.dist = (m->model == KGE_TRANSE || m->model == KGE_ROTATE) ? 1 : 0;
   const int kd = pl.parts * m->d + (pl.dist ? 3 : 0);
   pl.kp = (kd + 15) / 16 * 16;
-  KGE_REQUIRE(pl.kp <= 256, KGE_E_UNSUPPORTED, "K = %d too large for the tensor-core path", pl.kp);
+  KGE_REQUIRE(pl.kp <= KP_MAX, KGE_E_UNSUPPORTED, "K = %d too large for the tensor-core path (max %d)", pl.kp, KP_MAX);
   KGE_REQUIRE(k >= 1 && k <= 32, KGE_E_UNSUPPORTED, "k = %d too large for the tensor-core path (max 32)", k);
   KGE_REQUIRE(n_targets >= 1 && n_targets < (int64_t)CID_MASK * CH, KGE_E_UNSUPPORTED, "bad n_targets");
-  // Tile shape (TN targets per tile, NBUF accumulators per row half, NCOL column slices per tile).  SS-mode
-  // tcgen05.mma with N = 64 runs at well under half rate (operand fetch + per-instruction cost), so TN = 128:
-  //   (a) TN 128, NBUF 1, NCOL 1: 256 TMEM columns, two CTAs per SM = four accumulator streams per SM; a stream
-  //       that stalls (list compaction) leaves the tensor pipe to the other three          -- K <= 80
-  //   (f) TN 128, NBUF 2, NCOL 2: all 512 columns, one CTA of 16 epilogue warps and two MMA issuer warps per SM
-  //                                                                                          -- larger K
-  //   (c) TN 64,  NBUF 2, NCOL 1: one CTA per SM -- K so large that (f) has no room for a ring of tiles
-  // `shape` = 'a' | 'f' | 'c' forces one (tests, experiments; 0 = pick); the target image depends on TN only.
-  const size_t a_bytes = (size_t)MM * pl.kp * 2;
-  const size_t fixed = a_bytes + 32 * 8 + 2 * MM * 4 + 64;
-  const size_t two_per_sm = 112 * 1024, one_per_sm = 200 * 1024;   // 227 KB per SM, 1 KB reserved per CTA
-  KGE_REQUIRE(shape == 0 || shape == 'a' || shape == 'f' || shape == 'c', KGE_E_ARG, "unknown sweep shape %d", shape);
+  // Sweep shape (NH row halves of 128 queries per CTA, TN targets per tile, NBUF accumulators per row half, NCOL
+  // column slices per tile).  SS-mode tcgen05.mma with N = 64 runs at well under half rate (operand fetch + a
+  // per-instruction cost), so TN = 128 wherever it fits:
+  //   (a) NH 2, TN 128, NBUF 1, NCOL 1: 256 TMEM columns, two CTAs per SM = four accumulator streams per SM
+  //                                                                                          -- K <= 80
+  //   (f) NH 2, TN 128, NBUF 2, NCOL 2: all 512 columns, one CTA of 16 epilogue warps and two MMA issuer warps per
+  //       SM                                                                                 -- K <= ~190
+  //   (c) NH 2, TN 64,  NBUF 2, NCOL 1: one CTA per SM: (f) has no room for two whole tiles  -- K <= 256
+  //   (k) NH 1, TN 128, NBUF 2, NCOL 2: the queries of 256 rows no longer fit next to a ring, so a CTA keeps 128 rows
+  //       and the tiles stream through the ring in chunks of 64 K columns (RotatE d = 128 / 256: K = 272 / 528).
+  //       Every B element now serves 128 rows instead of 256: the sweep reads the image twice as often from L2
+  //       (~42 B/clk/SM at full tensor rate, about the chip's L2 limit), which bounds this shape   -- K <= 640
+  // `shape` = 'a' | 'f' | 'c' | 'k' forces one (tests, experiments; 0 = pick); the target image depends on TN only.
+  KGE_REQUIRE(shape == 0 || shape == 'a' || shape == 'f' || shape == 'c' || shape == 'k', KGE_E_ARG,
+              "unknown sweep shape %d", shape);
+  const size_t two_per_sm = 112 * 1024, one_per_sm = 200 * 1024, one_per_sm_max = 225 * 1024;   // 227 KB per SM
+  auto fixed_for = [&](int nh) { return (size_t)MH * nh * pl.kp * 2 + 32 * 8 + 2 * (size_t)MH * nh * 4 + 64; };
+  const size_t fixed2 = fixed_for(2);
   char cfg = (char)shape;
-  if (cfg == 'a' && fixed + 2 * (size_t)128 * pl.kp * 2 > two_per_sm) cfg = 0;
+  if (cfg == 'a' && fixed2 + 2 * (size_t)128 * pl.kp * 2 > two_per_sm) cfg = 0;
+  if (cfg == 'f' && fixed2 + 2 * (size_t)128 * pl.kp * 2 > one_per_sm) cfg = 0;
+  if (cfg == 'c' && fixed2 + 2 * (size_t)64 * pl.kp * 2 > one_per_sm) cfg = 0;
   if (!cfg) {
-    if (fixed + 3 * (size_t)128 * pl.kp * 2 <= two_per_sm) cfg = 'a';
-    else cfg = (fixed + 2 * (size_t)128 * pl.kp * 2 <= one_per_sm) ? 'f' : 'c';
+    if (fixed2 + 3 * (size_t)128 * pl.kp * 2 <= two_per_sm) cfg = 'a';
+    else if (fixed2 + 2 * (size_t)128 * pl.kp * 2 <= one_per_sm) cfg = 'f';
+    else cfg = (fixed2 + 2 * (size_t)64 * pl.kp * 2 <= one_per_sm) ? 'c' : 'k';
   }
+  pl.cfg = cfg;
+  pl.nh = cfg == 'k' ? 1 : 2;
   pl.tn = cfg == 'c' ? 64 : 128;
   pl.nbuf = cfg == 'a' ? 1 : 2;
-  pl.ncol = cfg == 'f' ? 2 : 1;
-  const size_t b_bytes = (size_t)pl.tn * pl.kp * 2;
-  size_t budget = cfg == 'a' ? two_per_sm : one_per_sm;
-  KGE_REQUIRE(fixed + 2 * b_bytes <= budget, KGE_E_UNSUPPORTED, "K = %d leaves no room for a pipeline", pl.kp);
+  pl.ncol = (cfg == 'f' || cfg == 'k') ? 2 : 1;
+  pl.kc = cfg == 'k' ? (pl.kp < 64 ? pl.kp : 64) : pl.kp;   // 16 KB stages: several chunks in flight ahead of the MMAs
+  pl.nkc = (pl.kp + pl.kc - 1) / pl.kc;
+  const int mm = MH * pl.nh;
+  const size_t fixed = fixed_for(pl.nh), a_bytes = (size_t)mm * pl.kp * 2;
+  const size_t s_bytes = (size_t)pl.tn * pl.kc * 2;
+  const size_t budget = cfg == 'a' ? two_per_sm : (cfg == 'k' ? one_per_sm_max : one_per_sm);
+  KGE_REQUIRE(fixed + 2 * s_bytes <= budget, KGE_E_UNSUPPORTED, "K = %d leaves no room for a pipeline", pl.kp);
   pl.ctas_per_sm = cfg == 'a' ? 2 : 1;
-  int stages = (int)((budget - fixed) / b_bytes);
+  int stages = (int)((budget - fixed) / s_bytes);
   if (stages > 8) stages = 8;
   pl.stages = stages;
-  pl.smem = a_bytes + (size_t)stages * b_bytes + (size_t)(2 * stages + 8) * 8 + 2 * MM * 4 + 64;
+  pl.smem = a_bytes + (size_t)stages * s_bytes + (size_t)(2 * stages + 8) * 8 + 2 * (size_t)mm * 4 + 64;
   // the setup stages one fp32 query row per warp in the ring
-  KGE_REQUIRE((size_t)stages * b_bytes >= (size_t)(8 * pl.ncol + 3) * pl.kp * 4, KGE_E_UNSUPPORTED, "ring too small");
+  const int n_warps = 4 * pl.nh * pl.ncol + 3;
+  KGE_REQUIRE((size_t)stages * s_bytes >= (size_t)n_warps * pl.kp * 4, KGE_E_UNSUPPORTED, "ring too small");
   pl.n_tiles = (n_targets + pl.tn - 1) / pl.tn;
-  pl.rows_pad = (n + MM - 1) / MM * MM;
+  pl.rows_pad = (n + mm - 1) / mm * mm;
   pl.unsafe_wpr = (pl.n_tiles * (pl.tn / CH) + 31) / 32;
-  // target splits: fill the resident CTA slots (2 per SM) when there are few row blocks
-  const int64_t row_blocks = pl.rows_pad / MM > 0 ? pl.rows_pad / MM : 1;
+  // target splits: fill the resident CTA slots when there are few row blocks
+  const int64_t row_blocks = pl.rows_pad / mm > 0 ? pl.rows_pad / mm : 1;
   const int64_t slots = (int64_t)kge_num_sms() * pl.ctas_per_sm;
   int64_t s = slots / row_blocks;
   if (s > MAX_SPLITS) s = MAX_SPLITS;
@@ -1422,6 +1424,8 @@ extern "C" int kge_full_sort_topk_mma(const kge_model_t* model, const int64_t* h
   a.kp = pl.kp;
   a.dist = pl.dist;
   a.stages = pl.stages;
+  a.kc = pl.kc;
+  a.nkc = pl.nkc;
   a.header = reinterpret_cast<const float*>(image);
   a.tiles = reinterpret_cast<const uint16_t*>(reinterpret_cast<const unsigned char*>(image) + IMG_HEADER);
   a.hist_off = hist_off;
@@ -1449,19 +1453,22 @@ extern "C" int kge_full_sort_topk_mma(const kge_model_t* model, const int64_t* h
                                                                        mask_first);
     KGE_LAUNCH_CHECK();
   }
-  const dim3 grid((unsigned)(pl.rows_pad / MM), (unsigned)pl.splits);
-#define KGE_SWEEP(TN_, NB_, NC_, NM_, DBG_)                                                                        \
+  const dim3 grid((unsigned)(pl.rows_pad / (MH * pl.nh)), (unsigned)pl.splits);
+#define KGE_SWEEP(NH_, TN_, NB_, NC_, NM_, DBG_)                                                                   \
   do {                                                                                                            \
-    KGE_CUDA(cudaFuncSetAttribute(fullsort_mma_kernel<TN_, NB_, NC_, NM_, DBG_>,                                  \
+    KGE_CUDA(cudaFuncSetAttribute(fullsort_mma_kernel<NH_, TN_, NB_, NC_, NM_, DBG_>,                             \
                                   cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pl.smem));                    \
-    fullsort_mma_kernel<TN_, NB_, NC_, NM_, DBG_><<<grid, sweep_threads(NC_, NM_), pl.smem, st>>>(a);             \
+    fullsort_mma_kernel<NH_, TN_, NB_, NC_, NM_, DBG_>                                                            \
+        <<<grid, sweep_threads(NH_, NC_, NM_), pl.smem, st>>>(a);                                                 \
   } while (0)
-  if (pl.tn == 128 && pl.nbuf == 1) {
-    if (debug_scores) KGE_SWEEP(128, 1, 1, KGE_MMA_A_NMMA, true); else KGE_SWEEP(128, 1, 1, KGE_MMA_A_NMMA, false);
-  } else if (pl.tn == 128) {
-    if (debug_scores) KGE_SWEEP(128, 2, 2, 2, true); else KGE_SWEEP(128, 2, 2, 2, false);
+  if (pl.cfg == 'a') {
+    if (debug_scores) KGE_SWEEP(2, 128, 1, 1, KGE_MMA_A_NMMA, true); else KGE_SWEEP(2, 128, 1, 1, KGE_MMA_A_NMMA, false);
+  } else if (pl.cfg == 'f') {
+    if (debug_scores) KGE_SWEEP(2, 128, 2, 2, 2, true); else KGE_SWEEP(2, 128, 2, 2, 2, false);
+  } else if (pl.cfg == 'c') {
+    if (debug_scores) KGE_SWEEP(2, 64, 2, 1, 2, true); else KGE_SWEEP(2, 64, 2, 1, 2, false);
   } else {
-    if (debug_scores) KGE_SWEEP(64, 2, 1, 2, true); else KGE_SWEEP(64, 2, 1, 2, false);
+    if (debug_scores) KGE_SWEEP(1, 128, 2, 2, 1, true); else KGE_SWEEP(1, 128, 2, 2, 1, false);
   }
 #undef KGE_SWEEP
   KGE_LAUNCH_CHECK();

@@ -589,9 +589,9 @@ class FusedKGEModel(KnowledgeRecommender):
 
     @staticmethod
     def _mma_shape() -> int:
-        """Sweep shape forced through KGE_MMA_CFG = a | f | c (tests, experiments); 0 = the library picks."""
+        """Sweep shape forced through KGE_MMA_CFG = a | f | c | k (tests, experiments); 0 = the library picks."""
         cfg = os.environ.get("KGE_MMA_CFG", "")
-        return ord(cfg[0]) if cfg[:1] in ("a", "f", "c") else 0
+        return ord(cfg[0]) if cfg[:1] in ("a", "f", "c", "k") else 0
 
     def _mma_supported(self, k: int, n_targets=None) -> bool:
         m = self._model_struct(False)

@@ -76,7 +76,7 @@ def _model_struct(kind, d, rows=1000):
 def test_sweep_plan_sizes(kind, d, tn):
     """plan_mma (csrc/mma_topk.cu) without a GPU: the operand image is tiles of TN rows of the padded K (fp16), the
     workspace holds one 128-entry list per (row, split, slice), the per-row scalars and bitmap, the row map and
-    the partial lists of the device-gated exact fallback; K > 256 and k > 32 are refused."""
+    the partial lists of the device-gated exact fallback; K > 640 and k > 32 are refused."""
     from hopwise_b200 import _abi
 
     lib = _abi.lib()
@@ -86,6 +86,7 @@ def test_sweep_plan_sizes(kind, d, tn):
     kd = parts * d + (3 if kind in ("TransE", "RotatE") else 0)
     kp = (kd + 15) // 16 * 16
     tiles = (n_targets + tn - 1) // tn
+    tiles128 = (n_targets + 127) // 128
     img = lib.kge_mma_image_bytes(C.byref(m), n_targets, 0)
     assert img == 128 + tiles * tn * kp * 2 + (n_targets * 4 + 127) // 128 * 128
     n, k = 75_776, 20
@@ -102,8 +103,10 @@ def test_sweep_plan_sizes(kind, d, tn):
             + a16(rows_pad * 4) + a16(exact))
     assert ws == want
     assert lib.kge_full_sort_topk_mma_workspace_bytes(C.byref(m), n, n_targets, 64, 0) == -1    # k > 32
-    big = _model_struct("ComplEx", 160)
-    assert lib.kge_mma_image_bytes(C.byref(big), n_targets, 0) == -1                          # K = 320 > 256
+    big = _model_struct("ComplEx", 160)                                                     # K = 320: shape (k)
+    assert lib.kge_mma_image_bytes(C.byref(big), n_targets, 0) == 128 + tiles128 * 128 * 320 * 2 + (n_targets * 4 + 127) // 128 * 128
+    huge = _model_struct("ComplEx", 330)
+    assert lib.kge_mma_image_bytes(C.byref(huge), n_targets, 0) == -1                         # K = 672 > 640
     # a forced shape is accepted ('c' always fits), an unknown one is refused
     assert lib.kge_mma_image_bytes(C.byref(m), n_targets, ord("c")) > 0
     assert lib.kge_mma_image_bytes(C.byref(m), n_targets, ord("x")) == -1

@@ -306,11 +306,14 @@ def test_mma_topk_equals_cuda_core_topk(name, d, I, k):
 
 @pytest.mark.parametrize("cfg,name,d,I,k", [("a", "DistMult", 64, 20000, 20), ("f", "DistMult", 64, 20000, 20),
                                             ("c", "DistMult", 64, 20000, 20), ("f", "RotatE", 20, 9000, 10),
-                                            ("", "RotatE", 120, 8300, 10), ("", "ComplEx", 128, 8300, 20)])
+                                            ("", "RotatE", 120, 8300, 10), ("", "ComplEx", 128, 8300, 20),
+                                            ("k", "DistMult", 64, 20000, 20), ("", "RotatE", 128, 8300, 10),
+                                            ("", "RotatE", 256, 8300, 20), ("", "TransE", 500, 8300, 20),
+                                            ("", "ComplEx", 300, 8300, 5)])
 def test_mma_tile_shapes(monkeypatch, cfg, name, d, I, k):
     """Every sweep shape (csrc/mma_topk.cu plan_mma: a = two CTAs per SM, f = column-sliced single CTA, c = 64-wide
-    tiles for K > 195) gives the CUDA-core kernel's ids and scores bit for bit; "" = the shape the plan picks
-    (K = 256 lands on c)."""
+    tiles for K > 195, k = 128-row CTAs with K-chunked tiles for K > 256: RotatE d = 128 / 256 are K = 272 / 528) gives
+    the CUDA-core kernel's ids and scores bit for bit; "" = the shape the plan picks (K = 256 lands on c)."""
     if cfg:
         monkeypatch.setenv("KGE_MMA_CFG", cfg)
     else:
