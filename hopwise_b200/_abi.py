@@ -13,7 +13,7 @@ import os
 
 from . import _build
 
-KGE_ABI_VERSION = 3
+KGE_ABI_VERSION = 4
 MODEL_KINDS = {"TransE": 0, "DistMult": 1, "RotatE": 2, "ComplEx": 3}
 
 
@@ -120,6 +120,11 @@ PROTOTYPES = {
     "kge_sample_negatives": (
         C.c_int,
         [_P, _P, C.c_int64, C.c_int32, _P, _P, C.c_int64, C.c_int64, _P, _P, _P],
+    ),
+    "kge_sample_alias_workspace_bytes": (C.c_int64, [C.c_int64]),
+    "kge_sample_negatives_alias": (
+        C.c_int,
+        [_P, _P, C.c_int64, C.c_int32, _P, _P, C.c_int64, _P, _P, _P, _P, _P, _P],
     ),
     "kge_mt19937_seed": (C.c_int, [_P, C.c_uint32, _P]),
 }

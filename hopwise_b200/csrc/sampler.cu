@@ -17,6 +17,11 @@
 //   the j-th open slot; then every drawn slot is checked against its key's sorted forbidden
 //   list (binary search) and the failing slots, compacted in ascending order like the reference's
 //   list comprehension, form the next round.
+// Popularity-biased candidates (sampler.py:68-116, AbstractSampler._build_alias_table / _pop_sampling): a round
+// of L open slots consumes randint(0, n_keys, L) -- the same masked rejection -- and then np.random.random(L):
+// two words per double, (w0 >> 5) * 2^26 + (w1 >> 6) over 2^53, a pair may straddle a 624-word block; slot j
+// takes keys[idx_j] when prob[idx_j] > p_j, else alias[idx_j].  The table itself is built on the host with the
+// reference's arithmetic (hopwise_b200/sampler.py build_alias_table).
 // The advanced state (624 words + pos) is written back so a later call -- or NumPy on the host
 // after a copy -- continues the same stream.
 #include "common.cuh"
@@ -103,6 +108,13 @@ struct SampleArgs {
   int32_t* check_a;
   int32_t* check_b;
   int max_rounds;
+  // popularity mode (pop_n > 0): alias table over pop_n keys, scratch for one round's indices and raw words
+  int64_t pop_n;
+  const int64_t* pop_keys;
+  const double* pop_prob;
+  const int64_t* pop_alias;
+  int32_t* idx_tmp;    // [total]
+  uint32_t* word_tmp;  // [2 * total]
 };
 
 __global__ void __launch_bounds__(SAMPLER_THREADS, 1) sample_kernel(const SampleArgs a) {
@@ -129,9 +141,10 @@ __global__ void __launch_bounds__(SAMPLER_THREADS, 1) sample_kernel(const Sample
     if (L == 0) break;
     if (++rounds > a.max_rounds) break;  // a key whose forbidden list covers the whole range
     // ---- draw L accepted values, in stream order, into the open slots -----------------------
+    const bool pop = a.pop_n > 0;
     if (t == 0) s_filled = 0;
     __syncthreads();
-    while (true) {
+    while (!(pop && a.rng == 0u)) {  // randint(0, 1, L) is all zeros and consumes nothing
       const int filled = s_filled;
       if (filled >= L) break;
       if (s_pos >= MT_N) {
@@ -154,14 +167,46 @@ __global__ void __launch_bounds__(SAMPLER_THREADS, 1) sample_kernel(const Sample
       if (t == 0) s_newpos = MT_N;
       __syncthreads();
       if (ok && rank < need) {
-        const int slot = identity ? (filled + rank) : check[filled + rank];
-        a.out[slot] = a.low + (int64_t)w;
+        if (pop) {
+          a.idx_tmp[filled + rank] = (int32_t)w;  // the j-th index of this round, j = position in the open list
+        } else {
+          const int slot = identity ? (filled + rank) : check[filled + rank];
+          a.out[slot] = a.low + (int64_t)w;
+        }
         if (rank == need - 1) s_newpos = i + 1;  // the word that produced the last needed value
       }
       __syncthreads();
       if (t == 0) {
         s_pos = s_newpos;  // MT_N when the whole rest of the block was consumed
         s_filled = filled + (tot < need ? tot : need);
+      }
+      __syncthreads();
+    }
+    if (pop) {
+      // ---- np.random.random(L): 2L raw words in stream order, then one double per slot ------------------
+      const int want = 2 * L;
+      int done = 0;
+      while (done < want) {
+        if (s_pos >= MT_N) {
+          __syncthreads();
+          mt_twist(mt);
+          if (t == 0) s_pos = 0;
+          __syncthreads();
+        }
+        const int pos = s_pos;
+        const int take = min(want - done, MT_N - pos);
+        if (t < take) a.word_tmp[done + t] = mt_temper(mt[pos + t]);
+        __syncthreads();
+        if (t == 0) s_pos = pos + take;
+        done += take;
+        __syncthreads();
+      }
+      for (int j = t; j < L; j += blockDim.x) {
+        const int slot = identity ? j : check[j];
+        const int32_t idx = a.rng == 0u ? 0 : a.idx_tmp[j];
+        const double hi = (double)(a.word_tmp[2 * j] >> 5), lo = (double)(a.word_tmp[2 * j + 1] >> 6);
+        const double p = (hi * 67108864.0 + lo) / 9007199254740992.0;
+        a.out[slot] = a.pop_prob[idx] > p ? a.pop_keys[idx] : a.pop_alias[idx];
       }
       __syncthreads();
     }
@@ -224,15 +269,21 @@ __global__ void mt_seed_kernel(uint32_t* state, uint32_t seed) {
 
 extern "C" int64_t kge_sample_workspace_bytes(int64_t total) { return total < 0 ? -1 : 2 * total * (int64_t)sizeof(int32_t); }
 
-extern "C" int kge_sample_negatives(uint32_t* mt_state, const int64_t* keys, int64_t n, int32_t num,
-                                    const int64_t* used_off, const int64_t* used_vals, int64_t low, int64_t high,
-                                    int64_t* out, void* workspace, kge_stream_t stream) {
+extern "C" int64_t kge_sample_alias_workspace_bytes(int64_t total) { return total < 0 ? -1 : 5 * total * (int64_t)sizeof(int32_t); }
+
+namespace {
+
+int launch_sampler(uint32_t* mt_state, const int64_t* keys, int64_t n, int32_t num, const int64_t* used_off,
+                   const int64_t* used_vals, int64_t low, int64_t high, int64_t pop_n, const int64_t* pop_keys,
+                   const double* pop_prob, const int64_t* pop_alias, int64_t* out, void* workspace,
+                   kge_stream_t stream) {
   KGE_REQUIRE(n >= 0 && num >= 1, KGE_E_ARG, "bad n / num");
   if (n == 0) return 0;
   KGE_REQUIRE(mt_state && keys && used_off && used_vals && out && workspace, KGE_E_ARG, "NULL argument");
-  KGE_REQUIRE(n * (int64_t)num < 0x7FFFFFFFll, KGE_E_UNSUPPORTED, "more than 2^31-1 samples in one call");
+  KGE_REQUIRE(n * (int64_t)num < 0x3FFFFFFFll, KGE_E_UNSUPPORTED, "more than 2^30-1 samples in one call");
   const int64_t rng = high - 1 - low;
-  KGE_REQUIRE(rng >= 1 && rng < 0xFFFFFFFFll, KGE_E_UNSUPPORTED,
+  // randint(low, low + 1) is the constant low and consumes no words: only the alias mode (one key) can ask for it
+  KGE_REQUIRE(rng >= (pop_n > 0 ? 0 : 1) && rng < 0xFFFFFFFFll, KGE_E_UNSUPPORTED,
               "randint range %lld outside the 32-bit masked path", (long long)rng);
   uint32_t mask = (uint32_t)rng;
   mask |= mask >> 1;
@@ -240,6 +291,7 @@ extern "C" int kge_sample_negatives(uint32_t* mt_state, const int64_t* keys, int
   mask |= mask >> 4;
   mask |= mask >> 8;
   mask |= mask >> 16;
+  const int64_t total = n * (int64_t)num;
   SampleArgs a;
   a.state = mt_state;
   a.keys = keys;
@@ -252,11 +304,35 @@ extern "C" int kge_sample_negatives(uint32_t* mt_state, const int64_t* keys, int
   a.mask = mask;
   a.out = out;
   a.check_a = reinterpret_cast<int32_t*>(workspace);
-  a.check_b = a.check_a + n * (int64_t)num;
+  a.check_b = a.check_a + total;
   a.max_rounds = 4096;
+  a.pop_n = pop_n;
+  a.pop_keys = pop_keys;
+  a.pop_prob = pop_prob;
+  a.pop_alias = pop_alias;
+  a.idx_tmp = pop_n > 0 ? a.check_b + total : nullptr;
+  a.word_tmp = pop_n > 0 ? reinterpret_cast<uint32_t*>(a.idx_tmp + total) : nullptr;
   sample_kernel<<<1, SAMPLER_THREADS, 0, (cudaStream_t)stream>>>(a);
   KGE_LAUNCH_CHECK();
   return 0;
+}
+
+}  // namespace
+
+extern "C" int kge_sample_negatives(uint32_t* mt_state, const int64_t* keys, int64_t n, int32_t num,
+                                    const int64_t* used_off, const int64_t* used_vals, int64_t low, int64_t high,
+                                    int64_t* out, void* workspace, kge_stream_t stream) {
+  return launch_sampler(mt_state, keys, n, num, used_off, used_vals, low, high, 0, nullptr, nullptr, nullptr, out,
+                        workspace, stream);
+}
+
+extern "C" int kge_sample_negatives_alias(uint32_t* mt_state, const int64_t* keys, int64_t n, int32_t num,
+                                          const int64_t* used_off, const int64_t* used_vals, int64_t pop_n,
+                                          const int64_t* pop_keys, const double* pop_prob, const int64_t* pop_alias,
+                                          int64_t* out, void* workspace, kge_stream_t stream) {
+  KGE_REQUIRE(pop_n >= 1 && pop_keys && pop_prob && pop_alias, KGE_E_ARG, "empty alias table");
+  return launch_sampler(mt_state, keys, n, num, used_off, used_vals, 0, pop_n, pop_n, pop_keys, pop_prob, pop_alias,
+                        out, workspace, stream);
 }
 
 extern "C" int kge_mt19937_seed(uint32_t* mt_state, uint32_t seed, kge_stream_t stream) {

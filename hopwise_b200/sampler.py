@@ -67,6 +67,12 @@ def _as_device_ids(x, device):
     return torch.as_tensor(np.asarray(x), dtype=torch.int64).to(device).contiguous()
 
 
+def _as_host_ids(x):
+    if torch.is_tensor(x):
+        return x.detach().cpu().numpy().astype(np.int64, copy=False).reshape(-1)
+    return np.asarray(x, dtype=np.int64).reshape(-1)
+
+
 def build_used_csr(keys, values, n_keys: int, device):
     """CSR (offsets[n_keys+1], sorted unique values) of `used_ids[key] = set(values)`."""
     keys = _as_device_ids(keys, device)
@@ -85,10 +91,51 @@ def build_used_csr(keys, values, n_keys: int, device):
     return off, v2.contiguous()
 
 
+def build_alias_table(candidates, alpha: float):
+    """The reference's alias table (sampler.py:68-100) as three arrays in its key order:
+    keys[n] int64 (first occurrence in `candidates`), prob[n] float64, alias[n] int64 (aliased key id, -1 = none).
+
+    Host set-up, run once per sampler.  Every float is produced by the same IEEE-754 double operations, in the same
+    order, as the reference's dict arithmetic (count / len, pow, the builtin sum, / total * n, and the running
+    prob[large] - (1 - prob[small]) of the pairing loop), so `prob > p` decides identically; the two FIFO queues
+    are deques instead of list.pop(0).
+    """
+    from collections import deque
+
+    cand = np.asarray(candidates, dtype=np.int64).reshape(-1)
+    if cand.size == 0:
+        raise ValueError("popularity sampling needs at least one candidate")
+    uniq, first, counts = np.unique(cand, return_index=True, return_counts=True)
+    order = np.argsort(first, kind="stable")          # dict(Counter(...)) iterates in first-occurrence order
+    keys = uniq[order]
+    n_cand, n_keys = int(cand.size), int(keys.size)
+    prob = [pow(c / n_cand, alpha) for c in counts[order].tolist()]
+    total = sum(prob)
+    large, small = deque(), deque()
+    for i in range(n_keys):
+        prob[i] = prob[i] / total * n_keys
+        if prob[i] > 1:
+            large.append(i)
+        elif prob[i] < 1:
+            small.append(i)
+    alias = [-1] * n_keys
+    while large and small:
+        lq, sq = large.popleft(), small.popleft()
+        alias[sq] = int(keys[lq])
+        prob[lq] = prob[lq] - (1 - prob[sq])
+        if prob[lq] < 1:
+            small.append(lq)
+        elif prob[lq] > 1:
+            large.append(lq)
+    return keys, np.asarray(prob, dtype=np.float64), np.asarray(alias, dtype=np.int64)
+
+
 class _FilteredUniformSampler:
-    """sample_by_key_ids with uniform candidates in [1, value_num) (sampler.py:140-183)."""
+    """sample_by_key_ids (sampler.py:140-183) with uniform candidates in [1, value_num), or -- after
+    ``set_popularity`` -- popularity-biased candidates from the alias table (sampler.py:102-116)."""
 
     def __init__(self, keys, values, n_keys: int, value_num: int, stream: MTStream, what: str):
+        self.pop = None        # (keys, prob, alias) on the device
         self.stream = stream
         self.device = stream.device
         self.to_host = False   # hand the ids back as a CPU tensor (inside hopwise's own CPU loaders)
@@ -105,6 +152,10 @@ class _FilteredUniformSampler:
                 # sampler.py:241-249 / 329-336 raise the same way
                 raise ValueError(f"Some {what} have interacted with all values, which we can not sample negatives for.")
 
+    def set_popularity(self, table):
+        """`table` = build_alias_table(...) (host arrays); shared between the phase copies of one sampler."""
+        self.pop = tuple(torch.from_numpy(np.ascontiguousarray(x)).to(self.device) for x in table)
+
     def sample_by_key_ids(self, key_ids, num: int = 1) -> torch.Tensor:
         keys = _as_device_ids(key_ids, self.device)
         n = keys.numel()
@@ -113,6 +164,19 @@ class _FilteredUniformSampler:
         if total == 0:
             return out
         lib = _abi.lib()
+        if self.pop is not None:
+            pk, pp, pa = self.pop
+            ws = torch.empty(max(lib.kge_sample_alias_workspace_bytes(total), 8), dtype=torch.uint8, device=self.device)
+            with torch.cuda.device(self.device):
+                _abi.check(
+                    lib.kge_sample_negatives_alias(
+                        self.stream.words.data_ptr(), keys.data_ptr(), n, int(num), self.used_off.data_ptr(),
+                        self.used_vals.data_ptr(), pk.numel(), pk.data_ptr(), pp.data_ptr(), pa.data_ptr(),
+                        out.data_ptr(), ws.data_ptr(), _abi.stream_ptr(),
+                    ),
+                    "kge_sample_negatives_alias",
+                )
+            return out.cpu() if self.to_host else out
         ws = torch.empty(max(lib.kge_sample_workspace_bytes(total), 8), dtype=torch.uint8, device=self.device)
         with torch.cuda.device(self.device):
             _abi.check(
@@ -140,15 +204,16 @@ def _sets_from_csr(off, vals, n_keys):
 class KGSampler(_FilteredUniformSampler):
     """Tail corruption filtered by the head's true tails (any relation), sampler.py:294-357.
 
-    ``KGSampler(dataset)`` reads ``dataset.head_entities / tail_entities / entity_num`` like the
-    reference; arrays can be given directly instead.  ``used_ids`` is the reference's attribute (an array of
+    ``KGSampler(dataset, distribution, alpha)`` reads ``dataset.head_entities / tail_entities / entity_num`` like
+    the reference; arrays can be given directly instead.  ``distribution="popularity"`` draws candidates from the
+    alias table over head+tail occurrences (sampler.py:68-116, 318-319).  ``used_ids`` is the reference's attribute (an array of
     sets indexed by head entity), materialised on first access.
     """
 
     def __init__(self, dataset=None, distribution="uniform", alpha=1.0, *, heads=None, tails=None, entity_num=None,
                  stream: MTStream | None = None, device="cuda"):
-        if distribution != "uniform":
-            raise NotImplementedError("only the uniform distribution is on the fused path")
+        if distribution not in ("uniform", "popularity"):
+            raise NotImplementedError(f"The sampling distribution [{distribution}] has not been implemented.")
         if dataset is not None:
             heads, tails, entity_num = dataset.head_entities, dataset.tail_entities, dataset.entity_num
         self.distribution, self.alpha = distribution, alpha
@@ -156,6 +221,10 @@ class KGSampler(_FilteredUniformSampler):
         stream = stream if stream is not None else MTStream(device=device)
         super().__init__(heads, tails, self.entity_num, self.entity_num, stream, "head entities")
         self._used_sets = None
+        if distribution == "popularity":
+            # sampler.py:318-319: every head occurrence, then every tail occurrence
+            cand = np.concatenate([_as_host_ids(heads), _as_host_ids(tails)])
+            self.set_popularity(build_alias_table(cand, alpha))
 
     @property
     def used_ids(self):
@@ -183,8 +252,8 @@ class RecSampler:
 
     def __init__(self, phases_or_users, datasets_or_items, n_users=None, n_items=None, distribution="uniform",
                  alpha=1.0, stream: MTStream | None = None, device="cuda"):
-        if distribution != "uniform":
-            raise NotImplementedError("only the uniform distribution is on the fused path")
+        if distribution not in ("uniform", "popularity"):
+            raise NotImplementedError(f"The sampling distribution [{distribution}] has not been implemented.")
         self.distribution, self.alpha = distribution, alpha
         self.stream = stream if stream is not None else MTStream(device=device)
         self.device = self.stream.device
@@ -212,6 +281,14 @@ class RecSampler:
             self._impl["train"] = _FilteredUniformSampler(phases_or_users, datasets_or_items, self.user_num,
                                                           self.item_num, self.stream, "users")
             self.phase = "train"
+            items = [_as_host_ids(datasets_or_items)]
+        if distribution == "popularity":
+            # sampler.py:220-224: the item column of every phase's dataset, concatenated -- one table for all phases
+            table = build_alias_table(np.concatenate([_as_host_ids(x) for x in items]), alpha)
+            first = next(iter(self._impl.values()))
+            first.set_popularity(table)
+            for impl in self._impl.values():
+                impl.pop = first.pop
 
     def set_phase(self, phase):
         """sampler.py:254-270: the copy of this sampler bound to `phase`."""
@@ -263,8 +340,11 @@ def install_device_samplers(train_data, device="cuda", to_host=True):
     stream = MTStream(state=np.random.get_state(), device=device)
     gen, kg = train_data.general_dataloader, train_data.kg_dataloader
     old = gen._sampler
-    rec = RecSampler(list(old.phases), list(old.datasets), stream=stream, device=device).set_phase(old.phase)
-    kgs = KGSampler(kg._dataset, stream=stream, device=device)
+    rec = RecSampler(list(old.phases), list(old.datasets), distribution=old.distribution, alpha=old.alpha,
+                     stream=stream, device=device).set_phase(old.phase)
+    old_kg = kg._sampler
+    kgs = KGSampler(kg._dataset, distribution=getattr(old_kg, "distribution", "uniform"),
+                    alpha=getattr(old_kg, "alpha", 1.0), stream=stream, device=device)
     kgs.to_host = to_host
     for impl in rec._impl.values():
         impl.to_host = to_host

@@ -25,7 +25,7 @@
 extern "C" {
 #endif
 
-#define KGE_ABI_VERSION 3
+#define KGE_ABI_VERSION 4
 
 typedef void* kge_stream_t; /* cudaStream_t */
 
@@ -232,6 +232,18 @@ int64_t kge_sample_workspace_bytes(int64_t total);
 int kge_sample_negatives(uint32_t* mt_state, const int64_t* keys, int64_t n, int32_t num, const int64_t* used_off,
                          const int64_t* used_vals, int64_t low, int64_t high, int64_t* out, void* workspace,
                          kge_stream_t stream);
+/* kge_sample_negatives_alias: the same rejection rounds with popularity-biased candidates
+ * (sampler.py:68-116: AbstractSampler._build_alias_table / _pop_sampling).  Each round of L open slots
+ * consumes np.random.randint(0, pop_n, L) and then np.random.random(L) from the stream; slot j takes
+ * pop_keys[idx_j] when pop_prob[idx_j] > p_j, else pop_alias[idx_j].  pop_keys / pop_prob / pop_alias
+ * [pop_n] (device): the alias table in the reference's key order (first occurrence in the candidates
+ * list), alias stored as the aliased key id (-1 where the reference leaves -1).
+ * workspace: kge_sample_alias_workspace_bytes(n*num) bytes. */
+int64_t kge_sample_alias_workspace_bytes(int64_t total);
+int kge_sample_negatives_alias(uint32_t* mt_state, const int64_t* keys, int64_t n, int32_t num,
+                               const int64_t* used_off, const int64_t* used_vals, int64_t pop_n,
+                               const int64_t* pop_keys, const double* pop_prob, const int64_t* pop_alias,
+                               int64_t* out, void* workspace, kge_stream_t stream);
 /* np.random.seed(seed) (legacy init_genrand) into a device state. */
 int kge_mt19937_seed(uint32_t* mt_state, uint32_t seed, kge_stream_t stream);
 

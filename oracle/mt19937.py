@@ -162,6 +162,53 @@ class MT19937:
         return out
 
 
+def random_sample(gen: "MT19937", size: int) -> np.ndarray:
+    """np.random.random(size) on the legacy stream: per double two words, (w0 >> 5) * 2^26 + (w1 >> 6) over 2^53
+    (numpy/random/src/mt19937/mt19937.h mt19937_next_double; numpy is a third-party dependency of the reference,
+    the call site is sampler.py:112)."""
+    w = gen.next_words(2 * size).astype(np.uint64)
+    a, b = w[0::2] >> np.uint64(5), w[1::2] >> np.uint64(6)
+    return (a.astype(np.float64) * 67108864.0 + b.astype(np.float64)) / 9007199254740992.0
+
+
+def build_alias_table(candidates, alpha: float):
+    """sampler.py:68-100 restated with the reference's own containers (dict in first-occurrence order, Python
+    floats, FIFO lists); returns (keys list, prob dict, alias dict)."""
+    cand = [int(x) for x in candidates]
+    prob = {}
+    for c in cand:
+        prob[c] = prob.get(c, 0) + 1
+    alias = {}
+    for i in prob:
+        alias[i] = -1
+        prob[i] = pow(prob[i] / len(cand), alpha)
+    norm = sum(prob.values())
+    large_q, small_q = [], []
+    for i in prob:
+        prob[i] = prob[i] / norm * len(prob)
+        if prob[i] > 1:
+            large_q.append(i)
+        elif prob[i] < 1:
+            small_q.append(i)
+    while large_q and small_q:
+        lq, sq = large_q.pop(0), small_q.pop(0)
+        alias[sq] = lq
+        prob[lq] = prob[lq] - (1 - prob[sq])
+        if prob[lq] < 1:
+            small_q.append(lq)
+        elif prob[lq] > 1:
+            large_q.append(lq)
+    return list(prob.keys()), prob, alias
+
+
+def pop_sampling(gen: "MT19937", table, size: int) -> np.ndarray:
+    """sampler.py:102-116: randint(0, n_keys, size), then random(size), then the alias rule."""
+    keys, prob, alias = table
+    idx = gen.randint(0, len(keys), size)
+    p = random_sample(gen, size)
+    return np.array([keys[i] if prob[keys[i]] > q else alias[keys[i]] for i, q in zip(idx, p)], dtype=np.int64)
+
+
 def build_used_csr(keys: np.ndarray, values: np.ndarray, n_keys: int):
     """CSR of sorted, de-duplicated values per key: the array form of the reference's
     `used_ids[key] = set(values)` (sampler.py:229-252, 321-336)."""
@@ -190,8 +237,9 @@ def _member(combined, keys, cand):
     return hit
 
 
-def sample_by_key_ids(gen: MT19937, key_ids, num: int, off, vals, low: int, high: int) -> np.ndarray:
-    """Filtered uniform negatives, j-major layout out[j*len(keys)+i] (sampler.py:140-183)."""
+def sample_by_key_ids(gen: MT19937, key_ids, num: int, off, vals, low: int, high: int, pop_table=None) -> np.ndarray:
+    """Filtered negatives, j-major layout out[j*len(keys)+i] (sampler.py:140-183); candidates are uniform in
+    [low, high) or, with `pop_table` = build_alias_table(...), popularity-biased (sampler.py:102-116)."""
     key_ids = np.asarray(key_ids, dtype=np.int64)
     keys = np.tile(key_ids, num)
     total = len(keys)
@@ -199,6 +247,9 @@ def sample_by_key_ids(gen: MT19937, key_ids, num: int, off, vals, low: int, high
     check = np.arange(total)
     combined = _combined(np.asarray(off), np.asarray(vals))
     while len(check) > 0:
-        out[check] = gen.randint(low, high, len(check))
+        if pop_table is None:
+            out[check] = gen.randint(low, high, len(check))
+        else:
+            out[check] = pop_sampling(gen, pop_table, len(check))
         check = check[_member(combined, keys[check], out[check])]
     return out

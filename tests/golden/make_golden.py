@@ -158,6 +158,48 @@ def golden_sampler():
     print("wrote sampler", [len(out[f'call{c}/neg_tails']) for c in calls])
 
 
+def golden_sampler_pop():
+    """Popularity-biased negatives (sampler.py:68-116) for the KG and the rec sampler, alpha 1.0 and 0.5, sharing one
+    stream; includes the alias table itself so the table build is pinned independently of the draws."""
+    rng = np.random.default_rng(SEED + 1)
+    E, U, I = 53, 29, 31
+    n_tri = 500
+    # skewed popularity: squares of uniforms concentrate on small ids
+    heads = 1 + (rng.random(n_tri) ** 2 * (E - 1)).astype(np.int64)
+    tails = 1 + (rng.random(n_tri) ** 3 * (E - 1)).astype(np.int64)
+    ru = rng.integers(1, U, 400)
+    ri = 1 + (rng.random(400) ** 2 * (I - 1)).astype(np.int64)
+    out = {"E": E, "U": U, "I": I, "heads": heads, "tails": tails, "rec_users": ru, "rec_items": ri}
+    for tag, alpha in (("a1", 1.0), ("a05", 0.5)):
+        ds = FakeDataset(U, I, E, 7, heads=heads, tails=tails)
+        kg = KGSampler(ds, distribution="popularity", alpha=alpha)
+        rec = Sampler("train", _RecDataset(ru, ri, U, I), distribution="popularity", alpha=alpha).set_phase("train")
+        for name, smp in (("kg", kg), ("rec", rec)):
+            keys = list(smp.prob.keys())
+            out[f"{tag}/{name}_keys"] = np.array(keys, dtype=np.int64)
+            out[f"{tag}/{name}_prob"] = np.array([smp.prob[k] for k in keys], dtype=np.float64)
+            out[f"{tag}/{name}_alias"] = np.array([smp.alias[k] for k in keys], dtype=np.int64)
+        np.random.seed(SEED + 7)
+        # an odd number of words consumed first: the doubles' word pairs then straddle the 624-word blocks
+        np.random.randint(0, 1 << 30, 3)
+        st = np.random.get_state()
+        out[f"{tag}/state0_key"], out[f"{tag}/state0_pos"] = st[1].copy(), st[2]
+        q_heads = [heads[rng.integers(0, len(heads), 350)], np.full(11, heads[0]), heads[rng.integers(0, len(heads), 27)]]
+        q_users = [ru[rng.integers(0, len(ru), 330)], ru[rng.integers(0, len(ru), 9)], np.full(6, ru[0])]
+        nums = [2, 3, 1]
+        for step, (qh, qu, num) in enumerate(zip(q_heads, q_users, nums)):
+            out[f"{tag}/call{step}/heads"], out[f"{tag}/call{step}/users"], out[f"{tag}/call{step}/num"] = qh, qu, num
+            out[f"{tag}/call{step}/neg_tails"] = kg.sample_by_entity_ids(qh, num).numpy()
+            st = np.random.get_state()
+            out[f"{tag}/call{step}/kg_key"], out[f"{tag}/call{step}/kg_pos"] = st[1].copy(), st[2]
+            out[f"{tag}/call{step}/neg_items"] = rec.sample_by_user_ids(qu, None, num).numpy()
+            st = np.random.get_state()
+            out[f"{tag}/call{step}/rec_key"], out[f"{tag}/call{step}/rec_pos"] = st[1].copy(), st[2]
+        out[f"{tag}/n_calls"] = len(nums)
+    np.savez_compressed(os.path.join(HERE, "sampler_pop.npz"), **out)
+    print("wrote sampler_pop", [len(out[f"a1/call{c}/neg_tails"]) for c in range(3)])
+
+
 def golden_eval():
     """Collector + Evaluator on masked random scores (no ties => torch.topk is canonical)."""
     rng = np.random.default_rng(SEED)
@@ -219,6 +261,6 @@ def golden_eval():
 
 if __name__ == "__main__":
     torch.set_num_threads(1)
-    golden_models()
-    golden_sampler()
-    golden_eval()
+    parts = {"models": golden_models, "sampler": golden_sampler, "sampler_pop": golden_sampler_pop, "eval": golden_eval}
+    for name in sys.argv[1:] or list(parts):   # e.g. `make_golden.py sampler_pop` regenerates one fixture
+        parts[name]()

@@ -118,3 +118,70 @@ def test_saturated_key_is_refused():
     tails = np.concatenate([np.arange(1, E), [5]])
     with pytest.raises(ValueError):
         KGSampler(heads=heads, tails=tails, entity_num=E)
+
+
+# ---- popularity-biased candidates (sampler.py:68-116) ---------------------------------------------------------
+
+@pytest.mark.parametrize("tag,alpha", [("a1", 1.0), ("a05", 0.5)])
+def test_popularity_golden_reference_stream(tag, alpha):
+    """KG and rec samplers in popularity mode on one stream: the reference's ids and MT19937 state, call by call."""
+    from hopwise_b200.sampler import KGSampler, MTStream, RecSampler
+
+    g = load_golden("sampler_pop.npz")
+    E, U, I = int(g["E"]), int(g["U"]), int(g["I"])
+    stream = MTStream(state=("MT19937", g[f"{tag}/state0_key"], int(g[f"{tag}/state0_pos"])))
+    kg = KGSampler(heads=g["heads"], tails=g["tails"], entity_num=E, stream=stream, distribution="popularity", alpha=alpha)
+    rec = RecSampler(g["rec_users"], g["rec_items"], U, I, stream=stream, distribution="popularity", alpha=alpha)
+    np.testing.assert_array_equal(kg.pop[0].cpu().numpy(), g[f"{tag}/kg_keys"])
+    np.testing.assert_array_equal(kg.pop[1].cpu().numpy(), g[f"{tag}/kg_prob"])
+    for c in range(int(g[f"{tag}/n_calls"])):
+        p = f"{tag}/call{c}/"
+        num = int(g[p + "num"])
+        neg_t = kg.sample_by_entity_ids(g[p + "heads"], num)
+        np.testing.assert_array_equal(neg_t.cpu().numpy(), g[p + "neg_tails"])
+        _state_equal(stream, g[p + "kg_key"], g[p + "kg_pos"])
+        neg_i = rec.sample_by_user_ids(g[p + "users"], None, num)
+        np.testing.assert_array_equal(neg_i.cpu().numpy(), g[p + "neg_items"])
+        _state_equal(stream, g[p + "rec_key"], g[p + "rec_pos"])
+    assert not stream.exhausted()
+
+
+@pytest.mark.parametrize("seed,E,n,num,alpha", [(2024, 34629, 2048, 1, 1.0), (7, 300, 2048, 4, 0.5), (3, 30001, 5000, 3, 0.75)])
+def test_popularity_against_oracle(seed, E, n, num, alpha):
+    from hopwise_b200.sampler import KGSampler, MTStream
+
+    rng = np.random.default_rng(seed)
+    n_tri = 20 * E if E < 1000 else 3 * E
+    heads = 1 + (rng.random(n_tri) ** 2 * (E - 1)).astype(np.int64)
+    tails = 1 + (rng.random(n_tri) ** 3 * (E - 1)).astype(np.int64)
+    q = heads[rng.integers(0, n_tri, n)]
+    off, vals = omt.build_used_csr(heads, tails, E)
+    table = omt.build_alias_table(np.concatenate([heads, tails]), alpha)
+    gen = omt.MT19937(seed)
+    want = omt.sample_by_key_ids(gen, q, num, off, vals, 1, E, pop_table=table)
+    stream = MTStream(seed=seed)
+    kg = KGSampler(heads=heads, tails=tails, entity_num=E, stream=stream, distribution="popularity", alpha=alpha)
+    got = kg.sample_by_entity_ids(q, num)
+    np.testing.assert_array_equal(got.cpu().numpy(), want)
+    _state_equal(stream, gen.key, gen.pos)
+    # the filter holds and NumPy can take over from the device state
+    got = got.cpu().numpy()
+    for j in (0, num - 1):
+        for i in range(0, n, 97):
+            assert got[j * n + i] not in set(vals[off[q[i]]:off[q[i] + 1]].tolist())
+    np.random.set_state(stream.get_state())
+    np.testing.assert_array_equal(np.random.random(5), omt.random_sample(gen, 5))
+
+
+def test_popularity_single_key_table():
+    """One candidate key: randint(0, 1, L) is constant and draws nothing, only the doubles advance the stream."""
+    from hopwise_b200.sampler import KGSampler, MTStream
+
+    heads, tails = np.array([3, 3, 3]), np.array([3, 3, 3])   # key 3 only; head 5 has no forbidden tails
+    stream = MTStream(seed=4)
+    kg = KGSampler(heads=heads, tails=tails, entity_num=9, stream=stream, distribution="popularity")
+    out = kg.sample_by_entity_ids(np.array([5, 5, 6, 7]), 2)
+    np.testing.assert_array_equal(out.cpu().numpy(), np.full(8, 3))
+    np.random.seed(4)
+    np.random.random(8)
+    _state_equal(stream, np.random.get_state()[1], np.random.get_state()[2])
