@@ -274,7 +274,7 @@ class DeviceKGLoader:
 
     def __init__(self, inter_user, inter_item, kg_head, kg_rel, kg_tail, rec_sampler, kg_sampler, batch_size: int,
                  seed: int, device="cuda", shuffle: bool = True, neg_sample_num: int = 1, gather=None,
-                 rank: int = 0, world: int = 1):
+                 rank: int = 0, world: int = 1, dynamic: bool = False, candidate_num: int = 0):
         self.device = torch.device(device)
         as_dev = lambda x: torch.as_tensor(np.asarray(x), dtype=torch.int64).to(self.device)  # noqa: E731
         self.inter_user, self.inter_item = as_dev(inter_user), as_dev(inter_item)
@@ -284,7 +284,30 @@ class DeviceKGLoader:
         self.rec_order = EpochOrder(self.inter_user.numel(), batch_size, seed, shuffle, rank, world)
         self.kg_order = EpochOrder(self.kg_head.numel(), batch_size, seed, True, rank, world)   # "must shuffle"
         self.neg_sample_num = int(neg_sample_num)
+        # train_neg_sample_args["dynamic"] / ["candidate_num"] (abstract_dataloader.py:166-183): the negative of a
+        # row is the best-scoring of `candidate_num` filtered candidates under the current weights
+        self.dynamic, self.candidate_num = bool(dynamic), int(candidate_num)
+        if self.dynamic and self.candidate_num < 1:
+            raise ValueError("dynamic negative sampling needs candidate_num >= 1")
+        self.model = None
         self._gather = gather or (lambda table, idx: table.index_select(0, idx))
+
+    def get_model(self, model):
+        """abstract_dataloader.py:214-215: the model dynamic negative sampling scores its candidates with."""
+        self.model = model
+
+    def _rec_negatives(self, user, item):
+        num = self.neg_sample_num
+        if not self.dynamic:
+            return self.rec_sampler.sample_by_user_ids(user, item, num)
+        if self.model is None:
+            raise RuntimeError("dynamic negative sampling: call get_model(model) first (trainer.py:306)")
+        cn = self.candidate_num
+        cand = self.rec_sampler.sample_by_user_ids(user, item, num * cn)   # j-major: [cn, num * len(user)]
+        with torch.no_grad():
+            scores = self.model.predict({"user_id": user.repeat(num * cn), "item_id": cand}).reshape(cn, -1)
+        best = torch.max(scores, dim=0)[1]
+        return cand.reshape(cn, -1).gather(0, best.unsqueeze(0)).view(-1)
 
     def __len__(self):
         return len(self.rec_order)
@@ -317,6 +340,8 @@ class DeviceKGLoader:
                 return
             ridx = self._index(ridx)
             user, item = self._gather(self.inter_user, ridx), self._gather(self.inter_item, ridx)
+            batch["neg_item_id"] = self._rec_negatives(user, item)
+            if self.neg_sample_num > 1:   # abstract_dataloader.py:191: the positives repeat once per negative
+                user, item = user.repeat(self.neg_sample_num), item.repeat(self.neg_sample_num)
             batch["user_id"], batch["item_id"] = user, item
-            batch["neg_item_id"] = self.rec_sampler.sample_by_user_ids(user, item, self.neg_sample_num)
             yield batch

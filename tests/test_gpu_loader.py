@@ -62,3 +62,67 @@ def test_device_kg_loader_feeds_the_fused_step():
             loss.backward()
         epoch_loss.append(tot)
     assert np.isfinite(epoch_loss).all() and epoch_loss[-1] < epoch_loss[0]
+
+
+def test_dynamic_negative_sampling_matches_oracle():
+    """train_neg_sample_args = {dynamic: True, candidate_num: 3, sample_num: 2} (abstract_dataloader.py:166-183):
+    candidates from the shared stream (KG draw first), scored by the model, best one kept per row; positives
+    repeat once per negative.  Checked against the oracle sampler + oracle model on the same index stream."""
+    from hopwise_b200.loader import DeviceKGLoader, EpochOrder
+    from hopwise_b200.sampler import KGSampler, MTStream, RecSampler
+    from kge_helpers import make_oracle_model, make_product_model
+    from oracle import mt19937 as omt
+
+    U, I, E, R, d, B, num, cn = 300, 200, 500, 6, 32, 512, 2, 3
+    rng = np.random.default_rng(17)
+    iu, ii = rng.integers(1, U, 1800), rng.integers(1, I, 1800)
+    kh, kr, kt = rng.integers(1, E, 2500), rng.integers(1, R - 1, 2500), rng.integers(1, E, 2500)
+    stream = MTStream(seed=5)
+    rec = RecSampler(iu, ii, U, I, stream=stream)
+    kg = KGSampler(heads=kh, tails=kt, entity_num=E, stream=stream)
+    loader = DeviceKGLoader(iu, ii, kh, kr, kt, rec, kg, batch_size=B, seed=7, neg_sample_num=num, dynamic=True,
+                            candidate_num=cn)
+    m = make_product_model("TransE", U, I, E, R, d)
+    ora = make_oracle_model("TransE", U, I, E, R, d)
+    with pytest.raises(RuntimeError):
+        next(iter(loader))
+    loader = DeviceKGLoader(iu, ii, kh, kr, kt, rec, kg, batch_size=B, seed=7, neg_sample_num=num, dynamic=True,
+                            candidate_num=cn)
+    stream.seed(5)
+    loader.get_model(m)
+
+    gen = omt.MT19937(5)
+    kg_off, kg_vals = omt.build_used_csr(kh, kt, E)
+    rec_off, rec_vals = omt.build_used_csr(iu, ii, U)
+    rec_o, kg_o = EpochOrder(len(iu), B, 7, True), EpochOrder(len(kh), B, 7, True)
+    kg_o.start()
+    rec_o.start()
+    steps, exact, rows = 0, 0, 0
+    for b in loader:
+        kidx = kg_o.next_indices().numpy()
+        np.testing.assert_array_equal(b["neg_tail_id"].cpu().numpy(),
+                                      omt.sample_by_key_ids(gen, kh[kidx], 1, kg_off, kg_vals, 1, E))
+        ridx = rec_o.next_indices().numpy()
+        n = len(ridx)
+        cand = omt.sample_by_key_ids(gen, iu[ridx], num * cn, rec_off, rec_vals, 1, I)
+        with torch.no_grad():
+            sc = ora.predict({"user_id": torch.from_numpy(np.tile(iu[ridx], num * cn)),
+                              "item_id": torch.from_numpy(cand)}).numpy().reshape(cn, -1)
+        want = cand.reshape(cn, -1)[sc.argmax(0), np.arange(num * n)]
+        got = b["neg_item_id"].cpu().numpy()
+        assert got.shape == (num * n,)
+        np.testing.assert_array_equal(b["user_id"].cpu().numpy(), np.tile(iu[ridx], num))
+        np.testing.assert_array_equal(b["item_id"].cpu().numpy(), np.tile(ii[ridx], num))
+        same = got == want
+        # a row may pick another candidate only when the two score within fp32 rounding of each other
+        for j in np.flatnonzero(~same):
+            col = cand.reshape(cn, -1)[:, j]
+            pick = np.flatnonzero(col == got[j])
+            assert len(pick) and sc[pick[0], j] >= sc[:, j].max() - 1e-5 * np.abs(sc[:, j]).max()
+        exact += int(same.sum())
+        rows += num * n
+        steps += 1
+    assert steps == 4 and exact >= 0.99 * rows
+    st = stream.get_state()
+    np.testing.assert_array_equal(st[1], gen.key)
+    assert st[2] == gen.pos
