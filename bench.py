@@ -484,6 +484,15 @@ def main():
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)
     rank, world, local = dist_info()
+    # stdout carries the one JSON line and nothing else: libraries that print to fd 1 (NCCL's version banner,
+    # hopwise's loggers) are pointed at stderr for the run
+    sys.stdout.flush()
+    json_fd = os.dup(1)
+    os.dup2(2, 1)
+
+    def emit(line):
+        sys.stdout.flush()
+        os.write(json_fd, (json.dumps(line) + "\n").encode())
     w = WORKLOADS[args.workload]
     triples_step = w["n_rec"] + w["n_kg"]
     config = {"workload": f"{args.workload}: {w['model']} d={w['d']} U={w['U']} I={w['I']} E={w['E']} R={w['R']} "
@@ -511,7 +520,7 @@ def main():
                 "gpu_launches": 0}
         if not args.no_extras:
             line["extras"] = {"cfg1_ml100k_pipeline": config1_pipeline("reference")}
-        print(json.dumps(line))
+        emit(line)
         return
 
     assert torch.cuda.is_available(), "bench.py --impl ours needs a CUDA device"
@@ -623,6 +632,25 @@ def main():
                "fwd_ms": float(f.mean()), "adam_ms": float(u.mean()), "bytes_per_triple": bx,
                "hbm_frac": t * bx / (ms * 1e-3) / 1e9 / peaks["hbm_gbs"],
                "hbm_frac_from_median": t * bx / (med * 1e-3) / 1e9 / peaks["hbm_gbs"]}
+        if t <= 8192 and ex is None:
+            # the reference's default batch is launch/latency bound: also time the trainer's one-call step
+            # (model.train_step: forward + Adam queued by one library call) back to back, as an epoch runs it
+            n_loop = 400
+            for i in range(20):
+                mx.train_step(db[i % 4])
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            torch.cuda.synchronize()
+            t0 = time.perf_counter()
+            e0.record()
+            for i in range(n_loop):
+                mx.train_step(db[i % 4])
+            e1.record()
+            host_s = time.perf_counter() - t0
+            torch.cuda.synchronize()
+            out["train_step_call"] = {
+                "what": f"{n_loop} back-to-back model.train_step calls (no L2 flush, no per-step sync)",
+                "device_ms_per_step": e0.elapsed_time(e1) / n_loop, "host_issue_ms_per_step": 1e3 * host_s / n_loop,
+                "triples_per_s": t / (e0.elapsed_time(e1) / n_loop * 1e-3)}
         if ex is not None:
             # split of the exchange (inside `adam_ms`, which covers backward = exchange + Adam): a few more steps
             for i in range(8):
@@ -676,21 +704,25 @@ def main():
                 it = iter(loader)
                 for _ in range(10):
                     b = next(it)
-                    mx.calculate_loss(b).backward()
+                    mx.train_step(b)
                 torch.cuda.synchronize()
                 stamps = [time.perf_counter()]
                 for _ in range(n_steps):
                     b = next(it)
-                    loss = mx.calculate_loss(b)
-                    loss.item()
-                    loss.backward()
+                    mx.train_step(b).item()     # the reference loop reads the loss every step (trainer.py:257-263)
                     stamps.append(time.perf_counter())
                 torch.cuda.synchronize()
                 per = np.diff(np.array(stamps))
+                # and as FusedKGTrainer runs an epoch: losses stay on the device, one sync at the end
+                t0 = time.perf_counter()
+                held = [mx.train_step(next(it)) for _ in range(n_steps)]
+                total = float(torch.stack(held).double().sum().item())
+                free_s = (time.perf_counter() - t0) / n_steps
                 extras["cfg2_b2048_device_loader"] = {
                     "what": "loader (order + gathers + KG and rec negative sampling) + fused step + loss.item(), wall clock",
                     "ms_per_step": float(per.mean()) * 1e3, "median_ms_per_step": float(np.median(per)) * 1e3,
-                    "triples_per_s": (wx["n_rec"] + wx["n_kg"]) / float(per.mean())}
+                    "triples_per_s": (wx["n_rec"] + wx["n_kg"]) / float(per.mean()),
+                    "ms_per_step_no_per_step_sync": free_s * 1e3, "loss_sum": total}
                 del mx, loader
                 torch.cuda.empty_cache()
             except Exception as exc:
@@ -739,7 +771,7 @@ def main():
                                           + ("hopwise's own model class from oracle/_ref" if kind == "reference"
                                              else "torch-CPU oracle port") + ", dense autograd + dense Adam)"}
     if rank == 0:
-        print(json.dumps(line))
+        emit(line)
     if world > 1:
         import torch.distributed as dist
 

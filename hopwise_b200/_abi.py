@@ -91,6 +91,7 @@ PROTOTYPES = {
     "kge_adam_table_fill": (C.c_int, [C.c_float, C.c_float, C.c_float, C.POINTER(C.c_float), C.c_int32]),
     "kge_train_forward": (C.c_int, [_MP, _BP, _AP, C.c_int, _P, _P]),
     "kge_adam_apply": (C.c_int, [_MP, _AP, C.c_float, _P, _P]),
+    "kge_train_step": (C.c_int, [_MP, _BP, _AP, C.c_float, _P, _P]),
     "kge_adam_flush": (C.c_int, [_MP, _AP, _P]),
     "kge_grad_discard": (C.c_int, [_MP, C.c_int32, _P]),
     "kge_grad_pack": (C.c_int, [_MP, C.c_int32, C.c_int32, _P, _P, _P, _P]),
@@ -116,6 +117,7 @@ PROTOTYPES = {
     ),
     "kge_topk_hits": (C.c_int, [_P, C.c_int64, C.c_int32, _P, _P, _P, _P]),
     "kge_topk_metric_sums": (C.c_int, [_P, C.c_int64, C.c_int32, _P, _P]),
+    "kge_gather_columns": (C.c_int, [_P, C.c_int32, C.c_int64, _P, C.c_int64, _P, _P, _P]),
     "kge_sample_workspace_bytes": (C.c_int64, [C.c_int64]),
     "kge_sample_negatives": (
         C.c_int,

@@ -66,6 +66,17 @@ def build(force: bool = False, verbose: bool = False) -> str:
         return LIB_PATH
     nvcc = _nvcc()
     os.makedirs(BUILD_DIR, exist_ok=True)
+    # one builder at a time: the ranks of a multi-GPU job all import the package at once and share the object files
+    import fcntl
+
+    with open(os.path.join(BUILD_DIR, ".lock"), "w") as lock:
+        fcntl.flock(lock, fcntl.LOCK_EX)
+        if not force and not needs_build():   # another process built it while this one waited
+            return LIB_PATH
+        return _build_locked(nvcc, force, verbose)
+
+
+def _build_locked(nvcc: str, force: bool, verbose: bool) -> str:
     header_mtime = max(
         os.path.getmtime(os.path.join(d, f))
         for d in (CSRC, INCLUDE)

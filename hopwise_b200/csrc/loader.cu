@@ -1,0 +1,63 @@
+// Batch assembly on the device: the row gathers of hopwise's loaders.
+//
+// Replaces (paths under /root/reference/hopwise/):
+//   data/dataloader/general_dataloader.py:66-70     TrainDataLoader.collate_fn: inter_feat[index]
+//   data/dataloader/knowledge_dataloader.py:69-75   KGDataLoader.collate_fn: kg_feat[index]
+//   data/interaction.py:130-139                     Interaction.__getitem__: every column indexed by the same index
+// One launch gathers every id column of a batch by the batch's index vector (the reference indexes the columns one
+// after another on the host): out[c][i] = column[c][index[i]].  Pure HBM/L2-bound int64 traffic: each index is read
+// once and reused for all columns, writes are coalesced.
+#include "common.cuh"
+
+namespace {
+
+constexpr int MAX_COLS = 8;
+
+struct GatherArgs {
+  const int64_t* cols[MAX_COLS];
+  int64_t* outs[MAX_COLS];
+  const int64_t* index;
+  int64_t n, rows;
+  int n_cols;
+  int32_t* status;  // set to 1 when an index falls outside [0, rows)
+};
+
+__global__ void __launch_bounds__(256) gather_columns_kernel(const GatherArgs a) {
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < a.n; i += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t r = __ldg(a.index + i);
+    if (r < 0 || r >= a.rows) {
+      if (a.status) *a.status = 1;
+      continue;
+    }
+#pragma unroll
+    for (int c = 0; c < MAX_COLS; ++c)
+      if (c < a.n_cols) a.outs[c][i] = __ldg(a.cols[c] + r);
+  }
+}
+
+}  // namespace
+
+extern "C" int kge_gather_columns(const int64_t* const* columns, int32_t n_columns, int64_t rows, const int64_t* index,
+                                  int64_t n, int64_t* const* outs, int32_t* status, kge_stream_t stream) {
+  KGE_REQUIRE(n >= 0 && rows >= 0 && n_columns >= 1 && n_columns <= MAX_COLS, KGE_E_ARG, "bad n / rows / n_columns");
+  if (n == 0) return 0;
+  KGE_REQUIRE(columns && outs && index, KGE_E_ARG, "NULL argument");
+  GatherArgs a = {};
+  for (int c = 0; c < n_columns; ++c) {
+    KGE_REQUIRE(columns[c] && outs[c], KGE_E_ARG, "NULL column %d", c);
+    a.cols[c] = columns[c];
+    a.outs[c] = outs[c];
+  }
+  a.index = index;
+  a.n = n;
+  a.rows = rows;
+  a.n_cols = n_columns;
+  a.status = status;
+  const int threads = 256;
+  int64_t grid = (n + threads - 1) / threads;
+  const int64_t cap = (int64_t)kge_num_sms() * 8;
+  if (grid > cap) grid = cap;
+  gather_columns_kernel<<<(int)grid, threads, 0, (cudaStream_t)stream>>>(a);
+  KGE_LAUNCH_CHECK();
+  return 0;
+}

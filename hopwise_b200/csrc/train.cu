@@ -855,6 +855,13 @@ extern "C" int kge_adam_apply(const kge_model_t* model, const kge_adam_t* adam, 
   return 0;
 }
 
+extern "C" int kge_train_step(const kge_model_t* model, const kge_batch_t* b, const kge_adam_t* adam,
+                              float grad_scale, float* loss_out, kge_stream_t stream) {
+  if (int e = kge_train_forward(model, b, adam, 1, loss_out, stream)) return e;
+  if (b->n_rec + b->n_kg == 0) return 0;
+  return kge_adam_apply(model, adam, grad_scale, nullptr, stream);
+}
+
 extern "C" int kge_adam_flush(const kge_model_t* model, const kge_adam_t* adam, kge_stream_t stream) {
   if (int e = check_model(model, true)) return e;
   KGE_REQUIRE(adam && adam->step >= 0, KGE_E_ARG, "bad adam");

@@ -16,10 +16,13 @@ cannot hide).
 
 from __future__ import annotations
 
+import ctypes as C
 from collections import deque
 
 import numpy as np
 import torch
+
+from . import _abi
 
 
 class PackedBatch:
@@ -204,6 +207,8 @@ class EpochOrder:
         self._perm = None
         self._pos = 0
         self._live = False
+        self.mirror = None       # a CUDA device: the epoch's index vector is uploaded once, batches are views of it
+        self._perm_dev = None
 
     @property
     def n_local(self) -> int:
@@ -254,6 +259,18 @@ class EpochOrder:
         self._pos += self.step
         return idx
 
+    def next_indices_device(self):
+        """next_indices() as a view of the device copy of the epoch's index vector (one upload per epoch instead of
+        one per batch); None once exhausted."""
+        had = self._perm is not None
+        idx = self.next_indices()
+        if idx is None:
+            return None
+        if not had or self._perm_dev is None:
+            self._perm_dev = self._perm.to(self.mirror)
+        pos = self._pos - self.step
+        return self._perm_dev[pos : pos + idx.numel()]
+
 
 class DeviceKGLoader:
     """KnowledgeBasedDataLoader in RSKG mode with the data, the gathers and both samplers on the GPU.
@@ -290,7 +307,14 @@ class DeviceKGLoader:
         if self.dynamic and self.candidate_num < 1:
             raise ValueError("dynamic negative sampling needs candidate_num >= 1")
         self.model = None
-        self._gather = gather or (lambda table, idx: table.index_select(0, idx))
+        # `gather(table, idx)` is the hook the CPU host-logic tests drive the loader through; on the GPU the id
+        # columns of a half are gathered by one kge_gather_columns launch
+        self._gather = gather
+        if gather is None and self.device.type != "cuda":
+            raise RuntimeError("DeviceKGLoader gathers on a CUDA device; there is no CPU fallback")
+        if gather is None:
+            self.rec_order.mirror = self.kg_order.mirror = self.device
+        self._col_ptrs = {}
 
     def get_model(self, model):
         """abstract_dataloader.py:214-215: the model dynamic negative sampling scores its candidates with."""
@@ -322,24 +346,50 @@ class DeviceKGLoader:
             idx = idx.pin_memory()
         return idx.to(self.device, non_blocking=True)
 
+    def _take(self, order, columns):
+        """The next batch of `order`: the id columns gathered by its index vector (interaction.py:130-139), or None
+        when the order is exhausted."""
+        if self._gather is not None:
+            idx = order.next_indices()
+            if idx is None:
+                return None
+            idx = self._index(idx)
+            return [self._gather(c, idx) for c in columns]
+        idx = order.next_indices_device()
+        if idx is None:
+            return None
+        n, nc = idx.numel(), len(columns)
+        out = torch.empty((nc, n), dtype=torch.int64, device=self.device)
+        key = id(columns[0])
+        src = self._col_ptrs.get(key)
+        if src is None:
+            src = self._col_ptrs[key] = (C.c_void_p * nc)(*[c.data_ptr() for c in columns])
+        base = out.data_ptr()
+        dst = (C.c_void_p * nc)(*[base + 8 * n * c for c in range(nc)])
+        with torch.cuda.device(self.device):
+            _abi.check(
+                _abi.lib().kge_gather_columns(src, nc, columns[0].numel(), idx.data_ptr(), n, dst, None,
+                                              _abi.stream_ptr()),
+                "kge_gather_columns",
+            )
+        return list(out.unbind(0))
+
     def __iter__(self):
         self.kg_order.start()    # knowledge_dataloader.py:131-135: kg iterator first, then the general one
         self.rec_order.start()
         while True:
-            kidx = self.kg_order.next_indices()
-            if kidx is None:     # :137-142 wraps a KG loader that ran out
+            kg_cols = (self.kg_head, self.kg_rel, self.kg_tail)
+            got = self._take(self.kg_order, kg_cols)
+            if got is None:      # :137-142 wraps a KG loader that ran out
                 self.kg_order.start()
-                kidx = self.kg_order.next_indices()
-            kidx = self._index(kidx)
-            head = self._gather(self.kg_head, kidx)
-            batch = {"head_id": head, "relation_id": self._gather(self.kg_rel, kidx),
-                     "tail_id": self._gather(self.kg_tail, kidx),
+                got = self._take(self.kg_order, kg_cols)
+            head, rel, tail = got
+            batch = {"head_id": head, "relation_id": rel, "tail_id": tail,
                      "neg_tail_id": self.kg_sampler.sample_by_entity_ids(head, 1)}   # knowledge_dataloader.py:51
-            ridx = self.rec_order.next_indices()
-            if ridx is None:
+            got = self._take(self.rec_order, (self.inter_user, self.inter_item))
+            if got is None:
                 return
-            ridx = self._index(ridx)
-            user, item = self._gather(self.inter_user, ridx), self._gather(self.inter_item, ridx)
+            user, item = got
             batch["neg_item_id"] = self._rec_negatives(user, item)
             if self.neg_sample_num > 1:   # abstract_dataloader.py:191: the positives repeat once per negative
                 user, item = user.repeat(self.neg_sample_num), item.repeat(self.neg_sample_num)

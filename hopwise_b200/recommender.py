@@ -452,6 +452,48 @@ class FusedKGEModel(KnowledgeRecommender):
         _plain_set(self, "_pending_loss", loss)
         return loss
 
+    LOSS_RING = 256
+
+    def train_step(self, interaction):
+        """``optimizer.zero_grad(); loss = calculate_loss(batch); loss.backward(); optimizer.step()`` of the
+        reference loop (trainer/trainer.py:247-266) as ONE library call: forward and the row-lazy Adam update are
+        queued back to back by ``kge_train_step`` with no autograd node in between.  Returns the step's loss, a
+        0-dim device tensor with no grad_fn (one slot of a zeroed ring that is replaced, never rewritten, every
+        LOSS_RING steps, so a loss a caller keeps stays valid).  With a gradient exchange installed (several GPUs)
+        the exchange has to run between the two kernels, and the call takes the two-launch route."""
+        if self._grad_sync is not None:
+            loss = self.calculate_loss(interaction)
+            loss.backward()
+            return loss.detach()
+        device = self._check_ready()
+        self._ensure_state(device)
+        lib = _abi.lib()
+        stream = _abi.stream_ptr()
+        if self._pending:  # a loss whose backward never ran: drop its gradient
+            m = self._model_struct(True)
+            _abi.check(lib.kge_grad_discard(C.byref(m), self._step + 1, stream), "kge_grad_discard")
+            _plain_set(self, "_pending", False)
+            _plain_set(self, "_pending_loss", None)
+        ring = self.__dict__.get("_loss_ring")
+        if ring is None or ring[2] == self.LOSS_RING or ring[0].device != device:
+            base = torch.zeros(self.LOSS_RING, device=device)
+            ring = [base, base.unbind(0), 0, base.data_ptr()]
+            self.__dict__["_loss_ring"] = ring
+        pos = ring[2]
+        ring[2] = pos + 1
+        m = self._model_struct(True)
+        b, keep = self._batch_struct(interaction, device)
+        a = self._adam_struct(self._step + 1)
+        _abi.check(
+            lib.kge_train_step(C.byref(m), C.byref(b), C.byref(a), float(self._grad_scale), ring[3] + 4 * pos, stream),
+            "kge_train_step",
+        )
+        _plain_set(self, "_keepalive", keep)
+        if b.n_rec + b.n_kg:
+            _plain_set(self, "_step", self._step + 1)
+            _plain_set(self, "_dirty", True)
+        return ring[1][pos]
+
     def flush(self):
         """Bring every row of every table to the current optimiser step (dense pass)."""
         if self._state is None or not self._dirty:

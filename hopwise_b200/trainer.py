@@ -136,15 +136,17 @@ class FusedKGTrainer(KGTrainer):
         model = self.model
         model.train()
         device = torch.device(self.device)
-        total = torch.zeros((), dtype=torch.float64, device=device)
         batches = DevicePrefetcher(train_data, device) if (self.prefetch and device.type == "cuda") else None
+        losses = []
         for interaction in (batches if batches is not None else train_data):
             if batches is None:
                 interaction = interaction.to(device)
-            loss = model.calculate_loss(interaction)
-            total += loss.detach()          # float64 += float32: the reference's `total_loss + losses.item()`
-            loss.backward()                 # the fused row-lazy Adam step (optimizer.step() has nothing to do)
-        total_loss = float(total.item())    # the epoch's only host synchronisation
+            # forward + the fused row-lazy Adam step in one library call (optimizer.step() has nothing to do); the
+            # loss stays on the device
+            losses.append(model.train_step(interaction))
+        # float64 sum of the float32 step losses: the reference's `total_loss + losses.item()`; the epoch's only
+        # host synchronisation
+        total_loss = float(torch.stack(losses).double().sum().item()) if losses else 0.0
         if math.isnan(total_loss):
             raise ValueError("Training loss is nan")   # trainer.py:337-339 (checked per epoch instead of per step)
         return total_loss

@@ -123,6 +123,13 @@ int kge_adam_apply(const kge_model_t* model, const kge_adam_t* adam, float grad_
  * weights are read by anything but this library (state_dict, predict, checkpoints). */
 int kge_adam_flush(const kge_model_t* model, const kge_adam_t* adam, kge_stream_t stream);
 
+/* kge_train_step: one whole optimisation step in one call -- kge_train_forward (with_grad) followed by
+ * kge_adam_apply on the same stream: what optimizer.zero_grad(); loss = model.calculate_loss(batch);
+ * loss.backward(); optimizer.step() amount to (trainer/trainer.py:247-266) on one GPU.  *loss_out must be
+ * zero on entry. */
+int kge_train_step(const kge_model_t* model, const kge_batch_t* batch, const kge_adam_t* adam, float grad_scale,
+                   float* loss_out, kge_stream_t stream);
+
 /* Drop a gradient that was accumulated but will not be applied. */
 int kge_grad_discard(const kge_model_t* model, int32_t step, kge_stream_t stream);
 
@@ -219,6 +226,14 @@ int kge_topk_hits(const int64_t* ids, int64_t n, int32_t k, const int64_t* pos_o
 /* kge_topk_metric_sums: metrics.py:67-69,93-101,164-165,191-207,231-232 summed over users:
  * sums[5*k] float64 = per-cutoff sums of recall, mrr, ndcg, hit, precision (caller zeroes). */
 int kge_topk_metric_sums(const int32_t* rec_topk, int64_t n, int32_t k, double* sums, kge_stream_t stream);
+
+/* ---- batch assembly ------------------------------------------------------------------------
+ * kge_gather_columns: Interaction.__getitem__ on the id columns of a batch (interaction.py:130-139 as called
+ * from general_dataloader.py:66-70 and knowledge_dataloader.py:69-75): outs[c][i] = columns[c][index[i]] for
+ * n_columns <= 8 int64 columns of `rows` entries in one launch.  columns / outs are HOST arrays of device
+ * pointers.  *status (device, may be NULL) becomes 1 when an index lies outside [0, rows). */
+int kge_gather_columns(const int64_t* const* columns, int32_t n_columns, int64_t rows, const int64_t* index,
+                       int64_t n, int64_t* const* outs, int32_t* status, kge_stream_t stream);
 
 /* ---- negative sampling -------------------------------------------------------------------
  * kge_sample_negatives: AbstractSampler.sample_by_key_ids with uniform sampling

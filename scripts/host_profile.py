@@ -8,16 +8,23 @@ w = bench.WORKLOADS["cfg2_transe_ml1m_b2048"]
 dev = torch.device("cuda", 0)
 model = bench.make_model(w, dev)
 batches = [{k: torch.from_numpy(v).to(dev) for k, v in b.items()} for b in bench.synth_batches(w, 4, 1)]
-def run(n, sync):
+def run(n, sync, one_call):
     for i in range(n):
-        loss = model.calculate_loss(batches[i % 4])
-        if sync:
-            loss.item()
-        loss.backward()
-run(200, True)
+        if one_call:
+            loss = model.train_step(batches[i % 4])
+            if sync:
+                loss.item()
+        else:
+            loss = model.calculate_loss(batches[i % 4])
+            if sync:
+                loss.item()
+            loss.backward()
+run(200, True, False)
+run(200, True, True)
 torch.cuda.synchronize()
-for sync in (False, True):
-    t0 = time.perf_counter(); run(3000, sync); torch.cuda.synchronize()
-    print(f"sync={sync}: {(time.perf_counter() - t0) / 3000 * 1e6:.1f} us/step")
-pr = cProfile.Profile(); pr.enable(); run(3000, False); pr.disable()
-pstats.Stats(pr).sort_stats("tottime").print_stats(22)
+for one_call in (False, True):
+    for sync in (False, True):
+        t0 = time.perf_counter(); run(3000, sync, one_call); torch.cuda.synchronize()
+        print(f"one_call={one_call} sync={sync}: {(time.perf_counter() - t0) / 3000 * 1e6:.1f} us/step")
+pr = cProfile.Profile(); pr.enable(); run(3000, False, True); pr.disable()
+pstats.Stats(pr).sort_stats("tottime").print_stats(14)

@@ -126,3 +126,37 @@ def test_dynamic_negative_sampling_matches_oracle():
     st = stream.get_state()
     np.testing.assert_array_equal(st[1], gen.key)
     assert st[2] == gen.pos
+
+
+def test_gather_columns_kernel():
+    """kge_gather_columns against numpy fancy indexing: 1..8 columns, empty index, repeated and boundary rows, and the
+    out-of-range flag."""
+    import ctypes as C
+
+    from hopwise_b200 import _abi
+
+    lib = _abi.lib()
+    rng = np.random.default_rng(0)
+    rows = 100_003
+    for nc, n in ((1, 1), (3, 2048), (8, 70_001), (2, 0)):
+        cols = [torch.from_numpy(rng.integers(0, 1 << 40, rows)).cuda() for _ in range(nc)]
+        idx = rng.integers(0, rows, n)
+        if n > 2:
+            idx[0], idx[1], idx[2] = 0, rows - 1, rows - 1
+        idx_d = torch.from_numpy(idx).cuda()
+        out = torch.full((nc, n), -1, dtype=torch.int64, device="cuda")
+        src = (C.c_void_p * nc)(*[c.data_ptr() for c in cols])
+        dst = (C.c_void_p * nc)(*[out.data_ptr() + 8 * n * c for c in range(nc)])
+        status = torch.zeros(1, dtype=torch.int32, device="cuda")
+        _abi.check(lib.kge_gather_columns(src, nc, rows, idx_d.data_ptr(), n, dst, status.data_ptr(), _abi.stream_ptr()),
+                   "kge_gather_columns")
+        for c in range(nc):
+            np.testing.assert_array_equal(out[c].cpu().numpy(), cols[c].cpu().numpy()[idx])
+        assert status.item() == 0
+    bad = torch.tensor([5, rows, -1, 7], device="cuda")
+    out = torch.full((1, 4), -1, dtype=torch.int64, device="cuda")
+    src = (C.c_void_p * 1)(cols[0].data_ptr())
+    dst = (C.c_void_p * 1)(out.data_ptr())
+    _abi.check(lib.kge_gather_columns(src, 1, rows, bad.data_ptr(), 4, dst, status.data_ptr(), _abi.stream_ptr()), "gather")
+    assert status.item() == 1 and out[0, 1].item() == -1 and out[0, 0].item() == cols[0][5].item()
+    assert lib.kge_gather_columns(src, 9, rows, bad.data_ptr(), 4, dst, None, _abi.stream_ptr()) != 0

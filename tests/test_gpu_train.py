@@ -348,3 +348,43 @@ def test_device_prefetcher_preserves_batches_and_training_result():
         m2.calculate_loss(db).backward()
     for (k1, v1), (_, v2) in zip(m1.state_dict().items(), m2.state_dict().items()):
         assert_weights_close(v2.cpu().numpy(), v1.cpu().numpy(), rtol=1e-5, atol=5e-7, err_msg=k1)
+
+
+@pytest.mark.parametrize("name", MODELS)
+def test_one_call_train_step_follows_the_golden_trajectory(name):
+    """model.train_step(batch) -- forward + Adam in one library call, what FusedKGTrainer's epoch loop uses -- on the
+    reference's golden trajectory; interleaved with the autograd route to show the two share all state."""
+    g = load_golden(f"model_{name}_d20.npz")
+    m = _golden_model(name, g)
+    held = []
+    for step, bi in enumerate(g["schedule"], start=1):
+        b = _gbatch(g, int(bi))
+        if step % 5 == 0:   # the two-launch route in between: same optimiser state, same step counter
+            loss = m.calculate_loss(b)
+            loss.backward()
+        else:
+            loss = m.train_step(b)
+            assert loss.grad_fn is None and loss.dim() == 0
+        held.append(loss.detach())
+        if step in (1, 4, 12):
+            for k, v in m.state_dict().items():
+                assert_weights_close(v.cpu().numpy(), g[f"step{step}/{k}"], rtol=RTOL, err_msg=f"{name} {k} step {step}")
+    # the losses stay valid after the fact (ring slots are never rewritten)
+    np.testing.assert_allclose(torch.stack(held).cpu().numpy(), g["losses"], rtol=RTOL)
+
+
+def test_train_step_loss_ring_rolls_over():
+    U, I, E, R, d = 50, 40, 90, 5, 16
+    rng = np.random.default_rng(3)
+    m = make_product_model("TransE", U, I, E, R, d)
+    ora = make_oracle_model("TransE", U, I, E, R, d)
+    opt = make_optimizer(ora)
+    n = m.LOSS_RING + 9
+    got, want = [], []
+    for _ in range(n):
+        b = random_batch(rng, U, I, E, R, 8, 8)
+        want.append(train_step(ora, opt, to_cpu_batch(b)))
+        got.append(m.train_step(to_device_batch(b)))
+    np.testing.assert_allclose(torch.stack(got).cpu().numpy(), np.array(want), rtol=1e-4)
+    for (k, vo), (_, vp) in zip(ora.state_dict().items(), m.state_dict().items()):
+        assert_weights_close(vp.cpu().numpy(), vo.numpy(), rtol=1e-4, atol=2e-6, err_msg=k)

@@ -41,7 +41,7 @@ def _loader(g):
     rec = _OracleSampler(gen, g["used_user"], g["used_item"], n_users, n_items)
     kg = _OracleSampler(gen, g["sampler_heads"], g["sampler_tails"], n_ent, n_ent)
     loader = DeviceKGLoader(g["inter_user"], g["inter_item"], g["kg_head"], g["kg_rel"], g["kg_tail"], rec, kg,
-                            batch_size=int(g["batch"]), seed=int(g["seed"]), device="cpu")
+                            batch_size=int(g["batch"]), seed=int(g["seed"]), device="cpu", gather=lambda table, idx: table.index_select(0, idx))
     return loader, gen
 
 
