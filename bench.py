@@ -546,7 +546,11 @@ def main():
         # in-switch vs NCCL: 8 B200 0.527 vs 0.564, 4 B200 0.487 vs 0.479, 2 B200 0.483 vs 0.462 (the two barriers
         # around the kernel cost more than NCCL's exchange until the ring gets long).  KGE_MULTIMEM=0 / 1 forces it.
         mm = os.environ.get("KGE_MULTIMEM")
-        exchange = enable_row_sparse_data_parallel(model, multimem=(world > 4) if mm is None else mm != "0")
+        # KGE_OWNER_ADAM=1: the optimiser step itself owner-sharded over the switch (one kernel: reduce 1/N of the
+        # gradient, dense Adam on it, multicast the weights) -- fits this workload, whose batch touches every row
+        owner = os.environ.get("KGE_OWNER_ADAM") == "1"
+        exchange = enable_row_sparse_data_parallel(model, multimem=(world > 4) if mm is None else mm != "0",
+                                                   owner_adam=owner)
         if os.environ.get("KGE_MULTIMEM_FUSED") == "0":   # A/B: host-launched barriers around the plain kernel
             exchange.fused_barriers = False
 
@@ -598,13 +602,17 @@ def main():
                     "ms_per_step": e2e_ms, "median_ms_per_step": e2e_median_ms, "max_ms_per_step": e2e_max_ms},
             # this library's kernels in the timed region: forward + Adam per step, plus the pack / add kernels of
             # the row-sparse exchange when a table takes that route (NCCL's own kernels are not counted)
-            "gpu_launches": args.steps * (2 + (exchange.kernels_per_step if exchange is not None else 0)),
+            "gpu_launches": args.steps * ((1 if exchange is not None and exchange.owner_adam else 2)
+                                          + (exchange.kernels_per_step if exchange is not None else 0)),
             "roofline": roof, "clocks": clk, "final_loss": last_loss}
     if exchange is not None:
         line["exchange_bytes_per_rank_per_step"] = exchange.bytes_per_step
-        line["exchange"] = ("nvls multimem all-reduce (csrc/collective.cu)"
-                            + (", barriers and touch marks inside the kernel" if exchange.fused_barriers else "")
-                            ) if exchange.multimem else "nccl all-reduce"
+        line["exchange"] = ("owner-sharded Adam over the switch: multimem.ld_reduce of 1/N of the gradient, dense Adam, "
+                            "multimem.st of the weights, barriers inside the kernel (csrc/collective.cu)"
+                            if exchange.owner_adam else
+                            ("nvls multimem all-reduce (csrc/collective.cu)"
+                             + (", barriers and touch marks inside the kernel" if exchange.fused_barriers else "")
+                             ) if exchange.multimem else "nccl all-reduce")
         line["exchange_routes_dense"] = list(exchange.dense)
 
     def train_leg(name, steps, world_, data_parallel=False):

@@ -105,6 +105,10 @@ PROTOTYPES = {
     ),
     "kge_copy_h2d_async": (C.c_int, [_P, _P, C.c_int64, _P]),
     "kge_multimem_all_reduce_f32": (C.c_int, [_P, C.c_int64, C.c_int32, C.c_int32, _P]),
+    "kge_owner_adam_step": (
+        C.c_int,
+        [_P, _P, _P, _P, _P, C.c_int64, C.c_int32, C.c_int32, _AP, C.c_float, _P, C.c_int32, _P, C.c_uint32, _P],
+    ),
     "kge_multimem_all_reduce_fused_f32": (
         C.c_int, [_P, C.c_int64, C.c_int32, C.c_int32, _P, C.c_int32, _P, C.c_uint32, _P, C.c_int64, C.c_int32, _P]),
     "kge_mma_image_bytes": (C.c_int64, [_MP, C.c_int64, C.c_int32]),

@@ -124,6 +124,82 @@ __global__ void __launch_bounds__(256) multimem_all_reduce_fused_kernel(float* _
   if (s_last) cross_rank_barrier(pads, rank, world, slot_base + world);
 }
 
+// ---- owner-sharded dense Adam over the switch ---------------------------------------------------------------------
+// One kernel per step instead of all-reduce + Adam: rank r owns the r-th slice of the flat parameter space.  It reads
+// the SUM of the N gradient copies of its slice straight from the switch (multimem.ld_reduce), takes the Adam step for
+// those elements with its (sharded) moments, and multicasts the new weights -- and zeros for the gradient -- to every
+// replica (multimem.st).  Every rank moves 1/N of the gradient in and 1/N of the weights out, and does 1/N of the
+// optimiser arithmetic; torch.optim.Adam's dense semantics (every element, every step), which is what the reference
+// trains with (trainer/trainer.py:131-170 builds optim.Adam over all parameters; DDP averages the gradients first).
+struct OwnerAdam {
+  float* g_mc;        // multicast address of the flat gradient buffer
+  float* w_mc;        // multicast address of the flat weight buffer
+  const float* w;     // this rank's replica of the weights (same layout)
+  float* m;           // moments: only [q_lo, q_hi) is ever touched on this rank
+  float* v;
+  int64_t q_lo, q_hi; // float4 units
+  float scale;        // 1 / world (DDP's mean) times the caller's loss scale
+  float lr_c, rsq_c;  // lr / (1 - b1^t), 1 / sqrt(1 - b2^t)
+  float b2, omb1, omb2, eps;
+};
+
+__device__ __forceinline__ void owner_adam_quad(const OwnerAdam& a, int64_t q, float4 g) {
+  const float4 w4 = *reinterpret_cast<const float4*>(a.w + 4 * q);
+  float4 m4 = *reinterpret_cast<const float4*>(a.m + 4 * q), v4 = *reinterpret_cast<const float4*>(a.v + 4 * q);
+  float wv[4] = {w4.x, w4.y, w4.z, w4.w}, mv[4] = {m4.x, m4.y, m4.z, m4.w}, vv[4] = {v4.x, v4.y, v4.z, v4.w};
+  const float gv[4] = {g.x, g.y, g.z, g.w};
+#pragma unroll
+  for (int e = 0; e < 4; ++e) {   // the arithmetic of adam_row (train.cu), element for element
+    const float ge = gv[e] * a.scale;
+    mv[e] += a.omb1 * (ge - mv[e]);
+    vv[e] = vv[e] * a.b2 + a.omb2 * ge * ge;
+    const float den = sqrtf(vv[e]) * a.rsq_c + a.eps;
+    wv[e] -= a.lr_c * (mv[e] / den);
+  }
+  *reinterpret_cast<float4*>(a.m + 4 * q) = make_float4(mv[0], mv[1], mv[2], mv[3]);
+  *reinterpret_cast<float4*>(a.v + 4 * q) = make_float4(vv[0], vv[1], vv[2], vv[3]);
+  multimem_st(a.w_mc + 4 * q, make_float4(wv[0], wv[1], wv[2], wv[3]));
+  multimem_st(a.g_mc + 4 * q, make_float4(0.f, 0.f, 0.f, 0.f));
+}
+
+__global__ void __launch_bounds__(256) owner_adam_kernel(const OwnerAdam a, uint32_t* const* pads, int rank, int world,
+                                                         int slot_base, uint32_t* local, uint32_t epoch) {
+  __shared__ int s_last;
+  // ---- barrier A (every rank's forward kernel has written its gradients), then release the grid
+  if (blockIdx.x == 0) {
+    cross_rank_barrier(pads, rank, world, slot_base);
+    __syncthreads();
+    if (threadIdx.x == 0) asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(local), "r"(epoch) : "memory");
+  } else {
+    if (threadIdx.x == 0) {
+      uint32_t seen, spins = 0;
+      do {
+        asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(seen) : "l"(local) : "memory");
+        if (++spins > COLL_SPIN_LIMIT) __trap();
+      } while (seen != epoch);
+    }
+    __syncthreads();
+  }
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  int64_t q = a.q_lo + (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  for (; q + stride < a.q_hi; q += 2 * stride) {   // two switch round trips in flight per thread
+    const float4 g0 = multimem_ld_reduce_add(a.g_mc + 4 * q), g1 = multimem_ld_reduce_add(a.g_mc + 4 * (q + stride));
+    owner_adam_quad(a, q, g0);
+    owner_adam_quad(a, q + stride, g1);
+  }
+  for (; q < a.q_hi; q += stride) owner_adam_quad(a, q, multimem_ld_reduce_add(a.g_mc + 4 * q));
+  __threadfence_system();
+  __syncthreads();
+  // ---- barrier B (every replica holds every slice's new weights and a zeroed gradient) by the last block
+  if (threadIdx.x == 0) {
+    const uint32_t done = atomicAdd(local + 1, 1u);
+    s_last = done == gridDim.x - 1;
+    if (s_last) local[1] = 0u;
+  }
+  __syncthreads();
+  if (s_last) cross_rank_barrier(pads, rank, world, slot_base + world);
+}
+
 }  // namespace
 
 extern "C" int kge_multimem_all_reduce_fused_f32(void* multicast_ptr, int64_t n_floats, int32_t rank, int32_t world,
@@ -166,6 +242,48 @@ extern "C" int kge_multimem_all_reduce_f32(void* multicast_ptr, int64_t n_floats
   if (grid > cap) grid = cap;
   multimem_all_reduce_kernel<<<(unsigned)grid, threads, 0, (cudaStream_t)stream>>>(reinterpret_cast<float*>(multicast_ptr),
                                                                                  lo, hi);
+  KGE_LAUNCH_CHECK();
+  return 0;
+}
+
+extern "C" int kge_owner_adam_step(void* grad_multicast, void* weight_multicast, const float* weight_local, float* m,
+                                   float* v, int64_t n_floats, int32_t rank, int32_t world, const kge_adam_t* adam,
+                                   float grad_scale, void* const* signal_pads_dev, int32_t slot_base,
+                                   uint32_t* local_flags, uint32_t epoch, kge_stream_t stream) {
+  KGE_REQUIRE(grad_multicast && weight_multicast && weight_local && m && v && adam, KGE_E_ARG, "NULL argument");
+  KGE_REQUIRE(n_floats >= 0 && (n_floats & 3) == 0 && world >= 1 && world <= 32 && rank >= 0 && rank < world, KGE_E_ARG,
+              "bad owner-Adam arguments");
+  KGE_REQUIRE(((reinterpret_cast<uintptr_t>(grad_multicast) | reinterpret_cast<uintptr_t>(weight_multicast) |
+                reinterpret_cast<uintptr_t>(weight_local) | reinterpret_cast<uintptr_t>(m) |
+                reinterpret_cast<uintptr_t>(v)) & 15) == 0, KGE_E_ARG, "buffers must be 16-byte aligned");
+  KGE_REQUIRE(signal_pads_dev && local_flags && slot_base >= 0 && epoch != 0 && adam->step >= 1, KGE_E_ARG,
+              "bad barrier / step arguments");
+  const int64_t quads = n_floats / 4;
+  const int64_t per = (quads + world - 1) / world;
+  const int64_t lo = per * rank < quads ? per * rank : quads, hi = lo + per < quads ? lo + per : quads;
+  OwnerAdam a;
+  a.g_mc = reinterpret_cast<float*>(grad_multicast);
+  a.w_mc = reinterpret_cast<float*>(weight_multicast);
+  a.w = weight_local;
+  a.m = m;
+  a.v = v;
+  a.q_lo = lo;
+  a.q_hi = hi;
+  a.scale = grad_scale;
+  // the bias corrections of kge_adam_table_fill (train.cu), formed in double like torch.optim.Adam's
+  const double bc1 = 1.0 - pow((double)adam->beta1, adam->step), bc2 = 1.0 - pow((double)adam->beta2, adam->step);
+  a.lr_c = (float)((double)adam->lr / bc1);
+  a.rsq_c = (float)(1.0 / sqrt(bc2));
+  a.b2 = adam->beta2;
+  a.omb1 = (float)(1.0 - (double)adam->beta1);
+  a.omb2 = (float)(1.0 - (double)adam->beta2);
+  a.eps = adam->eps;
+  const int threads = 256;
+  int64_t grid = hi > lo ? (hi - lo + 2 * threads - 1) / (2 * threads) : 1;
+  const int64_t cap = (int64_t)kge_num_sms() * 4;   // co-resident (the grid spins on a flag block 0 raises)
+  if (grid > cap) grid = cap;
+  owner_adam_kernel<<<(unsigned)grid, threads, 0, (cudaStream_t)stream>>>(
+      a, reinterpret_cast<uint32_t* const*>(signal_pads_dev), rank, world, slot_base, local_flags, epoch);
   KGE_LAUNCH_CHECK();
   return 0;
 }

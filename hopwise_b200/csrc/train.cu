@@ -40,6 +40,12 @@ struct AdamDev {
   const float2* table;  // {lr/(1-b1^j), 1/sqrt(1-b2^j)}
   int tlen;
 };
+// The table entries of the last ADAM_RECENT steps are staged in shared memory by the kernels that replay
+// (stage_recent_consts): the zero-gradient replay of a lagging row walks them one step after the other, and a
+// dependent L2 round trip per replayed step is what bounds the small-batch step (a third of the rows lag a few
+// steps there).  `recent` = that array (or nullptr: read the table in global memory).
+constexpr int ADAM_RECENT = 256;
+__device__ __forceinline__ int recent_lo(int step) { return step - (ADAM_RECENT - 1) > 0 ? step - (ADAM_RECENT - 1) : 0; }
 
 struct TrainArgs {
   kge_model_t m;
@@ -51,9 +57,20 @@ struct TrainArgs {
   float* loss;
 };
 
-__device__ __forceinline__ float2 adam_consts(const AdamDev& A, int j) {
+__device__ __forceinline__ float2 adam_consts(const AdamDev& A, int j, const float2* recent = nullptr) {
+  if (recent && j >= recent_lo(A.step)) return recent[j - recent_lo(A.step)];   // (j <= step always)
   if (j < A.tlen) return __ldg(A.table + j);
   return make_float2(A.lr, 1.f);
+}
+
+// All threads of the CTA: copy the constants of the last ADAM_RECENT steps into `smem`.  The caller synchronises the
+// CTA before the first adam_consts(A, j, smem).
+__device__ __forceinline__ void stage_recent_consts(const AdamDev& A, float2* smem) {
+  const int lo = recent_lo(A.step);
+  for (int i = threadIdx.x; i < ADAM_RECENT; i += blockDim.x) {
+    const int j = lo + i;
+    smem[i] = j < A.tlen ? __ldg(A.table + j) : make_float2(A.lr, 1.f);
+  }
 }
 
 // Zero-gradient Adam steps s+1 .. t_end on one row fragment (torch.optim.Adam with g = 0:
@@ -62,12 +79,12 @@ __device__ __forceinline__ float2 adam_consts(const AdamDev& A, int j) {
 // below fp32 resolution of the weights; m and v then decay in closed form.
 template <int E>
 __device__ __forceinline__ void adam_replay(float (&p)[E], float (&m)[E], float (&v)[E], int s, int t_end,
-                                            const AdamDev& A) {
+                                            const AdamDev& A, const float2* recent = nullptr) {
   const int n = t_end - s;
   if (n <= 0) return;
   const int nrep = n < A.cap ? n : A.cap;
   for (int j = s + 1; j <= s + nrep; ++j) {
-    const float2 c = adam_consts(A, j);
+    const float2 c = adam_consts(A, j, recent);
 #pragma unroll
     for (int e = 0; e < E; ++e) {
       m[e] -= A.omb1 * m[e];
@@ -99,20 +116,22 @@ __device__ __forceinline__ int2 row_state(const kge_table_t& T, int64_t row) {
 // pass would replay the same (growing, up to the cap) run of skipped steps for it again.
 template <int VEC, int G, int NCH>
 __device__ __forceinline__ void catch_up(const kge_table_t& T, int part, int64_t row, int2 st, int d, int gl,
-                                         const AdamDev& A, float (&x)[VEC * NCH], int mark) {
+                                         const AdamDev& A, float (&x)[VEC * NCH], int mark,
+                                         const float2* recent = nullptr) {
   const int last = st.x;
   if (last >= 0 && last < A.step - 1) {
     float m[VEC * NCH], v[VEC * NCH];
     frag_load<VEC, G, NCH>(T.m[part], row, d, gl, m);
     frag_load<VEC, G, NCH>(T.v[part], row, d, gl, v);
-    adam_replay<VEC * NCH>(x, m, v, last, A.step - 1, A);
-    if (mark && part == 0 && gl == 0 && st.y != A.step) T.row_state[2 * row + 1] = A.step;
+    adam_replay<VEC * NCH>(x, m, v, last, A.step - 1, A, recent);
+    if (mark && part == 0 && gl == 0 && st.y != A.step) T.row_state[2 * row + 1] = A.step;   // (last >= 0: has states)
   }
 }
 
 // Mark a row as touched in `step` (idempotent plain store; skipped when the loaded state shows it).
 __device__ __forceinline__ void mark_row(const kge_table_t& T, int64_t row, int seen_touch, int step, int gl) {
-  if (gl == 0 && seen_touch != step) T.row_state[2 * row + 1] = step;
+  // (tables without row states -- dense Adam on every element, owner-sharded over the switch -- keep no marks)
+  if (gl == 0 && seen_touch != step && T.row_state) T.row_state[2 * row + 1] = step;
 }
 
 __device__ __forceinline__ float softplusf(float z) { return fmaxf(z, 0.f) + log1pf(expf(-fabsf(z))); }
@@ -144,6 +163,8 @@ __global__ void __launch_bounds__(256, FwdBounds<MODEL, VEC, G, NCH>::MIN_CTAS) 
   constexpr int PR = (MODEL == KGE_COMPLEX) ? 2 : 1;                          // relation parts
   extern __shared__ float s_racc[];  // [PR][d] user->item relation gradient of this CTA
   __shared__ float s_loss[8];
+  __shared__ float2 s_recent[ADAM_RECENT];
+  stage_recent_consts(a.adam, s_recent);   // (the __syncthreads below covers it)
 
   const int d = a.m.d;
   const int gl = (threadIdx.x & 31) % G;
@@ -194,11 +215,11 @@ __global__ void __launch_bounds__(256, FwdBounds<MODEL, VEC, G, NCH>::MIN_CTAS) 
 #pragma unroll
     for (int p = 0; p < PH; ++p) frag_load<VEC, G, NCH>(ET.w[p], tn_id, d, gl, tnx[p]);
 #pragma unroll
-    for (int p = 0; p < PH; ++p) catch_up<VEC, G, NCH>(HT, p, h_id, sh, d, gl, a.adam, h[p], a.with_grad);
+    for (int p = 0; p < PH; ++p) catch_up<VEC, G, NCH>(HT, p, h_id, sh, d, gl, a.adam, h[p], a.with_grad, s_recent);
 #pragma unroll
-    for (int p = 0; p < PR; ++p) catch_up<VEC, G, NCH>(RT, p, r_id, sr, d, gl, a.adam, r[p], a.with_grad);
+    for (int p = 0; p < PR; ++p) catch_up<VEC, G, NCH>(RT, p, r_id, sr, d, gl, a.adam, r[p], a.with_grad, s_recent);
 #pragma unroll
-    for (int p = 0; p < PH; ++p) catch_up<VEC, G, NCH>(ET, p, tp_id, stp, d, gl, a.adam, tp[p], a.with_grad);
+    for (int p = 0; p < PH; ++p) catch_up<VEC, G, NCH>(ET, p, tp_id, stp, d, gl, a.adam, tp[p], a.with_grad, s_recent);
 
     // gradient fragments of the anchor, relation and positive tail
     float gh[PH][E], gr[PR][E], gtp[PH][E];
@@ -291,7 +312,7 @@ __global__ void __launch_bounds__(256, FwdBounds<MODEL, VEC, G, NCH>::MIN_CTAS) 
           for (int p = 0; p < PH; ++p) frag_load<VEC, G, NCH>(ET.w[p], tn_id, d, gl, tnx[p]);
         }
 #pragma unroll
-        for (int p = 0; p < PH; ++p) catch_up<VEC, G, NCH>(ET, p, t_id, st, d, gl, a.adam, t[p], a.with_grad);
+        for (int p = 0; p < PH; ++p) catch_up<VEC, G, NCH>(ET, p, t_id, st, d, gl, a.adam, t[p], a.with_grad, s_recent);
       }
 
       if (MODEL == KGE_TRANSE) {
@@ -492,7 +513,7 @@ __global__ void __launch_bounds__(256, FwdBounds<MODEL, VEC, G, NCH>::MIN_CTAS) 
       const int p = i / d, col = i - p * d;
       atomicAdd(RT.g[p] + (int64_t)a.m.ui_relation * d + col, s_racc[i]);
     }
-    if (threadIdx.x == 0) RT.row_state[2 * (int64_t)a.m.ui_relation + 1] = step;
+    if (threadIdx.x == 0 && RT.row_state) RT.row_state[2 * (int64_t)a.m.ui_relation + 1] = step;
   }
   lsum = warp_sum(lsum);
   if ((threadIdx.x & 31) == 0) s_loss[threadIdx.x >> 5] = lsum;
@@ -535,6 +556,38 @@ __device__ __forceinline__ void for_selected_rows(const kge_table_t& T, int win,
   }
 }
 
+// Whole-warp groups (G == 32: rows of 17..32 float4): the selected rows of a window are handed over U at a time, so
+// that their loads are in flight together -- a warp that walks its rows one dependent round trip after the other is
+// what bounds the small-batch optimiser step.  `body(rows[U], lasts[U], n)` runs with the warp converged, n in 1..U.
+template <int U, typename Pred, typename Body>
+__device__ __forceinline__ void for_selected_rows_batched(const kge_table_t& T, int win, Pred pred, Body body) {
+  const int lane = threadIdx.x & 31;
+  const int64_t warp_global = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int64_t n_warps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+  for (int64_t base = warp_global * win; base < T.rows; base += n_warps * win) {
+    const int64_t row = base + lane;
+    const bool mine = lane < win && row < T.rows;
+    int2 st = make_int2(-1, -1);
+    if (mine) st = *(reinterpret_cast<const int2*>(T.row_state) + row);
+    unsigned mask = __ballot_sync(0xffffffffu, mine && pred(st));
+    while (mask) {
+      int64_t rows[U];
+      int lasts[U];
+      int n = 0;
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
+        const int bit = mask ? (__ffs(mask) - 1) : 0;
+        const int last = __shfl_sync(0xffffffffu, st.x, bit);
+        rows[u] = base + bit;
+        lasts[u] = last;
+        if (mask) { ++n; mask &= mask - 1; }
+      }
+      body(rows, lasts, n);
+      __syncwarp();
+    }
+  }
+}
+
 struct ApplyArgs {
   kge_model_t m;
   AdamDev adam;
@@ -545,16 +598,16 @@ struct ApplyArgs {
 
 template <int VEC, int G, int NCH>
 __device__ __forceinline__ void adam_row(const kge_table_t& T, int64_t row, int last, int d, int gl, const AdamDev& A,
-                                         float scale) {
+                                         float scale, const float2* recent) {
   constexpr int E = VEC * NCH;
-  const float2 c = adam_consts(A, A.step);
+  const float2 c = adam_consts(A, A.step, recent);
   for (int part = 0; part < T.parts; ++part) {
     float p[E], m[E], v[E], g[E];
     frag_load<VEC, G, NCH>(T.w[part], row, d, gl, p);
     frag_load<VEC, G, NCH>(T.m[part], row, d, gl, m);
     frag_load<VEC, G, NCH>(T.v[part], row, d, gl, v);
     frag_load_cg<VEC, G, NCH>(T.g[part], row, d, gl, g);
-    if (last >= 0 && last < A.step - 1) adam_replay<E>(p, m, v, last, A.step - 1, A);
+    if (last >= 0 && last < A.step - 1) adam_replay<E>(p, m, v, last, A.step - 1, A, recent);
     float z[E];
 #pragma unroll
     for (int e = 0; e < E; ++e) {
@@ -573,21 +626,78 @@ __device__ __forceinline__ void adam_row(const kge_table_t& T, int64_t row, int 
   if (gl == 0) T.row_state[2 * row] = A.step;  // last_step; touch_step keeps `step` (stale from step+1 on)
 }
 
+// adam_row for up to U rows at once (whole-warp groups): all loads first, then the arithmetic, then the stores.
+template <int VEC, int G, int NCH, int U>
+__device__ __forceinline__ void adam_rows(const kge_table_t& T, const int64_t (&rows)[U], const int (&lasts)[U], int n,
+                                          int d, int gl, const AdamDev& A, float scale, const float2* recent) {
+  constexpr int E = VEC * NCH;
+  const float2 c = adam_consts(A, A.step, recent);
+  for (int part = 0; part < T.parts; ++part) {
+    float p[U][E], m[U][E], v[U][E], g[U][E];
+#pragma unroll
+    for (int u = 0; u < U; ++u)
+      if (u < n) {
+        frag_load<VEC, G, NCH>(T.w[part], rows[u], d, gl, p[u]);
+        frag_load<VEC, G, NCH>(T.m[part], rows[u], d, gl, m[u]);
+        frag_load<VEC, G, NCH>(T.v[part], rows[u], d, gl, v[u]);
+        frag_load_cg<VEC, G, NCH>(T.g[part], rows[u], d, gl, g[u]);
+      }
+#pragma unroll
+    for (int u = 0; u < U; ++u)
+      if (u < n) {
+        if (lasts[u] >= 0 && lasts[u] < A.step - 1) adam_replay<E>(p[u], m[u], v[u], lasts[u], A.step - 1, A, recent);
+        float z[E];
+#pragma unroll
+        for (int e = 0; e < E; ++e) {
+          const float ge = g[u][e] * scale;
+          m[u][e] += A.omb1 * (ge - m[u][e]);
+          v[u][e] = v[u][e] * A.b2 + A.omb2 * ge * ge;
+          const float den = sqrtf(v[u][e]) * c.y + A.eps;
+          p[u][e] -= c.x * (m[u][e] / den);
+          z[e] = 0.f;
+        }
+        frag_store<VEC, G, NCH>(T.w[part], rows[u], d, gl, p[u]);
+        frag_store<VEC, G, NCH>(T.m[part], rows[u], d, gl, m[u]);
+        frag_store<VEC, G, NCH>(T.v[part], rows[u], d, gl, v[u]);
+        frag_store<VEC, G, NCH>(T.g[part], rows[u], d, gl, z);
+      }
+  }
+#pragma unroll
+  for (int u = 0; u < U; ++u)
+    if (u < n && gl == 0) T.row_state[2 * rows[u]] = A.step;
+}
+
 template <int VEC, int G, int NCH>
-__global__ void __launch_bounds__(256) adam_apply_kernel(const ApplyArgs a) {
+__global__ void __launch_bounds__(256, 2) adam_apply_kernel(const ApplyArgs a) {
+  __shared__ float2 s_recent[ADAM_RECENT];
+  stage_recent_consts(a.adam, s_recent);
+  __syncthreads();
   const int gl = (threadIdx.x & 31) % G;
   const int step = a.adam.step;
   const float scale = a.scale_dev ? a.scale * __ldg(a.scale_dev) : a.scale;
   auto marked = [step](int2 st) { return st.y == step; };
+  if constexpr (G == 32 && VEC * NCH <= 8) {
+    constexpr int U = 2;
+    for_selected_rows_batched<U>(a.m.user, a.win[0], marked, [&](const int64_t (&rows)[U], const int (&lasts)[U], int n) {
+      adam_rows<VEC, G, NCH, U>(a.m.user, rows, lasts, n, a.m.d, gl, a.adam, scale, s_recent);
+    });
+    for_selected_rows_batched<U>(a.m.entity, a.win[1], marked, [&](const int64_t (&rows)[U], const int (&lasts)[U], int n) {
+      adam_rows<VEC, G, NCH, U>(a.m.entity, rows, lasts, n, a.m.d, gl, a.adam, scale, s_recent);
+    });
+    for_selected_rows_batched<U>(a.m.relation, a.win[2], marked, [&](const int64_t (&rows)[U], const int (&lasts)[U], int n) {
+      adam_rows<VEC, G, NCH, U>(a.m.relation, rows, lasts, n, a.m.d, gl, a.adam, scale, s_recent);
+    });
+    return;
+  }
   // (the tables are kernel parameters: index them by name, a pointer array would copy them to local memory)
   for_selected_rows<G>(a.m.user, a.win[0], marked, [&](int64_t row, int last) {
-    adam_row<VEC, G, NCH>(a.m.user, row, last, a.m.d, gl, a.adam, scale);
+    adam_row<VEC, G, NCH>(a.m.user, row, last, a.m.d, gl, a.adam, scale, s_recent);
   });
   for_selected_rows<G>(a.m.entity, a.win[1], marked, [&](int64_t row, int last) {
-    adam_row<VEC, G, NCH>(a.m.entity, row, last, a.m.d, gl, a.adam, scale);
+    adam_row<VEC, G, NCH>(a.m.entity, row, last, a.m.d, gl, a.adam, scale, s_recent);
   });
   for_selected_rows<G>(a.m.relation, a.win[2], marked, [&](int64_t row, int last) {
-    adam_row<VEC, G, NCH>(a.m.relation, row, last, a.m.d, gl, a.adam, scale);
+    adam_row<VEC, G, NCH>(a.m.relation, row, last, a.m.d, gl, a.adam, scale, s_recent);
   });
 }
 
@@ -721,13 +831,14 @@ int scan_window(int64_t rows) {
 // grid for a scan over `rows` row states: `win` rows per warp iteration, 8 warps per CTA
 int scan_grid(int64_t rows, int win, int ctas_per_sm) { return grid_for((rows + win - 1) / win, 8, ctas_per_sm); }
 
-bool table_has_state(const kge_table_t& T) {
+bool table_has_state(const kge_table_t& T, bool need_rows) {
   for (int p = 0; p < T.parts; ++p)
-    if (!T.m[p] || !T.v[p] || !T.g[p]) return false;
-  return T.row_state != nullptr;
+    if (!T.g[p] || (need_rows && (!T.m[p] || !T.v[p]))) return false;
+  return !need_rows || T.row_state != nullptr;
 }
 
-int check_model(const kge_model_t* m, bool need_state) {
+// need_state: gradient accumulators; need_rows: also moments and row states (the row-lazy Adam kernels)
+int check_model(const kge_model_t* m, bool need_state, bool need_rows = true) {
   KGE_REQUIRE(m, KGE_E_ARG, "model is NULL");
   KGE_REQUIRE(m->model >= KGE_TRANSE && m->model <= KGE_COMPLEX, KGE_E_ARG, "unknown model kind %d", m->model);
   const int ph = (m->model == KGE_ROTATE || m->model == KGE_COMPLEX) ? 2 : 1;
@@ -740,8 +851,8 @@ int check_model(const kge_model_t* m, bool need_state) {
   KGE_REQUIRE(kge_pick_rowcfg(m->d, c), KGE_E_UNSUPPORTED,
               "embedding_size %d unsupported (max 512, or 256 when not a multiple of 4)", m->d);
   if (need_state) {
-    KGE_REQUIRE(table_has_state(m->user) && table_has_state(m->entity) && table_has_state(m->relation), KGE_E_STATE,
-                "optimiser state buffers missing");
+    KGE_REQUIRE(table_has_state(m->user, need_rows) && table_has_state(m->entity, need_rows) &&
+                    table_has_state(m->relation, need_rows), KGE_E_STATE, "optimiser state buffers missing");
   }
   return 0;
 }
@@ -767,7 +878,9 @@ extern "C" int kge_adam_table_fill(float lr, float beta1, float beta2, float* ou
 
 extern "C" int kge_train_forward(const kge_model_t* model, const kge_batch_t* b, const kge_adam_t* adam,
                                  int with_grad, float* loss_out, kge_stream_t stream) {
-  if (int e = check_model(model, with_grad != 0)) return e;
+  // (a training pass without row states accumulates gradients for a dense optimiser step: kge_owner_adam_step)
+  const bool rows_given = model && (model->user.row_state || model->entity.row_state || model->relation.row_state);
+  if (int e = check_model(model, with_grad != 0, rows_given)) return e;
   KGE_REQUIRE(b && adam && loss_out, KGE_E_ARG, "NULL batch / adam / loss_out");
   KGE_REQUIRE(b->n_rec >= 0 && b->n_kg >= 0 && b->k_rec >= 1 && b->k_kg >= 1, KGE_E_ARG, "bad batch sizes");
   KGE_REQUIRE(adam->step >= 1, KGE_E_ARG, "adam.step is 1-based");
@@ -846,7 +959,8 @@ extern "C" int kge_adam_apply(const kge_model_t* model, const kge_adam_t* adam, 
   a.win[0] = scan_window(model->user.rows);
   a.win[1] = scan_window(model->entity.rows);
   a.win[2] = 4;
-  const int grid = scan_grid(max_rows, scan_window(max_rows), 4);
+  // (whole-warp groups take two rows at a time and ~100 registers: two CTAs per SM are resident)
+  const int grid = scan_grid(max_rows, scan_window(max_rows), (c.g == 32 && c.vec * c.nch <= 8) ? 2 : 4);
   cudaStream_t st = (cudaStream_t)stream;
 #define CALL(V, G, N) adam_apply_kernel<V, G, N><<<grid, threads, 0, st>>>(a)
   KGE_DISPATCH_ROWCFG(c, CALL);

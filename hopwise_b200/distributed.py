@@ -97,12 +97,14 @@ class RowSparseExchange:
     """Callable installed as ``model._grad_sync``; runs between the forward/gradient kernel and
     the Adam kernel of every step."""
 
-    def __init__(self, model, group=None, pack_fn=_cuda_pack, add_fn=_cuda_add, device=None, multimem=False):
+    def __init__(self, model, group=None, pack_fn=_cuda_pack, add_fn=_cuda_add, device=None, multimem=False,
+                 owner_adam=False):
         self.group = group
         self.symm = None           # symmetric-memory handle of the gradient buffer (multimem route)
         self.multimem = False
-        if multimem:
-            self._install_multimem(model)
+        self.owner_adam = False    # the optimiser step itself runs owner-sharded over the switch (kge_owner_adam_step)
+        if multimem or owner_adam:
+            self._install_multimem(model, owner_adam)
         self.world = dist.get_world_size(group)
         self.rank = dist.get_rank(group)
         self.pack_fn, self.add_fn = pack_fn, add_fn
@@ -122,10 +124,11 @@ class RowSparseExchange:
         self.timings = []          # [(pack_ms, collective_ms, add_ms)] of the timed steps, read by take_timings()
         self._events = []
 
-    def _install_multimem(self, model):
+    def _install_multimem(self, model, owner_adam=False):
         """Have the model allocate its flat gradient buffer in symmetric memory with a multicast mapping.
         Must run before the first training step (the optimiser state is created lazily there); every rank
-        reaches that allocation together, which makes the rendezvous inside it a proper collective."""
+        reaches that allocation together, which makes the rendezvous inside it a proper collective.
+        With `owner_adam` the weights move into a second such buffer and the model keeps no row-lazy state."""
         import torch.distributed._symmetric_memory as symm_mem
 
         if model._state is not None:
@@ -133,27 +136,42 @@ class RowSparseExchange:
         group = self.group if self.group is not None else dist.group.WORLD
         ex = self
 
-        def alloc(numel, device):
+        def symmetric(numel, device):
             padded = (numel + 3) // 4 * 4
+            buf = symm_mem.empty(padded, dtype=torch.float32, device=device)
+            buf.zero_()
+            hdl = symm_mem.rendezvous(buf, group)
+            if not hdl.has_multicast_support or not hdl.multicast_ptr:
+                raise RuntimeError("no NVLS multicast mapping for the buffer")
+            return buf, hdl, int(hdl.multicast_ptr) + (buf.data_ptr() - int(hdl.buffer_ptrs[hdl.rank]))
+
+        def alloc(numel, device):
             try:
-                buf = symm_mem.empty(padded, dtype=torch.float32, device=device)
-                buf.zero_()
-                hdl = symm_mem.rendezvous(buf, group)
-                if not hdl.has_multicast_support or not hdl.multicast_ptr:
-                    raise RuntimeError("no NVLS multicast mapping for the gradient buffer")
+                buf, hdl, mc = symmetric(numel, device)
             except Exception as exc:   # same hardware on every rank: all ranks take this branch together
+                if owner_adam:
+                    raise RuntimeError(f"owner-sharded Adam needs NVLS multicast memory ({exc})") from exc
                 import warnings
 
                 warnings.warn(f"multimem exchange unavailable ({exc}); the dense route uses NCCL's all-reduce")
                 ex.multimem = False
                 return torch.zeros(numel, device=device)
             ex.symm = hdl
-            ex._mc_base = int(hdl.multicast_ptr) + (buf.data_ptr() - int(hdl.buffer_ptrs[hdl.rank]))
+            ex._mc_base = mc
             ex._symm_keep = buf
             return buf[:numel]
 
+        def alloc_weights(numel, device):
+            buf, hdl, mc = symmetric(numel, device)
+            ex._w_symm, ex._w_mc_base, ex._w_keep = hdl, mc, buf
+            return buf
+
         object.__setattr__(model, "_g_alloc", alloc)
         self.multimem = True
+        if owner_adam:
+            object.__setattr__(model, "_w_alloc", alloc_weights)
+            object.__setattr__(model, "_owner_adam", True)
+            self.owner_adam = True
 
     SIGNAL_SLOT_BASE = 1024   # uint32 slots of the symmetric signal pad this library uses (torch's barrier channels
     #                           live at the front of the 9216-byte pad)
@@ -261,7 +279,29 @@ class RowSparseExchange:
         self._events = []
         return out
 
+    def _owner_step(self, model):
+        """Gradient reduction + Adam + weight broadcast in one kernel; every table takes it (dense Adam)."""
+        st = model._state
+        if self._local_flags is None:
+            self._local_flags = torch.zeros(2, dtype=torch.int32, device=st["g_flat"].device)
+            self.dense = [True, True, True]
+            self.bytes_per_step = 2 * 4 * st["w_flat"].numel() // self.world   # 1/N gradient in, 1/N weights out
+        self._epoch = self._epoch % 0x7FFFFFFF + 1
+        a = model._adam_struct(model._step + 1)
+        _abi.check(
+            _abi.lib().kge_owner_adam_step(
+                self._mc_base, self._w_mc_base, st["w_flat"].data_ptr(), st["m_flat"].data_ptr(),
+                st["v_flat"].data_ptr(), st["w_flat"].numel(), self.rank, self.world, C.byref(a),
+                float(model._grad_scale), int(self.symm.signal_pad_ptrs_dev), self.SIGNAL_SLOT_BASE,
+                self._local_flags.data_ptr(), self._epoch, _abi.stream_ptr()),
+            "kge_owner_adam_step",
+        )
+        self.kernels_per_step = 1
+        return True
+
     def __call__(self, model):
+        if self.owner_adam:
+            return self._owner_step(model)
         step = model._step + 1
         self._plan(model, model._touch_bounds)
         sparse = [w for w in range(3) if not self.dense[w]]
@@ -293,7 +333,7 @@ class RowSparseExchange:
         self._mark()
 
 
-def enable_row_sparse_data_parallel(model, group=None, multimem=False, max_batch_rows=None):
+def enable_row_sparse_data_parallel(model, group=None, multimem=False, max_batch_rows=None, owner_adam=False):
     """Turn a FusedKGEModel replica into a data-parallel one (call once, after model.to(device),
     on every rank, with identical initial weights: the reference gets that from DDP's rank-0
     broadcast, here `broadcast_weights` does it).  ``multimem=True``: dense tables are reduced in the
@@ -302,8 +342,15 @@ def enable_row_sparse_data_parallel(model, group=None, multimem=False, max_batch
 
     Every rank must plan with the same bounds on the rows a step can touch (message layout, collective sizes and the
     dense / sparse choice derive from them): they are agreed with one MAX all-reduce at the first step, or given as
-    ``max_batch_rows`` when later batches can be larger than the first."""
-    ex = RowSparseExchange(model, group=group, multimem=multimem)
+    ``max_batch_rows`` when later batches can be larger than the first.
+
+    ``owner_adam=True`` (implies multimem; for jobs whose batches touch most rows of every table, like the roofline
+    batches): the whole optimiser step moves into the exchange -- each rank reduces 1/world of the gradient in the
+    switch, applies dense Adam to it with its shard of the moments and multicasts the new weights
+    (``kge_owner_adam_step``): one kernel instead of all-reduce + Adam, 1/world of the optimiser work per rank.  The
+    weights then live in a symmetric buffer (the parameters become views of it), there is no row-lazy state, and
+    checkpoints carry weights only."""
+    ex = RowSparseExchange(model, group=group, multimem=multimem, owner_adam=owner_adam)
     if max_batch_rows is not None:   # (user rows, entity rows, relation rows) a step can touch, same on all ranks
         ex._agreed = tuple(int(x) for x in max_batch_rows)
     model._grad_sync = ex

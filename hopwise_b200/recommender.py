@@ -197,6 +197,7 @@ class FusedKGEModel(KnowledgeRecommender):
         self._state = None      # device-side optimiser state, allocated on first training step
         self._anchor = None
         self._grad_sync = None  # optional callable(model) run between forward and apply (multi-GPU)
+        self._owner_adam = False  # distributed.py: dense Adam, owner-sharded over the switch (no row-lazy state)
         self._grad_scale = 1.0  # 1 / world_size under data parallelism (DDP averages gradients)
         self._keepalive = None
         self._touch_bounds = (0, 0, 0)
@@ -255,15 +256,38 @@ class FusedKGEModel(KnowledgeRecommender):
         alloc = self.__dict__.get("_g_alloc")
         st["g_flat"] = alloc(g_numel, device) if alloc is not None else torch.zeros(g_numel, device=device)
         st["row_state_flat"] = torch.full((sum(rows for _, _, rows in fams), 2), -1, dtype=torch.int32, device=device)
+        # the moments share the gradient buffer's flat layout (an owner-sharded optimiser step walks the three
+        # buffers -- and the weights, below -- element for element)
+        flat_len = (g_numel + 3) // 4 * 4
+        st["m_flat"] = torch.zeros(flat_len, device=device)
+        st["v_flat"] = torch.zeros(flat_len, device=device)
+        w_alloc = self.__dict__.get("_w_alloc")
+        if w_alloc is not None:
+            # data-parallel owner-sharded Adam (distributed.py): the weights move into one symmetric buffer with the
+            # same layout; every parameter becomes a view of it
+            st["w_flat"] = w_alloc(flat_len, device)
+            w_off = 0
+            with torch.no_grad():
+                for _, names, rows in fams:
+                    for w in self._tables(names):
+                        view = st["w_flat"][w_off : w_off + rows * d].view(rows, d)
+                        view.copy_(w)
+                        w.data = view
+                        w_off += rows * d
+            self._ready_key = None
+            self._check_ready()
+            self.invalidate_target_image()
         g_off = rs_off = 0
         for fam, names, rows in fams:
-            g_views = []
+            g_views, m_views, v_views = [], [], []
             for _ in names:
                 g_views.append(st["g_flat"][g_off : g_off + rows * d].view(rows, d))
+                m_views.append(st["m_flat"][g_off : g_off + rows * d].view(rows, d))
+                v_views.append(st["v_flat"][g_off : g_off + rows * d].view(rows, d))
                 g_off += rows * d
             st[fam] = {
-                "m": [torch.zeros(rows, d, device=device) for _ in names],
-                "v": [torch.zeros(rows, d, device=device) for _ in names],
+                "m": m_views,
+                "v": v_views,
                 "g": g_views,
                 # [rows, 2] int32: {last_step, touch_step}
                 "row_state": st["row_state_flat"][rs_off : rs_off + rows],
@@ -322,8 +346,8 @@ class FusedKGEModel(KnowledgeRecommender):
                     t.m[p] = st[fam]["m"][p].data_ptr()
                     t.v[p] = st[fam]["v"][p].data_ptr()
                     t.g[p] = st[fam]["g"][p].data_ptr()
-            if st is not None:
-                t.row_state = st[fam]["row_state"].data_ptr()
+            if st is not None and not self._owner_adam:
+                t.row_state = st[fam]["row_state"].data_ptr()   # (owner-sharded dense Adam keeps no row states)
         if st is not None:
             m.adam_table = st["adam_table"].data_ptr()
             m.adam_table_len = st["adam_table_len"]
@@ -396,9 +420,7 @@ class FusedKGEModel(KnowledgeRecommender):
             self._ensure_state(device)
             lazy = True
         if self._pending:  # a loss whose backward never ran: drop its gradient
-            m = self._model_struct(True)
-            _abi.check(lib.kge_grad_discard(C.byref(m), self._step + 1, stream), "kge_grad_discard")
-            _plain_set(self, "_pending", False)
+            self._discard_pending(lib, stream)
         m = self._model_struct(lazy)
         b, keep = self._batch_struct(interaction, device)
         a = self._adam_struct(self._step + 1)
@@ -418,27 +440,43 @@ class FusedKGEModel(KnowledgeRecommender):
             _plain_set(self, "_pending", True)
         return loss.reshape(())
 
+    def _discard_pending(self, lib, stream):
+        if self._owner_adam:
+            self._state["g_flat"].zero_()
+        else:
+            m = self._model_struct(True)
+            _abi.check(lib.kge_grad_discard(C.byref(m), self._step + 1, stream), "kge_grad_discard")
+        _plain_set(self, "_pending", False)
+
     def _launch_apply(self, grad_out):
         if not self._pending:
             raise RuntimeError("backward called twice for one calculate_loss (the fused step keeps no graph)")
         lib = _abi.lib()
+        applied = False
         if self._grad_sync is not None:
-            self._grad_sync(self)
-        # the incoming grad stays on the device: no host sync inside backward (None: the direct
-        # loss.backward() of the trainer, whose incoming grad is 1)
-        g = grad_out
-        if g is not None and (g.dtype != torch.float32 or g.numel() != 1 or g.requires_grad):
-            g = g.detach().to(torch.float32).reshape(1).contiguous()
-        m = self._model_struct(True)
-        a = self._adam_struct(self._step + 1)
-        _abi.check(
-            lib.kge_adam_apply(C.byref(m), C.byref(a), float(self._grad_scale), _abi.ptr(g), _abi.stream_ptr()),
-            "kge_adam_apply",
-        )
+            applied = bool(self._grad_sync(self))   # True: the exchange kernel took the optimiser step as well
+        if self._owner_adam and not applied:
+            raise RuntimeError("owner-sharded Adam is enabled but the exchange did not take the step")
+        if applied and grad_out is not None:
+            raise RuntimeError("owner-sharded Adam takes loss.backward() directly (no incoming gradient)")
+        if not applied:
+            # the incoming grad stays on the device: no host sync inside backward (None: the direct
+            # loss.backward() of the trainer, whose incoming grad is 1)
+            g = grad_out
+            if g is not None and (g.dtype != torch.float32 or g.numel() != 1 or g.requires_grad):
+                g = g.detach().to(torch.float32).reshape(1).contiguous()
+            m = self._model_struct(True)
+            a = self._adam_struct(self._step + 1)
+            _abi.check(
+                lib.kge_adam_apply(C.byref(m), C.byref(a), float(self._grad_scale), _abi.ptr(g), _abi.stream_ptr()),
+                "kge_adam_apply",
+            )
         _plain_set(self, "_pending_loss", None)
         _plain_set(self, "_step", self._step + 1)
         _plain_set(self, "_pending", False)
-        _plain_set(self, "_dirty", True)
+        _plain_set(self, "_dirty", not applied)   # (a dense step leaves every row current)
+        if applied:
+            self.invalidate_target_image()
 
     def calculate_loss(self, interaction):
         """transe.py:75-98 / distmult.py:68-95 / rotate.py:98-131 / complex.py:95-128."""
@@ -470,9 +508,7 @@ class FusedKGEModel(KnowledgeRecommender):
         lib = _abi.lib()
         stream = _abi.stream_ptr()
         if self._pending:  # a loss whose backward never ran: drop its gradient
-            m = self._model_struct(True)
-            _abi.check(lib.kge_grad_discard(C.byref(m), self._step + 1, stream), "kge_grad_discard")
-            _plain_set(self, "_pending", False)
+            self._discard_pending(lib, stream)
             _plain_set(self, "_pending_loss", None)
         ring = self.__dict__.get("_loss_ring")
         if ring is None or ring[2] == self.LOSS_RING or ring[0].device != device:
@@ -500,9 +536,7 @@ class FusedKGEModel(KnowledgeRecommender):
             return
         lib = _abi.lib()
         if self._pending:
-            m = self._model_struct(True)
-            _abi.check(lib.kge_grad_discard(C.byref(m), self._step + 1, _abi.stream_ptr()), "kge_grad_discard")
-            self._pending = False
+            self._discard_pending(lib, _abi.stream_ptr())
         m = self._model_struct(True)
         a = self._adam_struct(self._step)
         _abi.check(lib.kge_adam_flush(C.byref(m), C.byref(a), _abi.stream_ptr()), "kge_adam_flush")
@@ -534,8 +568,8 @@ class FusedKGEModel(KnowledgeRecommender):
     @property
     def kge_optimizer_state(self):
         """Adam moments for checkpoints (rides in other_parameter(), trainer.py:296-304)."""
-        if self._state is None:
-            return None
+        if self._state is None or self._owner_adam:
+            return None   # (owner-sharded Adam: every rank holds 1/world of the moments; checkpoints carry weights only)
         self.flush()
         out = {"step": self._step}
         for fam in ("user", "entity", "relation"):

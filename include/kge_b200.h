@@ -166,6 +166,19 @@ int kge_multimem_all_reduce_fused_f32(void* multicast_ptr, int64_t n_floats, int
                                       uint32_t epoch, int32_t* row_state, int64_t n_mark_rows, int32_t step,
                                       kge_stream_t stream);
 
+/* kge_owner_adam_step: the optimiser step of a data-parallel job in ONE kernel, owner-sharded over the switch
+ * (replaces DDP's gradient all-reduce + optimizer.step(), trainer/trainer.py:82-112, 264-266, for replicas whose
+ * flat gradient and weight buffers are symmetric allocations with NVLS multicast mappings).  Rank `rank` reads the
+ * sum of the `world` gradient copies of its 1/world slice through multimem.ld_reduce, applies torch.optim.Adam's
+ * dense update (gradient scaled by grad_scale, bias corrections of adam->step) with its slice of the moments m / v
+ * (local buffers in the same flat layout), and multicasts the new weights -- and a zeroed gradient -- to every
+ * replica.  Barriers before (all gradients written) and after (all slices final) run inside the kernel: see
+ * kge_multimem_all_reduce_fused_f32 for signal_pads_dev / slot_base / local_flags / epoch. */
+int kge_owner_adam_step(void* grad_multicast, void* weight_multicast, const float* weight_local, float* m, float* v,
+                        int64_t n_floats, int32_t rank, int32_t world, const kge_adam_t* adam, float grad_scale,
+                        void* const* signal_pads_dev, int32_t slot_base, uint32_t* local_flags, uint32_t epoch,
+                        kge_stream_t stream);
+
 /* ---- scoring --------------------------------------------------------------------------
  * kge_predict: <Model>.predict / predict_kg (transe.py:100-110,128-137 and twins).
  * heads index the user tables when head_is_user != 0, else the entity tables; rels == NULL

@@ -44,7 +44,7 @@ def _shard(b, rank, k):
     return out
 
 
-def _worker(rank, world, port, name, route, out_dir, multimem=False):
+def _worker(rank, world, port, name, route, out_dir, multimem=False, owner=False):
     import torch.distributed as dist
 
     from hopwise_b200.distributed import broadcast_weights, enable_row_sparse_data_parallel
@@ -57,7 +57,7 @@ def _worker(rank, world, port, name, route, out_dir, multimem=False):
         SHAPE = SHAPES[route]
         m = make_product_model(name, device=dev, seed=2024 + rank, **SHAPE)   # different init: broadcast must fix it
         broadcast_weights(m)
-        ex = enable_row_sparse_data_parallel(m, multimem=multimem)
+        ex = enable_row_sparse_data_parallel(m, multimem=multimem, owner_adam=owner)
         batches, k = _batches(name, SHAPE)
         losses = []
         for b in batches:
@@ -67,7 +67,10 @@ def _worker(rank, world, port, name, route, out_dir, multimem=False):
         assert ex.bytes_per_step > 0
         if multimem:   # the in-switch reduction really ran (one launch of this library's kernel per step)
             assert ex.symm is not None and ex.kernels_per_step >= 1
-        assert ex.dense == ([True, True, True] if route == "dense" else [False, False, True])
+        if owner:      # the parameters are views of the symmetric weight buffer; no row-lazy state is kept
+            assert ex.owner_adam and m._state["w_flat"].data_ptr() == next(m.parameters()).data_ptr()
+            assert m.kge_optimizer_state is None
+        assert ex.dense == ([True, True, True] if route == "dense" or owner else [False, False, True])
         sd = {key: v.cpu().numpy() for key, v in m.state_dict().items()}
         np.savez(os.path.join(out_dir, f"rank{rank}.npz"), losses=np.array(losses), **sd)
     finally:
@@ -76,15 +79,20 @@ def _worker(rank, world, port, name, route, out_dir, multimem=False):
 
 @pytest.mark.parametrize("name,route,multimem", [("TransE", "dense", False), ("ComplEx", "dense", False),
                                                  ("TransE", "sparse", False), ("RotatE", "sparse", False),
-                                                 ("TransE", "dense", True), ("ComplEx", "dense", True)])
+                                                 ("TransE", "dense", True), ("ComplEx", "dense", True),
+                                                 ("TransE", "dense", "owner"), ("RotatE", "dense", "owner"),
+                                                 ("ComplEx", "sparse", "owner")])
 def test_two_rank_row_sparse_step_matches_single_gpu(name, route, multimem, tmp_path):
-    """multimem = the dense route reduced in the NVSwitch by kge_multimem_all_reduce_f32 instead of NCCL."""
+    """multimem = the dense route reduced in the NVSwitch by kge_multimem_all_reduce_f32 instead of NCCL;
+    "owner" = the whole optimiser step owner-sharded over the switch (kge_owner_adam_step; dense Adam on every table,
+    whatever share of the rows the batch touches)."""
     if torch.cuda.device_count() < 2:
         pytest.skip("needs 2 GPUs")
     import torch.multiprocessing as mp
 
     SHAPE = SHAPES[route]
-    mp.spawn(_worker, args=(2, _free_port(), name, route, str(tmp_path), multimem), nprocs=2, join=True)
+    owner = multimem == "owner"
+    mp.spawn(_worker, args=(2, _free_port(), name, route, str(tmp_path), bool(multimem), owner), nprocs=2, join=True)
     r0, r1 = np.load(tmp_path / "rank0.npz"), np.load(tmp_path / "rank1.npz")
     keys = [k_ for k_ in r0.files if k_ != "losses"]
     for key in keys:   # same values added in the same order on every rank

@@ -123,6 +123,9 @@ def test_dynamic_negative_sampling_matches_oracle():
         rows += num * n
         steps += 1
     assert steps == 4 and exact >= 0.99 * rows
+    # like the reference (knowledge_dataloader.py:137-145) the loader draws a KG batch before it finds the
+    # recommendation side exhausted: one more KG draw on the stream
+    omt.sample_by_key_ids(gen, kh[kg_o.next_indices().numpy()], 1, kg_off, kg_vals, 1, E)
     st = stream.get_state()
     np.testing.assert_array_equal(st[1], gen.key)
     assert st[2] == gen.pos
