@@ -40,13 +40,6 @@ struct AdamDev {
   const float2* table;  // {lr/(1-b1^j), 1/sqrt(1-b2^j)}
   int tlen;
 };
-// The table entries of the last ADAM_RECENT steps are staged in shared memory by the kernels that replay
-// (stage_recent_consts): the zero-gradient replay of a lagging row walks them one step after the other, and a
-// dependent L2 round trip per replayed step is what bounds the small-batch step (a third of the rows lag a few
-// steps there).  `recent` = that array (or nullptr: read the table in global memory).
-constexpr int ADAM_RECENT = 256;
-__device__ __forceinline__ int recent_lo(int step) { return step - (ADAM_RECENT - 1) > 0 ? step - (ADAM_RECENT - 1) : 0; }
-
 struct TrainArgs {
   kge_model_t m;
   kge_batch_t b;
@@ -57,20 +50,9 @@ struct TrainArgs {
   float* loss;
 };
 
-__device__ __forceinline__ float2 adam_consts(const AdamDev& A, int j, const float2* recent = nullptr) {
-  if (recent && j >= recent_lo(A.step)) return recent[j - recent_lo(A.step)];   // (j <= step always)
+__device__ __forceinline__ float2 adam_consts(const AdamDev& A, int j) {
   if (j < A.tlen) return __ldg(A.table + j);
   return make_float2(A.lr, 1.f);
-}
-
-// All threads of the CTA: copy the constants of the last ADAM_RECENT steps into `smem`.  The caller synchronises the
-// CTA before the first adam_consts(A, j, smem).
-__device__ __forceinline__ void stage_recent_consts(const AdamDev& A, float2* smem) {
-  const int lo = recent_lo(A.step);
-  for (int i = threadIdx.x; i < ADAM_RECENT; i += blockDim.x) {
-    const int j = lo + i;
-    smem[i] = j < A.tlen ? __ldg(A.table + j) : make_float2(A.lr, 1.f);
-  }
 }
 
 // Zero-gradient Adam steps s+1 .. t_end on one row fragment (torch.optim.Adam with g = 0:
@@ -79,12 +61,12 @@ __device__ __forceinline__ void stage_recent_consts(const AdamDev& A, float2* sm
 // below fp32 resolution of the weights; m and v then decay in closed form.
 template <int E>
 __device__ __forceinline__ void adam_replay(float (&p)[E], float (&m)[E], float (&v)[E], int s, int t_end,
-                                            const AdamDev& A, const float2* recent = nullptr) {
+                                            const AdamDev& A) {
   const int n = t_end - s;
   if (n <= 0) return;
   const int nrep = n < A.cap ? n : A.cap;
   for (int j = s + 1; j <= s + nrep; ++j) {
-    const float2 c = adam_consts(A, j, recent);
+    const float2 c = adam_consts(A, j);
 #pragma unroll
     for (int e = 0; e < E; ++e) {
       m[e] -= A.omb1 * m[e];
@@ -116,14 +98,13 @@ __device__ __forceinline__ int2 row_state(const kge_table_t& T, int64_t row) {
 // pass would replay the same (growing, up to the cap) run of skipped steps for it again.
 template <int VEC, int G, int NCH>
 __device__ __forceinline__ void catch_up(const kge_table_t& T, int part, int64_t row, int2 st, int d, int gl,
-                                         const AdamDev& A, float (&x)[VEC * NCH], int mark,
-                                         const float2* recent = nullptr) {
+                                         const AdamDev& A, float (&x)[VEC * NCH], int mark) {
   const int last = st.x;
   if (last >= 0 && last < A.step - 1) {
     float m[VEC * NCH], v[VEC * NCH];
     frag_load<VEC, G, NCH>(T.m[part], row, d, gl, m);
     frag_load<VEC, G, NCH>(T.v[part], row, d, gl, v);
-    adam_replay<VEC * NCH>(x, m, v, last, A.step - 1, A, recent);
+    adam_replay<VEC * NCH>(x, m, v, last, A.step - 1, A);
     if (mark && part == 0 && gl == 0 && st.y != A.step) T.row_state[2 * row + 1] = A.step;   // (last >= 0: has states)
   }
 }
@@ -163,8 +144,6 @@ __global__ void __launch_bounds__(256, FwdBounds<MODEL, VEC, G, NCH>::MIN_CTAS) 
   constexpr int PR = (MODEL == KGE_COMPLEX) ? 2 : 1;                          // relation parts
   extern __shared__ float s_racc[];  // [PR][d] user->item relation gradient of this CTA
   __shared__ float s_loss[8];
-  __shared__ float2 s_recent[ADAM_RECENT];
-  stage_recent_consts(a.adam, s_recent);   // (the __syncthreads below covers it)
 
   const int d = a.m.d;
   const int gl = (threadIdx.x & 31) % G;
@@ -215,11 +194,11 @@ __global__ void __launch_bounds__(256, FwdBounds<MODEL, VEC, G, NCH>::MIN_CTAS) 
 #pragma unroll
     for (int p = 0; p < PH; ++p) frag_load<VEC, G, NCH>(ET.w[p], tn_id, d, gl, tnx[p]);
 #pragma unroll
-    for (int p = 0; p < PH; ++p) catch_up<VEC, G, NCH>(HT, p, h_id, sh, d, gl, a.adam, h[p], a.with_grad, s_recent);
+    for (int p = 0; p < PH; ++p) catch_up<VEC, G, NCH>(HT, p, h_id, sh, d, gl, a.adam, h[p], a.with_grad);
 #pragma unroll
-    for (int p = 0; p < PR; ++p) catch_up<VEC, G, NCH>(RT, p, r_id, sr, d, gl, a.adam, r[p], a.with_grad, s_recent);
+    for (int p = 0; p < PR; ++p) catch_up<VEC, G, NCH>(RT, p, r_id, sr, d, gl, a.adam, r[p], a.with_grad);
 #pragma unroll
-    for (int p = 0; p < PH; ++p) catch_up<VEC, G, NCH>(ET, p, tp_id, stp, d, gl, a.adam, tp[p], a.with_grad, s_recent);
+    for (int p = 0; p < PH; ++p) catch_up<VEC, G, NCH>(ET, p, tp_id, stp, d, gl, a.adam, tp[p], a.with_grad);
 
     // gradient fragments of the anchor, relation and positive tail
     float gh[PH][E], gr[PR][E], gtp[PH][E];
@@ -312,7 +291,7 @@ __global__ void __launch_bounds__(256, FwdBounds<MODEL, VEC, G, NCH>::MIN_CTAS) 
           for (int p = 0; p < PH; ++p) frag_load<VEC, G, NCH>(ET.w[p], tn_id, d, gl, tnx[p]);
         }
 #pragma unroll
-        for (int p = 0; p < PH; ++p) catch_up<VEC, G, NCH>(ET, p, t_id, st, d, gl, a.adam, t[p], a.with_grad, s_recent);
+        for (int p = 0; p < PH; ++p) catch_up<VEC, G, NCH>(ET, p, t_id, st, d, gl, a.adam, t[p], a.with_grad);
       }
 
       if (MODEL == KGE_TRANSE) {
@@ -556,38 +535,6 @@ __device__ __forceinline__ void for_selected_rows(const kge_table_t& T, int win,
   }
 }
 
-// Whole-warp groups (G == 32: rows of 17..32 float4): the selected rows of a window are handed over U at a time, so
-// that their loads are in flight together -- a warp that walks its rows one dependent round trip after the other is
-// what bounds the small-batch optimiser step.  `body(rows[U], lasts[U], n)` runs with the warp converged, n in 1..U.
-template <int U, typename Pred, typename Body>
-__device__ __forceinline__ void for_selected_rows_batched(const kge_table_t& T, int win, Pred pred, Body body) {
-  const int lane = threadIdx.x & 31;
-  const int64_t warp_global = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-  const int64_t n_warps = ((int64_t)gridDim.x * blockDim.x) >> 5;
-  for (int64_t base = warp_global * win; base < T.rows; base += n_warps * win) {
-    const int64_t row = base + lane;
-    const bool mine = lane < win && row < T.rows;
-    int2 st = make_int2(-1, -1);
-    if (mine) st = *(reinterpret_cast<const int2*>(T.row_state) + row);
-    unsigned mask = __ballot_sync(0xffffffffu, mine && pred(st));
-    while (mask) {
-      int64_t rows[U];
-      int lasts[U];
-      int n = 0;
-#pragma unroll
-      for (int u = 0; u < U; ++u) {
-        const int bit = mask ? (__ffs(mask) - 1) : 0;
-        const int last = __shfl_sync(0xffffffffu, st.x, bit);
-        rows[u] = base + bit;
-        lasts[u] = last;
-        if (mask) { ++n; mask &= mask - 1; }
-      }
-      body(rows, lasts, n);
-      __syncwarp();
-    }
-  }
-}
-
 struct ApplyArgs {
   kge_model_t m;
   AdamDev adam;
@@ -598,16 +545,16 @@ struct ApplyArgs {
 
 template <int VEC, int G, int NCH>
 __device__ __forceinline__ void adam_row(const kge_table_t& T, int64_t row, int last, int d, int gl, const AdamDev& A,
-                                         float scale, const float2* recent) {
+                                         float scale) {
   constexpr int E = VEC * NCH;
-  const float2 c = adam_consts(A, A.step, recent);
+  const float2 c = adam_consts(A, A.step);
   for (int part = 0; part < T.parts; ++part) {
     float p[E], m[E], v[E], g[E];
     frag_load<VEC, G, NCH>(T.w[part], row, d, gl, p);
     frag_load<VEC, G, NCH>(T.m[part], row, d, gl, m);
     frag_load<VEC, G, NCH>(T.v[part], row, d, gl, v);
     frag_load_cg<VEC, G, NCH>(T.g[part], row, d, gl, g);
-    if (last >= 0 && last < A.step - 1) adam_replay<E>(p, m, v, last, A.step - 1, A, recent);
+    if (last >= 0 && last < A.step - 1) adam_replay<E>(p, m, v, last, A.step - 1, A);
     float z[E];
 #pragma unroll
     for (int e = 0; e < E; ++e) {
@@ -626,78 +573,21 @@ __device__ __forceinline__ void adam_row(const kge_table_t& T, int64_t row, int 
   if (gl == 0) T.row_state[2 * row] = A.step;  // last_step; touch_step keeps `step` (stale from step+1 on)
 }
 
-// adam_row for up to U rows at once (whole-warp groups): all loads first, then the arithmetic, then the stores.
-template <int VEC, int G, int NCH, int U>
-__device__ __forceinline__ void adam_rows(const kge_table_t& T, const int64_t (&rows)[U], const int (&lasts)[U], int n,
-                                          int d, int gl, const AdamDev& A, float scale, const float2* recent) {
-  constexpr int E = VEC * NCH;
-  const float2 c = adam_consts(A, A.step, recent);
-  for (int part = 0; part < T.parts; ++part) {
-    float p[U][E], m[U][E], v[U][E], g[U][E];
-#pragma unroll
-    for (int u = 0; u < U; ++u)
-      if (u < n) {
-        frag_load<VEC, G, NCH>(T.w[part], rows[u], d, gl, p[u]);
-        frag_load<VEC, G, NCH>(T.m[part], rows[u], d, gl, m[u]);
-        frag_load<VEC, G, NCH>(T.v[part], rows[u], d, gl, v[u]);
-        frag_load_cg<VEC, G, NCH>(T.g[part], rows[u], d, gl, g[u]);
-      }
-#pragma unroll
-    for (int u = 0; u < U; ++u)
-      if (u < n) {
-        if (lasts[u] >= 0 && lasts[u] < A.step - 1) adam_replay<E>(p[u], m[u], v[u], lasts[u], A.step - 1, A, recent);
-        float z[E];
-#pragma unroll
-        for (int e = 0; e < E; ++e) {
-          const float ge = g[u][e] * scale;
-          m[u][e] += A.omb1 * (ge - m[u][e]);
-          v[u][e] = v[u][e] * A.b2 + A.omb2 * ge * ge;
-          const float den = sqrtf(v[u][e]) * c.y + A.eps;
-          p[u][e] -= c.x * (m[u][e] / den);
-          z[e] = 0.f;
-        }
-        frag_store<VEC, G, NCH>(T.w[part], rows[u], d, gl, p[u]);
-        frag_store<VEC, G, NCH>(T.m[part], rows[u], d, gl, m[u]);
-        frag_store<VEC, G, NCH>(T.v[part], rows[u], d, gl, v[u]);
-        frag_store<VEC, G, NCH>(T.g[part], rows[u], d, gl, z);
-      }
-  }
-#pragma unroll
-  for (int u = 0; u < U; ++u)
-    if (u < n && gl == 0) T.row_state[2 * rows[u]] = A.step;
-}
-
 template <int VEC, int G, int NCH>
-__global__ void __launch_bounds__(256, 2) adam_apply_kernel(const ApplyArgs a) {
-  __shared__ float2 s_recent[ADAM_RECENT];
-  stage_recent_consts(a.adam, s_recent);
-  __syncthreads();
+__global__ void __launch_bounds__(256) adam_apply_kernel(const ApplyArgs a) {
   const int gl = (threadIdx.x & 31) % G;
   const int step = a.adam.step;
   const float scale = a.scale_dev ? a.scale * __ldg(a.scale_dev) : a.scale;
   auto marked = [step](int2 st) { return st.y == step; };
-  if constexpr (G == 32 && VEC * NCH <= 8) {
-    constexpr int U = 2;
-    for_selected_rows_batched<U>(a.m.user, a.win[0], marked, [&](const int64_t (&rows)[U], const int (&lasts)[U], int n) {
-      adam_rows<VEC, G, NCH, U>(a.m.user, rows, lasts, n, a.m.d, gl, a.adam, scale, s_recent);
-    });
-    for_selected_rows_batched<U>(a.m.entity, a.win[1], marked, [&](const int64_t (&rows)[U], const int (&lasts)[U], int n) {
-      adam_rows<VEC, G, NCH, U>(a.m.entity, rows, lasts, n, a.m.d, gl, a.adam, scale, s_recent);
-    });
-    for_selected_rows_batched<U>(a.m.relation, a.win[2], marked, [&](const int64_t (&rows)[U], const int (&lasts)[U], int n) {
-      adam_rows<VEC, G, NCH, U>(a.m.relation, rows, lasts, n, a.m.d, gl, a.adam, scale, s_recent);
-    });
-    return;
-  }
   // (the tables are kernel parameters: index them by name, a pointer array would copy them to local memory)
   for_selected_rows<G>(a.m.user, a.win[0], marked, [&](int64_t row, int last) {
-    adam_row<VEC, G, NCH>(a.m.user, row, last, a.m.d, gl, a.adam, scale, s_recent);
+    adam_row<VEC, G, NCH>(a.m.user, row, last, a.m.d, gl, a.adam, scale);
   });
   for_selected_rows<G>(a.m.entity, a.win[1], marked, [&](int64_t row, int last) {
-    adam_row<VEC, G, NCH>(a.m.entity, row, last, a.m.d, gl, a.adam, scale, s_recent);
+    adam_row<VEC, G, NCH>(a.m.entity, row, last, a.m.d, gl, a.adam, scale);
   });
   for_selected_rows<G>(a.m.relation, a.win[2], marked, [&](int64_t row, int last) {
-    adam_row<VEC, G, NCH>(a.m.relation, row, last, a.m.d, gl, a.adam, scale, s_recent);
+    adam_row<VEC, G, NCH>(a.m.relation, row, last, a.m.d, gl, a.adam, scale);
   });
 }
 
@@ -959,8 +849,7 @@ extern "C" int kge_adam_apply(const kge_model_t* model, const kge_adam_t* adam, 
   a.win[0] = scan_window(model->user.rows);
   a.win[1] = scan_window(model->entity.rows);
   a.win[2] = 4;
-  // (whole-warp groups take two rows at a time and ~100 registers: two CTAs per SM are resident)
-  const int grid = scan_grid(max_rows, scan_window(max_rows), (c.g == 32 && c.vec * c.nch <= 8) ? 2 : 4);
+  const int grid = scan_grid(max_rows, scan_window(max_rows), 4);
   cudaStream_t st = (cudaStream_t)stream;
 #define CALL(V, G, N) adam_apply_kernel<V, G, N><<<grid, threads, 0, st>>>(a)
   KGE_DISPATCH_ROWCFG(c, CALL);

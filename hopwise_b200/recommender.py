@@ -213,9 +213,16 @@ class FusedKGEModel(KnowledgeRecommender):
         return [getattr(self, n).weight for n in names]
 
     def _check_ready(self):
-        w = self._tables(self.ENTITY_TABLES)[0]
-        key = tuple(t.data_ptr() for names in (self.USER_TABLES, self.ENTITY_TABLES, self.RELATION_TABLES)
-                    for t in self._tables(names))
+        # (the Parameter objects are looked up once: nn.Module.__getattr__ is slow, and this runs every step; code
+        # that swaps a Parameter object -- not its .data -- drops the cache through _apply / load_state_dict)
+        plist = self.__dict__.get("_table_params")
+        if plist is None:
+            plist = [t for names in (self.USER_TABLES, self.ENTITY_TABLES, self.RELATION_TABLES)
+                     for t in self._tables(names)]
+            self.__dict__["_table_params"] = plist
+            self.__dict__["_entity0"] = self._tables(self.ENTITY_TABLES)[0]
+        w = self.__dict__["_entity0"]
+        key = tuple([t.data_ptr() for t in plist])
         if key == self._ready_key:   # same storages as the last (successful) check: nothing can have changed
             return w.device
         if not w.is_cuda:
@@ -367,7 +374,7 @@ class FusedKGEModel(KnowledgeRecommender):
     # ------------------------------------------------------------------ training
     @staticmethod
     def _ids(x, device):
-        if not torch.is_tensor(x):
+        if not isinstance(x, torch.Tensor):
             x = torch.as_tensor(x)
         if x.device != device:
             raise RuntimeError(f"batch ids are on {x.device}, the model is on {device} (call interaction.to(device))")
@@ -554,10 +561,12 @@ class FusedKGEModel(KnowledgeRecommender):
 
     def load_state_dict(self, state_dict, *args, **kwargs):
         self.flush()  # every row current before the weights are overwritten
+        self.__dict__.pop("_table_params", None)
         self.invalidate_target_image()
         return super().load_state_dict(state_dict, *args, **kwargs)
 
     def _apply(self, fn, *args, **kwargs):
+        self.__dict__.pop("_table_params", None)
         # .to(device): optimiser state is rebuilt lazily on the new device (after a flush)
         if self._state is not None:
             self.flush()

@@ -56,6 +56,15 @@ def _run(model_name, use_gpu, trainer_cls=None, steps_out=None):
             return loss
 
         model.calculate_loss = recording
+        if hasattr(model, "train_step"):   # FusedKGTrainer's epoch loop: forward + Adam in one call
+            inner_step = model.train_step
+
+            def recording_step(interaction):
+                loss = inner_step(interaction)
+                steps_out.append(loss.detach().clone())
+                return loss
+
+            model.train_step = recording_step
     _, valid_result = trainer.fit(train_data, valid_data, saved=False, show_progress=False)
     test_result = trainer.evaluate(test_data, load_best_model=False)
     return trainer, float(trainer.train_loss_dict[0]), valid_result, test_result
