@@ -546,9 +546,13 @@ def main():
         # in-switch vs NCCL: 8 B200 0.527 vs 0.564, 4 B200 0.487 vs 0.479, 2 B200 0.483 vs 0.462 (the two barriers
         # around the kernel cost more than NCCL's exchange until the ring gets long).  KGE_MULTIMEM=0 / 1 forces it.
         mm = os.environ.get("KGE_MULTIMEM")
-        # KGE_OWNER_ADAM=1: the optimiser step itself owner-sharded over the switch (one kernel: reduce 1/N of the
-        # gradient, dense Adam on it, multicast the weights) -- fits this workload, whose batch touches every row
-        owner = os.environ.get("KGE_OWNER_ADAM") == "1"
+        # The optimiser step itself runs owner-sharded over the switch when the fabric has multicast memory (one
+        # kernel: reduce 1/N of the gradient, dense Adam on it, multicast the weights) -- it fits this workload,
+        # whose batch touches every row.  Measured, ms/step at 8 / 2 B200: owner 0.417 / 0.406, in-switch
+        # all-reduce + Adam 0.463 / 0.441, NCCL all-reduce + Adam 0.489 / 0.440 (profiles/r2_bench_n8_*.json).
+        # KGE_OWNER_ADAM=0 / 1 and KGE_MULTIMEM=0 / 1 force a route.
+        oa = os.environ.get("KGE_OWNER_ADAM")
+        owner = "auto" if oa is None and mm is None else oa == "1"
         exchange = enable_row_sparse_data_parallel(model, multimem=(world > 4) if mm is None else mm != "0",
                                                    owner_adam=owner)
         if os.environ.get("KGE_MULTIMEM_FUSED") == "0":   # A/B: host-launched barriers around the plain kernel
@@ -571,6 +575,22 @@ def main():
     fwd_ms_avg = max_over_ranks(float(fwd.mean()), device, world)
     upd_ms_avg = max_over_ranks(float(upd.mean()), device, world)
     value = world * triples_step / (step_ms * 1e-3)
+
+    rank_split = None
+    if world > 1:
+        # what the synchronous step costs beyond the slowest rank's forward: per step, the slowest forward over the
+        # ranks and the shortest backward (the rank that arrives last waits for nobody: its backward is the exchange
+        # + optimiser cost proper; the others' include waiting for it)
+        import torch.distributed as dist
+
+        mine = torch.tensor(np.stack([fwd, upd]), dtype=torch.float64, device=device)
+        allr = [torch.empty_like(mine) for _ in range(world)]
+        dist.all_gather(allr, mine)
+        allr = torch.stack(allr).cpu().numpy()          # [world, 2, steps]
+        rank_split = {"fwd_ms_mean_over_ranks": float(allr[:, 0].mean()),
+                      "fwd_ms_slowest_rank_per_step": float(allr[:, 0].max(axis=0).mean()),
+                      "backward_ms_last_arriver_per_step": float(allr[:, 1].min(axis=0).mean()),
+                      "backward_ms_mean_over_ranks": float(allr[:, 1].mean())}
 
     e2e_ms, e2e_median_ms, e2e_max_ms = time_train_e2e(model, host_t, args.steps, args.warmup, world, device)
     e2e_ms = max_over_ranks(e2e_ms / args.steps, device, world)
@@ -606,6 +626,7 @@ def main():
                                           + (exchange.kernels_per_step if exchange is not None else 0)),
             "roofline": roof, "clocks": clk, "final_loss": last_loss}
     if exchange is not None:
+        line["rank_split"] = rank_split
         line["exchange_bytes_per_rank_per_step"] = exchange.bytes_per_step
         line["exchange"] = ("owner-sharded Adam over the switch: multimem.ld_reduce of 1/N of the gradient, dense Adam, "
                             "multimem.st of the weights, barriers inside the kernel (csrc/collective.cu)"

@@ -153,8 +153,8 @@ __device__ __forceinline__ void owner_adam_quad(const OwnerAdam& a, int64_t q, f
     const float ge = gv[e] * a.scale;
     mv[e] += a.omb1 * (ge - mv[e]);
     vv[e] = vv[e] * a.b2 + a.omb2 * ge * ge;
-    const float den = sqrtf(vv[e]) * a.rsq_c + a.eps;
-    wv[e] -= a.lr_c * (mv[e] / den);
+    const float den = sqrt_nonneg(vv[e]) * a.rsq_c + a.eps;
+    wv[e] -= a.lr_c * div_pos_den(mv[e], den);
   }
   *reinterpret_cast<float4*>(a.m + 4 * q) = make_float4(mv[0], mv[1], mv[2], mv[3]);
   *reinterpret_cast<float4*>(a.v + 4 * q) = make_float4(vv[0], vv[1], vv[2], vv[3]);

@@ -561,8 +561,8 @@ __device__ __forceinline__ void adam_row(const kge_table_t& T, int64_t row, int 
       const float ge = g[e] * scale;
       m[e] += A.omb1 * (ge - m[e]);
       v[e] = v[e] * A.b2 + A.omb2 * ge * ge;
-      const float den = sqrtf(v[e]) * c.y + A.eps;
-      p[e] -= c.x * (m[e] / den);
+      const float den = sqrt_nonneg(v[e]) * c.y + A.eps;
+      p[e] -= c.x * div_pos_den(m[e], den);
       z[e] = 0.f;
     }
     frag_store<VEC, G, NCH>(T.w[part], row, d, gl, p);
@@ -809,7 +809,10 @@ extern "C" int kge_train_forward(const kge_model_t* model, const kge_batch_t* b,
   // L2 the step is bound by bytes in flight, which the fatter threads (two CTAs per SM instead of four) halve: cfg5
   // 1.012 -> 1.055 ms/step, so that regime keeps one triple per warp.
   const double table_bytes = ((double)model->user.rows + (double)model->entity.rows) * model->d * 16.0;
+  // (a batch that does not fill the resident warps even once -- the reference's 2048 + 2048 -- is bound by the
+  // length of one warp's dependent instruction chain: one triple per warp halves it and doubles the warps)
   const bool two_per_warp = c.vec == 4 && c.g == 32 && c.nch == 1 && KGE_FWD_TWO_PER_WARP && table_bytes < 96e6 &&
+                            n_total >= (int64_t)kge_num_sms() * 256 &&
                             (model->model == KGE_TRANSE || model->model == KGE_DISTMULT);
   const int threads = 256;
   const int grid = grid_for(n_total, threads / (two_per_warp ? 16 : c.g), 8);

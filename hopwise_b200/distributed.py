@@ -333,6 +333,22 @@ class RowSparseExchange:
         self._mark()
 
 
+def multicast_available(device, group=None) -> bool:
+    """True when every rank can map a symmetric buffer with an NVLS multicast address (collective call)."""
+    ok = 1
+    try:
+        import torch.distributed._symmetric_memory as symm_mem
+
+        buf = symm_mem.empty(1024, dtype=torch.float32, device=device)
+        hdl = symm_mem.rendezvous(buf, group if group is not None else dist.group.WORLD)
+        ok = int(bool(hdl.has_multicast_support and hdl.multicast_ptr))
+    except Exception:
+        ok = 0
+    flag = torch.tensor([ok], dtype=torch.int32, device=device)
+    dist.all_reduce(flag, op=dist.ReduceOp.MIN, group=group)
+    return bool(flag.item())
+
+
 def enable_row_sparse_data_parallel(model, group=None, multimem=False, max_batch_rows=None, owner_adam=False):
     """Turn a FusedKGEModel replica into a data-parallel one (call once, after model.to(device),
     on every rank, with identical initial weights: the reference gets that from DDP's rank-0
@@ -349,7 +365,10 @@ def enable_row_sparse_data_parallel(model, group=None, multimem=False, max_batch
     switch, applies dense Adam to it with its shard of the moments and multicasts the new weights
     (``kge_owner_adam_step``): one kernel instead of all-reduce + Adam, 1/world of the optimiser work per rank.  The
     weights then live in a symmetric buffer (the parameters become views of it), there is no row-lazy state, and
-    checkpoints carry weights only."""
+    checkpoints carry weights only.  ``owner_adam="auto"`` takes that route when the fabric offers multicast memory
+    (probed collectively) and the plain exchange otherwise."""
+    if owner_adam == "auto":
+        owner_adam = multicast_available(next(model.parameters()).device, group)
     ex = RowSparseExchange(model, group=group, multimem=multimem, owner_adam=owner_adam)
     if max_batch_rows is not None:   # (user rows, entity rows, relation rows) a step can touch, same on all ranks
         ex._agreed = tuple(int(x) for x in max_batch_rows)

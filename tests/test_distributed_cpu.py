@@ -104,6 +104,10 @@ def _worker(rank, world, port, out_dir):
         ex.reset_bounds()
         ex(model3)
         assert ex.dense == [False, False, False] and ex.layout.caps == [5, 9, 2]
+        # no multicast memory on a CPU fabric: the probe agrees on False, and "auto" keeps the plain exchange
+        from hopwise_b200.distributed import multicast_available
+
+        assert multicast_available(torch.device("cpu")) is False
         # exact metric means from per-rank sums
         sums = torch.tensor([[1.0 + rank, 2.0], [3.0, 4.0 * (rank + 1)]], dtype=torch.float64)
         tot, n = reduce_metric_sums(sums, n_users=10 + rank)
