@@ -18,14 +18,14 @@ from oracle import ref as oref  # noqa: E402
 pytestmark = [pytest.mark.gpu, pytest.mark.skipif(not oref.ref_available(), reason="oracle/_ref is not built")]
 
 
-def _pipeline():
+def _pipeline(**extra):
     from hopwise.config import Config
     from hopwise.data import create_dataset, data_preparation
     from hopwise.utils import init_seed
 
     config = Config(model="TransE", dataset="ml-100k",
                     config_dict={"embedding_size": 16, "train_batch_size": 2048, "epochs": 1, "use_gpu": False, "gpu_id": "",
-                                 "show_progress": False, "seed": 2024})
+                                 "show_progress": False, "seed": 2024, **extra})
     init_seed(config["seed"], config["reproducibility"])
     dataset = create_dataset(config)
     train_data, valid_data, test_data = data_preparation(config, dataset)
@@ -84,3 +84,51 @@ def test_device_samplers_reproduce_the_reference_loader(tmp_path):
     kg_ref_used = train_ref.kg_dataloader._sampler.used_ids
     for h in (1, 50, 1000):
         assert kgs.used_ids[h] == set(int(x) for x in kg_ref_used[h])
+
+
+def test_popularity_and_dynamic_sampling_inside_the_reference_loader(tmp_path):
+    """train_neg_sample_args = {distribution: popularity, alpha: 0.5, dynamic: True, candidate_num: 3}: hopwise's own
+    `_neg_sampling` (abstract_dataloader.py:166-183) draws 3 popularity-biased candidates per row from the sampler and
+    keeps the one the model scores best.  With the device samplers installed -- and the fused model doing the scoring in
+    both arms -- the loader yields the batches it yields with the reference's CPU samplers."""
+    oref.import_ref()
+    import hopwise_b200
+    from hopwise.data.dataloader.knowledge_dataloader import KGDataLoaderState
+    from hopwise_b200.sampler import install_device_samplers
+
+    torch.zeros(1, device="cuda")
+    visible = os.environ.get("CUDA_VISIBLE_DEVICES")
+    args = {"train_neg_sample_args": {"distribution": "popularity", "sample_num": 1, "alpha": 0.5, "dynamic": True,
+                                      "candidate_num": 3}}
+    cwd = os.getcwd()
+    os.chdir(tmp_path)
+    try:
+        batches = {}
+        for arm in ("ref", "dev"):
+            config, train, _, _ = _pipeline(**args)
+            assert train.general_dataloader._sampler.distribution == "popularity"
+            torch.manual_seed(7)
+            model = hopwise_b200.TransE(config, train.dataset).to("cuda")
+            model.device = torch.device("cuda")   # (the config says cpu: this pipeline keeps hopwise's loaders on the host)
+            if arm == "dev":
+                install_device_samplers(train)
+                assert train.kg_dataloader._sampler.pop is not None
+            train.get_model(model)
+            train.set_mode(KGDataLoaderState.RSKG)
+            got = []
+            for i, b in enumerate(train):
+                got.append({k: v.clone() for k, v in b.interaction.items()})
+                if i == 5:
+                    break
+            batches[arm] = got
+    finally:
+        os.chdir(cwd)
+        if visible is None:
+            os.environ.pop("CUDA_VISIBLE_DEVICES", None)
+        else:
+            os.environ["CUDA_VISIBLE_DEVICES"] = visible
+    assert len(batches["ref"]) == len(batches["dev"]) == 6
+    for i, (a, b) in enumerate(zip(batches["dev"], batches["ref"])):
+        assert set(a) == set(b)
+        for k in b:
+            assert torch.equal(a[k], b[k]), f"batch {i} field {k}"
