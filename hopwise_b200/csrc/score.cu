@@ -63,6 +63,14 @@ __global__ void __launch_bounds__(256) predict_kernel(const ScoreArgs a, float* 
         s += x * x;
       }
       s = -sqrtf(group_sum<G>(s));
+    } else if (MODEL == KGE_TORUSE) {   // toruse.py:66-76 (padding lanes hold zeros: min(0, 1) = 0)
+#pragma unroll
+      for (int e = 0; e < E; ++e) {
+        const float x = (fracf_signed(h[0][e]) + fracf_signed(r[0][e])) - fracf_signed(t[0][e]);
+        const float x2 = x * x;
+        s += fminf(x2, 1.f - x2);
+      }
+      s = -(4.f * group_sum<G>(s));
     } else if (MODEL == KGE_DISTMULT) {
 #pragma unroll
       for (int e = 0; e < E; ++e) s += h[0][e] * r[0][e] * t[0][e];
@@ -128,6 +136,7 @@ __device__ __forceinline__ void build_queries(const ScoreArgs& a, const int64_t*
 }
 
 // Stage target rows [t0, t0+BT) x columns [c0, c0+KC) of one part into Ts (zero padded).
+template <bool FRAC>
 __device__ __forceinline__ void load_target_chunk(const float* __restrict__ W, int d, int64_t n_targets, int64_t t0,
                                                   int c0, float* Ts) {
   if ((d & 3) == 0) {
@@ -138,6 +147,7 @@ __device__ __forceinline__ void load_target_chunk(const float* __restrict__ W, i
       float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
       const int64_t t = t0 + j;
       if (t < n_targets && c < d) v = __ldg(reinterpret_cast<const float4*>(W + t * d + c));
+      if (FRAC) v = make_float4(fracf_signed(v.x), fracf_signed(v.y), fracf_signed(v.z), fracf_signed(v.w));
       *reinterpret_cast<float4*>(Ts + j * TS + q * 4) = v;
     }
   } else {
@@ -145,13 +155,18 @@ __device__ __forceinline__ void load_target_chunk(const float* __restrict__ W, i
       const int j = idx / KC, q = idx - j * KC;
       const int c = c0 + q;
       const int64_t t = t0 + j;
-      Ts[j * TS + q] = (t < n_targets && c < d) ? __ldg(W + t * d + c) : 0.f;
+      const float v = (t < n_targets && c < d) ? __ldg(W + t * d + c) : 0.f;
+      Ts[j * TS + q] = FRAC ? fracf_signed(v) : v;
     }
   }
 }
 
-template <bool DIST, bool TOPK>
+// MODE: how a (query, target) pair of rows is contracted -- 0 dot product, 1 squared distance (score = margin - sqrt),
+// 2 torus distance sum(min(x^2, 1 - x^2)) on frac()ed rows (score = -4 * sum).  Zero padding contributes 0 in all three.
+constexpr int MODE_DOT = 0, MODE_DIST = 1, MODE_TORUS = 2;
+template <int MODE, bool TOPK>
 __global__ void __launch_bounds__(TILE_THREADS) fullsort_tile_kernel(const TileArgs a) {
+  constexpr bool DIST = MODE == MODE_DIST;
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const int model = a.s.m.model;
   const int parts = (model == KGE_ROTATE || model == KGE_COMPLEX) ? 2 : 1;
@@ -247,7 +262,7 @@ __global__ void __launch_bounds__(TILE_THREADS) fullsort_tile_kernel(const TileA
       const float* W = a.s.m.entity.w[p];
       for (int c0 = 0; c0 < kpad; c0 += KC) {
         __syncthreads();  // previous chunk consumed
-        load_target_chunk(W, d, a.n_targets, t0, c0, Ts);
+        load_target_chunk<MODE == MODE_TORUS>(W, d, a.n_targets, t0, c0, Ts);
         __syncthreads();
         const float* qbase = Qs + (4 * tu) * qstride + p * kpad + c0;
 #pragma unroll
@@ -268,6 +283,14 @@ __global__ void __launch_bounds__(TILE_THREADS) fullsort_tile_kernel(const TileA
                 acc[x][y] = fmaf(e1, e1, acc[x][y]);
                 acc[x][y] = fmaf(e2, e2, acc[x][y]);
                 acc[x][y] = fmaf(e3, e3, acc[x][y]);
+              } else if (MODE == MODE_TORUS) {
+                const float e0 = qv[x].x - tv[y].x, e1 = qv[x].y - tv[y].y;
+                const float e2 = qv[x].z - tv[y].z, e3 = qv[x].w - tv[y].w;
+                const float s0 = e0 * e0, s1 = e1 * e1, s2 = e2 * e2, s3 = e3 * e3;
+                acc[x][y] += fminf(s0, 1.f - s0);
+                acc[x][y] += fminf(s1, 1.f - s1);
+                acc[x][y] += fminf(s2, 1.f - s2);
+                acc[x][y] += fminf(s3, 1.f - s3);
               } else {
                 acc[x][y] = fmaf(qv[x].x, tv[y].x, acc[x][y]);
                 acc[x][y] = fmaf(qv[x].y, tv[y].y, acc[x][y]);
@@ -290,7 +313,7 @@ __global__ void __launch_bounds__(TILE_THREADS) fullsort_tile_kernel(const TileA
         const int jo = lane + 32 * y;
         const int64_t j = t0 + jo;
         if (j >= a.n_targets) continue;
-        float sc = DIST ? (margin - sqrtf(acc[x][y])) : acc[x][y];
+        float sc = DIST ? (margin - sqrtf(acc[x][y])) : (MODE == MODE_TORUS ? -(4.f * acc[x][y]) : acc[x][y]);
         if (!TOPK) {
           a.out[rowid[u] * a.n_targets + j] = sc;
         } else {
@@ -465,7 +488,7 @@ __global__ void __launch_bounds__(256) topk_metric_sums_kernel(const int32_t* __
 
 int check_score_model(const kge_model_t* m) {
   KGE_REQUIRE(m, KGE_E_ARG, "model is NULL");
-  KGE_REQUIRE(m->model >= KGE_TRANSE && m->model <= KGE_COMPLEX, KGE_E_ARG, "unknown model kind %d", m->model);
+  KGE_REQUIRE(m->model >= KGE_TRANSE && m->model <= KGE_TORUSE, KGE_E_ARG, "unknown model kind %d", m->model);
   const int ph = (m->model == KGE_ROTATE || m->model == KGE_COMPLEX) ? 2 : 1;
   const int pr = (m->model == KGE_COMPLEX) ? 2 : 1;
   for (int p = 0; p < ph; ++p) KGE_REQUIRE(m->user.w[p] && m->entity.w[p], KGE_E_ARG, "NULL weight table");
@@ -507,7 +530,10 @@ int plan_tiles(const kge_model_t* m, int64_t n, int64_t n_targets, int k, bool t
   return 0;
 }
 
-bool is_dist(int model) { return model == KGE_TRANSE || model == KGE_ROTATE; }
+int tile_mode(int model) {
+  if (model == KGE_TORUSE) return MODE_TORUS;
+  return (model == KGE_TRANSE || model == KGE_ROTATE) ? MODE_DIST : MODE_DOT;
+}
 
 }  // namespace
 
@@ -537,6 +563,7 @@ extern "C" int kge_predict(const kge_model_t* model, const int64_t* heads, const
     case KGE_TRANSE: predict_kernel<KGE_TRANSE, V, G, N><<<grid, threads, 0, st>>>(a, out); break;     \
     case KGE_DISTMULT: predict_kernel<KGE_DISTMULT, V, G, N><<<grid, threads, 0, st>>>(a, out); break; \
     case KGE_ROTATE: predict_kernel<KGE_ROTATE, V, G, N><<<grid, threads, 0, st>>>(a, out); break;     \
+    case KGE_TORUSE: predict_kernel<KGE_TORUSE, V, G, N><<<grid, threads, 0, st>>>(a, out); break;     \
     default: predict_kernel<KGE_COMPLEX, V, G, N><<<grid, threads, 0, st>>>(a, out); break;            \
   }
   KGE_DISPATCH_ROWCFG(c, CALL);
@@ -545,9 +572,9 @@ extern "C" int kge_predict(const kge_model_t* model, const int64_t* heads, const
   return 0;
 }
 
-template <bool DIST, bool TOPK>
+template <int MODE, bool TOPK>
 static int launch_tile(const TileArgs& a, const TilePlan& pl, cudaStream_t st) {
-  auto kern = fullsort_tile_kernel<DIST, TOPK>;
+  auto kern = fullsort_tile_kernel<MODE, TOPK>;
   KGE_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pl.smem));
   // blockIdx.x is limited to 2^31-1 rows/BU: fine for any table that fits the device
   dim3 grid((unsigned)pl.n_blocks, (unsigned)pl.n_splits);
@@ -577,8 +604,11 @@ extern "C" int kge_full_sort_scores(const kge_model_t* model, const int64_t* hea
   a.tiles_per_split = pl.tiles_per_split;
   a.out = out;
   a.n_splits = 1;
-  return is_dist(model->model) ? launch_tile<true, false>(a, pl, (cudaStream_t)stream)
-                               : launch_tile<false, false>(a, pl, (cudaStream_t)stream);
+  switch (tile_mode(model->model)) {
+    case MODE_DIST: return launch_tile<MODE_DIST, false>(a, pl, (cudaStream_t)stream);
+    case MODE_TORUS: return launch_tile<MODE_TORUS, false>(a, pl, (cudaStream_t)stream);
+    default: return launch_tile<MODE_DOT, false>(a, pl, (cudaStream_t)stream);
+  }
 }
 
 extern "C" int64_t kge_full_sort_topk_workspace_bytes(const kge_model_t* model, int64_t n, int64_t n_targets,
@@ -623,7 +653,11 @@ extern "C" int kge_full_sort_topk(const kge_model_t* model, const int64_t* heads
   a.part_keys = reinterpret_cast<uint64_t*>(workspace);
   a.n_splits = pl.n_splits;
   cudaStream_t st = (cudaStream_t)stream;
-  if (int e = is_dist(model->model) ? launch_tile<true, true>(a, pl, st) : launch_tile<false, true>(a, pl, st)) return e;
+  const int mode = tile_mode(model->model);
+  if (int e = mode == MODE_DIST ? launch_tile<MODE_DIST, true>(a, pl, st)
+                                : (mode == MODE_TORUS ? launch_tile<MODE_TORUS, true>(a, pl, st)
+                                                      : launch_tile<MODE_DOT, true>(a, pl, st)))
+    return e;
   const int warps = 8;
   const int64_t mg = (n + warps - 1) / warps;
   topk_merge_kernel<<<(unsigned)mg, warps * 32, (size_t)warps * k * 8, st>>>(a.part_keys, n, pl.n_splits, k, ids_out,
@@ -689,8 +723,10 @@ int kge_topk_rows_indirect(const kge_model_t* model, const int64_t* heads, const
   a.k = k;
   a.row_map = row_map;
   a.row_count = row_count;
-  const bool dist = is_dist(model->model);
-  auto kern = dist ? fullsort_tile_kernel<true, true> : fullsort_tile_kernel<false, true>;
+  const int mode = tile_mode(model->model);
+  auto kern = mode == MODE_DIST ? fullsort_tile_kernel<MODE_DIST, true>
+                                : (mode == MODE_TORUS ? fullsort_tile_kernel<MODE_TORUS, true>
+                                                      : fullsort_tile_kernel<MODE_DOT, true>);
   KGE_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fp.tp.smem));
   const int warps = 8;
   const int64_t ra = n < FB_SPLIT_ROWS ? n : FB_SPLIT_ROWS;

@@ -48,6 +48,8 @@ __device__ __forceinline__ void warp_insert(uint64_t* list, int& len, int k, uin
   __syncwarp();
 }
 
+__device__ __forceinline__ float fracf_signed(float x) { return x - truncf(x); }   // torch.frac
+
 struct ScoreArgs {
   kge_model_t m;
   const int64_t* heads;
@@ -64,6 +66,7 @@ struct ScoreArgs {
 //   DistMult q = h * r                     (distmult.py:50-51)
 //   RotatE   q = rot(h, theta) = (re | im) (rotate.py:61-66)
 //   ComplEx  q = (hr*rr | hi*rr + hr*ri - hi*ri)   (complex.py:53-62 regrouped by tail part)
+//   TorusE   q = frac(h) + frac(r)         (toruse.py:66-76; torch.frac keeps the sign: x - trunc(x))
 __device__ __forceinline__ void query_value(const ScoreArgs& a, int64_t qrow, int c, float& q0, float& q1) {
   const int d = a.m.d;
   const int model = a.m.model;
@@ -75,6 +78,8 @@ __device__ __forceinline__ void query_value(const ScoreArgs& a, int64_t qrow, in
   q1 = 0.f;
   if (model == KGE_TRANSE) {
     q0 = h0 + r0;
+  } else if (model == KGE_TORUSE) {
+    q0 = fracf_signed(h0) + fracf_signed(r0);
   } else if (model == KGE_DISTMULT) {
     q0 = h0 * r0;
   } else if (model == KGE_ROTATE) {

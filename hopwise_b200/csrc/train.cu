@@ -732,7 +732,7 @@ bool table_has_state(const kge_table_t& T, bool need_rows) {
 // need_state: gradient accumulators; need_rows: also moments and row states (the row-lazy Adam kernels)
 int check_model(const kge_model_t* m, bool need_state, bool need_rows = true) {
   KGE_REQUIRE(m, KGE_E_ARG, "model is NULL");
-  KGE_REQUIRE(m->model >= KGE_TRANSE && m->model <= KGE_COMPLEX, KGE_E_ARG, "unknown model kind %d", m->model);
+  KGE_REQUIRE(m->model >= KGE_TRANSE && m->model <= KGE_TORUSE, KGE_E_ARG, "unknown model kind %d", m->model);
   const int ph = (m->model == KGE_ROTATE || m->model == KGE_COMPLEX) ? 2 : 1;
   const int pr = (m->model == KGE_COMPLEX) ? 2 : 1;
   KGE_REQUIRE(m->user.parts == ph && m->entity.parts == ph && m->relation.parts == pr, KGE_E_ARG,
@@ -793,7 +793,9 @@ extern "C" int kge_train_forward(const kge_model_t* model, const kge_batch_t* b,
   a.with_grad = with_grad;
   a.loss = loss_out;
   const double pr = (double)b->n_rec * b->k_rec, pk = (double)b->n_kg * b->k_kg;
-  if (model->model == KGE_TRANSE || model->model == KGE_DISTMULT) {
+  // (TorusE's training objective is TransE's: TripletMarginLoss on h + r, toruse.py:81-102)
+  const int kind = model->model == KGE_TORUSE ? KGE_TRANSE : model->model;
+  if (kind == KGE_TRANSE || kind == KGE_DISTMULT) {
     a.w_rec = a.w_kg = (float)(1.0 / (pr + pk));
     a.wpos_rec = a.wpos_kg = 0.f;
   } else {
@@ -815,20 +817,20 @@ extern "C" int kge_train_forward(const kge_model_t* model, const kge_batch_t* b,
   // length of one warp's dependent instruction chain: one triple per warp halves it and doubles the warps)
   const bool two_per_warp = c.vec == 4 && c.g == 32 && c.nch == 1 && KGE_FWD_TWO_PER_WARP && table_bytes < 96e6 &&
                             n_total >= (int64_t)kge_num_sms() * 256 &&
-                            (model->model == KGE_TRANSE || model->model == KGE_DISTMULT);
+                            (kind == KGE_TRANSE || kind == KGE_DISTMULT);
   const int threads = 256;
   const int grid = grid_for(n_total, threads / (two_per_warp ? 16 : c.g), 8);
   const size_t smem = (size_t)model->relation.parts * model->d * sizeof(float);
   cudaStream_t st = (cudaStream_t)stream;
 #define CALL(V, G, N)                                                                                   \
-  switch (model->model) {                                                                               \
+  switch (kind) {                                                                                       \
     case KGE_TRANSE: train_fwd_kernel<KGE_TRANSE, V, G, N><<<grid, threads, smem, st>>>(a); break;      \
     case KGE_DISTMULT: train_fwd_kernel<KGE_DISTMULT, V, G, N><<<grid, threads, smem, st>>>(a); break;  \
     case KGE_ROTATE: train_fwd_kernel<KGE_ROTATE, V, G, N><<<grid, threads, smem, st>>>(a); break;      \
     default: train_fwd_kernel<KGE_COMPLEX, V, G, N><<<grid, threads, smem, st>>>(a); break;             \
   }
   if (two_per_warp) {
-    if (model->model == KGE_TRANSE) train_fwd_kernel<KGE_TRANSE, 4, 16, 2><<<grid, threads, smem, st>>>(a);
+    if (kind == KGE_TRANSE) train_fwd_kernel<KGE_TRANSE, 4, 16, 2><<<grid, threads, smem, st>>>(a);
     else train_fwd_kernel<KGE_DISTMULT, 4, 16, 2><<<grid, threads, smem, st>>>(a);
   } else {
     KGE_DISPATCH_ROWCFG(c, CALL);

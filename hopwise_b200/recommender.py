@@ -846,4 +846,16 @@ class ComplEx(FusedKGEModel):
     UI_FULLSORT_BY_TOKEN = False  # complex.py:168-169 take weight[-1]
 
 
-MODELS = {"TransE": TransE, "DistMult": DistMult, "RotatE": RotatE, "ComplEx": ComplEx}
+class TorusE(FusedKGEModel):
+    """toruse.py: TransE's tables and TransE's training objective (TripletMarginLoss on h + r, toruse.py:81-102 -- the
+    fused step runs the TransE kernel), scored on the torus: -4 * sum(min(x^2, 1 - x^2)) with
+    x = frac(h) + frac(r) - frac(t) (toruse.py:66-76, 131-172).  The scorer is not a contraction, so full-sort
+    evaluation takes the CUDA-core kernels."""
+
+    KIND = "TorusE"
+    USER_TABLES = ("user_embedding",)
+    ENTITY_TABLES = ("entity_embedding",)
+    RELATION_TABLES = ("relation_embedding",)
+
+
+MODELS = {"TransE": TransE, "DistMult": DistMult, "RotatE": RotatE, "ComplEx": ComplEx, "TorusE": TorusE}

@@ -29,7 +29,10 @@ extern "C" {
 
 typedef void* kge_stream_t; /* cudaStream_t */
 
-enum kge_model_kind { KGE_TRANSE = 0, KGE_DISTMULT = 1, KGE_ROTATE = 2, KGE_COMPLEX = 3 };
+/* KGE_TORUSE (toruse.py): trains exactly like TransE (TripletMarginLoss on h + r, toruse.py:81-102: the train-step
+ * kernels take it as KGE_TRANSE) and scores on the torus: -4 * sum(min(x^2, 1 - x^2)), x = frac(h) + frac(r) - frac(t)
+ * (toruse.py:66-76, 131-172).  Not a contraction: CUDA-core scoring paths only. */
+enum kge_model_kind { KGE_TRANSE = 0, KGE_DISTMULT = 1, KGE_ROTATE = 2, KGE_COMPLEX = 3, KGE_TORUSE = 4 };
 
 enum kge_error {
   KGE_E_ARG = -1,         /* null pointer / negative size */

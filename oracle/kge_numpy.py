@@ -33,6 +33,10 @@ def score(model, h, r, t, margin=1.0):
     """h, r, t: lists of float64 arrays (1 or 2 parts) broadcastable on leading dims."""
     if model == "TransE":
         return -np.sqrt(((h[0] + r[0] - t[0]) ** 2).sum(-1))
+    if model == "TorusE":   # toruse.py:66-76
+        frac = lambda a: a - np.trunc(a)   # noqa: E731
+        x = (frac(h[0]) + frac(r[0])) - frac(t[0])
+        return -(4 * np.minimum(x * x, 1 - x * x).sum(-1))
     if model == "DistMult":
         return (h[0] * r[0] * t[0]).sum(-1)
     if model == "RotatE":
@@ -52,7 +56,7 @@ def pair_loss_and_grads(model, h, r, tp, tn, weight, margin=1.0):
 
     Returns (loss_sum, gh, gr, gtp, gtn); each g* is a list of arrays shaped like the input.
     """
-    if model == "TransE":
+    if model in ("TransE", "TorusE"):   # (TorusE trains with TransE's objective, toruse.py:81-102)
         x = h[0] + r[0]
         dp = x - tp[0] + EPS_PAIRWISE
         dn = x - tn[0] + EPS_PAIRWISE
@@ -123,7 +127,7 @@ def pair_loss_and_grads(model, h, r, tp, tn, weight, margin=1.0):
 
 def loss_weights(model, n_rec, n_kg):
     """Per-pair weights of the rec and KG segments in the scalar loss."""
-    if model in ("TransE", "DistMult"):
+    if model in ("TransE", "DistMult", "TorusE"):
         w = 1.0 / (n_rec + n_kg)
         return w, w
     return (0.5 / n_rec if n_rec else 0.0), (0.5 / n_kg if n_kg else 0.0)

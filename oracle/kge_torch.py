@@ -32,6 +32,8 @@ from torch import nn
 TABLE_NAMES = {
     "TransE": (["user_embedding"], ["entity_embedding"], ["relation_embedding"]),
     "DistMult": (["user_embedding"], ["entity_embedding"], ["relation_embedding"]),
+    # toruse.py:31-48: TransE's tables
+    "TorusE": (["user_embedding"], ["entity_embedding"], ["relation_embedding"]),
     "RotatE": (
         ["user_embedding", "user_embedding_im"],
         ["entity_embedding", "entity_embedding_im"],
@@ -90,7 +92,7 @@ class OracleKGE(nn.Module):
     def _ui_row(self, full_sort: bool) -> int:
         # TransE / DistMult always take weight[-1]; RotatE always the token id; ComplEx the
         # token id for loss/predict and weight[-1] for full_sort_predict.
-        if self.model in ("TransE", "DistMult"):
+        if self.model in ("TransE", "DistMult", "TorusE"):   # toruse.py:53, 121, 131
             return self.shapes.n_relations - 1
         if self.model == "ComplEx" and full_sort:
             return self.shapes.n_relations - 1
@@ -101,6 +103,9 @@ class OracleKGE(nn.Module):
         m = self.model
         if m == "TransE":
             return -torch.norm(h[0] + r[0] - t[0], p=2, dim=-1)
+        if m == "TorusE":   # toruse.py:66-76 (frac_ on detached copies: x - trunc(x), sign kept)
+            x = (torch.frac(h[0]) + torch.frac(r[0])) - torch.frac(t[0])
+            return -(4 * torch.min(x ** 2, 1 - x ** 2).sum(dim=-1))
         if m == "DistMult":
             return (h[0] * r[0] * t[0]).sum(dim=-1)
         if m == "RotatE":
@@ -134,7 +139,7 @@ class OracleKGE(nn.Module):
         kr = self._rows(self._r, rel)
         tp, tn = self._rows(self._e, tail), self._rows(self._e, neg_tail)
 
-        if self.model == "TransE":
+        if self.model in ("TransE", "TorusE"):   # toruse.py:81-102 is transe.py:75-98: the torus only scores
             anchor = torch.cat([u[0] + ur[0], h[0] + kr[0]])
             pos, neg = torch.cat([ip[0], tp[0]]), torch.cat([ineg[0], tn[0]])
             return nn.functional.triplet_margin_loss(anchor, pos, neg, margin=self.shapes.margin, p=2)

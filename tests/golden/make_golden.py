@@ -26,10 +26,11 @@ from hopwise.evaluator import Collector, Evaluator  # noqa: E402
 from hopwise.model.knowledge_graph_embedding_recommender.complex import ComplEx  # noqa: E402
 from hopwise.model.knowledge_graph_embedding_recommender.distmult import DistMult  # noqa: E402
 from hopwise.model.knowledge_graph_embedding_recommender.rotate import RotatE  # noqa: E402
+from hopwise.model.knowledge_graph_embedding_recommender.toruse import TorusE  # noqa: E402
 from hopwise.model.knowledge_graph_embedding_recommender.transe import TransE  # noqa: E402
 from hopwise.sampler import KGSampler, Sampler  # noqa: E402
 
-MODELS = {"TransE": TransE, "RotatE": RotatE, "DistMult": DistMult, "ComplEx": ComplEx}
+MODELS = {"TransE": TransE, "RotatE": RotatE, "DistMult": DistMult, "ComplEx": ComplEx, "TorusE": TorusE}
 SEED = 2024
 # (n_users, n_items, n_entities, n_relations, d)
 SHAPES = {"d20": (37, 23, 61, 7, 20), "d10": (19, 11, 29, 5, 10)}
@@ -58,13 +59,15 @@ def to_inter(b):
     return Interaction({k: torch.as_tensor(v, dtype=torch.long) for k, v in b.items()})
 
 
-def golden_models():
+def golden_models(only=None):
     for tag, (U, I, E, R, d) in SHAPES.items():
         rng = np.random.default_rng(SEED)
         # ragged rec/KG halves, duplicates guaranteed by the small id ranges; only a few
         # distinct batches so that some rows sit untouched for several Adam steps
         batches = make_batches(rng, U, I, E, R, 3, n_rec=13, n_kg=17)
         for name, cls in MODELS.items():
+            if only is not None and name not in only:
+                continue
             cfg = dict(REF_CONFIG, embedding_size=d, margin=1.0)
             ds = FakeDataset(U, I, E, R)
             torch.manual_seed(SEED)
@@ -261,6 +264,7 @@ def golden_eval():
 
 if __name__ == "__main__":
     torch.set_num_threads(1)
-    parts = {"models": golden_models, "sampler": golden_sampler, "sampler_pop": golden_sampler_pop, "eval": golden_eval}
-    for name in sys.argv[1:] or list(parts):   # e.g. `make_golden.py sampler_pop` regenerates one fixture
+    parts = {"models": golden_models, "sampler": golden_sampler, "sampler_pop": golden_sampler_pop, "eval": golden_eval,
+             "toruse": lambda: golden_models(only=("TorusE",))}   # (a model added later: the others stay untouched)
+    for name in sys.argv[1:] or [p for p in parts if p != "toruse"]:   # e.g. `make_golden.py sampler_pop`
         parts[name]()

@@ -21,7 +21,7 @@ def _score_atol(x):
 
 @pytest.mark.parametrize(
     "name,d", [("TransE", 100), ("TransE", 30), ("DistMult", 64), ("RotatE", 48), ("ComplEx", 64), ("ComplEx", 18),
-               ("RotatE", 256)]
+               ("RotatE", 256), ("TorusE", 100), ("TorusE", 30)]
 )
 def test_scores_against_oracle(name, d):
     U, I, E, R = 150, 333, 700, 9
@@ -138,7 +138,7 @@ def test_reference_metric_known_answers():
 
 
 @pytest.mark.parametrize("name,d,I,k", [("TransE", 100, 3001, 10), ("DistMult", 64, 5000, 20), ("ComplEx", 32, 1599, 10),
-                                        ("RotatE", 64, 777, 50), ("TransE", 22, 130, 128)])
+                                        ("RotatE", 64, 777, 50), ("TransE", 22, 130, 128), ("TorusE", 64, 2500, 20)])
 def test_topk_against_oracle(name, d, I, k):
     U, E, R = 400, I + 500, 9
     ora = make_oracle_model(name, U, I, E, R, d)
@@ -387,3 +387,35 @@ def test_topk_kg_against_dense_and_oracle(name, d, E, k, path):
     np.testing.assert_allclose(dense, o_dense, rtol=RTOL, atol=_score_atol(o_dense))
     o_ids, o_sc = ofs.topk_canonical(ofs.mask_scores(o_dense, np.array(hist_u), np.array(hist_i)), k)
     assert (ids != o_ids).mean() < 0.01
+
+
+def test_toruse_scores_with_weights_beyond_the_unit_interval():
+    """TorusE scores take frac() of every embedding (toruse.py:66-76; torch.frac keeps the sign): weights of magnitude
+    up to 3 exercise the truncation on both signs, on all four scoring entry points and the CUDA-core top-k; the
+    tensor-core path refuses the model (its scorer is not a contraction)."""
+    U, I, E, R, d = 90, 9000, 9100, 7, 40
+    ora = make_oracle_model("TorusE", U, I, E, R, d)
+    m = make_product_model("TorusE", U, I, E, R, d)
+    rng = np.random.default_rng(8)
+    with torch.no_grad():
+        for (_, po), (_, pp) in zip(ora.named_parameters(), m.named_parameters()):
+            w = torch.from_numpy(rng.uniform(-3, 3, tuple(po.shape)).astype(np.float32))
+            po.copy_(w)
+            pp.copy_(w.cuda())
+    m.invalidate_target_image()
+    users = torch.from_numpy(rng.integers(1, U, 64))
+    items = torch.from_numpy(rng.integers(0, I, 64))
+    with torch.no_grad():
+        want_p = ora.predict({"user_id": users, "item_id": items}).numpy()
+        want_fs = ora.full_sort_predict({"user_id": users}).numpy()
+    got_p = m.predict({"user_id": users.cuda(), "item_id": items.cuda()}).cpu().numpy()
+    got_fs = m.full_sort_predict({"user_id": users.cuda()}).cpu().numpy()
+    # sums of d terms of magnitude <= 1 with both signs: the absolute floor is that of the terms, not of the sum
+    np.testing.assert_allclose(got_p, want_p, rtol=RTOL, atol=4 * d * 1e-6)
+    np.testing.assert_allclose(got_fs, want_fs, rtol=RTOL, atol=4 * d * 1e-6)
+    ids, sc = m.full_sort_topk(users.cuda(), 20)           # "auto": 9,000 targets would take tcgen05 for a contraction
+    want_ids, want_sc = ofs.topk_canonical(ofs.mask_scores(got_fs), 20)
+    np.testing.assert_array_equal(ids.cpu().numpy(), want_ids)
+    np.testing.assert_array_equal(sc.cpu().numpy(), want_sc)
+    with pytest.raises(Exception):
+        m.full_sort_topk(users.cuda(), 20, path="mma")

@@ -21,7 +21,7 @@ from oracle import mt19937 as omt  # noqa: E402
 
 pytestmark = pytest.mark.skipif(not reference_available(), reason="reference tree not present")
 
-MODELS = ("TransE", "RotatE", "DistMult", "ComplEx")
+MODELS = ("TransE", "RotatE", "DistMult", "ComplEx", "TorusE")
 
 
 def _ref_classes():
@@ -30,9 +30,10 @@ def _ref_classes():
     from hopwise.model.knowledge_graph_embedding_recommender.complex import ComplEx
     from hopwise.model.knowledge_graph_embedding_recommender.distmult import DistMult
     from hopwise.model.knowledge_graph_embedding_recommender.rotate import RotatE
+    from hopwise.model.knowledge_graph_embedding_recommender.toruse import TorusE
     from hopwise.model.knowledge_graph_embedding_recommender.transe import TransE
 
-    return {"TransE": TransE, "RotatE": RotatE, "DistMult": DistMult, "ComplEx": ComplEx}, Interaction
+    return {"TransE": TransE, "RotatE": RotatE, "DistMult": DistMult, "ComplEx": ComplEx, "TorusE": TorusE}, Interaction
 
 
 @pytest.mark.parametrize("name", MODELS)
