@@ -37,7 +37,7 @@ template <int MODEL, int VEC, int G, int NCH>
 __global__ void __launch_bounds__(256) predict_kernel(const ScoreArgs a, float* __restrict__ out) {
   constexpr int E = VEC * NCH;
   constexpr int PH = (MODEL == KGE_ROTATE || MODEL == KGE_COMPLEX) ? 2 : 1;
-  constexpr int PR = (MODEL == KGE_COMPLEX) ? 2 : 1;
+  constexpr int PR = (MODEL == KGE_COMPLEX || MODEL == KGE_TRANSH) ? 2 : 1;
   const int d = a.m.d;
   const int gl = (threadIdx.x & 31) % G;
   const int groups_per_cta = blockDim.x / G;
@@ -60,6 +60,18 @@ __global__ void __launch_bounds__(256) predict_kernel(const ScoreArgs a, float* 
 #pragma unroll
       for (int e = 0; e < E; ++e) {
         const float x = h[0][e] + r[0][e] - t[0][e];
+        s += x * x;
+      }
+      s = -sqrtf(group_sum<G>(s));
+    } else if (MODEL == KGE_TRANSH) {   // transh.py:53-58, 73-74: project head and tail, then TransE's norm
+      float sw = 0.f;
+#pragma unroll
+      for (int e = 0; e < E; ++e) sw += r[1][e];
+      sw = group_sum<G>(sw);
+#pragma unroll
+      for (int e = 0; e < E; ++e) {
+        const float c = 1.f - sw * r[1][e];
+        const float x = (h[0][e] * c + r[0][e]) - t[0][e] * c;
         s += x * x;
       }
       s = -sqrtf(group_sum<G>(s));
@@ -122,23 +134,24 @@ struct TileArgs {
   int64_t row_begin, row_end;
 };
 
-__device__ __forceinline__ void build_queries(const ScoreArgs& a, const int64_t* rowid, int nrows, int kpad, float* Qs) {
+__device__ __forceinline__ void build_queries(const ScoreArgs& a, const int64_t* rowid, int nrows, int kpad, float* Qs,
+                                              const float* proj = nullptr) {
   const int d = a.m.d;
   const int parts = (a.m.model == KGE_ROTATE || a.m.model == KGE_COMPLEX) ? 2 : 1;
   const int qstride = parts * kpad;
   for (int idx = threadIdx.x; idx < BU * kpad; idx += blockDim.x) {
     const int u = idx / kpad, c = idx - u * kpad;
     float q0 = 0.f, q1 = 0.f;
-    if (u < nrows && c < d) query_value(a, rowid[u], c, q0, q1);
+    if (u < nrows && c < d) query_value(a, rowid[u], c, q0, q1, proj);
     Qs[u * qstride + c] = q0;
     if (parts == 2) Qs[u * qstride + kpad + c] = q1;
   }
 }
 
 // Stage target rows [t0, t0+BT) x columns [c0, c0+KC) of one part into Ts (zero padded).
-template <bool FRAC>
+template <bool FRAC, bool PROJ>
 __device__ __forceinline__ void load_target_chunk(const float* __restrict__ W, int d, int64_t n_targets, int64_t t0,
-                                                  int c0, float* Ts) {
+                                                  int c0, float* Ts, const float* Cs) {
   if ((d & 3) == 0) {
     // 8 float4 per row chunk; consecutive lanes take consecutive rows -> conflict-free STS.128
     for (int idx = threadIdx.x; idx < BT * (KC / 4); idx += blockDim.x) {
@@ -148,6 +161,9 @@ __device__ __forceinline__ void load_target_chunk(const float* __restrict__ W, i
       const int64_t t = t0 + j;
       if (t < n_targets && c < d) v = __ldg(reinterpret_cast<const float4*>(W + t * d + c));
       if (FRAC) v = make_float4(fracf_signed(v.x), fracf_signed(v.y), fracf_signed(v.z), fracf_signed(v.w));
+      if (PROJ) {   // (c < kpad always; Cs is zero beyond d like v)
+        v = make_float4(v.x * Cs[c], v.y * Cs[c + 1], v.z * Cs[c + 2], v.w * Cs[c + 3]);
+      }
       *reinterpret_cast<float4*>(Ts + j * TS + q * 4) = v;
     }
   } else {
@@ -156,17 +172,19 @@ __device__ __forceinline__ void load_target_chunk(const float* __restrict__ W, i
       const int c = c0 + q;
       const int64_t t = t0 + j;
       const float v = (t < n_targets && c < d) ? __ldg(W + t * d + c) : 0.f;
-      Ts[j * TS + q] = FRAC ? fracf_signed(v) : v;
+      Ts[j * TS + q] = FRAC ? fracf_signed(v) : (PROJ ? v * Cs[c] : v);
     }
   }
 }
 
 // MODE: how a (query, target) pair of rows is contracted -- 0 dot product, 1 squared distance (score = margin - sqrt),
 // 2 torus distance sum(min(x^2, 1 - x^2)) on frac()ed rows (score = -4 * sum).  Zero padding contributes 0 in all three.
-constexpr int MODE_DOT = 0, MODE_DIST = 1, MODE_TORUS = 2;
+// 3 = mode 1 on rows projected by one relation's factor c = 1 - sum(w) * w (TransH over items: every query row takes the
+// user->item relation, so one factor vector serves the whole launch; it is built once per CTA in shared memory).
+constexpr int MODE_DOT = 0, MODE_DIST = 1, MODE_TORUS = 2, MODE_PROJ = 3;
 template <int MODE, bool TOPK>
 __global__ void __launch_bounds__(TILE_THREADS) fullsort_tile_kernel(const TileArgs a) {
-  constexpr bool DIST = MODE == MODE_DIST;
+  constexpr bool DIST = MODE == MODE_DIST || MODE == MODE_PROJ;
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const int model = a.s.m.model;
   const int parts = (model == KGE_ROTATE || model == KGE_COMPLEX) ? 2 : 1;
@@ -186,6 +204,21 @@ __global__ void __launch_bounds__(TILE_THREADS) fullsort_tile_kernel(const TileA
   int* llen = cnt + (TOPK ? BU : 0);                                        // [BU]
   int64_t* cursor = reinterpret_cast<int64_t*>(llen + (TOPK ? BU : 0));     // [BU] (8-byte aligned by layout)
   int64_t* rowid = cursor + (TOPK ? BU : 0);                                // [BU] query row of each slot
+  float* Cs = reinterpret_cast<float*>(rowid + BU);                         // [kpad] projection factor (MODE_PROJ)
+  if (MODE == MODE_PROJ) {
+    // c = 1 - sum(w) * w of the user->item relation's hyperplane vector (relation part 1), zero beyond d
+    __shared__ float s_part[TILE_THREADS / 32];
+    const float* wv = a.s.m.relation.w[1] + (int64_t)a.s.rel_row * d;
+    float part = 0.f;
+    for (int c = threadIdx.x; c < d; c += blockDim.x) part += __ldg(wv + c);
+    part = warp_sum(part);
+    if ((threadIdx.x & 31) == 0) s_part[threadIdx.x >> 5] = part;
+    __syncthreads();
+    float sw = 0.f;
+    for (int i = 0; i < TILE_THREADS / 32; ++i) sw += s_part[i];
+    for (int c = threadIdx.x; c < kpad; c += blockDim.x) Cs[c] = c < d ? 1.f - sw * __ldg(wv + c) : 0.f;
+    __syncthreads();
+  }
 
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int tu = warp;  // users 4*tu .. 4*tu+3
@@ -201,7 +234,7 @@ __global__ void __launch_bounds__(TILE_THREADS) fullsort_tile_kernel(const TileA
   for (int u = threadIdx.x; u < BU; u += blockDim.x)
     rowid[u] = u < nrows ? (a.row_map ? (int64_t)__ldg(a.row_map + row0 + u) : row0 + u) : 0;
   __syncthreads();
-  build_queries(a.s, rowid, nrows, kpad, Qs);
+  build_queries(a.s, rowid, nrows, kpad, Qs, MODE == MODE_PROJ ? Cs : nullptr);
   if (TOPK) {
     for (int u = threadIdx.x; u < BU; u += blockDim.x) {
       thr[u] = 0ull;
@@ -262,7 +295,7 @@ __global__ void __launch_bounds__(TILE_THREADS) fullsort_tile_kernel(const TileA
       const float* W = a.s.m.entity.w[p];
       for (int c0 = 0; c0 < kpad; c0 += KC) {
         __syncthreads();  // previous chunk consumed
-        load_target_chunk<MODE == MODE_TORUS>(W, d, a.n_targets, t0, c0, Ts);
+        load_target_chunk<MODE == MODE_TORUS, MODE == MODE_PROJ>(W, d, a.n_targets, t0, c0, Ts, Cs);
         __syncthreads();
         const float* qbase = Qs + (4 * tu) * qstride + p * kpad + c0;
 #pragma unroll
@@ -488,9 +521,9 @@ __global__ void __launch_bounds__(256) topk_metric_sums_kernel(const int32_t* __
 
 int check_score_model(const kge_model_t* m) {
   KGE_REQUIRE(m, KGE_E_ARG, "model is NULL");
-  KGE_REQUIRE(m->model >= KGE_TRANSE && m->model <= KGE_TORUSE, KGE_E_ARG, "unknown model kind %d", m->model);
+  KGE_REQUIRE(m->model >= KGE_TRANSE && m->model <= KGE_TRANSH, KGE_E_ARG, "unknown model kind %d", m->model);
   const int ph = (m->model == KGE_ROTATE || m->model == KGE_COMPLEX) ? 2 : 1;
-  const int pr = (m->model == KGE_COMPLEX) ? 2 : 1;
+  const int pr = (m->model == KGE_COMPLEX || m->model == KGE_TRANSH) ? 2 : 1;
   for (int p = 0; p < ph; ++p) KGE_REQUIRE(m->user.w[p] && m->entity.w[p], KGE_E_ARG, "NULL weight table");
   for (int p = 0; p < pr; ++p) KGE_REQUIRE(m->relation.w[p], KGE_E_ARG, "NULL relation table");
   KGE_REQUIRE(m->d >= 1, KGE_E_UNSUPPORTED, "embedding_size %d unsupported", m->d);
@@ -509,6 +542,7 @@ int plan_tiles(const kge_model_t* m, int64_t n, int64_t n_targets, int k, bool t
   size_t smem = (size_t)BU * parts * pl.kpad * 4 + (size_t)BT * TS * 4;
   if (topk) smem += (size_t)BU * k * 8 + (size_t)BU * BT * 8 + BU * 8 + BU * (BT / 32) * 4 + BU * 4 * 2 + BU * 8;
   smem += BU * 8;   // rowid
+  if (m->model == KGE_TRANSH) smem += (size_t)pl.kpad * 4;   // projection factor
   pl.smem = smem;
   KGE_REQUIRE(smem <= 220 * 1024, KGE_E_UNSUPPORTED, "embedding_size %d needs %zu bytes of shared memory", m->d, smem);
   pl.n_blocks = (n + BU - 1) / BU;
@@ -532,6 +566,7 @@ int plan_tiles(const kge_model_t* m, int64_t n, int64_t n_targets, int k, bool t
 
 int tile_mode(int model) {
   if (model == KGE_TORUSE) return MODE_TORUS;
+  if (model == KGE_TRANSH) return MODE_PROJ;
   return (model == KGE_TRANSE || model == KGE_ROTATE) ? MODE_DIST : MODE_DOT;
 }
 
@@ -564,6 +599,7 @@ extern "C" int kge_predict(const kge_model_t* model, const int64_t* heads, const
     case KGE_DISTMULT: predict_kernel<KGE_DISTMULT, V, G, N><<<grid, threads, 0, st>>>(a, out); break; \
     case KGE_ROTATE: predict_kernel<KGE_ROTATE, V, G, N><<<grid, threads, 0, st>>>(a, out); break;     \
     case KGE_TORUSE: predict_kernel<KGE_TORUSE, V, G, N><<<grid, threads, 0, st>>>(a, out); break;     \
+    case KGE_TRANSH: predict_kernel<KGE_TRANSH, V, G, N><<<grid, threads, 0, st>>>(a, out); break;     \
     default: predict_kernel<KGE_COMPLEX, V, G, N><<<grid, threads, 0, st>>>(a, out); break;            \
   }
   KGE_DISPATCH_ROWCFG(c, CALL);
@@ -586,6 +622,8 @@ static int launch_tile(const TileArgs& a, const TilePlan& pl, cudaStream_t st) {
 extern "C" int kge_full_sort_scores(const kge_model_t* model, const int64_t* heads, const int64_t* rels, int64_t n,
                                     int head_is_user, int64_t n_targets, float* out, kge_stream_t stream) {
   if (int e = check_score_model(model)) return e;
+  KGE_REQUIRE(model->model != KGE_TRANSH || rels == nullptr, KGE_E_UNSUPPORTED,
+              "TransH full-sort takes the user->item relation only (transh.py:125-145; no KG scoring in the reference)");
   KGE_REQUIRE(n >= 0 && n_targets >= 1 && n_targets <= model->entity.rows, KGE_E_ARG, "bad n / n_targets");
   if (n == 0) return 0;
   KGE_REQUIRE(heads && out, KGE_E_ARG, "NULL heads / out");
@@ -607,6 +645,7 @@ extern "C" int kge_full_sort_scores(const kge_model_t* model, const int64_t* hea
   switch (tile_mode(model->model)) {
     case MODE_DIST: return launch_tile<MODE_DIST, false>(a, pl, (cudaStream_t)stream);
     case MODE_TORUS: return launch_tile<MODE_TORUS, false>(a, pl, (cudaStream_t)stream);
+    case MODE_PROJ: return launch_tile<MODE_PROJ, false>(a, pl, (cudaStream_t)stream);
     default: return launch_tile<MODE_DOT, false>(a, pl, (cudaStream_t)stream);
   }
 }
@@ -624,6 +663,8 @@ extern "C" int kge_full_sort_topk(const kge_model_t* model, const int64_t* heads
                                   const int64_t* hist_items, int mask_first, int32_t k, int64_t* ids_out,
                                   float* scores_out, void* workspace, int64_t workspace_bytes, kge_stream_t stream) {
   if (int e = check_score_model(model)) return e;
+  KGE_REQUIRE(model->model != KGE_TRANSH || rels == nullptr, KGE_E_UNSUPPORTED,
+              "TransH full-sort takes the user->item relation only (transh.py:125-145; no KG scoring in the reference)");
   KGE_REQUIRE(n >= 0 && n_targets >= 1 && n_targets <= model->entity.rows, KGE_E_ARG, "bad n / n_targets");
   KGE_REQUIRE(k >= 1 && k <= KMAX, KGE_E_UNSUPPORTED, "k=%d outside [1, %d]", k, KMAX);
   KGE_REQUIRE(k <= n_targets, KGE_E_ARG, "k=%d larger than the number of targets", k);
@@ -656,7 +697,8 @@ extern "C" int kge_full_sort_topk(const kge_model_t* model, const int64_t* heads
   const int mode = tile_mode(model->model);
   if (int e = mode == MODE_DIST ? launch_tile<MODE_DIST, true>(a, pl, st)
                                 : (mode == MODE_TORUS ? launch_tile<MODE_TORUS, true>(a, pl, st)
-                                                      : launch_tile<MODE_DOT, true>(a, pl, st)))
+                                   : (mode == MODE_PROJ ? launch_tile<MODE_PROJ, true>(a, pl, st)
+                                                        : launch_tile<MODE_DOT, true>(a, pl, st))))
     return e;
   const int warps = 8;
   const int64_t mg = (n + warps - 1) / warps;
@@ -726,7 +768,8 @@ int kge_topk_rows_indirect(const kge_model_t* model, const int64_t* heads, const
   const int mode = tile_mode(model->model);
   auto kern = mode == MODE_DIST ? fullsort_tile_kernel<MODE_DIST, true>
                                 : (mode == MODE_TORUS ? fullsort_tile_kernel<MODE_TORUS, true>
-                                                      : fullsort_tile_kernel<MODE_DOT, true>);
+                                   : (mode == MODE_PROJ ? fullsort_tile_kernel<MODE_PROJ, true>
+                                                        : fullsort_tile_kernel<MODE_DOT, true>));
   KGE_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fp.tp.smem));
   const int warps = 8;
   const int64_t ra = n < FB_SPLIT_ROWS ? n : FB_SPLIT_ROWS;

@@ -67,7 +67,10 @@ struct ScoreArgs {
 //   RotatE   q = rot(h, theta) = (re | im) (rotate.py:61-66)
 //   ComplEx  q = (hr*rr | hi*rr + hr*ri - hi*ri)   (complex.py:53-62 regrouped by tail part)
 //   TorusE   q = frac(h) + frac(r)         (toruse.py:66-76; torch.frac keeps the sign: x - trunc(x))
-__device__ __forceinline__ void query_value(const ScoreArgs& a, int64_t qrow, int c, float& q0, float& q1) {
+//   TransH   q = h * (1 - sum(w) * w) + r  (transh.py:53-58, 73-74; `proj` = the factor vector of the relation, built
+//                                           by the caller -- every query row shares the user->item relation)
+__device__ __forceinline__ void query_value(const ScoreArgs& a, int64_t qrow, int c, float& q0, float& q1,
+                                            const float* proj = nullptr) {
   const int d = a.m.d;
   const int model = a.m.model;
   const kge_table_t& HT = a.head_is_user ? a.m.user : a.m.entity;
@@ -80,6 +83,8 @@ __device__ __forceinline__ void query_value(const ScoreArgs& a, int64_t qrow, in
     q0 = h0 + r0;
   } else if (model == KGE_TORUSE) {
     q0 = fracf_signed(h0) + fracf_signed(r0);
+  } else if (model == KGE_TRANSH) {
+    q0 = h0 * proj[c] + r0;
   } else if (model == KGE_DISTMULT) {
     q0 = h0 * r0;
   } else if (model == KGE_ROTATE) {

@@ -141,7 +141,7 @@ template <int MODEL, int VEC, int G, int NCH>
 __global__ void __launch_bounds__(256, FwdBounds<MODEL, VEC, G, NCH>::MIN_CTAS) train_fwd_kernel(const TrainArgs a) {
   constexpr int E = VEC * NCH;
   constexpr int PH = (MODEL == KGE_ROTATE || MODEL == KGE_COMPLEX) ? 2 : 1;  // head / tail parts
-  constexpr int PR = (MODEL == KGE_COMPLEX) ? 2 : 1;                          // relation parts
+  constexpr int PR = (MODEL == KGE_COMPLEX || MODEL == KGE_TRANSH) ? 2 : 1;   // relation parts (TransH: r, w)
   extern __shared__ float s_racc[];  // [PR][d] user->item relation gradient of this CTA
   __shared__ float s_loss[8];
 
@@ -226,7 +226,28 @@ __global__ void __launch_bounds__(256, FwdBounds<MODEL, VEC, G, NCH>::MIN_CTAS) 
 #pragma unroll
     for (int e = 0; e < E; ++e) { c0[e] = c1[e] = c2[e] = c3[e] = 0.f; acc0[e] = acc1[e] = 0.f; }
     float nact = 0.f;
-    if (MODEL == KGE_TRANSE) {
+    float s_w = 0.f;   // TransH: sum of the hyperplane vector's components
+    if (MODEL == KGE_TRANSH) {
+      // transh.py:73-74: project(e) = e - (e * sum(w)) * w = e * (1 - sum(w) * w); c2 holds the factor.  Then TransE on
+      // the projected rows: c0 = x = h*c2 + r, c1 = w * unit(x - tp*c2 + eps), s_pos = ||x - tp*c2 + eps||
+      float sw = 0.f;
+#pragma unroll
+      for (int e = 0; e < E; ++e) sw += r[PR - 1][e];   // (padding lanes hold zeros)
+      s_w = group_sum<G>(sw);
+      float sp = 0.f;
+#pragma unroll
+      for (int e = 0; e < E; ++e) {
+        c2[e] = 1.f - s_w * r[PR - 1][e];
+        c0[e] = __fmaf_rn(h[0][e], c2[e], r[0][e]);
+        const float dp = frag_valid<VEC, G, NCH>(d, gl, e) ? (c0[e] - tp[0][e] * c2[e] + 1e-6f) : 0.f;
+        c1[e] = dp;
+        sp = __fmaf_rn(dp, dp, sp);
+      }
+      s_pos = sqrtf(group_sum<G>(sp));
+      const float inv_p = s_pos > 0.f ? 1.f / s_pos : 0.f;
+#pragma unroll
+      for (int e = 0; e < E; ++e) c1[e] = __fmul_rn(w, __fmul_rn(c1[e], inv_p));
+    } else if (MODEL == KGE_TRANSE) {
       float sp = 0.f;
 #pragma unroll
       for (int e = 0; e < E; ++e) {
@@ -296,7 +317,34 @@ __global__ void __launch_bounds__(256, FwdBounds<MODEL, VEC, G, NCH>::MIN_CTAS) 
         for (int p = 0; p < PH; ++p) catch_up<VEC, G, NCH>(ET, p, t_id, st, d, gl, a.adam, t[p], a.with_grad);
       }
 
-      if (MODEL == KGE_TRANSE) {
+      if (MODEL == KGE_TRANSH) {
+        float dnv[E];
+        float sn = 0.f;
+#pragma unroll
+        for (int e = 0; e < E; ++e) {
+          dnv[e] = frag_valid<VEC, G, NCH>(d, gl, e) ? (c0[e] - t[0][e] * c2[e] + 1e-6f) : 0.f;
+          sn = __fmaf_rn(dnv[e], dnv[e], sn);
+        }
+        const float nn_ = sqrtf(group_sum<G>(sn));
+        const float z = margin + s_pos - nn_;
+        if (z >= 0.f) {
+          inst_loss += z * w;
+          if (a.with_grad) {
+            const float inv_n = nn_ > 0.f ? 1.f / nn_ : 0.f;
+            nact += 1.f;
+#pragma unroll
+            for (int e = 0; e < E; ++e) {
+              const float gneg = __fmul_rn(w, __fmul_rn(dnv[e], inv_n));   // gradient of the PROJECTED negative tail
+              gh[0][e] += __fsub_rn(c1[e], gneg);                          // ... of x = proj(h) + r
+              gtp[0][e] -= c1[e];                                          // ... of the projected positive tail
+              acc0[e] = __fmaf_rn(gneg, t[0][e], acc0[e]);                 // ... of the factor c2, this tail's share
+              t[0][e] = gneg * c2[e];                                      // back through the projection
+            }
+            frag_atomic_add<VEC, G, NCH>(ET.g[0], t_id, d, gl, t[0]);
+            mark_row(ET, t_id, st.y, step, gl);
+          }
+        }
+      } else if (MODEL == KGE_TRANSE) {
         float sn = 0.f;
 #pragma unroll
         for (int e = 0; e < E; ++e) {
@@ -411,7 +459,28 @@ __global__ void __launch_bounds__(256, FwdBounds<MODEL, VEC, G, NCH>::MIN_CTAS) 
     }
 
     // ---- gradients of head, relation and positive tail from the accumulators ------------------------
-    if (MODEL == KGE_TRANSE) {
+    if (MODEL == KGE_TRANSH) {
+      if (nact > 0.f) {
+        any_grad = true;
+        // gh / gtp hold the gradients of x and of the projected positive tail.  The factor c2 = 1 - s_w * w gets
+        // g_c = g_x*h + g_tp'*tp + sum_j g_tn'_j*tn_j (acc0), and d c2_j / d w_i = -w_j - s_w * [i == j], so
+        // g_w = -s_w * g_c - <g_c, w> on every component.
+        float dot = 0.f;
+#pragma unroll
+        for (int e = 0; e < E; ++e) {
+          acc0[e] = __fmaf_rn(gh[0][e], h[0][e], __fmaf_rn(gtp[0][e], tp[0][e], acc0[e]));
+          dot = __fmaf_rn(acc0[e], r[PR - 1][e], dot);
+        }
+        dot = group_sum<G>(dot);
+#pragma unroll
+        for (int e = 0; e < E; ++e) {
+          gr[0][e] = gh[0][e];
+          gr[PR - 1][e] = frag_valid<VEC, G, NCH>(d, gl, e) ? (-s_w * acc0[e] - dot) : 0.f;
+          gh[0][e] *= c2[e];
+          gtp[0][e] *= c2[e];
+        }
+      }
+    } else if (MODEL == KGE_TRANSE) {
       if (nact > 0.f) {
         any_grad = true;
 #pragma unroll
@@ -732,9 +801,9 @@ bool table_has_state(const kge_table_t& T, bool need_rows) {
 // need_state: gradient accumulators; need_rows: also moments and row states (the row-lazy Adam kernels)
 int check_model(const kge_model_t* m, bool need_state, bool need_rows = true) {
   KGE_REQUIRE(m, KGE_E_ARG, "model is NULL");
-  KGE_REQUIRE(m->model >= KGE_TRANSE && m->model <= KGE_TORUSE, KGE_E_ARG, "unknown model kind %d", m->model);
+  KGE_REQUIRE(m->model >= KGE_TRANSE && m->model <= KGE_TRANSH, KGE_E_ARG, "unknown model kind %d", m->model);
   const int ph = (m->model == KGE_ROTATE || m->model == KGE_COMPLEX) ? 2 : 1;
-  const int pr = (m->model == KGE_COMPLEX) ? 2 : 1;
+  const int pr = (m->model == KGE_COMPLEX || m->model == KGE_TRANSH) ? 2 : 1;
   KGE_REQUIRE(m->user.parts == ph && m->entity.parts == ph && m->relation.parts == pr, KGE_E_ARG,
               "table parts do not match the model kind");
   for (int p = 0; p < ph; ++p) KGE_REQUIRE(m->user.w[p] && m->entity.w[p], KGE_E_ARG, "NULL weight table");
@@ -795,7 +864,7 @@ extern "C" int kge_train_forward(const kge_model_t* model, const kge_batch_t* b,
   const double pr = (double)b->n_rec * b->k_rec, pk = (double)b->n_kg * b->k_kg;
   // (TorusE's training objective is TransE's: TripletMarginLoss on h + r, toruse.py:81-102)
   const int kind = model->model == KGE_TORUSE ? KGE_TRANSE : model->model;
-  if (kind == KGE_TRANSE || kind == KGE_DISTMULT) {
+  if (kind == KGE_TRANSE || kind == KGE_DISTMULT || kind == KGE_TRANSH) {
     a.w_rec = a.w_kg = (float)(1.0 / (pr + pk));
     a.wpos_rec = a.wpos_kg = 0.f;
   } else {
@@ -827,6 +896,7 @@ extern "C" int kge_train_forward(const kge_model_t* model, const kge_batch_t* b,
     case KGE_TRANSE: train_fwd_kernel<KGE_TRANSE, V, G, N><<<grid, threads, smem, st>>>(a); break;      \
     case KGE_DISTMULT: train_fwd_kernel<KGE_DISTMULT, V, G, N><<<grid, threads, smem, st>>>(a); break;  \
     case KGE_ROTATE: train_fwd_kernel<KGE_ROTATE, V, G, N><<<grid, threads, smem, st>>>(a); break;      \
+    case KGE_TRANSH: train_fwd_kernel<KGE_TRANSH, V, G, N><<<grid, threads, smem, st>>>(a); break;      \
     default: train_fwd_kernel<KGE_COMPLEX, V, G, N><<<grid, threads, smem, st>>>(a); break;             \
   }
   if (two_per_warp) {

@@ -858,4 +858,33 @@ class TorusE(FusedKGEModel):
     RELATION_TABLES = ("relation_embedding",)
 
 
-MODELS = {"TransE": TransE, "DistMult": DistMult, "RotatE": RotatE, "ComplEx": ComplEx, "TorusE": TorusE}
+class TransH(FusedKGEModel):
+    """transh.py: TransE on rows projected per relation.  The second relation table `norm_vec` holds the hyperplane
+    vector w; the reference's ``project`` is ``ent - (ent * w.sum()) * w`` (transh.py:73-74), applied to head and both
+    tails before TransE's TripletMarginLoss (transh.py:76-107) and norm (transh.py:53-58).  Recommendation triples
+    read ``relation_embedding.weight[-1]`` but ``norm_vec(ui_relation)`` (transh.py:63, 90): the kernels take one row
+    for both, so a dataset whose [UI-Relation] token is not the last relation id is refused (hopwise's datasets append
+    the token last).  The reference scores users against items only; so does this class."""
+
+    KIND = "TransH"
+    USER_TABLES = ("user_embedding",)
+    ENTITY_TABLES = ("entity_embedding",)
+    RELATION_TABLES = ("relation_embedding", "norm_vec")
+
+    def __init__(self, config, dataset):
+        super().__init__(config, dataset)
+        token_row = int(dataset.field2token_id["relation_id"][dataset.ui_relation])
+        if token_row != self.n_relations - 1:
+            raise NotImplementedError(
+                f"TransH: [UI-Relation] is relation {token_row}, not the last row {self.n_relations - 1}; "
+                "relation_embedding.weight[-1] and norm_vec(ui_relation) would name different rows (transh.py:63, 90)")
+
+    def predict_kg(self, interaction):
+        raise NotImplementedError("the reference TransH has no KG scoring entry points (transh.py)")
+
+    def full_sort_predict_kg(self, interaction):
+        raise NotImplementedError("the reference TransH has no KG scoring entry points (transh.py)")
+
+
+MODELS = {"TransE": TransE, "DistMult": DistMult, "RotatE": RotatE, "ComplEx": ComplEx, "TorusE": TorusE,
+          "TransH": TransH}

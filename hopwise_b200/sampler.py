@@ -211,7 +211,7 @@ class KGSampler(_FilteredUniformSampler):
     """
 
     def __init__(self, dataset=None, distribution="uniform", alpha=1.0, *, heads=None, tails=None, entity_num=None,
-                 stream: MTStream | None = None, device="cuda"):
+                 stream: MTStream | None = None, device="cuda", alias_table=None):
         if distribution not in ("uniform", "popularity"):
             raise NotImplementedError(f"The sampling distribution [{distribution}] has not been implemented.")
         if dataset is not None:
@@ -224,7 +224,7 @@ class KGSampler(_FilteredUniformSampler):
         if distribution == "popularity":
             # sampler.py:318-319: every head occurrence, then every tail occurrence
             cand = np.concatenate([_as_host_ids(heads), _as_host_ids(tails)])
-            self.set_popularity(build_alias_table(cand, alpha))
+            self.set_popularity(alias_table if alias_table is not None else build_alias_table(cand, alpha))
 
     @property
     def used_ids(self):
@@ -251,7 +251,7 @@ class RecSampler:
     """
 
     def __init__(self, phases_or_users, datasets_or_items, n_users=None, n_items=None, distribution="uniform",
-                 alpha=1.0, stream: MTStream | None = None, device="cuda"):
+                 alpha=1.0, stream: MTStream | None = None, device="cuda", alias_table=None):
         if distribution not in ("uniform", "popularity"):
             raise NotImplementedError(f"The sampling distribution [{distribution}] has not been implemented.")
         self.distribution, self.alpha = distribution, alpha
@@ -284,7 +284,11 @@ class RecSampler:
             items = [_as_host_ids(datasets_or_items)]
         if distribution == "popularity":
             # sampler.py:220-224: the item column of every phase's dataset, concatenated -- one table for all phases
-            table = build_alias_table(np.concatenate([_as_host_ids(x) for x in items]), alpha)
+            # (the table depends on the ORDER of the interactions at this moment -- the key order is that of first
+            # occurrence -- and hopwise's evaluation loaders sort their datasets by user later on,
+            # general_dataloader.py:92: a sampler that replaces an existing one takes over its table, `alias_table`)
+            table = alias_table if alias_table is not None else build_alias_table(
+                np.concatenate([_as_host_ids(x) for x in items]), alpha)
             first = next(iter(self._impl.values()))
             first.set_popularity(table)
             for impl in self._impl.values():
@@ -329,6 +333,17 @@ class RecSampler:
         return self.sample_by_key_ids(user_ids, num)
 
 
+def _table_of(sampler):
+    """(keys, prob, alias) arrays of a reference sampler's alias table (sampler.py:68-100: the dicts `prob` and
+    `alias`, in key order), or None when it samples uniformly."""
+    if getattr(sampler, "distribution", "uniform") != "popularity":
+        return None
+    keys = list(sampler.prob.keys())
+    return (np.array([int(k) for k in keys], dtype=np.int64),
+            np.array([float(sampler.prob[k]) for k in keys], dtype=np.float64),
+            np.array([int(sampler.alias[k]) for k in keys], dtype=np.int64))
+
+
 def install_device_samplers(train_data, device="cuda", to_host=True):
     """Swap the two CPU samplers of a hopwise ``KnowledgeBasedDataLoader`` for the device ones, in place:
     ``train_data.general_dataloader._sampler`` (rec negatives) and ``train_data.kg_dataloader._sampler`` (KG
@@ -341,10 +356,10 @@ def install_device_samplers(train_data, device="cuda", to_host=True):
     gen, kg = train_data.general_dataloader, train_data.kg_dataloader
     old = gen._sampler
     rec = RecSampler(list(old.phases), list(old.datasets), distribution=old.distribution, alpha=old.alpha,
-                     stream=stream, device=device).set_phase(old.phase)
+                     stream=stream, device=device, alias_table=_table_of(old)).set_phase(old.phase)
     old_kg = kg._sampler
     kgs = KGSampler(kg._dataset, distribution=getattr(old_kg, "distribution", "uniform"),
-                    alpha=getattr(old_kg, "alpha", 1.0), stream=stream, device=device)
+                    alpha=getattr(old_kg, "alpha", 1.0), stream=stream, device=device, alias_table=_table_of(old_kg))
     kgs.to_host = to_host
     for impl in rec._impl.values():
         impl.to_host = to_host

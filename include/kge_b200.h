@@ -31,8 +31,14 @@ typedef void* kge_stream_t; /* cudaStream_t */
 
 /* KGE_TORUSE (toruse.py): trains exactly like TransE (TripletMarginLoss on h + r, toruse.py:81-102: the train-step
  * kernels take it as KGE_TRANSE) and scores on the torus: -4 * sum(min(x^2, 1 - x^2)), x = frac(h) + frac(r) - frac(t)
- * (toruse.py:66-76, 131-172).  Not a contraction: CUDA-core scoring paths only. */
-enum kge_model_kind { KGE_TRANSE = 0, KGE_DISTMULT = 1, KGE_ROTATE = 2, KGE_COMPLEX = 3, KGE_TORUSE = 4 };
+ * (toruse.py:66-76, 131-172).  Not a contraction: CUDA-core scoring paths only.
+ * KGE_TRANSH (transh.py): TransE on rows projected per relation.  The relation table has two parts, the translation
+ * r and the hyperplane vector w (`norm_vec`); the reference's project() is ent - (ent * sum(w)) * w (transh.py:73-74:
+ * the SUM of w's components, not <ent, w>), i.e. ent * (1 - sum(w) * w) element-wise, applied to head and both tails
+ * before TransE's TripletMarginLoss / norm (transh.py:53-58, 76-107).  Recommendation triples take row
+ * `ui_relation` of both parts.  Scoring: predict and full-sort over items (transh.py:109-145); the reference has no
+ * KG scoring entry points for this model.  CUDA-core scoring paths only. */
+enum kge_model_kind { KGE_TRANSE = 0, KGE_DISTMULT = 1, KGE_ROTATE = 2, KGE_COMPLEX = 3, KGE_TORUSE = 4, KGE_TRANSH = 5 };
 
 enum kge_error {
   KGE_E_ARG = -1,         /* null pointer / negative size */

@@ -33,6 +33,9 @@ def score(model, h, r, t, margin=1.0):
     """h, r, t: lists of float64 arrays (1 or 2 parts) broadcastable on leading dims."""
     if model == "TransE":
         return -np.sqrt(((h[0] + r[0] - t[0]) ** 2).sum(-1))
+    if model == "TransH":   # transh.py:53-58, 73-74
+        c = 1.0 - r[1].sum(-1, keepdims=True) * r[1]
+        return -np.sqrt((((h[0] - t[0]) * c + r[0]) ** 2).sum(-1))
     if model == "TorusE":   # toruse.py:66-76
         frac = lambda a: a - np.trunc(a)   # noqa: E731
         x = (frac(h[0]) + frac(r[0])) - frac(t[0])
@@ -68,6 +71,25 @@ def pair_loss_and_grads(model, h, r, tp, tn, weight, margin=1.0):
         un = np.where(n_n > 0, dn / np.where(n_n > 0, n_n, 1.0), 0.0)
         gx = act * (up - un)
         return (np.maximum(z, 0).sum() * weight, [gx], [gx.copy()], [-act * up], [act * un])
+    if model == "TransH":
+        # transh.py:73-107: TransE on rows scaled by c = 1 - sum(w) * w (project(e) = e - (e * w.sum()) * w).
+        # d c_j / d w_i = -w_j - sum(w) * [i == j]  =>  g_w = -sum(w) * g_c - <g_c, w>
+        w_ = r[1]
+        sw = w_.sum(-1, keepdims=True)
+        c = 1.0 - sw * w_
+        x = h[0] * c + r[0]
+        dp = x - tp[0] * c + EPS_PAIRWISE
+        dn = x - tn[0] * c + EPS_PAIRWISE
+        n_p = np.sqrt((dp * dp).sum(-1, keepdims=True))
+        n_n = np.sqrt((dn * dn).sum(-1, keepdims=True))
+        z = margin + n_p - n_n
+        act = (z >= 0).astype(np.float64) * weight
+        up = np.where(n_p > 0, dp / np.where(n_p > 0, n_p, 1.0), 0.0)
+        un = np.where(n_n > 0, dn / np.where(n_n > 0, n_n, 1.0), 0.0)
+        gx, gtp_, gtn_ = act * (up - un), -act * up, act * un
+        gc = gx * h[0] + gtp_ * tp[0] + gtn_ * tn[0]
+        gw = -sw * gc - (gc * w_).sum(-1, keepdims=True)
+        return (np.maximum(z, 0).sum() * weight, [gx * c], [gx, gw], [gtp_ * c], [gtn_ * c])
     if model == "DistMult":
         sp = (h[0] * r[0] * tp[0]).sum(-1, keepdims=True)
         sn = (h[0] * r[0] * tn[0]).sum(-1, keepdims=True)
@@ -127,7 +149,7 @@ def pair_loss_and_grads(model, h, r, tp, tn, weight, margin=1.0):
 
 def loss_weights(model, n_rec, n_kg):
     """Per-pair weights of the rec and KG segments in the scalar loss."""
-    if model in ("TransE", "DistMult", "TorusE"):
+    if model in ("TransE", "DistMult", "TorusE", "TransH"):
         w = 1.0 / (n_rec + n_kg)
         return w, w
     return (0.5 / n_rec if n_rec else 0.0), (0.5 / n_kg if n_kg else 0.0)

@@ -34,6 +34,8 @@ TABLE_NAMES = {
     "DistMult": (["user_embedding"], ["entity_embedding"], ["relation_embedding"]),
     # toruse.py:31-48: TransE's tables
     "TorusE": (["user_embedding"], ["entity_embedding"], ["relation_embedding"]),
+    # transh.py:31-48: the second relation table is the hyperplane vector
+    "TransH": (["user_embedding"], ["entity_embedding"], ["relation_embedding", "norm_vec"]),
     "RotatE": (
         ["user_embedding", "user_embedding_im"],
         ["entity_embedding", "entity_embedding_im"],
@@ -94,6 +96,11 @@ class OracleKGE(nn.Module):
         # token id for loss/predict and weight[-1] for full_sort_predict.
         if self.model in ("TransE", "DistMult", "TorusE"):   # toruse.py:53, 121, 131
             return self.shapes.n_relations - 1
+        if self.model == "TransH":
+            # transh.py:63, 90: relation_embedding.weight[-1] but norm_vec(ui_relation) -- one row only when the token
+            # is the last relation id, which is the case the product supports
+            assert self.shapes.ui_relation == self.shapes.n_relations - 1
+            return self.shapes.n_relations - 1
         if self.model == "ComplEx" and full_sort:
             return self.shapes.n_relations - 1
         return self.shapes.ui_relation
@@ -103,6 +110,11 @@ class OracleKGE(nn.Module):
         m = self.model
         if m == "TransE":
             return -torch.norm(h[0] + r[0] - t[0], p=2, dim=-1)
+        if m == "TransH":   # transh.py:53-58, 73-74: project(e) = e - (e * w.sum()) * w
+            w = r[1]
+            sw = w.sum(dim=-1, keepdim=True)
+            proj = lambda e: e - (e * sw) * w   # noqa: E731
+            return -torch.norm(proj(h[0]) + r[0] - proj(t[0]), p=2, dim=-1)
         if m == "TorusE":   # toruse.py:66-76 (frac_ on detached copies: x - trunc(x), sign kept)
             x = (torch.frac(h[0]) + torch.frac(r[0])) - torch.frac(t[0])
             return -(4 * torch.min(x ** 2, 1 - x ** 2).sum(dim=-1))
@@ -142,6 +154,14 @@ class OracleKGE(nn.Module):
         if self.model in ("TransE", "TorusE"):   # toruse.py:81-102 is transe.py:75-98: the torus only scores
             anchor = torch.cat([u[0] + ur[0], h[0] + kr[0]])
             pos, neg = torch.cat([ip[0], tp[0]]), torch.cat([ineg[0], tn[0]])
+            return nn.functional.triplet_margin_loss(anchor, pos, neg, margin=self.shapes.margin, p=2)
+        if self.model == "TransH":   # transh.py:76-107: project every row with its triple's relation, then TransE's loss
+            def proj(e, rr):
+                return e - (e * rr[1].sum(dim=1, keepdim=True)) * rr[1]
+
+            anchor = torch.cat([proj(u[0], ur) + ur[0], proj(h[0], kr) + kr[0]])
+            pos = torch.cat([proj(ip[0], ur), proj(tp[0], kr)])
+            neg = torch.cat([proj(ineg[0], ur), proj(tn[0], kr)])
             return nn.functional.triplet_margin_loss(anchor, pos, neg, margin=self.shapes.margin, p=2)
         if self.model == "DistMult":
             cat = lambda a, b: [torch.cat([x, y]) for x, y in zip(a, b)]  # noqa: E731

@@ -86,10 +86,11 @@ def test_device_samplers_reproduce_the_reference_loader(tmp_path):
         assert kgs.used_ids[h] == set(int(x) for x in kg_ref_used[h])
 
 
-def test_popularity_and_dynamic_sampling_inside_the_reference_loader(tmp_path):
-    """train_neg_sample_args = {distribution: popularity, alpha: 0.5, dynamic: True, candidate_num: 3}: hopwise's own
-    `_neg_sampling` (abstract_dataloader.py:166-183) draws 3 popularity-biased candidates per row from the sampler and
-    keeps the one the model scores best.  With the device samplers installed -- and the fused model doing the scoring in
+@pytest.mark.parametrize("mode", ["popularity", "dynamic", "popularity+dynamic"])
+def test_popularity_and_dynamic_sampling_inside_the_reference_loader(tmp_path, mode):
+    """train_neg_sample_args with distribution: popularity (alpha 0.5) and / or dynamic: True (candidate_num 3):
+    hopwise's own `_neg_sampling` (abstract_dataloader.py:166-183) draws the candidates from the sampler and keeps
+    the one the model scores best.  With the device samplers installed -- and the fused model doing the scoring in
     both arms -- the loader yields the batches it yields with the reference's CPU samplers."""
     oref.import_ref()
     import hopwise_b200
@@ -98,22 +99,24 @@ def test_popularity_and_dynamic_sampling_inside_the_reference_loader(tmp_path):
 
     torch.zeros(1, device="cuda")
     visible = os.environ.get("CUDA_VISIBLE_DEVICES")
-    args = {"train_neg_sample_args": {"distribution": "popularity", "sample_num": 1, "alpha": 0.5, "dynamic": True,
-                                      "candidate_num": 3}}
+    pop, dyn = "popularity" in mode, "dynamic" in mode
+    args = {"train_neg_sample_args": {"distribution": "popularity" if pop else "uniform", "sample_num": 1,
+                                      "alpha": 0.5 if pop else 1.0, "dynamic": dyn, "candidate_num": 3 if dyn else 0}}
     cwd = os.getcwd()
     os.chdir(tmp_path)
     try:
         batches = {}
         for arm in ("ref", "dev"):
             config, train, _, _ = _pipeline(**args)
-            assert train.general_dataloader._sampler.distribution == "popularity"
+            assert train.general_dataloader._sampler.distribution == ("popularity" if pop else "uniform")
             torch.manual_seed(7)
             model = hopwise_b200.TransE(config, train.dataset).to("cuda")
             model.device = torch.device("cuda")   # (the config says cpu: this pipeline keeps hopwise's loaders on the host)
             if arm == "dev":
                 install_device_samplers(train)
-                assert train.kg_dataloader._sampler.pop is not None
-            train.get_model(model)
+                assert (train.kg_dataloader._sampler.pop is not None) == pop
+            if dyn:
+                train.get_model(model)
             train.set_mode(KGDataLoaderState.RSKG)
             got = []
             for i, b in enumerate(train):
@@ -130,5 +133,8 @@ def test_popularity_and_dynamic_sampling_inside_the_reference_loader(tmp_path):
     assert len(batches["ref"]) == len(batches["dev"]) == 6
     for i, (a, b) in enumerate(zip(batches["dev"], batches["ref"])):
         assert set(a) == set(b)
+        for k in ("neg_tail_id", "head_id", "user_id", "item_id", "neg_item_id"):
+            bad = (a[k] != b[k]).nonzero().flatten()
+            assert bad.numel() == 0, f"batch {i} field {k}: {bad.numel()} of {a[k].numel()} differ, first at {bad[:5].tolist()}"
         for k in b:
             assert torch.equal(a[k], b[k]), f"batch {i} field {k}"

@@ -57,11 +57,12 @@ def test_scores_match_reference(name, tag):
     b = _batch(g, 0)
     with torch.no_grad():
         np.testing.assert_allclose(m.predict(b).numpy(), g["predict"], rtol=1e-6, atol=1e-7)
-        np.testing.assert_allclose(m.predict_kg(b).numpy(), g["predict_kg"], rtol=1e-6, atol=1e-7)
         fs = m.full_sort_predict({"user_id": torch.from_numpy(g["fullsort_users"])})
         np.testing.assert_allclose(fs.numpy(), g["fullsort"], rtol=1e-6, atol=1e-7)
-        kb = {"head_id": b["head_id"][:5], "relation_id": b["relation_id"][:5]}
-        np.testing.assert_allclose(m.full_sort_predict_kg(kb).numpy(), g["fullsort_kg"], rtol=1e-6, atol=1e-7)
+        if "predict_kg" in g.files:   # (transh.py scores users against items only)
+            np.testing.assert_allclose(m.predict_kg(b).numpy(), g["predict_kg"], rtol=1e-6, atol=1e-7)
+            kb = {"head_id": b["head_id"][:5], "relation_id": b["relation_id"][:5]}
+            np.testing.assert_allclose(m.full_sort_predict_kg(kb).numpy(), g["fullsort_kg"], rtol=1e-6, atol=1e-7)
 
 
 @pytest.mark.parametrize("name", MODELS)

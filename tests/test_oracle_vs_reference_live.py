@@ -21,7 +21,7 @@ from oracle import mt19937 as omt  # noqa: E402
 
 pytestmark = pytest.mark.skipif(not reference_available(), reason="reference tree not present")
 
-MODELS = ("TransE", "RotatE", "DistMult", "ComplEx", "TorusE")
+MODELS = ("TransE", "RotatE", "DistMult", "ComplEx", "TorusE", "TransH")
 
 
 def _ref_classes():
@@ -32,8 +32,10 @@ def _ref_classes():
     from hopwise.model.knowledge_graph_embedding_recommender.rotate import RotatE
     from hopwise.model.knowledge_graph_embedding_recommender.toruse import TorusE
     from hopwise.model.knowledge_graph_embedding_recommender.transe import TransE
+    from hopwise.model.knowledge_graph_embedding_recommender.transh import TransH
 
-    return {"TransE": TransE, "RotatE": RotatE, "DistMult": DistMult, "ComplEx": ComplEx, "TorusE": TorusE}, Interaction
+    return {"TransE": TransE, "RotatE": RotatE, "DistMult": DistMult, "ComplEx": ComplEx, "TorusE": TorusE,
+            "TransH": TransH}, Interaction
 
 
 @pytest.mark.parametrize("name", MODELS)
@@ -62,21 +64,26 @@ def test_loss_gradients_and_scores_match_the_reference(name, case):
         assert kr == ko
         gr = pr.grad.numpy() if pr.grad is not None else np.zeros_like(pr.detach().numpy())
         go = po.grad.numpy() if po.grad is not None else np.zeros_like(gr)
-        np.testing.assert_allclose(go, gr, rtol=1e-5, atol=1e-8, err_msg=kr)
+        # (TransH: the reference looks the hyperplane row up twice per projection, so its autograd adds the two
+        # paths' fp32 contributions in another order; elements that nearly cancel differ by ~1e-8 absolute)
+        np.testing.assert_allclose(go, gr, rtol=1e-5, atol=5e-8 if name == "TransH" else 1e-8, err_msg=kr)
 
     with torch.no_grad():
         np.testing.assert_allclose(ora.predict(to_cpu_batch(b)).numpy(), ref.predict(inter).numpy(), rtol=1e-5, atol=1e-6)
-        np.testing.assert_allclose(ora.predict_kg(to_cpu_batch(b)).numpy(), ref.predict_kg(inter).numpy(), rtol=1e-5,
-                                   atol=1e-6)
+        has_kg = hasattr(ref, "predict_kg")   # transh.py scores users against items only
+        if has_kg:
+            np.testing.assert_allclose(ora.predict_kg(to_cpu_batch(b)).numpy(), ref.predict_kg(inter).numpy(), rtol=1e-5,
+                                       atol=1e-6)
         users = torch.as_tensor(rng.integers(1, U, 6), dtype=torch.long)
         fr = ref.full_sort_predict(Interaction({"user_id": users})).view(-1, I).numpy()
         fo = ora.full_sort_predict({"user_id": users}).numpy()
         np.testing.assert_allclose(fo, fr, rtol=1e-5, atol=1e-6)
-        kb = {"head_id": torch.as_tensor(b["head_id"][:5], dtype=torch.long),
-              "relation_id": torch.as_tensor(b["relation_id"][:5], dtype=torch.long)}
-        fr = ref.full_sort_predict_kg(Interaction(kb)).view(-1, E).numpy()
-        fo = ora.full_sort_predict_kg(kb).numpy()
-        np.testing.assert_allclose(fo, fr, rtol=1e-5, atol=1e-6)
+        if has_kg:
+            kb = {"head_id": torch.as_tensor(b["head_id"][:5], dtype=torch.long),
+                  "relation_id": torch.as_tensor(b["relation_id"][:5], dtype=torch.long)}
+            fr = ref.full_sort_predict_kg(Interaction(kb)).view(-1, E).numpy()
+            fo = ora.full_sort_predict_kg(kb).numpy()
+            np.testing.assert_allclose(fo, fr, rtol=1e-5, atol=1e-6)
 
 
 @pytest.mark.parametrize("case", range(5))
