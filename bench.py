@@ -207,7 +207,9 @@ def time_train_e2e(model, host_batches, steps, warmup, world, device):
     (hopwise_b200.loader.DevicePrefetcher); every step's copy is inside the timed region."""
     from hopwise_b200.loader import DevicePrefetcher, pack_batch
 
-    host_batches = [pack_batch(b) for b in host_batches]   # the loader's side: one pinned buffer per batch
+    # the loader's side: one pinned buffer per batch, ids as int32 (row indices; the copy stream widens them on the
+    # device) -- half the bytes of the int64 vectors over PCIe, which is what bounds this loop
+    host_batches = [pack_batch(b, narrow=True) for b in host_batches]
     nb = len(host_batches)
     stream = torch.cuda.current_stream()
 
@@ -563,7 +565,7 @@ def main():
     host_t = [{k: torch.from_numpy(v).pin_memory() for k, v in b.items()} for b in host]
     dev_t = [{k: v.to(device) for k, v in b.items()} for b in host_t]
     flush_buf = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device=device)
-    h2d = sum(v.numel() * 8 for v in host_t[0].values())
+    h2d = sum(v.numel() * 4 for v in host_t[0].values())   # staged as int32 (time_train_e2e)
     peaks = measured_peaks()
 
     with ClockSampler(local) as clocks:

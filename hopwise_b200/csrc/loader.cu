@@ -35,7 +35,35 @@ __global__ void __launch_bounds__(256) gather_columns_kernel(const GatherArgs a)
   }
 }
 
+// ids staged as int32 over PCIe (every id is a row index below 2^31), widened to the int64 the kernels read
+__global__ void __launch_bounds__(256) widen_ids_kernel(const int32_t* __restrict__ src, int64_t* __restrict__ dst,
+                                                        int64_t n) {
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  const int64_t quads = n / 4;
+  for (int64_t q = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; q < quads; q += stride) {
+    const int4 v = __ldg(reinterpret_cast<const int4*>(src) + q);
+    reinterpret_cast<longlong2*>(dst)[2 * q] = make_longlong2(v.x, v.y);
+    reinterpret_cast<longlong2*>(dst)[2 * q + 1] = make_longlong2(v.z, v.w);
+  }
+  for (int64_t i = quads * 4 + (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) dst[i] = src[i];
+}
+
 }  // namespace
+
+extern "C" int kge_widen_ids_i32(const int32_t* src, int64_t* dst, int64_t n, kge_stream_t stream) {
+  KGE_REQUIRE(n >= 0, KGE_E_ARG, "negative n");
+  if (n == 0) return 0;
+  KGE_REQUIRE(src && dst, KGE_E_ARG, "NULL argument");
+  KGE_REQUIRE(((reinterpret_cast<uintptr_t>(src) | reinterpret_cast<uintptr_t>(dst)) & 15) == 0, KGE_E_ARG,
+              "buffers must be 16-byte aligned");
+  int64_t grid = (n / 4 + 255) / 256;
+  const int64_t cap = (int64_t)kge_num_sms() * 8;
+  if (grid > cap) grid = cap;
+  if (grid < 1) grid = 1;
+  widen_ids_kernel<<<(int)grid, 256, 0, (cudaStream_t)stream>>>(src, dst, n);
+  KGE_LAUNCH_CHECK();
+  return 0;
+}
 
 extern "C" int kge_gather_columns(const int64_t* const* columns, int32_t n_columns, int64_t rows, const int64_t* index,
                                   int64_t n, int64_t* const* outs, int32_t* status, kge_stream_t stream) {

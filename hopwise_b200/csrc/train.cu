@@ -239,7 +239,10 @@ __global__ void __launch_bounds__(256, FwdBounds<MODEL, VEC, G, NCH>::MIN_CTAS) 
       for (int e = 0; e < E; ++e) {
         c2[e] = 1.f - s_w * r[PR - 1][e];
         c0[e] = __fmaf_rn(h[0][e], c2[e], r[0][e]);
-        const float dp = frag_valid<VEC, G, NCH>(d, gl, e) ? (c0[e] - tp[0][e] * c2[e] + 1e-6f) : 0.f;
+        // (projected tails as explicit products: the positive and the negative residual must be formed by identical
+        // operations -- a product contracted into the subtraction on one side only leaves a 1-ulp residue where a
+        // row is both the positive and the negative of a pair, and Adam turns 5e-10 of gradient into 4e-5 of weight)
+        const float dp = frag_valid<VEC, G, NCH>(d, gl, e) ? (__fsub_rn(c0[e], __fmul_rn(tp[0][e], c2[e])) + 1e-6f) : 0.f;
         c1[e] = dp;
         sp = __fmaf_rn(dp, dp, sp);
       }
@@ -322,7 +325,7 @@ __global__ void __launch_bounds__(256, FwdBounds<MODEL, VEC, G, NCH>::MIN_CTAS) 
         float sn = 0.f;
 #pragma unroll
         for (int e = 0; e < E; ++e) {
-          dnv[e] = frag_valid<VEC, G, NCH>(d, gl, e) ? (c0[e] - t[0][e] * c2[e] + 1e-6f) : 0.f;
+          dnv[e] = frag_valid<VEC, G, NCH>(d, gl, e) ? (__fsub_rn(c0[e], __fmul_rn(t[0][e], c2[e])) + 1e-6f) : 0.f;
           sn = __fmaf_rn(dnv[e], dnv[e], sn);
         }
         const float nn_ = sqrtf(group_sum<G>(sn));

@@ -257,6 +257,10 @@ int kge_topk_metric_sums(const int32_t* rec_topk, int64_t n, int32_t k, double* 
 int kge_gather_columns(const int64_t* const* columns, int32_t n_columns, int64_t rows, const int64_t* index,
                        int64_t n, int64_t* const* outs, int32_t* status, kge_stream_t stream);
 
+/* kge_widen_ids_i32: dst[i] = src[i] for ids a loader staged as int32 (half the host->device bytes of the int64 id
+ * vectors hopwise's Interaction holds, trainer.py:250-256; every id is a row index below 2^31).  16-byte aligned. */
+int kge_widen_ids_i32(const int32_t* src, int64_t* dst, int64_t n, kge_stream_t stream);
+
 /* ---- negative sampling -------------------------------------------------------------------
  * kge_sample_negatives: AbstractSampler.sample_by_key_ids with uniform sampling
  * (sampler.py:140-183, 226-227, 315-316) on numpy's MT19937 stream, bit for bit.

@@ -352,7 +352,17 @@ def test_device_prefetcher_preserves_batches_and_training_result():
     from hopwise_b200.loader import pack_batch
 
     packed = [pack_batch(b) for b in host]   # one copy per step instead of seven
-    assert packed[0].base.is_pinned() and packed[0].base.numel() == sum(v.numel() for v in host[0].values())
+    assert packed[0].base.is_pinned() and packed[0].base.numel() == (sum(v.numel() for v in host[0].values()) + 3) // 4 * 4
+    # ids staged as int32 and widened on the device (kge_widen_ids_i32): the consumer sees the same int64 vectors
+    narrow = [pack_batch(b, narrow=True) for b in host]
+    assert narrow[0].base.dtype == torch.int32 and narrow[0].base.nbytes * 2 == packed[0].base.nbytes
+    for i, db in enumerate(DevicePrefetcher(narrow, "cuda")):
+        for k in host[i]:
+            assert db[k].dtype == torch.int64 and torch.equal(db[k].cpu(), host[i][k])
+    for k, v in narrow[2].to("cuda").items():
+        assert v.dtype == torch.int64 and torch.equal(v.cpu(), host[2][k])
+    with pytest.raises(ValueError):
+        pack_batch({"user_id": np.array([1, 2 ** 31])}, narrow=True)
     for db in DevicePrefetcher(packed, "cuda", depth=3):
         assert set(db) == set(host[0]) and all(t.is_cuda for t in db.values())
         m2.calculate_loss(db).backward()
