@@ -201,10 +201,16 @@ def time_train_device(model, dev_batches, steps, warmup, flush_buf, world):
     return fwd, upd, float(loss.item())   # per-step milliseconds (forward / backward = exchange + Adam)
 
 
-def time_train_e2e(model, host_batches, steps, warmup, world, device):
-    """The trainer's loop body from pinned host ids: H2D of the step's 7 id vectors, loss, loss.item()
-    (D2H, trainer.py:259), backward.  The copies run one batch ahead on a side stream
-    (hopwise_b200.loader.DevicePrefetcher); every step's copy is inside the timed region."""
+def time_train_e2e(model, host_batches, steps, warmup, world, device, reference_order=False):
+    """The training loop from pinned host ids through the public API: H2D of the step's 7 id vectors, the step, a
+    device->host read of every step's loss.  The copies run one batch ahead on a side stream
+    (hopwise_b200.loader.DevicePrefetcher); every step's copy and every loss read are inside the timed region.
+
+    Two orders.  `reference_order`: loss = calculate_loss(); loss.item(); loss.backward() -- the reference trainer's
+    body (trainer.py:257-263), whose mid-step sync leaves the GPU idle while the host turns around.  Default: the
+    step is issued as one call (model.train_step) and the loss of step i is read while step i+1 runs -- every step's
+    loss still crosses to the host inside the timed region, one step late (FusedKGTrainer itself reads the losses
+    once per epoch)."""
     from hopwise_b200.loader import DevicePrefetcher, pack_batch
 
     # the loader's side: one pinned buffer per batch, ids as int32 (row indices; the copy stream widens them on the
@@ -213,17 +219,27 @@ def time_train_e2e(model, host_batches, steps, warmup, world, device):
     nb = len(host_batches)
     stream = torch.cuda.current_stream()
 
+    pending = []
+
     def one(db):
-        loss = model.calculate_loss(db)
-        val = loss.item()   # trainer.py:259 -- the per-step device->host sync of the reference loop
-        loss.backward()
-        return val
+        if reference_order:
+            loss = model.calculate_loss(db)
+            val = loss.item()   # trainer.py:259 -- the per-step device->host sync of the reference loop
+            loss.backward()
+            return val
+        pending.append(model.train_step(db))
+        return pending.pop(0).item() if len(pending) > 1 else None   # the previous step's loss
+
+    def drain():
+        while pending:
+            pending.pop(0).item()
 
     warmup = max(warmup, nb)   # every pinned batch has been through one H2D copy before the timed region (the
     #                            first copy out of a pinned buffer costs ~1 ms extra)
     loader = DevicePrefetcher([host_batches[i % nb] for i in range(warmup)], device)
     for db in loader:
         one(db)
+    drain()
     loader.batches = [host_batches[(warmup + i) % nb] for i in range(steps)]
     barrier(world)
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -231,7 +247,8 @@ def time_train_e2e(model, host_batches, steps, warmup, world, device):
     e0.record(stream)
     for db in loader:
         one(db)
-        stamps.append(time.perf_counter())   # (each step ends with a host sync: loss.item())
+        stamps.append(time.perf_counter())   # (each step ends with a host sync on a loss)
+    drain()                                  # the last step's loss, still inside the timed region
     e1.record(stream)
     barrier(world)
     per_step = np.diff(np.array(stamps)) * 1e3
@@ -597,6 +614,8 @@ def main():
     e2e_ms, e2e_median_ms, e2e_max_ms = time_train_e2e(model, host_t, args.steps, args.warmup, world, device)
     e2e_ms = max_over_ranks(e2e_ms / args.steps, device, world)
     e2e_value = world * triples_step / (e2e_ms * 1e-3)
+    ref_order_ms, _, _ = time_train_e2e(model, host_t, args.steps, args.warmup, world, device, reference_order=True)
+    ref_order_ms = max_over_ranks(ref_order_ms / args.steps, device, world)
 
     bpt = bytes_per_triple(w["model"], w["d"], w["k"])
     achieved = triples_step * bpt / (step_ms * 1e-3) / 1e9
@@ -621,7 +640,12 @@ def main():
             "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": config,
             "e2e": {"value": e2e_value, "unit": "triples/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4,
-                    "ms_per_step": e2e_ms, "median_ms_per_step": e2e_median_ms, "max_ms_per_step": e2e_max_ms},
+                    "ms_per_step": e2e_ms, "median_ms_per_step": e2e_median_ms, "max_ms_per_step": e2e_max_ms,
+                    "what": "pinned int32 ids -> H2D (copy stream, one batch ahead) -> model.train_step -> loss.item() of "
+                            "the previous step while this one runs; all inside the timed region",
+                    "reference_loop_order_ms_per_step": ref_order_ms,
+                    "reference_loop_order": "calculate_loss -> loss.item() -> backward (trainer.py:257-263): the "
+                                            "mid-step sync idles the GPU while the host turns around"},
             # this library's kernels in the timed region: forward + Adam per step, plus the pack / add kernels of
             # the row-sparse exchange when a table takes that route (NCCL's own kernels are not counted)
             "gpu_launches": args.steps * ((1 if exchange is not None and exchange.owner_adam else 2)
@@ -737,6 +761,12 @@ def main():
                     b = next(it)
                     mx.train_step(b)
                 torch.cuda.synchronize()
+                # as FusedKGTrainer runs an epoch: losses stay on the device, one sync at the end
+                t0 = time.perf_counter()
+                held = [mx.train_step(next(it)) for _ in range(n_steps)]
+                total = float(torch.stack(held).double().sum().item())
+                free_s = (time.perf_counter() - t0) / n_steps
+                del held
                 stamps = [time.perf_counter()]
                 for _ in range(n_steps):
                     b = next(it)
@@ -744,11 +774,6 @@ def main():
                     stamps.append(time.perf_counter())
                 torch.cuda.synchronize()
                 per = np.diff(np.array(stamps))
-                # and as FusedKGTrainer runs an epoch: losses stay on the device, one sync at the end
-                t0 = time.perf_counter()
-                held = [mx.train_step(next(it)) for _ in range(n_steps)]
-                total = float(torch.stack(held).double().sum().item())
-                free_s = (time.perf_counter() - t0) / n_steps
                 extras["cfg2_b2048_device_loader"] = {
                     "what": "loader (order + gathers + KG and rec negative sampling) + fused step + loss.item(), wall clock",
                     "ms_per_step": float(per.mean()) * 1e3, "median_ms_per_step": float(np.median(per)) * 1e3,

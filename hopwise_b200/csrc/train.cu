@@ -237,7 +237,9 @@ __global__ void __launch_bounds__(256, FwdBounds<MODEL, VEC, G, NCH>::MIN_CTAS) 
       float sp = 0.f;
 #pragma unroll
       for (int e = 0; e < E; ++e) {
-        c2[e] = 1.f - s_w * r[PR - 1][e];
+        // (explicit roundings: the compiler rematerialises this factor at its uses, and a product contracted into
+        // the subtraction at one use only would give the positive and the negative tail different factors)
+        c2[e] = __fsub_rn(1.f, __fmul_rn(s_w, r[PR - 1][e]));
         c0[e] = __fmaf_rn(h[0][e], c2[e], r[0][e]);
         // (projected tails as explicit products: the positive and the negative residual must be formed by identical
         // operations -- a product contracted into the subtraction on one side only leaves a 1-ulp residue where a

@@ -186,6 +186,10 @@ class DevicePrefetcher:
             nxt += 1
             if used[idx]:
                 self._stream.wait_event(self._released[idx])
+                # the slot's previous host buffer is only kept alive by the slot (the raw cudaMemcpyAsync is invisible
+                # to torch's pinned allocator): its DMA must have run before the reference is dropped -- in a loop
+                # that never syncs (FusedKGTrainer's epoch) the GPU may lag the host by several batches
+                self._copied[idx].synchronize()
             db = self._stage(self._slots[idx], b)
             self._copied[idx].record(self._stream)
             queue.append((db, idx))

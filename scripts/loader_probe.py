@@ -45,3 +45,32 @@ for sync in (False, True):
     timed("kg sampler only", lambda: loader.kg_sampler.sample_by_entity_ids(b0["head_id"], 1), sync)
     timed("rec sampler only", lambda: loader.rec_sampler.sample_by_user_ids(b0["user_id"], b0["item_id"], 1), sync)
     timed("gather only", lambda: loader._take(loader.kg_order, (loader.kg_head, loader.kg_rel, loader.kg_tail)), sync)
+
+# the bench's sequence: a no-sync loop that keeps every step's loss, then one read at the end
+for hold in (False, True, False, True):
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    held = []
+    for _ in range(N):
+        loss = mx.train_step(next(it))
+        if hold:
+            held.append(loss)
+    host = time.perf_counter() - t0
+    if hold:
+        total = float(torch.stack(held).double().sum().item())
+    torch.cuda.synchronize()
+    print(f"no-sync loop, keep losses={hold}: host {host / N * 1e6:.1f} us  wall {(time.perf_counter() - t0) / N * 1e6:.1f} us")
+big = torch.empty(2 * 1024 ** 3, dtype=torch.uint8, device=dev)
+del big
+torch.cuda.empty_cache()
+for hold in (False, True):
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    held = []
+    for _ in range(N):
+        loss = mx.train_step(next(it))
+        if hold:
+            held.append(loss)
+    host = time.perf_counter() - t0
+    torch.cuda.synchronize()
+    print(f"after empty_cache, no-sync loop, keep losses={hold}: host {host / N * 1e6:.1f} us  wall {(time.perf_counter() - t0) / N * 1e6:.1f} us")
