@@ -48,6 +48,7 @@ for sync in (False, True):
 
 # the bench's sequence: a no-sync loop that keeps every step's loss, then one read at the end
 for hold in (False, True, False, True):
+    it = iter(loader)
     torch.cuda.synchronize()
     t0 = time.perf_counter()
     held = []
@@ -64,6 +65,7 @@ big = torch.empty(2 * 1024 ** 3, dtype=torch.uint8, device=dev)
 del big
 torch.cuda.empty_cache()
 for hold in (False, True):
+    it = iter(loader)
     torch.cuda.synchronize()
     t0 = time.perf_counter()
     held = []
