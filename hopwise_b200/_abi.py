@@ -174,6 +174,33 @@ def ptr(t):
     return None if t is None else t.data_ptr()
 
 
+class on_device:
+    """``with on_device(dev):`` like torch.cuda.device(dev), but free when `dev` is already current (the usual case;
+    torch's guard costs ~5 us of host time per use, which the reference-batch loop pays several times per step)."""
+
+    __slots__ = ("idx", "prev")
+
+    def __init__(self, device):
+        import torch
+
+        idx = getattr(device, "index", device)
+        self.idx = torch.cuda.current_device() if idx is None else int(idx)
+
+    def __enter__(self):
+        import torch
+
+        self.prev = torch.cuda.current_device()
+        if self.prev != self.idx:
+            torch.cuda.set_device(self.idx)
+
+    def __exit__(self, *exc):
+        if self.prev != self.idx:
+            import torch
+
+            torch.cuda.set_device(self.prev)
+        return False
+
+
 def stream_ptr():
     """cudaStream_t of torch's current stream on the current device (the raw getter: torch.cuda.current_stream()
     builds a Stream object, ~10 us of host time per call on the step's critical path)."""

@@ -48,7 +48,7 @@ class PackedBatch:
         dev = self.base.to(device, non_blocking=True)
         if self.narrow:
             wide = torch.empty(dev.numel(), dtype=torch.int64, device=dev.device)
-            with torch.cuda.device(dev.device):
+            with _abi.on_device(dev.device):
                 _widen(dev, wide, _abi.stream_ptr())
             dev = wide
         return self.views(dev)
@@ -159,7 +159,7 @@ class DevicePrefetcher:
                     with torch.cuda.stream(self._stream):
                         wide = torch.empty(base.numel(), dtype=torch.int64, device=self.device)
                     slot["dev:__wide__"] = wide
-                with torch.cuda.device(self.device):
+                with _abi.on_device(self.device):
                     _widen(base, wide[: base.numel()], sptr)
                 base = wide[: base.numel()]
             return batch.views(base)
@@ -324,7 +324,7 @@ class DeviceKGLoader:
 
     def __init__(self, inter_user, inter_item, kg_head, kg_rel, kg_tail, rec_sampler, kg_sampler, batch_size: int,
                  seed: int, device="cuda", shuffle: bool = True, neg_sample_num: int = 1, gather=None,
-                 rank: int = 0, world: int = 1, dynamic: bool = False, candidate_num: int = 0, prefetch=None):
+                 rank: int = 0, world: int = 1, dynamic: bool = False, candidate_num: int = 0):
         self.device = torch.device(device)
         as_dev = lambda x: torch.as_tensor(np.asarray(x), dtype=torch.int64).to(self.device)  # noqa: E731
         self.inter_user, self.inter_item = as_dev(inter_user), as_dev(inter_item)
@@ -348,14 +348,6 @@ class DeviceKGLoader:
         if gather is None:
             self.rec_order.mirror = self.kg_order.mirror = self.device
         self._col_ptrs = {}
-        # One batch ahead on a side stream: the gathers and the two single-CTA sampler kernels of batch i+1 run while
-        # step i trains (and while the host waits on a per-step loss read); same batches in the same order -- the
-        # loader is the only user of the MT19937 stream and its launches stay in order on the side stream.  Not with
-        # dynamic negatives, which score their candidates under the weights of the step they belong to.
-        self.prefetch = (gather is None and not self.dynamic) if prefetch is None else bool(prefetch)
-        if self.prefetch and (gather is not None or self.dynamic):
-            raise ValueError("prefetch needs the CUDA gathers and static negative sampling")
-        self._side = None
 
     def get_model(self, model):
         """abstract_dataloader.py:214-215: the model dynamic negative sampling scores its candidates with."""
@@ -407,7 +399,7 @@ class DeviceKGLoader:
             src = self._col_ptrs[key] = (C.c_void_p * nc)(*[c.data_ptr() for c in columns])
         base = out.data_ptr()
         dst = (C.c_void_p * nc)(*[base + 8 * n * c for c in range(nc)])
-        with torch.cuda.device(self.device):
+        with _abi.on_device(self.device):
             _abi.check(
                 _abi.lib().kge_gather_columns(src, nc, columns[0].numel(), idx.data_ptr(), n, dst, None,
                                               _abi.stream_ptr()),
@@ -416,35 +408,6 @@ class DeviceKGLoader:
         return list(out.unbind(0))
 
     def __iter__(self):
-        if not self.prefetch:
-            yield from self._batches()
-            return
-        if self._side is None:
-            self._side = torch.cuda.Stream(self.device)
-        side, main = self._side, torch.cuda.current_stream(self.device)
-        side.wait_stream(main)   # (the sampler state and the id tables were written on the consumer's stream)
-        gen = self._batches()
-
-        def produce():
-            with torch.cuda.stream(side):
-                b = next(gen, None)
-                ev = torch.cuda.Event()
-                ev.record(side)
-            return b, ev
-
-        nxt = produce()
-        while nxt[0] is not None:
-            b, ev = nxt
-            nxt = produce()
-            main = torch.cuda.current_stream(self.device)
-            main.wait_event(ev)
-            for t in b.values():   # allocated from the side stream's pool, consumed on this one
-                t.record_stream(main)
-            yield b
-        # (the draw that found the recommendation side exhausted advanced the sampler state on the side stream)
-        torch.cuda.current_stream(self.device).wait_stream(side)
-
-    def _batches(self):
         self.kg_order.start()    # knowledge_dataloader.py:131-135: kg iterator first, then the general one
         self.rec_order.start()
         while True:

@@ -41,7 +41,7 @@ class MTStream:
         seed = int(seed)
         if not 0 <= seed <= 0xFFFFFFFF:
             raise ValueError("legacy integer seed must fit 32 bits")
-        with torch.cuda.device(self.device):
+        with _abi.on_device(self.device):
             _abi.check(_abi.lib().kge_mt19937_seed(self.words.data_ptr(), seed, _abi.stream_ptr()), "kge_mt19937_seed")
 
     def set_state(self, state):
@@ -167,7 +167,7 @@ class _FilteredUniformSampler:
         if self.pop is not None:
             pk, pp, pa = self.pop
             ws = torch.empty(max(lib.kge_sample_alias_workspace_bytes(total), 8), dtype=torch.uint8, device=self.device)
-            with torch.cuda.device(self.device):
+            with _abi.on_device(self.device):
                 _abi.check(
                     lib.kge_sample_negatives_alias(
                         self.stream.words.data_ptr(), keys.data_ptr(), n, int(num), self.used_off.data_ptr(),
@@ -178,7 +178,7 @@ class _FilteredUniformSampler:
                 )
             return out.cpu() if self.to_host else out
         ws = torch.empty(max(lib.kge_sample_workspace_bytes(total), 8), dtype=torch.uint8, device=self.device)
-        with torch.cuda.device(self.device):
+        with _abi.on_device(self.device):
             _abi.check(
                 lib.kge_sample_negatives(
                     self.stream.words.data_ptr(), keys.data_ptr(), n, int(num), self.used_off.data_ptr(),

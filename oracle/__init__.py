@@ -1,13 +1,13 @@
 """CPU oracle for the KGE hot path.  TEST INFRASTRUCTURE ONLY.
 
 This package restates, on the CPU, the algorithms that tail-unica/hopwise runs for
-TransE / RotatE / DistMult / ComplEx training, KG negative sampling and full-sort
+TransE / RotatE / DistMult / ComplEx (and TorusE / TransH) training, KG negative sampling and full-sort
 top-k evaluation.  It is the checker the CUDA path is compared against; it is never
 the thing that is shipped or measured as the product.
 
 Who may import it: ``tests/``, ``__graft_entry__.smoke()`` and the ``cpu_baseline`` /
 ``--impl reference`` legs of ``bench.py``.  Nothing under ``hopwise_b200/`` imports it,
-and ``tests/test_no_oracle_in_product.py`` enforces that.
+and ``tests/test_abi_cpu.py::test_product_has_no_cpu_fallback_and_no_oracle_import`` enforces that.
 
 Parity status: PINNED.  Every function here is checked against outputs of the
 reference itself (hopwise v0.9.1.post1 imported from /root/reference in the build
