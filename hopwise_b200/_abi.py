@@ -123,6 +123,12 @@ PROTOTYPES = {
     "kge_topk_metric_sums": (C.c_int, [_P, C.c_int64, C.c_int32, _P, _P]),
     "kge_gather_columns": (C.c_int, [_P, C.c_int32, C.c_int64, _P, C.c_int64, _P, _P, _P]),
     "kge_widen_ids_i32": (C.c_int, [_P, _P, C.c_int64, _P]),
+    "kge_assemble_batch_workspace_bytes": (C.c_int64, [C.c_int64, C.c_int64, C.c_int32]),
+    "kge_assemble_batch": (
+        C.c_int,
+        [_P, _P, _P, _P, C.c_int64, _P, C.c_int64, _P, _P, C.c_int64, _P, _P, C.c_int64, _P, C.c_int64, C.c_int32,
+         _P, _P, C.c_int64, _P, _P, _P],
+    ),
     "kge_sample_workspace_bytes": (C.c_int64, [C.c_int64]),
     "kge_sample_negatives": (
         C.c_int,

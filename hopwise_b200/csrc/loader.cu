@@ -89,3 +89,46 @@ extern "C" int kge_gather_columns(const int64_t* const* columns, int32_t n_colum
   KGE_LAUNCH_CHECK();
   return 0;
 }
+
+// One training batch of the reference's RSKG loader in one library call: the KG half is drawn first (gather the
+// triples by the batch's index vector, corrupt the tails), then the recommendation half, both samplers on the one
+// MT19937 stream (knowledge_dataloader.py:131-145, general_dataloader.py:66-70, abstract_dataloader.py:185-198).
+// Four launches queued back to back; what it saves over calling the pieces is host time, which bounds the loop at the
+// reference's batch size.  out: head | relation | tail | neg_tail | user | item | neg_item (neg_item: neg_num per row,
+// j-major), uniform candidates.
+extern "C" int64_t kge_assemble_batch_workspace_bytes(int64_t n_kg, int64_t n_rec, int32_t neg_num) {
+  if (n_kg < 0 || n_rec < 0 || neg_num < 1) return -1;
+  const int64_t a = kge_sample_workspace_bytes(n_kg), b = kge_sample_workspace_bytes(n_rec * neg_num);
+  return a > b ? a : b;
+}
+
+extern "C" int kge_assemble_batch(uint32_t* mt_state, const int64_t* kg_head, const int64_t* kg_rel,
+                                  const int64_t* kg_tail, int64_t kg_rows, const int64_t* kg_index, int64_t n_kg,
+                                  const int64_t* kg_used_off, const int64_t* kg_used_vals, int64_t entity_num,
+                                  const int64_t* inter_user, const int64_t* inter_item, int64_t inter_rows,
+                                  const int64_t* rec_index, int64_t n_rec, int32_t neg_num,
+                                  const int64_t* rec_used_off, const int64_t* rec_used_vals, int64_t item_num,
+                                  int64_t* out, void* workspace, kge_stream_t stream) {
+  KGE_REQUIRE(n_kg >= 0 && n_rec >= 0 && neg_num >= 1 && out, KGE_E_ARG, "bad sizes / NULL out");
+  int64_t* head = out;
+  int64_t* neg_tail = out + 3 * n_kg;
+  int64_t* user = neg_tail + n_kg;
+  int64_t* neg_item = user + 2 * n_rec;
+  if (n_kg > 0) {
+    const int64_t* cols[3] = {kg_head, kg_rel, kg_tail};
+    int64_t* outs[3] = {head, head + n_kg, head + 2 * n_kg};
+    if (int e = kge_gather_columns(cols, 3, kg_rows, kg_index, n_kg, outs, nullptr, stream)) return e;
+    if (int e = kge_sample_negatives(mt_state, head, n_kg, 1, kg_used_off, kg_used_vals, 1, entity_num, neg_tail, workspace,
+                                     stream))
+      return e;
+  }
+  if (n_rec > 0) {
+    const int64_t* cols[2] = {inter_user, inter_item};
+    int64_t* outs[2] = {user, user + n_rec};
+    if (int e = kge_gather_columns(cols, 2, inter_rows, rec_index, n_rec, outs, nullptr, stream)) return e;
+    if (int e = kge_sample_negatives(mt_state, user, n_rec, neg_num, rec_used_off, rec_used_vals, 1, item_num, neg_item,
+                                     workspace, stream))
+      return e;
+  }
+  return 0;
+}

@@ -407,7 +407,62 @@ class DeviceKGLoader:
             )
         return list(out.unbind(0))
 
+    def _fast_path(self):
+        """True when a whole batch can be assembled by one kge_assemble_batch call: CUDA gathers, both samplers this
+        package's uniform ones on one stream, handing ids over on the device, static negatives."""
+        from .sampler import KGSampler, RecSampler
+
+        kg, rec = self.kg_sampler, self.rec_sampler
+        if self._gather is not None or self.dynamic or not isinstance(kg, KGSampler) or not isinstance(rec, RecSampler):
+            return False
+        if rec.phase is None or kg.pop is not None or kg.to_host:
+            return False
+        impl = rec._impl[rec.phase]
+        return impl.pop is None and not impl.to_host and impl.stream is kg.stream and kg.device == self.device
+
+    def _assembled(self):
+        """The epoch's batches through kge_assemble_batch: per step two index views, one output buffer, one call."""
+        lib = _abi.lib()
+        kg, impl = self.kg_sampler, self.rec_sampler._impl[self.rec_sampler.phase]
+        num = self.neg_sample_num
+        ws, ws_bytes = None, -1
+        self.kg_order.start()
+        self.rec_order.start()
+        while True:
+            kidx = self.kg_order.next_indices_device()
+            if kidx is None:
+                self.kg_order.start()
+                kidx = self.kg_order.next_indices_device()
+            ridx = self.rec_order.next_indices_device()
+            n_kg = kidx.numel()
+            n_rec = 0 if ridx is None else ridx.numel()
+            need = lib.kge_assemble_batch_workspace_bytes(n_kg, n_rec, num)
+            if need > ws_bytes:
+                ws, ws_bytes = torch.empty(max(need, 8), dtype=torch.uint8, device=self.device), need
+            out = torch.empty(4 * n_kg + (2 + num) * n_rec, dtype=torch.int64, device=self.device)
+            with _abi.on_device(self.device):
+                _abi.check(
+                    lib.kge_assemble_batch(
+                        kg.stream.words.data_ptr(), self.kg_head.data_ptr(), self.kg_rel.data_ptr(),
+                        self.kg_tail.data_ptr(), self.kg_head.numel(), kidx.data_ptr(), n_kg, kg.used_off.data_ptr(),
+                        kg.used_vals.data_ptr(), kg.value_num, self.inter_user.data_ptr(), self.inter_item.data_ptr(),
+                        self.inter_user.numel(), None if ridx is None else ridx.data_ptr(), n_rec, num,
+                        impl.used_off.data_ptr(), impl.used_vals.data_ptr(), impl.value_num, out.data_ptr(),
+                        ws.data_ptr(), _abi.stream_ptr()),
+                    "kge_assemble_batch",
+                )
+            if ridx is None:     # (the KG draw before the recommendation side is found exhausted: like the reference)
+                return
+            head, rel, tail, neg_tail, user, item, neg_item = out.split([n_kg] * 4 + [n_rec, n_rec, num * n_rec])
+            if num > 1:
+                user, item = user.repeat(num), item.repeat(num)
+            yield {"head_id": head, "relation_id": rel, "tail_id": tail, "neg_tail_id": neg_tail, "user_id": user,
+                   "item_id": item, "neg_item_id": neg_item}
+
     def __iter__(self):
+        if self._fast_path():
+            yield from self._assembled()
+            return
         self.kg_order.start()    # knowledge_dataloader.py:131-135: kg iterator first, then the general one
         self.rec_order.start()
         while True:

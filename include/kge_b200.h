@@ -257,6 +257,19 @@ int kge_topk_metric_sums(const int32_t* rec_topk, int64_t n, int32_t k, double* 
 int kge_gather_columns(const int64_t* const* columns, int32_t n_columns, int64_t rows, const int64_t* index,
                        int64_t n, int64_t* const* outs, int32_t* status, kge_stream_t stream);
 
+/* kge_assemble_batch: one RSKG training batch in one call (knowledge_dataloader.py:131-145: the KG half first --
+ * kg_feat[index] then sample_by_entity_ids --, then general_dataloader.py:66-70 + abstract_dataloader.py:185-198:
+ * inter_feat[index] then sample_by_user_ids), both samplers on the one MT19937 stream, uniform candidates.
+ * out (device, 4*n_kg + (2 + neg_num)*n_rec int64): head | relation | tail | neg_tail | user | item | neg_item
+ * (neg_item j-major).  workspace: kge_assemble_batch_workspace_bytes(...) bytes. */
+int64_t kge_assemble_batch_workspace_bytes(int64_t n_kg, int64_t n_rec, int32_t neg_num);
+int kge_assemble_batch(uint32_t* mt_state, const int64_t* kg_head, const int64_t* kg_rel, const int64_t* kg_tail,
+                       int64_t kg_rows, const int64_t* kg_index, int64_t n_kg, const int64_t* kg_used_off,
+                       const int64_t* kg_used_vals, int64_t entity_num, const int64_t* inter_user,
+                       const int64_t* inter_item, int64_t inter_rows, const int64_t* rec_index, int64_t n_rec,
+                       int32_t neg_num, const int64_t* rec_used_off, const int64_t* rec_used_vals, int64_t item_num,
+                       int64_t* out, void* workspace, kge_stream_t stream);
+
 /* kge_widen_ids_i32: dst[i] = src[i] for ids a loader staged as int32 (half the host->device bytes of the int64 id
  * vectors hopwise's Interaction holds, trainer.py:250-256; every id is a row index below 2^31).  16-byte aligned. */
 int kge_widen_ids_i32(const int32_t* src, int64_t* dst, int64_t n, kge_stream_t stream);

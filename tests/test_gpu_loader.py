@@ -163,3 +163,38 @@ def test_gather_columns_kernel():
     _abi.check(lib.kge_gather_columns(src, 1, rows, bad.data_ptr(), 4, dst, status.data_ptr(), _abi.stream_ptr()), "gather")
     assert status.item() == 1 and out[0, 1].item() == -1 and out[0, 0].item() == cols[0][5].item()
     assert lib.kge_gather_columns(src, 9, rows, bad.data_ptr(), 4, dst, None, _abi.stream_ptr()) != 0
+
+
+def test_one_call_batch_assembly_equals_the_piecewise_path():
+    """kge_assemble_batch (one library call per batch) against the loader's piecewise path (gather hook + separate
+    sampler calls): same batches, 2 negatives per interaction, KG wrap-around, same final sampler state."""
+    from hopwise_b200.loader import DeviceKGLoader
+    from hopwise_b200.sampler import KGSampler, MTStream, RecSampler
+
+    U, I, E, R, B, num = 300, 200, 500, 6, 256, 2
+    rng = np.random.default_rng(23)
+    iu, ii = rng.integers(1, U, 3000), rng.integers(1, I, 3000)
+    kh, kr, kt = rng.integers(1, E, 1100), rng.integers(1, R - 1, 1100), rng.integers(1, E, 1100)   # 5 KG batches < 12 rec
+
+    def run(fast):
+        stream = MTStream(seed=9)
+        rec = RecSampler(iu, ii, U, I, stream=stream)
+        kg = KGSampler(heads=kh, tails=kt, entity_num=E, stream=stream)
+        hook = None if fast else (lambda table, idx: table.index_select(0, idx))
+        loader = DeviceKGLoader(iu, ii, kh, kr, kt, rec, kg, batch_size=B, seed=3, neg_sample_num=num, gather=hook)
+        assert loader._fast_path() == fast
+        out = []
+        for _ in range(2):
+            out += [{k: v.cpu().numpy().copy() for k, v in b.items()} for b in loader]
+        return out, stream.get_state()
+
+    a, sa = run(True)
+    b, sb = run(False)
+    assert len(a) == len(b) == 24
+    for x, y in zip(a, b):
+        assert set(x) == set(y) == set(DeviceKGLoader.KEYS)
+        for k in x:
+            np.testing.assert_array_equal(x[k], y[k], err_msg=k)
+        assert len(x["user_id"]) == len(x["neg_item_id"]) == num * (len(x["neg_item_id"]) // num)
+    np.testing.assert_array_equal(sa[1], sb[1])
+    assert sa[2] == sb[2]
