@@ -107,7 +107,7 @@ PROTOTYPES = {
     "kge_multimem_all_reduce_f32": (C.c_int, [_P, C.c_int64, C.c_int32, C.c_int32, _P]),
     "kge_owner_adam_step": (
         C.c_int,
-        [_P, _P, _P, _P, _P, C.c_int64, C.c_int32, C.c_int32, _AP, C.c_float, _P, C.c_int32, _P, C.c_uint32, _P],
+        [_P, _P, _P, _P, _P, _P, C.c_int64, C.c_int32, C.c_int32, _AP, C.c_float, _P, C.c_int32, _P, C.c_uint32, _P],
     ),
     "kge_multimem_all_reduce_fused_f32": (
         C.c_int, [_P, C.c_int64, C.c_int32, C.c_int32, _P, C.c_int32, _P, C.c_uint32, _P, C.c_int64, C.c_int32, _P]),

@@ -127,7 +127,7 @@ __global__ void __launch_bounds__(256) multimem_all_reduce_fused_kernel(float* _
 // ---- owner-sharded dense Adam over the switch ---------------------------------------------------------------------
 // One kernel per step instead of all-reduce + Adam: rank r owns the r-th slice of the flat parameter space.  It reads
 // the SUM of the N gradient copies of its slice straight from the switch (multimem.ld_reduce), takes the Adam step for
-// those elements with its (sharded) moments, and multicasts the new weights -- and zeros for the gradient -- to every
+// those elements with its (sharded) moments, and multicasts the new weights to every
 // replica (multimem.st).  Every rank moves 1/N of the gradient in and 1/N of the weights out, and does 1/N of the
 // optimiser arithmetic; torch.optim.Adam's dense semantics (every element, every step), which is what the reference
 // trains with (trainer/trainer.py:131-170 builds optim.Adam over all parameters; DDP averages the gradients first).
@@ -158,7 +158,6 @@ __device__ __forceinline__ void owner_adam_quad(const OwnerAdam& a, int64_t q, f
   *reinterpret_cast<float4*>(a.m + 4 * q) = make_float4(mv[0], mv[1], mv[2], mv[3]);
   *reinterpret_cast<float4*>(a.v + 4 * q) = make_float4(vv[0], vv[1], vv[2], vv[3]);
   multimem_st(a.w_mc + 4 * q, make_float4(wv[0], wv[1], wv[2], wv[3]));
-  multimem_st(a.g_mc + 4 * q, make_float4(0.f, 0.f, 0.f, 0.f));
 }
 
 // U quads of one thread: every load first (the switch round trip of the gradient and the three local reads of each
@@ -263,11 +262,13 @@ extern "C" int kge_multimem_all_reduce_f32(void* multicast_ptr, int64_t n_floats
   return 0;
 }
 
-extern "C" int kge_owner_adam_step(void* grad_multicast, void* weight_multicast, const float* weight_local, float* m,
-                                   float* v, int64_t n_floats, int32_t rank, int32_t world, const kge_adam_t* adam,
+extern "C" int kge_owner_adam_step(void* grad_multicast, float* grad_local, void* weight_multicast,
+                                   const float* weight_local, float* m, float* v, int64_t n_floats, int32_t rank,
+                                   int32_t world, const kge_adam_t* adam,
                                    float grad_scale, void* const* signal_pads_dev, int32_t slot_base,
                                    uint32_t* local_flags, uint32_t epoch, kge_stream_t stream) {
-  KGE_REQUIRE(grad_multicast && weight_multicast && weight_local && m && v && adam, KGE_E_ARG, "NULL argument");
+  KGE_REQUIRE(grad_multicast && grad_local && weight_multicast && weight_local && m && v && adam, KGE_E_ARG,
+              "NULL argument");
   KGE_REQUIRE(n_floats >= 0 && (n_floats & 3) == 0 && world >= 1 && world <= 32 && rank >= 0 && rank < world, KGE_E_ARG,
               "bad owner-Adam arguments");
   KGE_REQUIRE(((reinterpret_cast<uintptr_t>(grad_multicast) | reinterpret_cast<uintptr_t>(weight_multicast) |
@@ -302,5 +303,9 @@ extern "C" int kge_owner_adam_step(void* grad_multicast, void* weight_multicast,
   owner_adam_kernel<<<(unsigned)grid, threads, 0, (cudaStream_t)stream>>>(
       a, reinterpret_cast<uint32_t* const*>(signal_pads_dev), rank, world, slot_base, local_flags, epoch);
   KGE_LAUNCH_CHECK();
+  // The kernel's barrier B means every rank has finished reading every copy of the gradient: this rank's copy is
+  // zeroed locally for the next step (zeroing through the multicast address instead doubles what every GPU receives
+  // over NVLink per step: N slices of weights AND N slices of zeros).
+  KGE_CUDA(cudaMemsetAsync(grad_local, 0, (size_t)n_floats * sizeof(float), (cudaStream_t)stream));
   return 0;
 }

@@ -290,7 +290,7 @@ class RowSparseExchange:
         a = model._adam_struct(model._step + 1)
         _abi.check(
             _abi.lib().kge_owner_adam_step(
-                self._mc_base, self._w_mc_base, st["w_flat"].data_ptr(), st["m_flat"].data_ptr(),
+                self._mc_base, self._symm_keep.data_ptr(), self._w_mc_base, st["w_flat"].data_ptr(), st["m_flat"].data_ptr(),
                 st["v_flat"].data_ptr(), st["w_flat"].numel(), self.rank, self.world, C.byref(a),
                 float(model._grad_scale), int(self.symm.signal_pad_ptrs_dev), self.SIGNAL_SLOT_BASE,
                 self._local_flags.data_ptr(), self._epoch, _abi.stream_ptr()),

@@ -180,11 +180,12 @@ int kge_multimem_all_reduce_fused_f32(void* multicast_ptr, int64_t n_floats, int
  * flat gradient and weight buffers are symmetric allocations with NVLS multicast mappings).  Rank `rank` reads the
  * sum of the `world` gradient copies of its 1/world slice through multimem.ld_reduce, applies torch.optim.Adam's
  * dense update (gradient scaled by grad_scale, bias corrections of adam->step) with its slice of the moments m / v
- * (local buffers in the same flat layout), and multicasts the new weights -- and a zeroed gradient -- to every
- * replica.  Barriers before (all gradients written) and after (all slices final) run inside the kernel: see
+ * (local buffers in the same flat layout), and multicasts the new weights to every replica; this rank's gradient
+ * copy (grad_local) is zeroed behind the kernel, whose closing barrier means every rank is done reading it.  Barriers before (all gradients written) and after (all slices final) run inside the kernel: see
  * kge_multimem_all_reduce_fused_f32 for signal_pads_dev / slot_base / local_flags / epoch. */
-int kge_owner_adam_step(void* grad_multicast, void* weight_multicast, const float* weight_local, float* m, float* v,
-                        int64_t n_floats, int32_t rank, int32_t world, const kge_adam_t* adam, float grad_scale,
+int kge_owner_adam_step(void* grad_multicast, float* grad_local, void* weight_multicast, const float* weight_local,
+                        float* m, float* v, int64_t n_floats, int32_t rank, int32_t world, const kge_adam_t* adam,
+                        float grad_scale,
                         void* const* signal_pads_dev, int32_t slot_base, uint32_t* local_flags, uint32_t epoch,
                         kge_stream_t stream);
 
