@@ -125,7 +125,7 @@ __device__ __forceinline__ float sigmoidf(float z) { return 1.f / (1.f + expf(-z
 template <int MODEL, int VEC, int G, int NCH>
 struct FwdBounds {
   static constexpr int E = VEC * NCH;
-  static constexpr int PH = (MODEL == KGE_ROTATE || MODEL == KGE_COMPLEX) ? 2 : 1;
+  static constexpr int PH = (MODEL == KGE_ROTATE || MODEL == KGE_COMPLEX || MODEL == KGE_TRANSD) ? 2 : 1;
   // resident CTAs per SM the register budget is shaped for (more warps = more loads in flight)
 #ifdef KGE_FWD_MIN_CTAS
   static constexpr int MIN_CTAS = KGE_FWD_MIN_CTAS;   // experiment knob (scripts/build_variant.sh)
@@ -140,8 +140,8 @@ struct FwdBounds {
 template <int MODEL, int VEC, int G, int NCH>
 __global__ void __launch_bounds__(256, FwdBounds<MODEL, VEC, G, NCH>::MIN_CTAS) train_fwd_kernel(const TrainArgs a) {
   constexpr int E = VEC * NCH;
-  constexpr int PH = (MODEL == KGE_ROTATE || MODEL == KGE_COMPLEX) ? 2 : 1;  // head / tail parts
-  constexpr int PR = (MODEL == KGE_COMPLEX || MODEL == KGE_TRANSH) ? 2 : 1;   // relation parts (TransH: r, w)
+  constexpr int PH = (MODEL == KGE_ROTATE || MODEL == KGE_COMPLEX || MODEL == KGE_TRANSD) ? 2 : 1;  // head / tail parts
+  constexpr int PR = (MODEL == KGE_COMPLEX || MODEL == KGE_TRANSH || MODEL == KGE_TRANSD) ? 2 : 1;   // relation parts
   extern __shared__ float s_racc[];  // [PR][d] user->item relation gradient of this CTA
   __shared__ float s_loss[8];
 
@@ -227,7 +227,33 @@ __global__ void __launch_bounds__(256, FwdBounds<MODEL, VEC, G, NCH>::MIN_CTAS) 
     for (int e = 0; e < E; ++e) { c0[e] = c1[e] = c2[e] = c3[e] = 0.f; acc0[e] = acc1[e] = 0.f; }
     float nact = 0.f;
     float s_w = 0.f;   // TransH: sum of the hyperplane vector's components
-    if (MODEL == KGE_TRANSH) {
+    float s_h = 0.f, s_tp = 0.f;   // TransD: <h, h_p>, <tp, tp_p>
+    if (MODEL == KGE_TRANSD) {
+      // transd.py:86-91: proj(e) = e + r_p * <e, e_p> (parts: [0] embedding, [1] transfer vector).  Then TransE on the
+      // projected rows: c0 = x = proj(h) + r, c1 = w * unit(x - proj(tp) + eps).  Products and dot products by explicit
+      // fmas in one order, so that the projections of equal rows are equal bit for bit wherever they are formed.
+      float a0 = 0.f, a1 = 0.f;
+#pragma unroll
+      for (int e = 0; e < E; ++e) {
+        a0 = __fmaf_rn(h[0][e], h[PH - 1][e], a0);
+        a1 = __fmaf_rn(tp[0][e], tp[PH - 1][e], a1);
+      }
+      s_h = group_sum<G>(a0);
+      s_tp = group_sum<G>(a1);
+      float sp = 0.f;
+#pragma unroll
+      for (int e = 0; e < E; ++e) {
+        c0[e] = __fmaf_rn(r[PR - 1][e], s_h, h[0][e]) + r[0][e];
+        const float tproj = __fmaf_rn(r[PR - 1][e], s_tp, tp[0][e]);
+        const float dp = frag_valid<VEC, G, NCH>(d, gl, e) ? (__fsub_rn(c0[e], tproj) + 1e-6f) : 0.f;
+        c1[e] = dp;
+        sp = __fmaf_rn(dp, dp, sp);
+      }
+      s_pos = sqrtf(group_sum<G>(sp));
+      const float inv_p = s_pos > 0.f ? 1.f / s_pos : 0.f;
+#pragma unroll
+      for (int e = 0; e < E; ++e) c1[e] = __fmul_rn(w, __fmul_rn(c1[e], inv_p));
+    } else if (MODEL == KGE_TRANSH) {
       // transh.py:73-74: project(e) = e - (e * sum(w)) * w = e * (1 - sum(w) * w); c2 holds the factor.  Then TransE on
       // the projected rows: c0 = x = h*c2 + r, c1 = w * unit(x - tp*c2 + eps), s_pos = ||x - tp*c2 + eps||
       float sw = 0.f;
@@ -322,7 +348,48 @@ __global__ void __launch_bounds__(256, FwdBounds<MODEL, VEC, G, NCH>::MIN_CTAS) 
         for (int p = 0; p < PH; ++p) catch_up<VEC, G, NCH>(ET, p, t_id, st, d, gl, a.adam, t[p], a.with_grad);
       }
 
-      if (MODEL == KGE_TRANSH) {
+      if (MODEL == KGE_TRANSD) {
+        float a0 = 0.f;
+#pragma unroll
+        for (int e = 0; e < E; ++e) a0 = __fmaf_rn(t[0][e], t[PH - 1][e], a0);
+        const float s_tn = group_sum<G>(a0);
+        float dnv[E];
+        float sn = 0.f;
+#pragma unroll
+        for (int e = 0; e < E; ++e) {
+          const float tproj = __fmaf_rn(r[PR - 1][e], s_tn, t[0][e]);
+          dnv[e] = frag_valid<VEC, G, NCH>(d, gl, e) ? (__fsub_rn(c0[e], tproj) + 1e-6f) : 0.f;
+          sn = __fmaf_rn(dnv[e], dnv[e], sn);
+        }
+        const float nn_ = sqrtf(group_sum<G>(sn));
+        const float z = margin + s_pos - nn_;
+        if (z >= 0.f) {
+          inst_loss += z * w;
+          if (a.with_grad) {
+            const float inv_n = nn_ > 0.f ? 1.f / nn_ : 0.f;
+            nact += 1.f;
+            float dotn = 0.f;
+#pragma unroll
+            for (int e = 0; e < E; ++e) {
+              dnv[e] = __fmul_rn(w, __fmul_rn(dnv[e], inv_n));   // gradient of the PROJECTED negative tail
+              gh[0][e] += __fsub_rn(c1[e], dnv[e]);              // ... of x = proj(h) + r
+              gtp[0][e] -= c1[e];                                // ... of the projected positive tail
+              acc1[e] = __fmaf_rn(dnv[e], s_tn, acc1[e]);        // ... of r_p, this tail's share
+              dotn = __fmaf_rn(dnv[e], r[PR - 1][e], dotn);
+            }
+            dotn = group_sum<G>(dotn);
+            float gv[E];
+#pragma unroll
+            for (int e = 0; e < E; ++e) {   // back through proj(t) = t + r_p * <t, t_p>
+              gv[e] = t[0][e] * dotn;
+              dnv[e] = __fmaf_rn(t[PH - 1][e], dotn, dnv[e]);
+            }
+            frag_atomic_add<VEC, G, NCH>(ET.g[0], t_id, d, gl, dnv);
+            frag_atomic_add<VEC, G, NCH>(ET.g[PH - 1], t_id, d, gl, gv);
+            mark_row(ET, t_id, st.y, step, gl);
+          }
+        }
+      } else if (MODEL == KGE_TRANSH) {
         float dnv[E];
         float sn = 0.f;
 #pragma unroll
@@ -464,7 +531,30 @@ __global__ void __launch_bounds__(256, FwdBounds<MODEL, VEC, G, NCH>::MIN_CTAS) 
     }
 
     // ---- gradients of head, relation and positive tail from the accumulators ------------------------
-    if (MODEL == KGE_TRANSH) {
+    if (MODEL == KGE_TRANSD) {
+      if (nact > 0.f) {
+        any_grad = true;
+        // gh[0] / gtp[0] hold the gradients of x and of the projected positive tail; back through
+        // proj(e) = e + r_p * <e, e_p>:  g_e = g + e_p * <g, r_p>,  g_ep = e * <g, r_p>,  g_rp += g * <e, e_p>
+        float dh = 0.f, dt = 0.f;
+#pragma unroll
+        for (int e = 0; e < E; ++e) {
+          dh = __fmaf_rn(gh[0][e], r[PR - 1][e], dh);
+          dt = __fmaf_rn(gtp[0][e], r[PR - 1][e], dt);
+        }
+        dh = group_sum<G>(dh);
+        dt = group_sum<G>(dt);
+#pragma unroll
+        for (int e = 0; e < E; ++e) {
+          gr[0][e] = gh[0][e];
+          gr[PR - 1][e] = __fmaf_rn(gh[0][e], s_h, __fmaf_rn(gtp[0][e], s_tp, acc1[e]));
+          gh[PH - 1][e] = h[0][e] * dh;
+          gh[0][e] = __fmaf_rn(h[PH - 1][e], dh, gh[0][e]);
+          gtp[PH - 1][e] = tp[0][e] * dt;
+          gtp[0][e] = __fmaf_rn(tp[PH - 1][e], dt, gtp[0][e]);
+        }
+      }
+    } else if (MODEL == KGE_TRANSH) {
       if (nact > 0.f) {
         any_grad = true;
         // gh / gtp hold the gradients of x and of the projected positive tail.  The factor c2 = 1 - s_w * w gets
@@ -806,9 +896,9 @@ bool table_has_state(const kge_table_t& T, bool need_rows) {
 // need_state: gradient accumulators; need_rows: also moments and row states (the row-lazy Adam kernels)
 int check_model(const kge_model_t* m, bool need_state, bool need_rows = true) {
   KGE_REQUIRE(m, KGE_E_ARG, "model is NULL");
-  KGE_REQUIRE(m->model >= KGE_TRANSE && m->model <= KGE_TRANSH, KGE_E_ARG, "unknown model kind %d", m->model);
-  const int ph = (m->model == KGE_ROTATE || m->model == KGE_COMPLEX) ? 2 : 1;
-  const int pr = (m->model == KGE_COMPLEX || m->model == KGE_TRANSH) ? 2 : 1;
+  KGE_REQUIRE(m->model >= KGE_TRANSE && m->model <= KGE_TRANSD, KGE_E_ARG, "unknown model kind %d", m->model);
+  const int ph = (m->model == KGE_ROTATE || m->model == KGE_COMPLEX || m->model == KGE_TRANSD) ? 2 : 1;
+  const int pr = (m->model == KGE_COMPLEX || m->model == KGE_TRANSH || m->model == KGE_TRANSD) ? 2 : 1;
   KGE_REQUIRE(m->user.parts == ph && m->entity.parts == ph && m->relation.parts == pr, KGE_E_ARG,
               "table parts do not match the model kind");
   for (int p = 0; p < ph; ++p) KGE_REQUIRE(m->user.w[p] && m->entity.w[p], KGE_E_ARG, "NULL weight table");
@@ -869,7 +959,7 @@ extern "C" int kge_train_forward(const kge_model_t* model, const kge_batch_t* b,
   const double pr = (double)b->n_rec * b->k_rec, pk = (double)b->n_kg * b->k_kg;
   // (TorusE's training objective is TransE's: TripletMarginLoss on h + r, toruse.py:81-102)
   const int kind = model->model == KGE_TORUSE ? KGE_TRANSE : model->model;
-  if (kind == KGE_TRANSE || kind == KGE_DISTMULT || kind == KGE_TRANSH) {
+  if (kind == KGE_TRANSE || kind == KGE_DISTMULT || kind == KGE_TRANSH || kind == KGE_TRANSD) {
     a.w_rec = a.w_kg = (float)(1.0 / (pr + pk));
     a.wpos_rec = a.wpos_kg = 0.f;
   } else {
@@ -902,6 +992,7 @@ extern "C" int kge_train_forward(const kge_model_t* model, const kge_batch_t* b,
     case KGE_DISTMULT: train_fwd_kernel<KGE_DISTMULT, V, G, N><<<grid, threads, smem, st>>>(a); break;  \
     case KGE_ROTATE: train_fwd_kernel<KGE_ROTATE, V, G, N><<<grid, threads, smem, st>>>(a); break;      \
     case KGE_TRANSH: train_fwd_kernel<KGE_TRANSH, V, G, N><<<grid, threads, smem, st>>>(a); break;      \
+    case KGE_TRANSD: train_fwd_kernel<KGE_TRANSD, V, G, N><<<grid, threads, smem, st>>>(a); break;      \
     default: train_fwd_kernel<KGE_COMPLEX, V, G, N><<<grid, threads, smem, st>>>(a); break;             \
   }
   if (two_per_warp) {

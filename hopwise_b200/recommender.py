@@ -151,6 +151,7 @@ class FusedKGEModel(KnowledgeRecommender):
     ENTITY_TABLES: tuple = ()
     RELATION_TABLES: tuple = ()
     HAS_MARGIN = True
+    CREATION_ORDER: tuple = ()    # table names in the reference constructor's order when it is not user, entity, relation
     # rotate.py:43 / complex.py:38 look the [UI-Relation] token up; transe/distmult take weight[-1]
     UI_BY_TOKEN = False
     UI_FULLSORT_BY_TOKEN = False
@@ -165,12 +166,10 @@ class FusedKGEModel(KnowledgeRecommender):
             self.ui_relation = int(dataset.field2token_id["relation_id"][dataset.ui_relation])
         # tables in the reference's creation order (fixes the RNG stream of the initialisation)
         d = self.embedding_size
-        for name in self.USER_TABLES:
-            setattr(self, name, nn.Embedding(self.n_users, d))
-        for name in self.ENTITY_TABLES:
-            setattr(self, name, nn.Embedding(self.n_entities, d))
-        for name in self.RELATION_TABLES:
-            setattr(self, name, nn.Embedding(self.n_relations, d))
+        rows = {**{n: self.n_users for n in self.USER_TABLES}, **{n: self.n_entities for n in self.ENTITY_TABLES},
+                **{n: self.n_relations for n in self.RELATION_TABLES}}
+        for name in (self.CREATION_ORDER or self.USER_TABLES + self.ENTITY_TABLES + self.RELATION_TABLES):
+            setattr(self, name, nn.Embedding(rows[name], d))
         self.apply(_xavier_normal_initialization)
         if self.KIND == "RotatE":
             nn.init.uniform_(self.relation_embedding.weight, 0, 2 * math.pi)  # rotate.py:59
@@ -886,5 +885,122 @@ class TransH(FusedKGEModel):
         raise NotImplementedError("the reference TransH has no KG scoring entry points (transh.py)")
 
 
+class TransD(FusedKGEModel):
+    """transd.py: every table has an embedding and a transfer vector; ``forward(ent, ent_vec, rel_vec) = rel_vec *
+    <ent, ent_vec> + ent`` (transd.py:86-91) projects head and both tails before TransE's TripletMarginLoss
+    (transd.py:93-133).  The train step is one fused kernel like the others (KGE_TRANSD).  Scoring composes two
+    library calls: ``kge_transd_project`` writes the projected rows, and since the projection of an item does not
+    depend on the user, the rest IS TransE on projected tables -- a private TransE view of those buffers runs
+    predict, dense full-sort and the fused top-k (tensor-core path included).  ``full_sort_predict_kg`` is refused:
+    the reference's version projects the head with <h, h> and broadcasts a relation per row over all tails
+    (transd.py:192-217), which no projected table expresses."""
+
+    KIND = "TransD"
+    USER_TABLES = ("user_embedding", "user_vec_embedding")
+    ENTITY_TABLES = ("entity_embedding", "entity_vec_embedding")
+    RELATION_TABLES = ("relation_embedding", "relation_vec_embedding")
+    CREATION_ORDER = ("user_embedding", "entity_embedding", "relation_embedding", "user_vec_embedding",
+                      "entity_vec_embedding", "relation_vec_embedding")   # transd.py:41-47
+
+    # ---- projected rows ---------------------------------------------------------------------------------------
+    def _project(self, family, ids, rel_ids=None):
+        """[len(ids), d] projected rows of `family` ("user" / "entity"); rel_ids None = the user->item relation."""
+        device = self._check_ready()
+        self.flush()
+        emb, vec = self._tables(self.USER_TABLES if family == "user" else self.ENTITY_TABLES)
+        rvec = self.relation_vec_embedding.weight
+        ids = self._ids(ids, device)
+        n = ids.numel()
+        rel_ids = None if rel_ids is None else self._ids(rel_ids, device)
+        out = torch.empty(n, self.embedding_size, dtype=torch.float32, device=device)
+        _abi.check(
+            _abi.lib().kge_transd_project(emb.data_ptr(), vec.data_ptr(), _abi.ptr(ids), n, self.embedding_size,
+                                          rvec.data_ptr(), _abi.ptr(rel_ids), self.n_relations - 1, out.data_ptr(),
+                                          _abi.stream_ptr()),
+            "kge_transd_project",
+        )
+        return out
+
+    def _projected_items(self):
+        """Rows [0, n_items) of the entity table projected with the user->item relation, cached per weight version."""
+        tabs = self._tables(self.ENTITY_TABLES) + [self.relation_vec_embedding.weight]
+        key = (self._step, tuple(t.data_ptr() for t in tabs), tuple(t._version for t in tabs))
+        hit = self.__dict__.get("_items_cache")
+        if hit is None or hit[0] != key:
+            ids = torch.arange(self.n_items, device=tabs[0].device)
+            hit = (key, self._project("entity", ids))
+            self.__dict__["_items_cache"] = hit
+            view = self.__dict__.get("_view")
+            if view is not None:
+                view.invalidate_target_image()
+        return hit[1]
+
+    def invalidate_target_image(self):
+        super().invalidate_target_image()
+        self.__dict__.pop("_items_cache", None)
+
+    def _transe_view(self, users, entities):
+        """The private TransE model over projected tables: `users` [n, d] rows, `entities` [m, d] rows, the
+        relation table shared with this model."""
+        view = self.__dict__.get("_view")
+        if view is None:
+            cfg = {"USER_ID_FIELD": self.USER_ID, "ITEM_ID_FIELD": self.ITEM_ID, "NEG_PREFIX": self.NEG_ITEM_ID[: -len(self.ITEM_ID)],
+                   "ENTITY_ID_FIELD": self.ENTITY_ID, "RELATION_ID_FIELD": self.RELATION_ID,
+                   "HEAD_ENTITY_ID_FIELD": self.HEAD_ENTITY_ID, "TAIL_ENTITY_ID_FIELD": self.TAIL_ENTITY_ID,
+                   "device": self.device, "embedding_size": self.embedding_size, "margin": self.margin}
+
+            class _Shape:
+                def num(_, field):
+                    return {self.RELATION_ID: self.n_relations}.get(field, 1)
+
+            view = TransE(cfg, _Shape())
+            view.eval()
+            self.__dict__["_view"] = view   # (not a submodule: its tables are scratch, not parameters of this model)
+        with torch.no_grad():
+            view.user_embedding.weight.data = users
+            view.entity_embedding.weight.data = entities
+            view.relation_embedding.weight.data = self.relation_embedding.weight.data
+        view.n_users, view.n_items, view.n_entities = users.shape[0], entities.shape[0], entities.shape[0]
+        view.__dict__.pop("_table_params", None)
+        return view
+
+    # ---- scoring ----------------------------------------------------------------------------------------------
+    def predict(self, interaction):
+        users, items = interaction[self.USER_ID], interaction[self.ITEM_ID]
+        view = self._transe_view(self._project("user", users), self._project("entity", items))
+        view.invalidate_target_image()
+        idx = torch.arange(view.n_users, device=view.user_embedding.weight.device)
+        return view.predict({self.USER_ID: idx, self.ITEM_ID: idx})
+
+    def predict_kg(self, interaction):
+        heads, rels, tails = (interaction[k] for k in (self.HEAD_ENTITY_ID, self.RELATION_ID, self.TAIL_ENTITY_ID))
+        both = torch.cat([self._project("entity", heads, rels), self._project("entity", tails, rels)])
+        n = both.shape[0] // 2
+        view = self._transe_view(both[:1], both)
+        view.invalidate_target_image()
+        idx = torch.arange(n, device=both.device)
+        return view.predict_kg({self.HEAD_ENTITY_ID: idx, self.RELATION_ID: self._ids(rels, both.device),
+                                self.TAIL_ENTITY_ID: idx + n})
+
+    def _rec_view(self, user_ids):
+        view = self._transe_view(self._project("user", user_ids), self._projected_items())
+        return view, torch.arange(view.n_users, device=view.user_embedding.weight.device)
+
+    def full_sort_predict(self, interaction):
+        view, idx = self._rec_view(interaction[self.USER_ID])
+        return view.full_sort_predict({self.USER_ID: idx})
+
+    def full_sort_predict_kg(self, interaction):
+        raise NotImplementedError("TransD.full_sort_predict_kg: the reference projects the head with <h, h> and a "
+                                  "relation per row over all tails (transd.py:192-217); not built")
+
+    def full_sort_topk(self, user_ids, k, hist_off=None, hist_items=None, mask_pad=True, return_scores=True,
+                       path="auto", _debug_scores=False, relation_ids=None):
+        if relation_ids is not None:
+            raise NotImplementedError("TransD scores users against items only (see full_sort_predict_kg)")
+        view, idx = self._rec_view(user_ids)
+        return view.full_sort_topk(idx, k, hist_off, hist_items, mask_pad, return_scores, path, _debug_scores)
+
+
 MODELS = {"TransE": TransE, "DistMult": DistMult, "RotatE": RotatE, "ComplEx": ComplEx, "TorusE": TorusE,
-          "TransH": TransH}
+          "TransH": TransH, "TransD": TransD}

@@ -244,7 +244,7 @@ _KGE_PACKAGE = "hopwise.model.knowledge_graph_embedding_recommender"
 _installed: dict = {}
 
 
-def install(models=("TransE", "DistMult", "RotatE", "ComplEx", "TorusE", "TransH")):
+def install(models=("TransE", "DistMult", "RotatE", "ComplEx", "TorusE", "TransH", "TransD")):
     """Make hopwise resolve these model names to the fused classes and FusedKGTrainer.
 
     ``get_model(name)`` imports ``hopwise.model.knowledge_graph_embedding_recommender.<name>`` and takes the

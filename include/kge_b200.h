@@ -37,8 +37,15 @@ typedef void* kge_stream_t; /* cudaStream_t */
  * the SUM of w's components, not <ent, w>), i.e. ent * (1 - sum(w) * w) element-wise, applied to head and both tails
  * before TransE's TripletMarginLoss / norm (transh.py:53-58, 76-107).  Recommendation triples take row
  * `ui_relation` of both parts.  Scoring: predict and full-sort over items (transh.py:109-145); the reference has no
- * KG scoring entry points for this model.  CUDA-core scoring paths only. */
-enum kge_model_kind { KGE_TRANSE = 0, KGE_DISTMULT = 1, KGE_ROTATE = 2, KGE_COMPLEX = 3, KGE_TORUSE = 4, KGE_TRANSH = 5 };
+ * KG scoring entry points for this model.  CUDA-core scoring paths only.
+ * KGE_TRANSD (transd.py): every table has two parts, the embedding and a transfer vector; an entity e with transfer
+ * vector e_p is projected with the relation's r_p as e + r_p * <e, e_p> (transd.py:86-91) before TransE's
+ * TripletMarginLoss (transd.py:93-133).  TRAIN STEP ONLY: scoring goes through kge_transd_project, which writes
+ * projected rows, and the KGE_TRANSE scoring entry points on those (the projection of an item does not depend on the
+ * user, so full-sort over items is TransE over a projected table). */
+enum kge_model_kind {
+  KGE_TRANSE = 0, KGE_DISTMULT = 1, KGE_ROTATE = 2, KGE_COMPLEX = 3, KGE_TORUSE = 4, KGE_TRANSH = 5, KGE_TRANSD = 6
+};
 
 enum kge_error {
   KGE_E_ARG = -1,         /* null pointer / negative size */
@@ -188,6 +195,13 @@ int kge_owner_adam_step(void* grad_multicast, float* grad_local, void* weight_mu
                         float grad_scale,
                         void* const* signal_pads_dev, int32_t slot_base, uint32_t* local_flags, uint32_t epoch,
                         kge_stream_t stream);
+
+/* kge_transd_project: out[i, :] = E[id_i] + RP[rel_i] * <E[id_i], EP[id_i]>  (TransD.forward, transd.py:86-91).
+ * ids == NULL: rows 0..n-1 in order; rel_ids == NULL: relation row `rel_row` for every i.  emb / vec: [rows, d]
+ * tables of the projected family (user or entity), rel_vec: the relation transfer-vector table. */
+int kge_transd_project(const float* emb, const float* vec, const int64_t* ids, int64_t n, int32_t d,
+                       const float* rel_vec, const int64_t* rel_ids, int64_t rel_row, float* out,
+                       kge_stream_t stream);
 
 /* ---- scoring --------------------------------------------------------------------------
  * kge_predict: <Model>.predict / predict_kg (transe.py:100-110,128-137 and twins).

@@ -33,6 +33,9 @@ def score(model, h, r, t, margin=1.0):
     """h, r, t: lists of float64 arrays (1 or 2 parts) broadcastable on leading dims."""
     if model == "TransE":
         return -np.sqrt(((h[0] + r[0] - t[0]) ** 2).sum(-1))
+    if model == "TransD":   # transd.py:86-91, 135-176
+        proj = lambda e: e[0] + r[1] * (e[0] * e[1]).sum(-1, keepdims=True)   # noqa: E731
+        return -np.sqrt(((proj(h) + r[0] - proj(t)) ** 2).sum(-1))
     if model == "TransH":   # transh.py:53-58, 73-74
         c = 1.0 - r[1].sum(-1, keepdims=True) * r[1]
         return -np.sqrt((((h[0] - t[0]) * c + r[0]) ** 2).sum(-1))
@@ -71,6 +74,25 @@ def pair_loss_and_grads(model, h, r, tp, tn, weight, margin=1.0):
         un = np.where(n_n > 0, dn / np.where(n_n > 0, n_n, 1.0), 0.0)
         gx = act * (up - un)
         return (np.maximum(z, 0).sum() * weight, [gx], [gx.copy()], [-act * up], [act * un])
+    if model == "TransD":
+        # transd.py:86-133: TransE on proj(e) = e + r_p * <e, e_p>.  With G the gradient of a projected row:
+        # g_e = G + e_p * <G, r_p>,  g_ep = e * <G, r_p>,  g_rp += G * <e, e_p>
+        rp = r[1]
+        dot = lambda a_, b_: (a_ * b_).sum(-1, keepdims=True)   # noqa: E731
+        s_h, s_p, s_n = dot(h[0], h[1]), dot(tp[0], tp[1]), dot(tn[0], tn[1])
+        x = h[0] + rp * s_h + r[0]
+        dp = x - (tp[0] + rp * s_p) + EPS_PAIRWISE
+        dn = x - (tn[0] + rp * s_n) + EPS_PAIRWISE
+        n_p = np.sqrt((dp * dp).sum(-1, keepdims=True))
+        n_n = np.sqrt((dn * dn).sum(-1, keepdims=True))
+        z = margin + n_p - n_n
+        act = (z >= 0).astype(np.float64) * weight
+        up = np.where(n_p > 0, dp / np.where(n_p > 0, n_p, 1.0), 0.0)
+        un = np.where(n_n > 0, dn / np.where(n_n > 0, n_n, 1.0), 0.0)
+        gx, gp, gn = act * (up - un), -act * up, act * un
+        back = lambda G, e: ([G + e[1] * dot(G, rp), e[0] * dot(G, rp)])   # noqa: E731
+        grp = gx * s_h + gp * s_p + gn * s_n
+        return (np.maximum(z, 0).sum() * weight, back(gx, h), [gx, grp], back(gp, tp), back(gn, tn))
     if model == "TransH":
         # transh.py:73-107: TransE on rows scaled by c = 1 - sum(w) * w (project(e) = e - (e * w.sum()) * w).
         # d c_j / d w_i = -w_j - sum(w) * [i == j]  =>  g_w = -sum(w) * g_c - <g_c, w>
@@ -149,7 +171,7 @@ def pair_loss_and_grads(model, h, r, tp, tn, weight, margin=1.0):
 
 def loss_weights(model, n_rec, n_kg):
     """Per-pair weights of the rec and KG segments in the scalar loss."""
-    if model in ("TransE", "DistMult", "TorusE", "TransH"):
+    if model in ("TransE", "DistMult", "TorusE", "TransH", "TransD"):
         w = 1.0 / (n_rec + n_kg)
         return w, w
     return (0.5 / n_rec if n_rec else 0.0), (0.5 / n_kg if n_kg else 0.0)

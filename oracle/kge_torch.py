@@ -36,6 +36,9 @@ TABLE_NAMES = {
     "TorusE": (["user_embedding"], ["entity_embedding"], ["relation_embedding"]),
     # transh.py:31-48: the second relation table is the hyperplane vector
     "TransH": (["user_embedding"], ["entity_embedding"], ["relation_embedding", "norm_vec"]),
+    # transd.py:41-47: an embedding and a transfer vector per table (created embeddings first, then the vectors)
+    "TransD": (["user_embedding", "user_vec_embedding"], ["entity_embedding", "entity_vec_embedding"],
+               ["relation_embedding", "relation_vec_embedding"]),
     "RotatE": (
         ["user_embedding", "user_embedding_im"],
         ["entity_embedding", "entity_embedding_im"],
@@ -75,12 +78,13 @@ class OracleKGE(nn.Module):
         self.shapes = shapes
         d = shapes.embedding_size
         unames, enames, rnames = TABLE_NAMES[model]
-        for n in unames:
-            setattr(self, n, nn.Embedding(shapes.n_users, d))
-        for n in enames:
-            setattr(self, n, nn.Embedding(shapes.n_entities, d))
-        for n in rnames:
-            setattr(self, n, nn.Embedding(shapes.n_relations, d))
+        rows = {**{n: shapes.n_users for n in unames}, **{n: shapes.n_entities for n in enames},
+                **{n: shapes.n_relations for n in rnames}}
+        order = unames + enames + rnames
+        if model == "TransD":   # the reference constructor's order (it fixes the RNG stream of the initialisation)
+            order = [unames[0], enames[0], rnames[0], unames[1], enames[1], rnames[1]]
+        for n in order:
+            setattr(self, n, nn.Embedding(rows[n], d))
         for mod in self.modules():  # same traversal order as nn.Module.apply on children
             if isinstance(mod, nn.Embedding):
                 nn.init.xavier_normal_(mod.weight.data)
@@ -94,7 +98,7 @@ class OracleKGE(nn.Module):
     def _ui_row(self, full_sort: bool) -> int:
         # TransE / DistMult always take weight[-1]; RotatE always the token id; ComplEx the
         # token id for loss/predict and weight[-1] for full_sort_predict.
-        if self.model in ("TransE", "DistMult", "TorusE"):   # toruse.py:53, 121, 131
+        if self.model in ("TransE", "DistMult", "TorusE", "TransD"):   # toruse.py:53, 121, 131; transd.py:60, 69
             return self.shapes.n_relations - 1
         if self.model == "TransH":
             # transh.py:63, 90: relation_embedding.weight[-1] but norm_vec(ui_relation) -- one row only when the token
@@ -110,6 +114,9 @@ class OracleKGE(nn.Module):
         m = self.model
         if m == "TransE":
             return -torch.norm(h[0] + r[0] - t[0], p=2, dim=-1)
+        if m == "TransD":   # transd.py:86-91, 135-176: proj(e) = r_p * <e, e_p> + e on head and tail, then TransE's norm
+            proj = lambda e: r[1] * (e[0] * e[1]).sum(dim=-1, keepdim=True) + e[0]   # noqa: E731
+            return -torch.norm(proj(h) + r[0] - proj(t), p=2, dim=-1)
         if m == "TransH":   # transh.py:53-58, 73-74: project(e) = e - (e * w.sum()) * w
             w = r[1]
             sw = w.sum(dim=-1, keepdim=True)
@@ -154,6 +161,14 @@ class OracleKGE(nn.Module):
         if self.model in ("TransE", "TorusE"):   # toruse.py:81-102 is transe.py:75-98: the torus only scores
             anchor = torch.cat([u[0] + ur[0], h[0] + kr[0]])
             pos, neg = torch.cat([ip[0], tp[0]]), torch.cat([ineg[0], tn[0]])
+            return nn.functional.triplet_margin_loss(anchor, pos, neg, margin=self.shapes.margin, p=2)
+        if self.model == "TransD":   # transd.py:93-133
+            def projd(e, rr):
+                return rr[1] * (e[0] * e[1]).sum(dim=1, keepdim=True) + e[0]
+
+            anchor = torch.cat([projd(u, ur) + ur[0], projd(h, kr) + kr[0]])
+            pos = torch.cat([projd(ip, ur), projd(tp, kr)])
+            neg = torch.cat([projd(ineg, ur), projd(tn, kr)])
             return nn.functional.triplet_margin_loss(anchor, pos, neg, margin=self.shapes.margin, p=2)
         if self.model == "TransH":   # transh.py:76-107: project every row with its triple's relation, then TransE's loss
             def proj(e, rr):

