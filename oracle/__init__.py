@@ -1,7 +1,7 @@
 """CPU oracle for the KGE hot path.  TEST INFRASTRUCTURE ONLY.
 
 This package restates, on the CPU, the algorithms that tail-unica/hopwise runs for
-TransE / RotatE / DistMult / ComplEx (and TorusE / TransH) training, KG negative sampling and full-sort
+TransE / RotatE / DistMult / ComplEx (and TorusE / TransH / TransD) training, KG negative sampling and full-sort
 top-k evaluation.  It is the checker the CUDA path is compared against; it is never
 the thing that is shipped or measured as the product.
 
