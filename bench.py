@@ -177,6 +177,25 @@ def barrier(world):
     torch.cuda.synchronize()
 
 
+class no_gc:
+    """Timed regions run with the cyclic collector off (collected right before): a generation-2 pass between two kernel
+    launches of a block is tens of milliseconds of idle GPU inside that block's events."""
+
+    def __enter__(self):
+        import gc
+
+        gc.collect()
+        self._was = gc.isenabled()
+        gc.disable()
+
+    def __exit__(self, *exc):
+        import gc
+
+        if self._was:
+            gc.enable()
+        return False
+
+
 # ---- timed legs -------------------------------------------------------------------------------
 def time_train_device(model, dev_batches, steps, warmup, flush_buf, world):
     """K steps with ids resident in HBM; per-step CUDA events, L2 flushed (untimed) in between."""
@@ -185,17 +204,18 @@ def time_train_device(model, dev_batches, steps, warmup, flush_buf, world):
     for i in range(warmup):
         model.calculate_loss(dev_batches[i % nb]).backward()
     ev = [[torch.cuda.Event(enable_timing=True) for _ in range(3)] for _ in range(steps)]
-    barrier(world)
-    for i in range(steps):
-        if flush_buf is not None:
-            flush_buf.zero_()
-        b = dev_batches[(warmup + i) % nb]
-        ev[i][0].record()
-        loss = model.calculate_loss(b)
-        ev[i][1].record()
-        loss.backward()
-        ev[i][2].record()
-    barrier(world)
+    with no_gc():
+        barrier(world)
+        for i in range(steps):
+            if flush_buf is not None:
+                flush_buf.zero_()
+            b = dev_batches[(warmup + i) % nb]
+            ev[i][0].record()
+            loss = model.calculate_loss(b)
+            ev[i][1].record()
+            loss.backward()
+            ev[i][2].record()
+        barrier(world)
     fwd = np.array([e[0].elapsed_time(e[1]) for e in ev])
     upd = np.array([e[1].elapsed_time(e[2]) for e in ev])
     return fwd, upd, float(loss.item())   # per-step milliseconds (forward / backward = exchange + Adam)
@@ -258,16 +278,17 @@ def time_train_e2e(model, host_batches, steps, warmup, world, device, reference_
         one(db)
     drain()
     loader.batches = [host_batches[(warmup + i) % nb] for i in range(steps)]
-    barrier(world)
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    stamps = [time.perf_counter()]
-    e0.record(stream)
-    for db in loader:
-        one(db)
-        stamps.append(time.perf_counter())   # (each step ends with a host sync on a loss)
-    drain()                                  # the last step's loss, still inside the timed region
-    e1.record(stream)
-    barrier(world)
+    with no_gc():
+        barrier(world)
+        stamps = [time.perf_counter()]
+        e0.record(stream)
+        for db in loader:
+            one(db)
+            stamps.append(time.perf_counter())   # (each step ends with a host sync on a loss)
+        drain()                                  # the last step's loss, still inside the timed region
+        e1.record(stream)
+        barrier(world)
     per_step = np.diff(np.array(stamps)) * 1e3
     return e0.elapsed_time(e1), float(np.median(per_step)), float(per_step.max())
 
@@ -287,14 +308,15 @@ def time_fullsort(fs, device, n_users_step, steps, warmup, world, rank, path="au
     for i in range(max(warmup, len(blocks))):   # every block once before the timed region (first-touch effects)
         u, o, h = blocks[i % len(blocks)]
         m.full_sort_topk(u, fs["k"], o, h, return_scores=False, path=path)
-    barrier(world)
     ev = [torch.cuda.Event(enable_timing=True) for _ in range(steps + 1)]
-    ev[0].record()
-    for i in range(steps):
-        u, o, h = blocks[i % len(blocks)]
-        ids, _ = m.full_sort_topk(u, fs["k"], o, h, return_scores=False, path=path)
-        ev[i + 1].record()
-    barrier(world)
+    with no_gc():
+        barrier(world)
+        ev[0].record()
+        for i in range(steps):
+            u, o, h = blocks[i % len(blocks)]
+            ids, _ = m.full_sort_topk(u, fs["k"], o, h, return_scores=False, path=path)
+            ev[i + 1].record()
+        barrier(world)
     ms = ev[0].elapsed_time(ev[-1])
     in_order = [ev[i].elapsed_time(ev[i + 1]) for i in range(steps)]
     per_rep = sorted(in_order)
@@ -341,12 +363,13 @@ def full_eval_leg(fs, device, world, rank):
         return metrics_from_sums(sums, total, [fs["k"]], decimals=None)
 
     run()   # warm-up: operand image, workspaces, first touches
-    barrier(world)
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e0.record()
-    result = run()   # ends with the D2H read of the metric sums
-    e1.record()
-    barrier(world)
+    with no_gc():
+        barrier(world)
+        e0.record()
+        result = run()   # ends with the D2H read of the metric sums
+        e1.record()
+        barrier(world)
     ms = max_over_ranks(e0.elapsed_time(e1), device, world)
     fb = m._mma_total_fallback_rows
     del m
