@@ -96,6 +96,7 @@ PROTOTYPES = {
     "kge_grad_discard": (C.c_int, [_MP, C.c_int32, _P]),
     "kge_grad_pack": (C.c_int, [_MP, C.c_int32, C.c_int32, _P, _P, _P, _P]),
     "kge_grad_add": (C.c_int, [_MP, C.c_int32, C.c_int32, _P, _P, _P, C.c_int64, _P]),
+    "kge_transh_project": (C.c_int, [_P, _P, C.c_int64, C.c_int32, _P, _P, C.c_int64, _P, _P]),
     "kge_transd_project": (C.c_int, [_P, _P, _P, C.c_int64, C.c_int32, _P, _P, C.c_int64, _P, _P]),
     "kge_predict": (C.c_int, [_MP, _P, _P, _P, C.c_int64, C.c_int, _P, _P]),
     "kge_full_sort_scores": (C.c_int, [_MP, _P, _P, C.c_int64, C.c_int, C.c_int64, _P, _P]),

@@ -138,6 +138,32 @@ __global__ void __launch_bounds__(256) transd_project_kernel(const float* __rest
   }
 }
 
+// ---- TransH projection: out[i] = E[id_i] * (1 - sum(w) * w), w = W[rel_i]  (transh.py:73-74) ---------------------
+template <int VEC, int G, int NCH>
+__global__ void __launch_bounds__(256) transh_project_kernel(const float* __restrict__ emb, const int64_t* __restrict__ ids,
+                                                             int64_t n, int d, const float* __restrict__ norm_vec,
+                                                             const int64_t* __restrict__ rel_ids, int64_t rel_row,
+                                                             float* __restrict__ out) {
+  constexpr int E = VEC * NCH;
+  const int gl = (threadIdx.x & 31) % G;
+  const int groups_per_cta = blockDim.x / G;
+  const int64_t n_groups = (int64_t)gridDim.x * groups_per_cta;
+  for (int64_t i = (int64_t)blockIdx.x * groups_per_cta + threadIdx.x / G; i < n; i += n_groups) {
+    const int64_t row = ids ? __ldg(ids + i) : i;
+    const int64_t rr = rel_ids ? __ldg(rel_ids + i) : rel_row;
+    float e0[E], w[E];
+    frag_load<VEC, G, NCH>(emb, row, d, gl, e0);
+    frag_load<VEC, G, NCH>(norm_vec, rr, d, gl, w);
+    float s = 0.f;
+#pragma unroll
+    for (int e = 0; e < E; ++e) s += w[e];
+    s = group_sum<G>(s);
+#pragma unroll
+    for (int e = 0; e < E; ++e) e0[e] *= __fsub_rn(1.f, __fmul_rn(s, w[e]));
+    frag_store<VEC, G, NCH>(out, i, d, gl, e0);
+  }
+}
+
 // ---- the tile kernel ---------------------------------------------------------------------------
 struct TileArgs {
   ScoreArgs s;
@@ -651,6 +677,25 @@ extern "C" int kge_transd_project(const float* emb, const float* vec, const int6
   cudaStream_t st = (cudaStream_t)stream;
 #define CALL(V, G, N) \
   transd_project_kernel<V, G, N><<<grid, threads, 0, st>>>(emb, vec, ids, n, d, rel_vec, rel_ids, rel_row, out)
+  KGE_DISPATCH_ROWCFG(c, CALL);
+#undef CALL
+  KGE_LAUNCH_CHECK();
+  return 0;
+}
+
+extern "C" int kge_transh_project(const float* emb, const int64_t* ids, int64_t n, int32_t d, const float* norm_vec,
+                                  const int64_t* rel_ids, int64_t rel_row, float* out, kge_stream_t stream) {
+  KGE_REQUIRE(n >= 0 && d >= 1, KGE_E_ARG, "bad n / d");
+  if (n == 0) return 0;
+  KGE_REQUIRE(emb && norm_vec && out && (rel_ids || rel_row >= 0), KGE_E_ARG, "NULL argument");
+  RowCfg c = {};
+  KGE_REQUIRE(kge_pick_rowcfg(d, c), KGE_E_UNSUPPORTED, "embedding_size %d unsupported", d);
+  const int threads = 256;
+  int64_t g = (n + threads / c.g - 1) / (threads / c.g);
+  const int64_t cap = (int64_t)kge_num_sms() * 8;
+  const int grid = (int)(g < cap ? g : cap);
+  cudaStream_t st = (cudaStream_t)stream;
+#define CALL(V, G, N) transh_project_kernel<V, G, N><<<grid, threads, 0, st>>>(emb, ids, n, d, norm_vec, rel_ids, rel_row, out)
   KGE_DISPATCH_ROWCFG(c, CALL);
 #undef CALL
   KGE_LAUNCH_CHECK();

@@ -652,6 +652,32 @@ class FusedKGEModel(KnowledgeRecommender):
     def full_sort_predict_kg(self, interaction):
         return self._full_sort(interaction[self.HEAD_ENTITY_ID], interaction[self.RELATION_ID], False, self.n_entities)
 
+    # ------------------------------------------------------------------ projected-table scoring (TransD, TransH)
+    def _transe_view(self, users, entities):
+        """The private TransE model over projected tables: `users` [n, d] rows, `entities` [m, d] rows, the
+        relation table shared with this model."""
+        view = self.__dict__.get("_view")
+        if view is None:
+            cfg = {"USER_ID_FIELD": self.USER_ID, "ITEM_ID_FIELD": self.ITEM_ID, "NEG_PREFIX": self.NEG_ITEM_ID[: -len(self.ITEM_ID)],
+                   "ENTITY_ID_FIELD": self.ENTITY_ID, "RELATION_ID_FIELD": self.RELATION_ID,
+                   "HEAD_ENTITY_ID_FIELD": self.HEAD_ENTITY_ID, "TAIL_ENTITY_ID_FIELD": self.TAIL_ENTITY_ID,
+                   "device": self.device, "embedding_size": self.embedding_size, "margin": self.margin}
+
+            class _Shape:
+                def num(_, field):
+                    return {self.RELATION_ID: self.n_relations}.get(field, 1)
+
+            view = TransE(cfg, _Shape())
+            view.eval()
+            self.__dict__["_view"] = view   # (not a submodule: its tables are scratch, not parameters of this model)
+        with torch.no_grad():
+            view.user_embedding.weight.data = users
+            view.entity_embedding.weight.data = entities
+            view.relation_embedding.weight.data = self.relation_embedding.weight.data
+        view.n_users, view.n_items, view.n_entities = users.shape[0], entities.shape[0], entities.shape[0]
+        view.__dict__.pop("_table_params", None)
+        return view
+
     # ------------------------------------------------------------------ fused full-sort top-k
     def _topk_exact(self, m, users, k, hist_off, hist_items, mask_pad, ids, scores, rels=None, n_targets=None):
         lib = _abi.lib()
@@ -884,6 +910,60 @@ class TransH(FusedKGEModel):
     def full_sort_predict_kg(self, interaction):
         raise NotImplementedError("the reference TransH has no KG scoring entry points (transh.py)")
 
+    # A large item set is scored as TransE over projected tables (users and items scaled by the user->item relation's
+    # factor, `kge_transh_project`): that is the route to the tensor-core top-k.  Dense rows and top-k always take
+    # the same route, so that the top-k of a user equals the top-k of its dense row bit for bit.
+    VIEW_MIN_ITEMS = 8192
+
+    def _project(self, family, ids):
+        device = self._check_ready()
+        self.flush()
+        emb = (self.user_embedding if family == "user" else self.entity_embedding).weight
+        ids = self._ids(ids, device)
+        out = torch.empty(ids.numel(), self.embedding_size, dtype=torch.float32, device=device)
+        _abi.check(
+            _abi.lib().kge_transh_project(emb.data_ptr(), ids.data_ptr(), ids.numel(), self.embedding_size,
+                                          self.norm_vec.weight.data_ptr(), None, self.n_relations - 1, out.data_ptr(),
+                                          _abi.stream_ptr()),
+            "kge_transh_project",
+        )
+        return out
+
+    def _projected_items(self):
+        tabs = [self.entity_embedding.weight, self.norm_vec.weight]
+        key = (self._step, tuple(t.data_ptr() for t in tabs), tuple(t._version for t in tabs))
+        hit = self.__dict__.get("_items_cache")
+        if hit is None or hit[0] != key:
+            hit = (key, self._project("entity", torch.arange(self.n_items, device=tabs[0].device)))
+            self.__dict__["_items_cache"] = hit
+            view = self.__dict__.get("_view")
+            if view is not None:
+                view.invalidate_target_image()
+        return hit[1]
+
+    def invalidate_target_image(self):
+        super().invalidate_target_image()
+        self.__dict__.pop("_items_cache", None)
+
+    def _rec_view(self, user_ids):
+        view = self._transe_view(self._project("user", user_ids), self._projected_items())
+        return view, torch.arange(view.n_users, device=view.user_embedding.weight.device)
+
+    def full_sort_predict(self, interaction):
+        if self.n_items < self.VIEW_MIN_ITEMS:
+            return super().full_sort_predict(interaction)
+        view, idx = self._rec_view(interaction[self.USER_ID])
+        return view.full_sort_predict({self.USER_ID: idx})
+
+    def full_sort_topk(self, user_ids, k, hist_off=None, hist_items=None, mask_pad=True, return_scores=True,
+                       path="auto", _debug_scores=False, relation_ids=None):
+        if relation_ids is not None:
+            raise NotImplementedError("the reference TransH has no KG scoring entry points (transh.py)")
+        if self.n_items < self.VIEW_MIN_ITEMS:
+            return super().full_sort_topk(user_ids, k, hist_off, hist_items, mask_pad, return_scores, path, _debug_scores)
+        view, idx = self._rec_view(user_ids)
+        return view.full_sort_topk(idx, k, hist_off, hist_items, mask_pad, return_scores, path, _debug_scores)
+
 
 class TransD(FusedKGEModel):
     """transd.py: every table has an embedding and a transfer vector; ``forward(ent, ent_vec, rel_vec) = rel_vec *
@@ -938,31 +1018,6 @@ class TransD(FusedKGEModel):
     def invalidate_target_image(self):
         super().invalidate_target_image()
         self.__dict__.pop("_items_cache", None)
-
-    def _transe_view(self, users, entities):
-        """The private TransE model over projected tables: `users` [n, d] rows, `entities` [m, d] rows, the
-        relation table shared with this model."""
-        view = self.__dict__.get("_view")
-        if view is None:
-            cfg = {"USER_ID_FIELD": self.USER_ID, "ITEM_ID_FIELD": self.ITEM_ID, "NEG_PREFIX": self.NEG_ITEM_ID[: -len(self.ITEM_ID)],
-                   "ENTITY_ID_FIELD": self.ENTITY_ID, "RELATION_ID_FIELD": self.RELATION_ID,
-                   "HEAD_ENTITY_ID_FIELD": self.HEAD_ENTITY_ID, "TAIL_ENTITY_ID_FIELD": self.TAIL_ENTITY_ID,
-                   "device": self.device, "embedding_size": self.embedding_size, "margin": self.margin}
-
-            class _Shape:
-                def num(_, field):
-                    return {self.RELATION_ID: self.n_relations}.get(field, 1)
-
-            view = TransE(cfg, _Shape())
-            view.eval()
-            self.__dict__["_view"] = view   # (not a submodule: its tables are scratch, not parameters of this model)
-        with torch.no_grad():
-            view.user_embedding.weight.data = users
-            view.entity_embedding.weight.data = entities
-            view.relation_embedding.weight.data = self.relation_embedding.weight.data
-        view.n_users, view.n_items, view.n_entities = users.shape[0], entities.shape[0], entities.shape[0]
-        view.__dict__.pop("_table_params", None)
-        return view
 
     # ---- scoring ----------------------------------------------------------------------------------------------
     def predict(self, interaction):

@@ -203,6 +203,12 @@ int kge_transd_project(const float* emb, const float* vec, const int64_t* ids, i
                        const float* rel_vec, const int64_t* rel_ids, int64_t rel_row, float* out,
                        kge_stream_t stream);
 
+/* kge_transh_project: out[i, :] = E[id_i] * (1 - sum(w) * w), w = W[rel_i]  (TransH.project, transh.py:73-74).
+ * Lets full-sort over a large item set run as KGE_TRANSE over projected tables (tensor-core path included); the
+ * KGE_TRANSH scoring entry points compute the same scores directly on the CUDA cores. */
+int kge_transh_project(const float* emb, const int64_t* ids, int64_t n, int32_t d, const float* norm_vec,
+                       const int64_t* rel_ids, int64_t rel_row, float* out, kge_stream_t stream);
+
 /* ---- scoring --------------------------------------------------------------------------
  * kge_predict: <Model>.predict / predict_kg (transe.py:100-110,128-137 and twins).
  * heads index the user tables when head_is_user != 0, else the entity tables; rels == NULL
