@@ -8,7 +8,10 @@ Public surface (mirrors the reference names so a hopwise user can switch imports
   DevicePrefetcher                       host->device batch staging one step ahead (loader.py)
 """
 
-from .recommender import ComplEx, DistMult, FusedKGEModel, KnowledgeRecommender, RotatE, TorusE, TransD, TransE, TransH, MODELS  # noqa: F401
+from .recommender import (  # noqa: F401
+    MODELS, ComplEx, DistMult, FusedKGEModel, KnowledgeRecommender, RotatE, TorusE, TransD, TransE, TransH,
+)
 
-__all__ = ["TransE", "DistMult", "RotatE", "ComplEx", "TorusE", "TransH", "TransD", "FusedKGEModel", "KnowledgeRecommender", "MODELS"]
+__all__ = ["TransE", "DistMult", "RotatE", "ComplEx", "TorusE", "TransH", "TransD", "FusedKGEModel",
+           "KnowledgeRecommender", "MODELS"]
 __version__ = "0.1.0"

@@ -658,7 +658,8 @@ class FusedKGEModel(KnowledgeRecommender):
         relation table shared with this model."""
         view = self.__dict__.get("_view")
         if view is None:
-            cfg = {"USER_ID_FIELD": self.USER_ID, "ITEM_ID_FIELD": self.ITEM_ID, "NEG_PREFIX": self.NEG_ITEM_ID[: -len(self.ITEM_ID)],
+            cfg = {"USER_ID_FIELD": self.USER_ID, "ITEM_ID_FIELD": self.ITEM_ID,
+                   "NEG_PREFIX": self.NEG_ITEM_ID[: -len(self.ITEM_ID)],
                    "ENTITY_ID_FIELD": self.ENTITY_ID, "RELATION_ID_FIELD": self.RELATION_ID,
                    "HEAD_ENTITY_ID_FIELD": self.HEAD_ENTITY_ID, "TAIL_ENTITY_ID_FIELD": self.TAIL_ENTITY_ID,
                    "device": self.device, "embedding_size": self.embedding_size, "margin": self.margin}
