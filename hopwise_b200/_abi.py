@@ -13,7 +13,7 @@ import os
 
 from . import _build
 
-KGE_ABI_VERSION = 4
+KGE_ABI_VERSION = 5
 MODEL_KINDS = {"TransE": 0, "DistMult": 1, "RotatE": 2, "ComplEx": 3, "TorusE": 4, "TransH": 5, "TransD": 6}
 
 
