@@ -122,3 +122,35 @@ def test_epoch_order_matches_torch_distributed_sampler(n, step, world, shuffle):
             assert len(got) == len(want)
             for a, b in zip(got, want):
                 assert torch.equal(a, b)
+
+
+def test_pack_batch_layouts_on_the_host():
+    """pack_batch: one contiguous buffer (int64, or int32 with narrow=True), padded to a multiple of four ids, named
+    views at their offsets; ids beyond 32 bits are refused for the narrow layout."""
+    from hopwise_b200.loader import pack_batch
+
+    rng = np.random.default_rng(0)
+    batch = {"user_id": rng.integers(0, 1000, 7), "item_id": rng.integers(0, 2 ** 31 - 1, 7), "neg_item_id": rng.integers(0, 9, 14)}
+    for narrow in (False, True):
+        pb = pack_batch(batch, pin=False, narrow=narrow)
+        assert pb.narrow == narrow and pb.base.dtype == (torch.int32 if narrow else torch.int64)
+        assert pb.base.numel() == 28 and pb.base.numel() % 4 == 0
+        views = pb.views()
+        assert list(views) == list(batch)
+        for k, v in batch.items():
+            np.testing.assert_array_equal(views[k].numpy().astype(np.int64), v)
+        off = [pb.slices[k][0] for k in batch]
+        assert off == [0, 7, 14]
+    with pytest.raises(ValueError):
+        pack_batch({"user_id": np.array([3, 2 ** 31])}, pin=False, narrow=True)
+    assert pack_batch({"user_id": np.array([3, 2 ** 31])}, pin=False).base[1].item() == 2 ** 31
+
+
+def test_device_loader_refuses_the_cpu_without_a_gather_hook():
+    from hopwise_b200.loader import DeviceKGLoader
+
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        DeviceKGLoader([1], [1], [1], [1], [1], None, None, batch_size=1, seed=0, device="cpu")
+    with pytest.raises(ValueError, match="candidate_num"):
+        DeviceKGLoader([1], [1], [1], [1], [1], None, None, batch_size=1, seed=0, device="cpu", dynamic=True,
+                       gather=lambda t, i: t.index_select(0, i))
