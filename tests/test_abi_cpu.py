@@ -6,6 +6,7 @@ import os
 import re
 
 import pytest
+import torch
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 HEADER = os.path.join(ROOT, "include", "kge_b200.h")
@@ -52,6 +53,16 @@ def test_host_only_entry_points():
     assert abs(buf[3] - 1 / (1 - 0.999) ** 0.5) < 1e-3
     assert abs(buf[2 * (n - 1)] - 1e-3) < 1e-10 and abs(buf[2 * (n - 1) + 1] - 1.0) < 1e-6
     assert lib.kge_sample_workspace_bytes(100) == 800
+    assert lib.kge_sample_alias_workspace_bytes(100) == 2000       # two open-slot lists, round indices, 2 words / slot
+    assert lib.kge_assemble_batch_workspace_bytes(2048, 2048, 3) == lib.kge_sample_workspace_bytes(2048 * 3)
+    assert lib.kge_assemble_batch_workspace_bytes(-1, 0, 1) == -1
+    # the entry points added in round 2 refuse bad arguments the same way
+    assert lib.kge_gather_columns(None, 9, 10, None, 4, None, None, None) < 0
+    assert lib.kge_widen_ids_i32(None, None, 8, None) < 0
+    assert lib.kge_transd_project(None, None, None, 4, 16, None, None, 0, None, None) < 0
+    assert lib.kge_transh_project(None, None, 4, 16, None, None, 0, None, None) < 0
+    assert lib.kge_sample_negatives_alias(None, None, 4, 1, None, None, 0, None, None, None, None, None, None) < 0
+    assert lib.kge_owner_adam_step(None, None, None, None, None, None, 16, 0, 2, None, 1.0, None, 0, None, 1, None) < 0
     # argument errors come back as codes + message, never exceptions or crashes
     assert lib.kge_train_forward(None, None, None, 1, None, None) < 0
     assert b"NULL" in lib.kge_last_error()
@@ -135,7 +146,7 @@ def test_product_has_no_cpu_fallback_and_no_oracle_import():
 def test_state_dict_keys_match_reference_names(golden):
     from kge_helpers import make_product_model
 
-    for name in ("TransE", "RotatE", "DistMult", "ComplEx"):
+    for name in ("TransE", "RotatE", "DistMult", "ComplEx", "TorusE", "TransH", "TransD"):
         g = golden(f"model_{name}_d10.npz")
         U, I, E, R, d = (int(x) for x in g["shape"])
         m = make_product_model(name, U, I, E, R, d, device="cpu")
@@ -147,7 +158,15 @@ def test_state_dict_keys_match_reference_names(golden):
 
 
 def test_unsupported_configs_are_refused():
-    from kge_helpers import make_product_model
+    from kge_helpers import ShapeDataset, make_product_model
+    import hopwise_b200
+    from kge_helpers import BASE_CONFIG
+
+    # TransH reads relation_embedding.weight[-1] but norm_vec(ui_relation): one row only when the token is last
+    cfg = dict(BASE_CONFIG, embedding_size=16, margin=1.0, device=torch.device("cpu"))
+    with pytest.raises(NotImplementedError, match="UI-Relation"):
+        hopwise_b200.TransH(cfg, ShapeDataset(10, 8, 20, 5, ui_token_id=2))
+    hopwise_b200.TransH(cfg, ShapeDataset(10, 8, 20, 5))
 
     with pytest.raises(NotImplementedError):
         make_product_model("TransE", 10, 8, 20, 5, 16, device="cpu", learner="sgd")
