@@ -76,7 +76,12 @@ class kge_adam_t(C.Structure):
         ("eps", C.c_float),
         ("step", C.c_int32),
         ("replay_cap", C.c_int32),
+        ("optimizer", C.c_int32),
+        ("reserved", C.c_int32),
     ]
+
+
+OPTIMIZERS = {"adam": 0, "sgd": 1, "adagrad": 2, "rmsprop": 3}   # enum kge_optimizer
 
 
 _P = C.c_void_p

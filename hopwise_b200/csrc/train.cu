@@ -37,6 +37,7 @@ struct AdamDev {
   float lr, b1, b2, eps, omb1, omb2;
   int step;  // update being produced
   int cap;
+  int opt;   // enum kge_optimizer
   const float2* table;  // {lr/(1-b1^j), 1/sqrt(1-b2^j)}
   int tlen;
 };
@@ -100,7 +101,7 @@ template <int VEC, int G, int NCH>
 __device__ __forceinline__ void catch_up(const kge_table_t& T, int part, int64_t row, int2 st, int d, int gl,
                                          const AdamDev& A, float (&x)[VEC * NCH], int mark) {
   const int last = st.x;
-  if (last >= 0 && last < A.step - 1) {
+  if (last >= 0 && last < A.step - 1 && A.opt == KGE_OPT_ADAM) {   // (only Adam moves a row that has no gradient)
     float m[VEC * NCH], v[VEC * NCH];
     frag_load<VEC, G, NCH>(T.m[part], row, d, gl, m);
     frag_load<VEC, G, NCH>(T.v[part], row, d, gl, v);
@@ -714,26 +715,44 @@ __device__ __forceinline__ void adam_row(const kge_table_t& T, int64_t row, int 
                                          float scale) {
   constexpr int E = VEC * NCH;
   const float2 c = adam_consts(A, A.step);
+  // RMSprop: the second moment of a row that skipped n steps decayed by alpha^n meanwhile (torch multiplies it by
+  // alpha once per step, gradient or not); a row never touched before has v = 0
+  const float lag_decay = (A.opt == KGE_OPT_RMSPROP && last >= 0 && last < A.step - 1)
+                              ? powf(A.b2, (float)(A.step - 1 - last)) : 1.f;
   for (int part = 0; part < T.parts; ++part) {
     float p[E], m[E], v[E], g[E];
     frag_load<VEC, G, NCH>(T.w[part], row, d, gl, p);
-    frag_load<VEC, G, NCH>(T.m[part], row, d, gl, m);
-    frag_load<VEC, G, NCH>(T.v[part], row, d, gl, v);
+    if (A.opt == KGE_OPT_ADAM) frag_load<VEC, G, NCH>(T.m[part], row, d, gl, m);
+    if (A.opt != KGE_OPT_SGD) frag_load<VEC, G, NCH>(T.v[part], row, d, gl, v);
     frag_load_cg<VEC, G, NCH>(T.g[part], row, d, gl, g);
-    if (last >= 0 && last < A.step - 1) adam_replay<E>(p, m, v, last, A.step - 1, A);
     float z[E];
+    if (A.opt == KGE_OPT_ADAM) {
+      if (last >= 0 && last < A.step - 1) adam_replay<E>(p, m, v, last, A.step - 1, A);
 #pragma unroll
-    for (int e = 0; e < E; ++e) {
-      const float ge = g[e] * scale;
-      m[e] += A.omb1 * (ge - m[e]);
-      v[e] = v[e] * A.b2 + A.omb2 * ge * ge;
-      const float den = sqrt_nonneg(v[e]) * c.y + A.eps;
-      p[e] -= c.x * div_pos_den(m[e], den);
-      z[e] = 0.f;
+      for (int e = 0; e < E; ++e) {
+        const float ge = g[e] * scale;
+        m[e] += A.omb1 * (ge - m[e]);
+        v[e] = v[e] * A.b2 + A.omb2 * ge * ge;
+        const float den = sqrt_nonneg(v[e]) * c.y + A.eps;
+        p[e] -= c.x * div_pos_den(m[e], den);
+        z[e] = 0.f;
+      }
+      frag_store<VEC, G, NCH>(T.m[part], row, d, gl, m);
+    } else {
+#pragma unroll
+      for (int e = 0; e < E; ++e) {
+        const float ge = g[e] * scale;
+        if (A.opt == KGE_OPT_SGD) {
+          p[e] -= A.lr * ge;
+        } else {
+          v[e] = A.opt == KGE_OPT_ADAGRAD ? __fmaf_rn(ge, ge, v[e]) : __fmaf_rn(A.omb2 * ge, ge, v[e] * lag_decay * A.b2);
+          p[e] -= A.lr * div_pos_den(ge, sqrt_nonneg(v[e]) + A.eps);
+        }
+        z[e] = 0.f;
+      }
     }
     frag_store<VEC, G, NCH>(T.w[part], row, d, gl, p);
-    frag_store<VEC, G, NCH>(T.m[part], row, d, gl, m);
-    frag_store<VEC, G, NCH>(T.v[part], row, d, gl, v);
+    if (A.opt != KGE_OPT_SGD) frag_store<VEC, G, NCH>(T.v[part], row, d, gl, v);
     frag_store<VEC, G, NCH>(T.g[part], row, d, gl, z);
   }
   if (gl == 0) T.row_state[2 * row] = A.step;  // last_step; touch_step keeps `step` (stale from step+1 on)
@@ -768,6 +787,16 @@ __global__ void __launch_bounds__(256) adam_flush_kernel(const kge_table_t T, in
       [&](int64_t row, int last) {
         for (int part = 0; part < T.parts; ++part) {
           float p[E], m[E], v[E];
+          if (A.opt != KGE_OPT_ADAM) {   // the weights of an idle row do not move; RMSprop's second moment decays
+            if (A.opt == KGE_OPT_RMSPROP) {
+              frag_load<VEC, G, NCH>(T.v[part], row, d, gl, v);
+              const float f = powf(A.b2, (float)(A.step - last));
+#pragma unroll
+              for (int e = 0; e < E; ++e) v[e] *= f;
+              frag_store<VEC, G, NCH>(T.v[part], row, d, gl, v);
+            }
+            continue;
+          }
           frag_load<VEC, G, NCH>(T.w[part], row, d, gl, p);
           frag_load<VEC, G, NCH>(T.m[part], row, d, gl, m);
           frag_load<VEC, G, NCH>(T.v[part], row, d, gl, v);
@@ -863,6 +892,7 @@ AdamDev make_adam_dev(const kge_model_t* m, const kge_adam_t* a) {
   A.omb1 = (float)(1.0 - (double)a->beta1);
   A.omb2 = (float)(1.0 - (double)a->beta2);
   A.step = a->step;
+  A.opt = a->optimizer;
   A.cap = a->replay_cap > 0 ? a->replay_cap : 200;
   A.table = reinterpret_cast<const float2*>(m->adam_table);
   A.tlen = m->adam_table ? m->adam_table_len : 0;
@@ -940,6 +970,8 @@ extern "C" int kge_train_forward(const kge_model_t* model, const kge_batch_t* b,
   KGE_REQUIRE(b && adam && loss_out, KGE_E_ARG, "NULL batch / adam / loss_out");
   KGE_REQUIRE(b->n_rec >= 0 && b->n_kg >= 0 && b->k_rec >= 1 && b->k_kg >= 1, KGE_E_ARG, "bad batch sizes");
   KGE_REQUIRE(adam->step >= 1, KGE_E_ARG, "adam.step is 1-based");
+  KGE_REQUIRE(adam->optimizer >= KGE_OPT_ADAM && adam->optimizer <= KGE_OPT_RMSPROP, KGE_E_ARG, "unknown optimizer %d",
+              adam->optimizer);
   const int64_t n_total = b->n_rec + b->n_kg;
   if (n_total == 0) return 0;
   KGE_REQUIRE(b->n_rec == 0 || (b->user && b->item && b->neg_item), KGE_E_ARG, "NULL rec id array");

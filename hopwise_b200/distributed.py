@@ -133,6 +133,8 @@ class RowSparseExchange:
 
         if model._state is not None:
             raise RuntimeError("multimem exchange must be enabled before the first training step")
+        if owner_adam and getattr(model, "learner", "adam") != "adam":
+            raise NotImplementedError("owner-sharded optimiser step implements Adam only")
         group = self.group if self.group is not None else dist.group.WORLD
         ex = self
 

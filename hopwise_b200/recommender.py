@@ -176,9 +176,20 @@ class FusedKGEModel(KnowledgeRecommender):
 
         # optimiser hyper-parameters: the trainer's (trainer.py:165-206); anything the fused
         # update does not reproduce is refused instead of silently diverging
+        # (trainer.py:189-205: adam, adamw, sgd, adagrad, rmsprop; an unrecognised name falls back to Adam there too.
+        # AdamW with weight_decay 0 IS Adam; sparse_adam needs sparse gradients, which these dense tables never give
+        # the reference either)
         learner = str(_cfg_get(config, "learner", "adam")).lower()
-        if learner != "adam":
-            raise NotImplementedError(f"fused KGE step implements learner 'adam' only, got {learner!r}")
+        if learner == "sparse_adam":
+            raise NotImplementedError("learner 'sparse_adam' needs sparse embedding gradients (nn.Embedding(sparse=True))")
+        if learner == "adamw":
+            learner = "adam"
+        if learner not in _abi.OPTIMIZERS:
+            import warnings
+
+            warnings.warn(f"unrecognized learner {learner!r}: Adam, as the reference trainer does (trainer.py:203-205)")
+            learner = "adam"
+        self.learner = learner
         if float(_cfg_get(config, "weight_decay", 0.0) or 0.0) != 0.0:
             raise NotImplementedError("fused KGE step implements weight_decay 0.0 only")
         if _cfg_get(config, "clip_grad_norm", None):
@@ -186,8 +197,10 @@ class FusedKGEModel(KnowledgeRecommender):
         if _cfg_get(config, "enable_amp", False) or _cfg_get(config, "enable_scaler", False):
             raise NotImplementedError("AMP / GradScaler are not supported: the kernels are fp32")
         self.learning_rate = float(_cfg_get(config, "learning_rate", 1e-3))
-        self.betas = (0.9, 0.999)
-        self.adam_eps = 1e-8
+        # torch's defaults for the learner (the trainer passes lr and weight_decay only): Adam betas (0.9, 0.999) eps
+        # 1e-8; Adagrad eps 1e-10; RMSprop alpha 0.99 (carried in the beta2 slot) eps 1e-8
+        self.betas = (0.9, 0.99) if learner == "rmsprop" else (0.9, 0.999)
+        self.adam_eps = 1e-10 if learner == "adagrad" else 1e-8
         self.replay_cap = int(_cfg_get(config, "kge_replay_cap", 200))
 
         self._step = 0          # optimiser steps applied so far
@@ -365,6 +378,7 @@ class FusedKGEModel(KnowledgeRecommender):
         if a is None or a[0] != hp:   # one struct per hyper-parameter set; only the step changes between calls
             s = _abi.kge_adam_t()
             s.lr, s.beta1, s.beta2, s.eps, s.replay_cap = hp
+            s.optimizer = _abi.OPTIMIZERS[self.learner]
             a = (hp, s)
             self.__dict__["_adam_cache"] = a
         a[1].step = step

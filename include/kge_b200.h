@@ -104,10 +104,22 @@ typedef struct {
 } kge_batch_t;
 
 /* torch.optim.Adam hyper-parameters (trainer.py:189-190) + the step about to be applied. */
+/* The optimiser hopwise's trainer builds (trainer/trainer.py:165-206), applied to the touched rows:
+ *   KGE_OPT_ADAM     torch.optim.Adam(lr) (also AdamW with weight_decay 0): beta1, beta2, eps; rows that skipped steps
+ *                    are caught up with the zero-gradient steps dense Adam gives them
+ *   KGE_OPT_SGD      torch.optim.SGD(lr): p -= lr * g
+ *   KGE_OPT_ADAGRAD  torch.optim.Adagrad(lr): v += g^2; p -= lr * g / (sqrt(v) + eps)          (eps 1e-10)
+ *   KGE_OPT_RMSPROP  torch.optim.RMSprop(lr): v = beta2 * v + (1 - beta2) * g^2; p -= lr * g / (sqrt(v) + eps)
+ *                    (beta2 = alpha 0.99, eps 1e-8; v of a row that skipped n steps decays by alpha^n)
+ * Under the last three a row without a gradient does not move, so nothing is replayed. */
+enum kge_optimizer { KGE_OPT_ADAM = 0, KGE_OPT_SGD = 1, KGE_OPT_ADAGRAD = 2, KGE_OPT_RMSPROP = 3 };
+
 typedef struct {
   float lr, beta1, beta2, eps;
   int32_t step;       /* 1-based index of the update this batch produces */
   int32_t replay_cap; /* zero-gradient steps replayed exactly per row before the closed-form tail */
+  int32_t optimizer;  /* enum kge_optimizer */
+  int32_t reserved;
 } kge_adam_t;
 
 int kge_abi_version(void);

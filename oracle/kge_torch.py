@@ -224,8 +224,12 @@ class OracleKGE(nn.Module):
         return self.score(h, r, t)
 
 
-def make_optimizer(model: nn.Module, lr: float = 1e-3, weight_decay: float = 0.0):
-    return torch.optim.Adam(model.parameters(), lr=lr, weight_decay=weight_decay)
+def make_optimizer(model: nn.Module, lr: float = 1e-3, weight_decay: float = 0.0, learner: str = "adam"):
+    """The optimiser the reference trainer builds for `learner` (trainer/trainer.py:189-205): torch's defaults apart
+    from lr and weight_decay."""
+    cls = {"adam": torch.optim.Adam, "adamw": torch.optim.AdamW, "sgd": torch.optim.SGD, "adagrad": torch.optim.Adagrad,
+           "rmsprop": torch.optim.RMSprop}[learner.lower()]
+    return cls(model.parameters(), lr=lr, weight_decay=weight_decay)
 
 
 def train_step(model: OracleKGE, opt, batch: dict) -> float:

@@ -38,7 +38,7 @@ def test_struct_layout_matches_header():
     assert C.sizeof(_abi.kge_table_t) == 8 + 4 + 4 + 4 * 16 + 8
     assert C.sizeof(_abi.kge_model_t) == 4 * 6 + 8 + 3 * C.sizeof(_abi.kge_table_t) + 8 + 8
     assert C.sizeof(_abi.kge_batch_t) == 3 * 8 + 8 + 4 * 8 + 8 + 8
-    assert C.sizeof(_abi.kge_adam_t) == 24
+    assert C.sizeof(_abi.kge_adam_t) == 32
 
 
 def test_host_only_entry_points():
@@ -169,7 +169,11 @@ def test_unsupported_configs_are_refused():
     hopwise_b200.TransH(cfg, ShapeDataset(10, 8, 20, 5))
 
     with pytest.raises(NotImplementedError):
-        make_product_model("TransE", 10, 8, 20, 5, 16, device="cpu", learner="sgd")
+        make_product_model("TransE", 10, 8, 20, 5, 16, device="cpu", learner="sparse_adam")
+    for learner, want in (("sgd", "sgd"), ("Adagrad", "adagrad"), ("rmsprop", "rmsprop"), ("adamw", "adam")):
+        assert make_product_model("TransE", 10, 8, 20, 5, 16, device="cpu", learner=learner).learner == want
+    with pytest.warns(UserWarning, match="unrecognized learner"):
+        assert make_product_model("TransE", 10, 8, 20, 5, 16, device="cpu", learner="lion").learner == "adam"
     with pytest.raises(NotImplementedError):
         make_product_model("TransE", 10, 8, 20, 5, 16, device="cpu", weight_decay=0.1)
     with pytest.raises(NotImplementedError):

@@ -413,3 +413,35 @@ def test_train_step_loss_ring_rolls_over():
     np.testing.assert_allclose(torch.stack(got).cpu().numpy(), np.array(want), rtol=1e-4)
     for (k, vo), (_, vp) in zip(ora.state_dict().items(), m.state_dict().items()):
         assert_weights_close(vp.cpu().numpy(), vo.numpy(), rtol=1e-4, atol=2e-6, err_msg=k)
+
+
+@pytest.mark.parametrize("learner,lr", [("sgd", 0.5), ("adagrad", 0.05), ("rmsprop", 1e-3), ("adamw", 1e-3)])
+@pytest.mark.parametrize("name", ["TransE", "ComplEx", "TransD"])
+def test_other_learners_follow_torch(name, learner, lr):
+    """trainer.py:189-205: sgd / adagrad / rmsprop (and adamw, which is Adam at weight_decay 0) applied to the touched
+    rows only, against torch.optim's dense versions on the oracle: rows idle for several steps in between (RMSprop's
+    second moment keeps decaying on them), checkpoint flush in the middle."""
+    U, I, E, R, d = 120, 80, 300, 7, 36
+    ora = make_oracle_model(name, U, I, E, R, d)
+    m = make_product_model(name, U, I, E, R, d, learner=learner, lr=lr)
+    assert m.learner == ("adam" if learner == "adamw" else learner)
+    opt_o = make_optimizer(ora, lr=lr, learner=learner)
+    rng = np.random.default_rng(11)
+    pool = [random_batch(rng, U, I, E, R, 64, 48, 2, 1) for _ in range(4)]
+    for step in range(14):
+        b = pool[(step * step) % 4]
+        want = train_step(ora, opt_o, to_cpu_batch(tile_batch(b, 2, 1)))
+        got = m.train_step(to_device_batch(b)) if step % 2 else _trainer_step(m, torch.optim.SGD(m.parameters(), lr=0.1),
+                                                                              to_device_batch(b))
+        np.testing.assert_allclose(float(got), want, rtol=RTOL, err_msg=f"loss at step {step + 1}")
+        if step == 6:
+            m.state_dict()   # flushes: every row current, RMSprop's idle rows decayed
+    for (k, vo), (_, vp) in zip(ora.state_dict().items(), m.state_dict().items()):
+        assert_weights_close(vp.cpu().numpy(), vo.numpy(), rtol=RTOL, atol=5e-7, err_msg=f"{learner} {k}")
+    if learner in ("adagrad", "rmsprop"):   # the second moments too (torch keeps them per parameter)
+        st = m.kge_optimizer_state
+        key = "sum" if learner == "adagrad" else "square_avg"
+        for fam, names in (("user", m.USER_TABLES), ("entity", m.ENTITY_TABLES), ("relation", m.RELATION_TABLES)):
+            for p, tname in enumerate(names):
+                want_v = opt_o.state[getattr(ora, tname).weight][key].numpy()
+                np.testing.assert_allclose(st[fam]["v"][p].numpy(), want_v, rtol=2e-5, atol=1e-12, err_msg=f"{learner} v {tname}")
