@@ -36,7 +36,7 @@ def test_struct_layout_matches_header():
 
     # sizes computed from the header's field lists (LP64)
     assert C.sizeof(_abi.kge_table_t) == 8 + 4 + 4 + 4 * 16 + 8
-    assert C.sizeof(_abi.kge_model_t) == 4 * 6 + 8 + 3 * C.sizeof(_abi.kge_table_t) + 8 + 8
+    assert C.sizeof(_abi.kge_model_t) == 4 * 6 + 8 + 3 * C.sizeof(_abi.kge_table_t) + 8 + 8 + 16
     assert C.sizeof(_abi.kge_batch_t) == 3 * 8 + 8 + 4 * 8 + 8 + 8
     assert C.sizeof(_abi.kge_adam_t) == 32
 
