@@ -116,7 +116,7 @@ __device__ __forceinline__ void touch_row(const kge_table_t& T, int64_t row, int
   if (tl.on && tl.m.touch_list) {
     if (atomicExch(&T.row_state[2 * row + 1], step) != step) {
       const int64_t base = tl.which == 0 ? 0 : (tl.which == 1 ? tl.m.user.rows : tl.m.user.rows + tl.m.entity.rows);
-      tl.m.touch_list[base + atomicAdd(tl.m.touch_count + tl.which, 1)] = (int32_t)row;
+      tl.m.touch_list[base + atomicAdd(tl.m.touch_count + 3 * (step & 1) + tl.which, 1)] = (int32_t)row;
     }
   } else {
     T.row_state[2 * row + 1] = step;
@@ -793,7 +793,11 @@ __global__ void __launch_bounds__(256) adam_apply_kernel(const ApplyArgs a) {
     const int32_t* ul = a.m.touch_list;
     const int32_t* el = ul + a.m.user.rows;
     const int32_t* rl = el + a.m.entity.rows;
-    const int nu = __ldg(a.m.touch_count), ne = __ldg(a.m.touch_count + 1), nr = __ldg(a.m.touch_count + 2);
+    // (two sets of counters, by step parity: this kernel zeroes the set the NEXT forward pass will count into --
+    // nobody reads or writes it while this kernel runs -- which saves a memset node in front of every forward pass)
+    const int32_t* cnt = a.m.touch_count + 3 * (step & 1);
+    const int nu = cnt[0], ne = cnt[1], nr = cnt[2];
+    if (blockIdx.x == 0 && threadIdx.x < 3) a.m.touch_count[3 * ((step + 1) & 1) + threadIdx.x] = 0;
     for (int64_t i = group; i < nu; i += n_groups) {
       const int64_t row = __ldg(ul + i);
       adam_row<VEC, G, NCH>(a.m.user, row, a.m.user.row_state[2 * row], a.m.d, gl, a.adam, scale);
@@ -1063,7 +1067,6 @@ extern "C" int kge_train_forward(const kge_model_t* model, const kge_batch_t* b,
                             (kind == KGE_TRANSE || kind == KGE_DISTMULT);
   const int threads = 256;
   const int grid = grid_for(n_total, threads / (two_per_warp ? 16 : c.g), 8);
-  if (model->touch_count && with_grad) KGE_CUDA(cudaMemsetAsync(model->touch_count, 0, 3 * sizeof(int32_t), (cudaStream_t)stream));
   const size_t smem = (size_t)model->relation.parts * model->d * sizeof(float);
   cudaStream_t st = (cudaStream_t)stream;
 #define CALL(V, G, N)                                                                                   \

@@ -277,7 +277,7 @@ class FusedKGEModel(KnowledgeRecommender):
         st["row_state_flat"] = torch.full((sum(rows for _, _, rows in fams), 2), -1, dtype=torch.int32, device=device)
         # small batches: the rows a step touches, listed by the forward pass for the optimiser kernel (kge_model_t)
         st["touch_list"] = torch.empty(sum(rows for _, _, rows in fams), dtype=torch.int32, device=device)
-        st["touch_count"] = torch.zeros(3, dtype=torch.int32, device=device)
+        st["touch_count"] = torch.zeros(6, dtype=torch.int32, device=device)   # two sets, by step parity
         # the moments share the gradient buffer's flat layout (an owner-sharded optimiser step walks the three
         # buffers -- and the weights, below -- element for element)
         flat_len = (g_numel + 3) // 4 * 4
@@ -477,12 +477,20 @@ class FusedKGEModel(KnowledgeRecommender):
     def _lists_touched_rows(self, b) -> bool:
         """Whether this step lists its touched rows for the optimiser kernel (LIST_ROWS_MAX): single replica only --
         an exchange marks rows itself -- and small enough that one atomic per first touch is cheap."""
-        if self._grad_sync is not None or self._owner_adam:
-            return False
-        refs = int(b.n_rec) * (2 + int(b.k_rec)) + int(b.n_kg) * (3 + int(b.k_kg))
-        return refs <= self.LIST_ROWS_MAX
+        listed = False
+        if self._grad_sync is None and not self._owner_adam and self._state is not None:
+            refs = int(b.n_rec) * (2 + int(b.k_rec)) + int(b.n_kg) * (3 + int(b.k_kg))
+            listed = refs <= self.LIST_ROWS_MAX
+        # the optimiser kernel of a listed step zeroes the counters of the next one; after a step that was not listed
+        # (or never applied) they are stale
+        if listed and not self.__dict__.get("_listed_last", False):
+            self._state["touch_count"].zero_()
+        _plain_set(self, "_listed_last", listed)
+        return listed
 
     def _discard_pending(self, lib, stream):
+        self._state["touch_count"].zero_()   # (the dropped step's rows were counted; the optimiser kernel never ran)
+        _plain_set(self, "_listed_last", False)
         if self._owner_adam:
             self._state["g_flat"].zero_()
         else:

@@ -85,8 +85,10 @@ typedef struct {
   int32_t _pad2;
   /* Optional (both or neither; small batches): the training pass appends every row it touches, once, to
    * touch_list -- user rows at [0, user.rows), entity rows from user.rows, relation rows behind them -- and counts
-   * them per table in touch_count[3]; kge_adam_apply then walks the three lists instead of scanning every row state.
-   * kge_train_forward zeroes the counts.  Leave NULL when anything else marks rows (the data-parallel exchange). */
+   * them per table in touch_count[6] (two sets of three, by step parity; zero before the first step);
+   * kge_adam_apply walks the three lists instead of scanning every row state and zeroes the other parity's set for
+   * the next step.  A gradient that is dropped instead of applied leaves its set to be zeroed by the caller.  Leave
+   * both NULL when anything else marks rows (the data-parallel exchange). */
   int32_t* touch_list;
   int32_t* touch_count;
 } kge_model_t;

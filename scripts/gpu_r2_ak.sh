@@ -1,7 +1,7 @@
 #!/bin/bash
 # round 2, GPU session AK (1 GPU): touched-row lists for small batches -- train tests, reference-batch timings
 mkdir -p gpurun_out
-timeout 600 python -m pytest tests/test_gpu_train.py tests/test_gpu_loader.py -m gpu -q -x 2>&1 | tail -n 4
+timeout 600 python -m pytest tests/test_gpu_train.py tests/test_gpu_loader.py tests/test_gpu_trainer_e2e.py -m gpu -q 2>&1 | tail -n 6
 python - <<'PY'
 import subprocess, json
 out = subprocess.run("python bench.py --steps 20 --warmup 5 --no-cpu-baseline", shell=True, capture_output=True, text=True).stdout

@@ -449,3 +449,39 @@ def test_other_learners_follow_torch(name, learner, lr):
             for p, tname in enumerate(names):
                 want_v = opt_o.state[getattr(ora, tname).weight][key].numpy()
                 np.testing.assert_allclose(st[fam]["v"][p].numpy(), want_v, rtol=2e-4, atol=1e-10, err_msg=f"{learner} v {tname}")
+
+
+@pytest.mark.parametrize("name", ["TransE", "RotatE"])
+def test_listed_and_scanned_steps_interleave(name):
+    """Small batches hand the optimiser kernel a list of the touched rows, large ones let it scan the row states
+    (FusedKGEModel.LIST_ROWS_MAX): steps of both kinds in any order, with a gradient that is dropped in between
+    (its rows were counted but never applied), follow the oracle's trajectory."""
+    U, I, E, R, d = 150, 100, 400, 7, 32
+    ora = make_oracle_model(name, U, I, E, R, d)
+    m = make_product_model(name, U, I, E, R, d)
+    opt_o = make_optimizer(ora)
+    rng = np.random.default_rng(5)
+    pool = [random_batch(rng, U, I, E, R, 96, 80) for _ in range(5)]
+    listed_seen = []
+    plan = [True, True, False, True, "drop", True, False, False, True, True, "drop", False, True]
+    for step, mode in enumerate(plan):
+        b = pool[step % 5]
+        if mode == "drop":   # a loss whose backward never runs
+            m.LIST_ROWS_MAX = 1 << 20
+            m.calculate_loss(to_device_batch(pool[(step + 2) % 5]))
+            continue
+        m.LIST_ROWS_MAX = (1 << 20) if mode else 10
+        want = train_step(ora, opt_o, to_cpu_batch(b))
+        if step % 2:
+            got = float(m.train_step(to_device_batch(b)))
+        else:
+            loss = m.calculate_loss(to_device_batch(b))
+            got = float(loss.item())
+            loss.backward()
+        listed_seen.append(m._listed_last)
+        np.testing.assert_allclose(got, want, rtol=RTOL, err_msg=f"loss at step {step + 1}")
+    assert listed_seen == [x for x in plan if x != "drop"]
+    for (k, vo), (_, vp) in zip(ora.state_dict().items(), m.state_dict().items()):
+        assert_weights_close(vp.cpu().numpy(), vo.numpy(), rtol=RTOL, atol=5e-7, err_msg=k)
+    cnt = m._state["touch_count"].cpu().numpy()
+    assert (cnt >= 0).all() and cnt.sum() <= U + E + R
