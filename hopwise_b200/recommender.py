@@ -348,8 +348,12 @@ class FusedKGEModel(KnowledgeRecommender):
         return m
 
     # A step that can touch at most this many rows hands the optimiser kernel a list of them (no scan of the row
-    # states, no imbalance between the scanning warps): what bounds a small batch is the longest warp's chain.
-    LIST_ROWS_MAX = 65536
+    # states, no imbalance between the scanning warps).  Off by default (0).  Measured at the reference batch
+    # (2048 + 2048, cfg2): the optimiser kernel 21 -> 16 us and the back-to-back step 32.6 -> 29.6 us of device time,
+    # but every first touch now costs the forward pass two dependent atomic round trips (exchange the mark, then take
+    # a list slot), and with a cold L2 -- how bench.py times its legs -- the step goes 43.7 -> 58.6 us.  Set it to
+    # e.g. 65536 for long runs of small batches over tables that stay in L2.
+    LIST_ROWS_MAX = 0
 
     def _build_model_struct(self, with_state: bool, listed: bool = False) -> _abi.kge_model_t:
         m = _abi.kge_model_t()
