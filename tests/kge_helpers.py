@@ -85,12 +85,15 @@ def assert_weights_close(got, want, rtol=1e-5, atol=5e-7, outlier_frac=5e-4, out
     (|g| ~ eps = 1e-8, e.g. duplicate rows whose contributions cancel): d(update)/dg peaks at
     lr / (4 eps) = 2.5e4, so two correct fp32 implementations that sum in a different order can
     differ by up to ~1e-5..1e-4 on such an element.  Those elements are allowed, but only
-    `outlier_frac` of a table and never beyond `outlier_atol` (a tenth of one Adam step).
+    `outlier_frac` of a table (two at least) and never beyond `outlier_atol` (a tenth of one Adam step).
     """
     got, want = np.asarray(got), np.asarray(want)
     assert got.shape == want.shape, err_msg
     diff = np.abs(got - want)
     bad = diff > atol + rtol * np.abs(want)
     assert np.isfinite(got).all(), err_msg
-    assert bad.mean() <= outlier_frac, f"{err_msg}: {bad.sum()} / {bad.size} elements beyond rtol={rtol}, atol={atol}"
+    # (at least two elements per table: the float atomics of the gradient scatter add in a different order every run, so
+    # WHICH nearly cancelled element lands beyond the tolerance varies from run to run on small tables)
+    allowed = max(2, int(outlier_frac * bad.size))
+    assert bad.sum() <= allowed, f"{err_msg}: {bad.sum()} / {bad.size} elements beyond rtol={rtol}, atol={atol}"
     assert diff.max() <= outlier_atol, f"{err_msg}: max abs diff {diff.max()} > {outlier_atol}"
