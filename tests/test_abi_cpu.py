@@ -178,3 +178,21 @@ def test_unsupported_configs_are_refused():
         make_product_model("TransE", 10, 8, 20, 5, 16, device="cpu", weight_decay=0.1)
     with pytest.raises(NotImplementedError):
         make_product_model("TransE", 10, 8, 20, 5, 16, device="cpu", clip_grad_norm={"max_norm": 5})
+
+
+def test_entry_points_the_reference_does_not_offer_are_refused_before_any_device_work():
+    """TransH has no KG scoring in the reference (transh.py); TransD's dense KG full-sort is not mirrored
+    (transd.py:192-217).  Both refuse by name, on any device."""
+    from kge_helpers import make_product_model
+
+    h = make_product_model("TransH", 10, 8, 20, 5, 16, device="cpu")
+    d = make_product_model("TransD", 10, 8, 20, 5, 16, device="cpu")
+    b = {"head_id": torch.tensor([1]), "relation_id": torch.tensor([1]), "tail_id": torch.tensor([2])}
+    for call in (lambda: h.predict_kg(b), lambda: h.full_sort_predict_kg(b), lambda: d.full_sort_predict_kg(b),
+                 lambda: d.full_sort_topk(torch.tensor([1]), 3, relation_ids=torch.tensor([1]))):
+        with pytest.raises(NotImplementedError):
+            call()
+    # and the compute paths of every model refuse CPU tensors instead of falling back
+    for m in (h, d):
+        with pytest.raises(RuntimeError, match="CUDA only"):
+            m.predict({"user_id": torch.tensor([1]), "item_id": torch.tensor([2])})
