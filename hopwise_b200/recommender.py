@@ -484,7 +484,7 @@ class FusedKGEModel(KnowledgeRecommender):
         listed = False
         if self._grad_sync is None and not self._owner_adam and self._state is not None:
             refs = int(b.n_rec) * (2 + int(b.k_rec)) + int(b.n_kg) * (3 + int(b.k_kg))
-            listed = refs <= self.LIST_ROWS_MAX
+            listed = 0 < refs <= self.LIST_ROWS_MAX
         # the optimiser kernel of a listed step zeroes the counters of the next one; after a step that was not listed
         # (or never applied) they are stale
         if listed and not self.__dict__.get("_listed_last", False):
